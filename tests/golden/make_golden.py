@@ -1,0 +1,176 @@
+#!/usr/bin/env python
+"""Generate golden vectors by running the UNMODIFIED reference code.
+
+Run in the build container only (needs /root/reference); the outputs
+(``tests/golden/*.npz``) are committed, this script is how they were made.
+
+  python tests/golden/make_golden.py
+
+1. ``evlfu_c1_*.npz``   -- /root/reference/cache_algo/EvLFU_C1.py driven one request
+   at a time on synthetic Zipf traces with a stub ``storage_manager`` whose rows
+   encode (table,row), so the returned tensors reveal which backing row answered.
+   Per request: hit vector, evicted keys, flushed keys, answering (table,row);
+   plus the final per-bucket FIFO lists.
+2. ``codecs.npz``       -- the reference's offline quantisers / dequantisers
+   (script/reduce_precision.py) evaluated on a fixed vector of floats.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+T = 26
+DIM = 36                     # the reference's hard-coded EV_DIMENSION
+KEY_SHIFT = 40
+
+
+def zipf_trace(rng, rows, n_req, alpha=1.05):
+    """[n_req, T] int64: per table, rank ~ r^-alpha mapped through a fixed permutation."""
+    out = np.empty((n_req, T), dtype=np.int64)
+    for t in range(T):
+        n = rows[t]
+        w = np.arange(1, n + 1, dtype=np.float64) ** (-alpha)
+        cdf = np.cumsum(w) / w.sum()
+        ranks = np.searchsorted(cdf, rng.random(n_req), side="left")
+        perm = np.random.default_rng(7 + t).permutation(n)
+        out[:, t] = perm[np.minimum(ranks, n - 1)]
+    return out
+
+
+class LogList(list):
+    """list that records pop(0) -- the only way EvLFU_C1 removes victims (:40,:55)."""
+
+    def __init__(self, events, bucket):
+        super().__init__()
+        self.events = events
+        self.bucket = bucket
+
+    def pop(self, i=-1):
+        k = super().pop(i)
+        self.events.append(("pop", self.bucket, k))
+        return k
+
+
+def str_key_to_int(k):
+    t, r = k.split("-")
+    return ((int(t) - 1) << KEY_SHIFT) | int(r)
+
+
+def run_reference_evlfu(trace, cap, approx_thres):
+    # stub storage_manager: row value = [table0, row, 0.5, ...] (exact in fp32)
+    sm = types.ModuleType("storage_manager")
+
+    def get_val(table_id, row_id):
+        v = [0.5] * DIM
+        v[0] = float(table_id - 1)
+        v[1] = float(row_id)
+        return v
+
+    sm.get_val_from_storage = get_val
+    sm.get_arr_val_from_storage = lambda keys: [get_val(t, r) for t, r in keys]
+    sys.modules["storage_manager"] = sm
+    sys.path.insert(0, os.path.join(REF, "cache_algo"))
+    sys.modules.pop("EvLFU_C1", None)
+    import EvLFU_C1 as ref  # noqa: the reference module itself
+
+    ref.init(cap)
+    events = []
+    for b in range(T + 1):
+        ref.lists_C1[b] = LogList(events, b)
+
+    def ref_print(*a, **k):           # the reference announces a flush with print (:37)
+        if a and a[0] == "flushing!":
+            events.append(("flush",))
+
+    ref.print = ref_print             # module-global lookup wins over the builtin
+    nf = int(0.3 * cap) + 1           # :39 -- pops that follow the announcement are the flush
+    n = len(trace)
+    hits = np.zeros((n, T), dtype=bool)
+    src_t = np.zeros((n, T), dtype=np.int32)
+    src_r = np.zeros((n, T), dtype=np.int64)
+    ev_keys, ev_off = [], [0]
+    fl_keys, fl_off = [], [0]
+    for i in range(n):
+        events.clear()
+        hit, embs = ref.request_to_ev_lfu([int(x) for x in trace[i]], False, approx_thres, DIM)
+        hits[i] = hit
+        for t in range(T):
+            v = embs[t][0]
+            tt, rr = float(v[0]), float(v[1])
+            if v[2] == 0.5 and tt == int(tt) and 0 <= tt < T:
+                src_t[i, t], src_r[i, t] = int(tt), int(rr)
+            else:                       # the reference's random fill (:104-107)
+                src_t[i, t], src_r[i, t] = -1, 0
+        flush_left = 0
+        for e in events:
+            if e[0] == "flush":
+                flush_left = nf
+            elif flush_left > 0:
+                assert e[1] == T
+                fl_keys.append(str_key_to_int(e[2]))
+                flush_left -= 1
+            else:
+                ev_keys.append(str_key_to_int(e[2]))
+        ev_off.append(len(ev_keys))
+        fl_off.append(len(fl_keys))
+    state_keys, state_off = [], [0]
+    for b in range(T + 1):
+        state_keys.extend(str_key_to_int(k) for k in ref.lists_C1[b])
+        state_off.append(len(state_keys))
+    return dict(hits=np.packbits(hits, axis=1), src_t=src_t.astype(np.int8), src_r=src_r.astype(np.int32),
+                ev_keys=np.array(ev_keys, dtype=np.int64), ev_off=np.array(ev_off, dtype=np.int32),
+                fl_keys=np.array(fl_keys, dtype=np.int64), fl_off=np.array(fl_off, dtype=np.int32),
+                state_keys=np.array(state_keys, dtype=np.int64), state_off=np.array(state_off, dtype=np.int32),
+                n_perfect=np.int64(ref.n_perfect_item_C1), min_bucket=np.int64(ref.min_C1))
+
+
+def golden_evlfu():
+    cases = [
+        # name, rows per table, n_req, cap, approx_thres, seed
+        ("evlfu_c1_small", [40 + 13 * t for t in range(T)], 2500, 300, -1, 42),
+        ("evlfu_c1_skew", [3, 5, 4000, 2500, 7, 4, 60, 9, 3, 300, 50, 3500, 40, 4, 80, 3000,
+                           5, 45, 30, 4, 3800, 6, 5, 600, 11, 400], 4000, 1500, -1, 43),
+        ("evlfu_c1_flush", [4 + (t % 3) for t in range(T)], 3000, 110, -1, 44),   # tiny tables -> perfect hits -> flushes
+        ("evlfu_c1_approx", [40 + 13 * t for t in range(T)], 2000, 400, 20, 45),
+    ]
+    for name, rows, n_req, cap, thres, seed in cases:
+        rng = np.random.default_rng(seed)
+        trace = zipf_trace(rng, rows, n_req)
+        g = run_reference_evlfu(trace, cap, thres)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), trace=trace.astype(np.int32),
+                            rows=np.array(rows, dtype=np.int64), cap=np.int64(cap),
+                            approx_thres=np.int64(thres), **g)
+        print(name, "requests", n_req, "evictions", len(g["ev_keys"]), "flushed", len(g["fl_keys"]),
+              "hit rate %.3f" % np.unpackbits(g["hits"], axis=1)[:, :T].mean())
+
+
+def golden_codecs():
+    sys.path.insert(0, os.path.join(REF, "script"))
+    sys.modules.pop("reduce_precision", None)
+    import reduce_precision as rp  # the reference's quantisers
+
+    rng = np.random.default_rng(99)
+    x = np.concatenate([
+        rng.uniform(-0.65, 0.65, 3000), rng.uniform(-1.0, 1.0, 1000), rng.normal(0, 0.01, 1000),
+        np.array([0.0, -0.0, 0.65, -0.65, 0.6501, -0.6501, 1.0, -1.0, 0.25, -0.25, 0.8, -0.8, 0.6, 0.4,
+                  0.015, 0.00025, -0.015, -0.00025, 1e-7, -1e-7, 0.999, -0.999]),
+    ]).astype(np.float32)
+    # the reference applies the lambdas to a float32 pandas column under NumPy 1.x, where
+    # np.float32 (op) python-float promotes to float64; feed python floats to get that.
+    xs = [float(v) for v in x]
+    q16 = np.array([rp.convert_ev_float_to_ushort(v) for v in xs], dtype=np.int64)
+    d16 = np.array([rp.convert_ushort_to_evfloat(int(v)) for v in q16], dtype=np.float64)
+    q8 = np.array([round(((v + 1) / 2) * 254) for v in xs], dtype=np.int64)          # :270
+    d8 = np.array([round(((int(v) / 254) * 2) - 1, 3) for v in q8], dtype=np.float64)  # :283
+    q4 = np.array([rp.convert_to_4bit_int_posit(v) for v in xs], dtype=np.int64)
+    d4 = np.array([rp.convert_from_4bit_int_posit(int(min(v, 14))) for v in q4], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "codecs.npz"), x=x, q16=q16, d16=d16, q8=q8, d8=d8, q4=q4, d4=d4)
+    print("codecs", len(x), "values; q16 max", q16.max(), "q4 range", q4.min(), q4.max())
+
+
+if __name__ == "__main__":
+    golden_evlfu()
+    golden_codecs()
