@@ -1,0 +1,215 @@
+"""Host-side handle of the GPU cache: the runtime-configured counterpart of the reference's
+mixed_precs_caching/cache_manager.cpp (whose configuration is compile-time #defines).
+
+``EvStore`` owns one evs_handle (include/evstore_b200.h).  Device tensors go straight to
+``evs_lookup_batch``; host arrays go through ``evs_lookup_batch_host``.  There is no CPU
+fallback: construction raises when the CUDA library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _native
+from .codecs import encode_table, row_bytes
+
+
+@dataclass
+class CacheConfig:
+    """Mirrors cache_manager.cpp:13-20 (+ EV_DIMENSION / N_EV_TABLE)."""
+    n_layers: int = 1                 # N_CACHING_LAYER
+    main_precision: int = 32          # MAIN_PRECISION
+    secondary_precision: int = 0      # SECONDARY_PRECISION
+    total_size: int = 75425           # TOTAL_SIZE (fp32-row units)
+    size_proportion: str = ""         # SIZE_PROPORTION "c1-c2-c3"
+    max_batch: int = 2048
+    approx_emb_thres: int = -1        # EvLFU_C1.request_to_ev_lfu(approx_emb_thres)
+    device: int = 0
+    n_tables_total: int = 0           # agg_hit range; 0 = n_tables
+    table_base: int = 0
+    store_in_hbm: bool = False
+    record_events: bool = False
+    flush_rate: float = 0.0
+    perfect_item_cap: float = 0.0
+    high_agghit_threshold: int = 0
+    extra: dict = field(default_factory=dict)
+
+    def proportions(self):
+        if not self.size_proportion:
+            return 0, 0, 0
+        a, b, c = (int(x) for x in self.size_proportion.split("-"))
+        return a, b, c
+
+
+def _ptr_array(arrays):
+    arr = (C.c_void_p * len(arrays))()
+    for i, a in enumerate(arrays):
+        arr[i] = a.ctypes.data
+    return arr
+
+
+class EvStore:
+    def __init__(self, tables_fp32, cfg: CacheConfig, stores: dict | None = None, alt_keys=None):
+        """tables_fp32: list of [rows, dim] float32 arrays (the trained embedding tables).
+        stores: optional {precision: [raw rows per table]} if the quantised files already exist;
+        otherwise they are derived from the fp32 tables with the reference's quantisers."""
+        self.lib = _native.load_library()
+        self.cfg = cfg
+        self.n_tables = len(tables_fp32)
+        self.dim = int(tables_fp32[0].shape[1])
+        self.rows = np.array([t.shape[0] for t in tables_fp32], dtype=np.int64)
+        stores = dict(stores or {})
+        need = [cfg.main_precision] + ([cfg.secondary_precision] if cfg.n_layers >= 2 else [])
+        self._stores = {}
+        for p in need:
+            rb = row_bytes(self.dim, p)
+            tabs = stores.get(p) or [encode_table(t, p) for t in tables_fp32]
+            for t, a in zip(tables_fp32, tabs):
+                if not a.flags["C_CONTIGUOUS"] or a.nbytes != t.shape[0] * rb:
+                    raise ValueError(f"backing rows at {p} bits must be C-contiguous [rows, {rb} B]")
+            self._stores[p] = tabs                                   # keep alive: the GPU reads them in place
+        self._alt = None
+        c = _native.EvsConfig()
+        c.device = cfg.device
+        c.n_tables = self.n_tables
+        c.n_tables_total = cfg.n_tables_total or self.n_tables
+        c.table_base = cfg.table_base
+        c.dim = self.dim
+        c.n_layers = cfg.n_layers
+        c.main_precision = cfg.main_precision
+        c.secondary_precision = cfg.secondary_precision
+        c.total_size = cfg.total_size
+        c.prop_c1, c.prop_c2, c.prop_c3 = cfg.proportions()
+        c.max_batch = cfg.max_batch
+        c.approx_emb_thres = cfg.approx_emb_thres
+        c.high_agghit_threshold = cfg.high_agghit_threshold
+        c.flush_rate = cfg.flush_rate
+        c.perfect_item_cap = cfg.perfect_item_cap
+        c.rows = self.rows.ctypes.data_as(C.POINTER(C.c_int64))
+        self._main_ptrs = _ptr_array(self._stores[cfg.main_precision])
+        c.store_main = C.cast(self._main_ptrs, C.POINTER(C.c_void_p))
+        if cfg.n_layers >= 2:
+            self._sec_ptrs = _ptr_array(self._stores[cfg.secondary_precision])
+            c.store_secondary = C.cast(self._sec_ptrs, C.POINTER(C.c_void_p))
+        if cfg.n_layers == 3:
+            if alt_keys is None:
+                raise ValueError("n_layers == 3 needs alt_keys (one uint32 array per table)")
+            self._alt = [np.ascontiguousarray(a, dtype=np.uint32) for a in alt_keys]
+            self._alt_ptrs = _ptr_array(self._alt)
+            c.alt_keys = C.cast(self._alt_ptrs, C.POINTER(C.c_void_p))
+        c.store_in_hbm = int(cfg.store_in_hbm)
+        c.record_events = int(cfg.record_events)
+        self._c = c
+        self.handle = C.c_void_p()
+        _native.check(self.lib.evs_create(C.byref(c), C.byref(self.handle)), "evs_create")
+
+    # ---- hot path ------------------------------------------------------------------------
+    def lookup(self, lS_i, out=None, hit=None, agg_in=None, stream=None):
+        """lS_i: int64 CUDA tensor [n_tables, B].  Returns (out [B, n_tables, dim] fp32, hit [B, n_tables] uint8)."""
+        import torch
+        assert lS_i.is_cuda and lS_i.dtype == torch.int64 and lS_i.is_contiguous()
+        T, B = lS_i.shape
+        assert T == self.n_tables
+        if out is None:
+            out = torch.empty((B, T, self.dim), dtype=torch.float32, device=lS_i.device)
+        if hit is None:
+            hit = torch.empty((B, T), dtype=torch.uint8, device=lS_i.device)
+        st = stream if stream is not None else torch.cuda.current_stream(lS_i.device).cuda_stream
+        stride = out.stride(0)
+        rc = self.lib.evs_lookup_batch(self.handle, lS_i.data_ptr(), B, out.data_ptr(), stride, hit.data_ptr(),
+                                       agg_in.data_ptr() if agg_in is not None else None, st)
+        _native.check(rc, "evs_lookup_batch")
+        return out, hit
+
+    def probe(self, lS_i, agg_out=None, stream=None):
+        import torch
+        T, B = lS_i.shape
+        if agg_out is None:
+            agg_out = torch.empty((B,), dtype=torch.uint8, device=lS_i.device)
+        st = stream if stream is not None else torch.cuda.current_stream(lS_i.device).cuda_stream
+        _native.check(self.lib.evs_probe_batch(self.handle, lS_i.data_ptr(), B, agg_out.data_ptr(), st), "evs_probe_batch")
+        return agg_out
+
+    def lookup_host(self, idx: np.ndarray, out: np.ndarray | None = None, hit: np.ndarray | None = None):
+        """idx: int64 host array [n_tables, B] (numpy or a pinned torch tensor's numpy view)."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        T, B = idx.shape
+        assert T == self.n_tables
+        if out is None:
+            out = np.empty((B, T, self.dim), dtype=np.float32)
+        if hit is None:
+            hit = np.empty((B, T), dtype=np.uint8)
+        rc = self.lib.evs_lookup_batch_host(self.handle, idx.ctypes.data, B, out.ctypes.data, hit.ctypes.data)
+        _native.check(rc, "evs_lookup_batch_host")
+        return out, hit
+
+    def lookup_host_ptr(self, idx_ptr: int, B: int, out_ptr: int, hit_ptr: int = 0):
+        _native.check(self.lib.evs_lookup_batch_host(self.handle, idx_ptr, B, out_ptr, hit_ptr or None),
+                      "evs_lookup_batch_host")
+
+    def interact(self, x, ly, out=None, stream=None):
+        """dlrm interact_features (dot): x [B, d], ly [B, n_f, d] -> [B, d + (n_f+1) n_f / 2]."""
+        import torch
+        B, d = x.shape
+        n_f = ly.shape[1]
+        if out is None:
+            out = torch.empty((B, d + (n_f + 1) * n_f // 2), dtype=torch.float32, device=x.device)
+        st = stream if stream is not None else torch.cuda.current_stream(x.device).cuda_stream
+        _native.check(self.lib.evs_interact(x.data_ptr(), ly.data_ptr(), out.data_ptr(), B, n_f, d, st), "evs_interact")
+        return out
+
+    # ---- bookkeeping ---------------------------------------------------------------------
+    def sync(self):
+        _native.check(self.lib.evs_sync(self.handle), "evs_sync")
+
+    def stats(self, reset: bool = False) -> dict:
+        s = _native.EvsStats()
+        _native.check(self.lib.evs_stats(self.handle, C.byref(s), int(reset)), "evs_stats")
+        return s.as_dict()
+
+    def last_events(self, tier: int = 0):
+        cap_e = self.cfg.max_batch * self.n_tables
+        cap_f = int(self.stats()["capacity"][tier] * 0.35) + 8
+        ev = np.empty(cap_e, dtype=np.int64)
+        fl = np.empty(cap_f, dtype=np.int64)
+        ne, nf = C.c_int64(cap_e), C.c_int64(cap_f)
+        _native.check(self.lib.evs_last_events(self.handle, tier, ev.ctypes.data, C.byref(ne), fl.ctypes.data, C.byref(nf)),
+                      "evs_last_events")
+        return ev[:ne.value].copy(), fl[:nf.value].copy()
+
+    def dump_state(self, tier: int = 0):
+        """Per agg_hit bucket, the resident keys in eviction (FIFO) order, and n_perfect."""
+        st = self.stats()
+        cap = int(st["size"][tier]) + 8
+        keys = np.empty(cap, dtype=np.int64)
+        nb = (self.cfg.n_tables_total or self.n_tables) + 2
+        off = np.zeros(nb, dtype=np.int64)
+        n = C.c_int64(cap)
+        npf = C.c_int64(0)
+        _native.check(self.lib.evs_dump_state(self.handle, tier, keys.ctypes.data, C.byref(n), off.ctypes.data, C.byref(npf)),
+                      "evs_dump_state")
+        return [keys[off[b]:off[b + 1]].tolist() for b in range(nb - 1)], int(npf.value)
+
+    def dump_c3(self):
+        st = self.stats()
+        cap = int(st["c3_capacity"]) + 8
+        keys = np.empty(cap, dtype=np.int64)
+        alt = np.empty(cap, dtype=np.uint32)
+        rec = np.empty(cap, dtype=np.uint8)
+        n = C.c_int64(cap)
+        _native.check(self.lib.evs_dump_c3(self.handle, keys.ctypes.data, alt.ctypes.data, rec.ctypes.data, C.byref(n)),
+                      "evs_dump_c3")
+        return keys[:n.value].copy(), alt[:n.value].copy(), rec[:n.value].copy()
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.evs_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

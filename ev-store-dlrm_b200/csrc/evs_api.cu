@@ -1,0 +1,641 @@
+// C-ABI implementation (include/evstore_b200.h): handle life cycle, per-batch kernel
+// sequence, host-buffer path, stats / introspection, legacy libcachemanager.so symbols.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "evs_host.h"
+#include "evs_interact.cuh"
+#include "evs_kernels.cuh"
+#include "evs_tiers.cuh"
+
+namespace evs {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+static unsigned next_pow2(unsigned long long v) {
+    unsigned long long p = 1;
+    while (p < v) p <<= 1;
+    return static_cast<unsigned>(p);
+}
+
+// Entry capacities exactly as the reference's constructors compute them, quirks included:
+//   cache_manager.cpp:22-52   cacheSize = TOTAL_SIZE, TOTAL_SIZE/2 (2 layers); main 16 -> *2, main 4 -> *8,
+//                             main 8 gets TOTAL_SIZE and splits inside its constructor
+//   evlfu_32.cpp:99-105       C2 of a 32-bit C1: 16 -> cap*2, 8 -> EVLFU_8BIT(cap*4), 4 -> cap*8
+//   evlfu_16.cpp:93-98        C2 of a 16-bit C1: 8 -> EVLFU_8BIT(cap*2), 4 -> cap*4
+//   evlfu_8.cpp:57-95         EVLFU_8BIT(total): 1 layer total*4; 2 layers total/2*4 and total/2*8;
+//                             3 layers (p*total/100)*4, *8, *36 or total/3*4, *8, *36
+//     -> an 8-bit C2 is constructed through that same constructor, so it is multiplied by 4 twice.
+//   The literal 36 is EV_DIMENSION (one fp32 row holds EV_DIMENSION 4-byte alt keys); we use cfg.dim.
+int compute_caps(const evs_config &cfg, Caps &out) {
+    const long long total = cfg.total_size;
+    const int mp = cfg.main_precision, sp = cfg.secondary_precision;
+    if (total <= 0) return EVS_ERR_INVALID;
+    auto prec_ok = [](int p) { return p == 32 || p == 16 || p == 8 || p == 4; };
+    if (!prec_ok(mp)) return EVS_ERR_INVALID;
+    out = Caps();
+    if (cfg.n_layers == 1) {
+        out.c1 = total * (32 / mp);
+        return EVS_OK;
+    }
+    if (!prec_ok(sp) || sp >= mp) return EVS_ERR_INVALID;
+    if (cfg.n_layers == 2) {
+        const long long cs = total / 2;
+        if (mp == 32) {
+            out.c1 = cs;
+            out.c2 = (sp == 16) ? cs * 2 : (sp == 8) ? cs * 4 * 4 : cs * 8;
+        } else if (mp == 16) {
+            out.c1 = cs * 2;
+            out.c2 = (sp == 8) ? out.c1 * 2 * 4 : out.c1 * 4;
+        } else if (mp == 8) {
+            out.c1 = cs * 4;
+            out.c2 = cs * 8;
+        } else {
+            return EVS_ERR_INVALID;
+        }
+        return EVS_OK;
+    }
+    if (cfg.n_layers == 3) {
+        if (mp != 8 || sp != 4) return EVS_ERR_INVALID;      // cache_manager.cpp:212-220
+        if (cfg.prop_c1 || cfg.prop_c2 || cfg.prop_c3) {
+            if (cfg.prop_c1 + cfg.prop_c2 + cfg.prop_c3 != 100) return EVS_ERR_INVALID;
+            out.c1 = (cfg.prop_c1 * total / 100) * 4;
+            out.c2 = (cfg.prop_c2 * total / 100) * 8;
+            out.c3 = (cfg.prop_c3 * total / 100) * cfg.dim;
+        } else {
+            out.c1 = total / 3 * 4;
+            out.c2 = total / 3 * 8;
+            out.c3 = total / 3 * cfg.dim;
+        }
+        return EVS_OK;
+    }
+    return EVS_ERR_INVALID;
+}
+
+template <typename T>
+static int dev_alloc(std::vector<void *> &owner, T **p, size_t n, bool zero = true) {
+    void *q = nullptr;
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    EVS_CUDA(cudaMalloc(&q, bytes));
+    owner.push_back(q);
+    if (zero) EVS_CUDA(cudaMemset(q, 0, bytes));
+    *p = static_cast<T *>(q);
+    return EVS_OK;
+}
+
+static int make_store(evs_handle h, const void *const *ptrs, int prec, std::vector<const unsigned char *> &out) {
+    const evs_config &c = h->cfg;
+    out.clear();
+    for (int t = 0; t < c.n_tables; ++t) {
+        const size_t bytes = static_cast<size_t>(h->rows[t]) * c.dim * prec / 8;
+        if (ptrs == nullptr || ptrs[t] == nullptr) {
+            set_error("backing store pointer missing for table " + std::to_string(t));
+            return EVS_ERR_INVALID;
+        }
+        if (c.store_in_hbm) {
+            unsigned char *d = nullptr;
+            int rc = dev_alloc(h->dev_allocs, &d, bytes + 16, false);
+            if (rc) return rc;
+            EVS_CUDA(cudaMemcpy(d, ptrs[t], bytes, cudaMemcpyHostToDevice));
+            out.push_back(d);
+        } else {
+            void *hp = const_cast<void *>(ptrs[t]);
+            cudaError_t e = cudaHostRegister(hp, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+            if (e == cudaSuccess) {
+                h->registered.push_back(hp);
+            } else if (e == cudaErrorHostMemoryAlreadyRegistered) {
+                cudaGetLastError();
+            } else {
+                set_error(std::string("cudaHostRegister(table ") + std::to_string(t) + ", " + std::to_string(bytes) +
+                          " B) -> " + cudaGetErrorString(e));
+                cudaGetLastError();
+                return EVS_ERR_CUDA;
+            }
+            void *dp = nullptr;
+            EVS_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+            out.push_back(static_cast<const unsigned char *>(dp));
+        }
+    }
+    return EVS_OK;
+}
+
+static int build_tier(evs_handle h, Tier &tr, int prec, long long cap, const void *const *store) {
+    const evs_config &c = h->cfg;
+    const long long n_max = static_cast<long long>(c.max_batch) * c.n_tables;
+    if (cap < 32) {
+        set_error("tier capacity below 32 entries");
+        return EVS_ERR_INVALID;
+    }
+    const long long rows_total = cap + n_max;
+    if (rows_total >= static_cast<long long>(kRowMask)) {
+        set_error("tier too large: rows must fit 27 bits");
+        return EVS_ERR_INVALID;
+    }
+    TierDev &d = tr.dev;
+    tr.prec = prec;
+    d.prec = prec;
+    d.cap = static_cast<unsigned>(cap);
+    d.rows_total = static_cast<unsigned>(rows_total);
+    d.row_bytes = static_cast<unsigned>(c.dim * prec / 8);
+    d.row_stride = (d.row_bytes + 15u) & ~15u;
+    const float pic = c.perfect_item_cap > 0 ? c.perfect_item_cap : 0.95f;
+    const float fr = c.flush_rate > 0 ? c.flush_rate : 0.3f;
+    d.max_perfect = static_cast<unsigned>(static_cast<int>(static_cast<double>(cap) * static_cast<double>(pic)));
+    d.flush_n = static_cast<unsigned>(static_cast<int>(static_cast<double>(fr) * static_cast<double>(cap))) + 1u;
+    d.n_buckets = c.n_tables_total + 1;
+    const unsigned hash_cap = next_pow2(static_cast<unsigned long long>(rows_total) * 2);
+    d.hash_mask = hash_cap - 1;
+    d.ring_cap = next_pow2(static_cast<unsigned long long>(std::max(2 * rows_total, rows_total + 4 * n_max)));
+    int rc;
+    if ((rc = dev_alloc(tr.allocs, &d.slots, hash_cap, false))) return rc;
+    if ((rc = dev_alloc(tr.allocs, &d.slab, static_cast<size_t>(rows_total) * d.row_stride, true))) return rc;
+    if ((rc = dev_alloc(tr.allocs, &d.row_meta, rows_total, false))) return rc;
+    if ((rc = dev_alloc(tr.allocs, &d.row_key, rows_total, false))) return rc;
+    if ((rc = dev_alloc(tr.allocs, &d.row_slot, rows_total, false))) return rc;
+    if ((rc = dev_alloc(tr.allocs, &d.free_rows, rows_total, false))) return rc;
+    if ((rc = dev_alloc(tr.allocs, &d.ring, static_cast<size_t>(d.n_buckets) * d.ring_cap, false))) return rc;
+    if ((rc = dev_alloc(tr.allocs, &d.ctl, 1, true))) return rc;
+    const long long n_chunks = (c.max_batch + kSamplesPerCta - 1) / kSamplesPerCta;
+    if ((rc = dev_alloc(tr.allocs, &d.flags, n_max, true))) return rc;
+    if ((rc = dev_alloc(tr.allocs, &d.pos_slot, n_max, true))) return rc;
+    if ((rc = dev_alloc(tr.allocs, &d.miss_list, n_max, true))) return rc;
+    if ((rc = dev_alloc(tr.allocs, &d.hist, n_chunks * kMaxBuckets, true))) return rc;
+    if ((rc = dev_alloc(tr.allocs, &d.evicted, n_max, true))) return rc;
+    d.flushed = nullptr;
+    if (c.record_events)
+        if ((rc = dev_alloc(tr.allocs, &d.flushed, d.flush_n, true))) return rc;
+
+    if ((rc = make_store(h, store, prec, tr.store_dev))) return rc;
+    const unsigned char **dstore = nullptr;
+    if ((rc = dev_alloc(tr.allocs, &dstore, c.n_tables, false))) return rc;
+    EVS_CUDA(cudaMemcpy(dstore, tr.store_dev.data(), sizeof(void *) * c.n_tables, cudaMemcpyHostToDevice));
+    d.store = dstore;
+
+    k_init_tier<<<592, 256, 0, h->stream>>>(d);
+    EVS_CUDA(cudaGetLastError());
+    TierCtl init{};
+    init.free_top = d.rows_total;
+    EVS_CUDA(cudaMemcpyAsync(d.ctl, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+    EVS_CUDA(cudaStreamSynchronize(h->stream));
+    tr.ub_used = 0;
+    return EVS_OK;
+}
+
+static void free_all(evs_handle h) {
+    if (h == nullptr) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < EVS_MAX_TIERS; ++i)
+        for (void *p : h->tier[i].allocs) cudaFree(p);
+    for (void *p : h->c3_allocs) cudaFree(p);
+    for (void *p : h->dev_allocs) cudaFree(p);
+    for (void *p : h->registered) cudaHostUnregister(p);
+    delete h->c3;
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+}
+
+// Keep every bucket ring from overflowing: the host only tracks an upper bound of the
+// occupancy and looks at the real head/tail when that bound gets close to the ring size.
+static int maintain_rings(evs_handle h, Tier &tr, cudaStream_t st) {
+    const unsigned long long n_max = static_cast<unsigned long long>(h->cfg.max_batch) * h->cfg.n_tables;
+    if (tr.ub_used + 2 * n_max <= tr.dev.ring_cap) return EVS_OK;
+    TierCtl ctl;
+    EVS_CUDA(cudaStreamSynchronize(st));
+    EVS_CUDA(cudaMemcpy(&ctl, tr.dev.ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
+    bool any = false;
+    for (int b = 0; b < tr.dev.n_buckets; ++b) {
+        if (ctl.tail[b] - ctl.head[b] + 2 * n_max > tr.dev.ring_cap) {
+            k_compact<<<1, 1024, 0, st>>>(tr.dev, b);
+            any = true;
+        }
+    }
+    EVS_CUDA(cudaGetLastError());
+    if (any) {
+        EVS_CUDA(cudaStreamSynchronize(st));
+        EVS_CUDA(cudaMemcpy(&ctl, tr.dev.ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
+    }
+    unsigned long long mx = 0;
+    for (int b = 0; b < tr.dev.n_buckets; ++b) mx = std::max(mx, ctl.tail[b] - ctl.head[b]);
+    tr.ub_used = mx;
+    return EVS_OK;
+}
+
+template <int PREC>
+static void launch_single_tier(evs_handle h, Tier &tr, const LookupArgs &a, cudaStream_t st) {
+    const int n_chunks = (a.B + kSamplesPerCta - 1) / kSamplesPerCta;
+    k_lookup<PREC><<<n_chunks, kLookupThreads, 0, st>>>(tr.dev, a);
+    const int miss_ctas = std::min(n_chunks, 592);
+    k_miss<PREC><<<miss_ctas, 256, 8 * tr.dev.row_stride, st>>>(tr.dev, a);
+    k_hist_scan<<<1, 1024, 0, st>>>(tr.dev, n_chunks);
+    k_append<<<n_chunks, kLookupThreads, 0, st>>>(tr.dev, a.B, a.T);
+    k_evict<<<1, 1024, 0, st>>>(tr.dev, a.g);
+}
+
+static int check_device_errors(evs_handle h) {
+    GlobalCtl g;
+    EVS_CUDA(cudaMemcpy(&g, h->g, sizeof(g), cudaMemcpyDeviceToHost));
+    if (g.error) {
+        unsigned zero = 0;
+        cudaMemcpy(&h->g->error, &zero, sizeof(zero), cudaMemcpyHostToDevice);
+        set_error("an index was outside [0, rows[table])");
+        return EVS_ERR_INDEX;
+    }
+    for (int i = 0; i < h->n_tiers; ++i) {
+        TierCtl c;
+        EVS_CUDA(cudaMemcpy(&c, h->tier[i].dev.ctl, sizeof(c), cudaMemcpyDeviceToHost));
+        if (c.error) {
+            set_error("tier " + std::to_string(i) + ": internal capacity error " + std::to_string(c.error));
+            return EVS_ERR_CAPACITY;
+        }
+    }
+    return EVS_OK;
+}
+
+}  // namespace evs
+
+using namespace evs;
+
+extern "C" {
+
+int evs_version(void) { return 100; }
+
+const char *evs_last_error(void) { return g_last_error.c_str(); }
+
+int evs_create(const evs_config *cfg, evs_handle *out) {
+    if (cfg == nullptr || out == nullptr) return EVS_ERR_INVALID;
+    *out = nullptr;
+    if (cfg->n_tables < 1 || cfg->n_tables > EVS_MAX_TABLES || cfg->dim < 1 || cfg->max_batch < 1 ||
+        cfg->rows == nullptr || cfg->n_layers < 1 || cfg->n_layers > 3) {
+        set_error("evs_create: bad n_tables / dim / max_batch / rows / n_layers");
+        return EVS_ERR_INVALID;
+    }
+    evs_handle h = new evs_handle_s();
+    h->cfg = *cfg;
+    if (h->cfg.n_tables_total <= 0) h->cfg.n_tables_total = cfg->n_tables;
+    if (h->cfg.n_tables_total > 31 || h->cfg.n_tables_total < cfg->n_tables + 0 * cfg->table_base) {
+        set_error("evs_create: n_tables_total must be in [n_tables, 31]");
+        delete h;
+        return EVS_ERR_INVALID;
+    }
+    if (h->cfg.high_agghit_threshold <= 0) h->cfg.high_agghit_threshold = 23;
+    if ((static_cast<long long>(cfg->dim) * cfg->main_precision) % 8 != 0) {
+        set_error("evs_create: dim*precision must be a whole number of bytes");
+        delete h;
+        return EVS_ERR_INVALID;
+    }
+    h->rows.assign(cfg->rows, cfg->rows + cfg->n_tables);
+    h->cfg.rows = h->rows.data();
+    for (int t = 0; t < cfg->n_tables; ++t) {
+        if (h->rows[t] < 1 || h->rows[t] >= (1ll << kKeyShift)) {
+            set_error("evs_create: rows[t] out of range");
+            delete h;
+            return EVS_ERR_INVALID;
+        }
+    }
+    int rc = compute_caps(h->cfg, h->caps);
+    if (rc) {
+        set_error("evs_create: unsupported layer / precision / size combination");
+        delete h;
+        return rc;
+    }
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) {
+        set_error(std::string("cudaSetDevice -> ") + cudaGetErrorString(e));
+        delete h;
+        return EVS_ERR_CUDA;
+    }
+    auto fail = [&](int code) {
+        free_all(h);
+        return code;
+    };
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        return fail(EVS_ERR_CUDA);
+    }
+    const long long n_max = static_cast<long long>(cfg->max_batch) * cfg->n_tables;
+    if ((rc = dev_alloc(h->dev_allocs, &h->g, 1))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &h->d_rows, cfg->n_tables))) return fail(rc);
+    if (cudaMemcpy(h->d_rows, h->rows.data(), sizeof(int64_t) * cfg->n_tables, cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(EVS_ERR_CUDA);
+    if ((rc = dev_alloc(h->dev_allocs, &h->d_agg, cfg->max_batch))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &h->d_idx, n_max))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &h->d_out, n_max * cfg->dim))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &h->d_hit, n_max))) return fail(rc);
+
+    h->n_tiers = cfg->n_layers >= 2 ? 2 : 1;
+    if ((rc = build_tier(h, h->tier[0], cfg->main_precision, h->caps.c1, cfg->store_main))) return fail(rc);
+    if (h->n_tiers == 2)
+        if ((rc = build_tier(h, h->tier[1], cfg->secondary_precision, h->caps.c2, cfg->store_secondary))) return fail(rc);
+    if (cfg->n_layers == 3 && h->caps.c3 > 0) {
+        if ((rc = c3_build(h))) return fail(rc);
+        h->c3_active = true;
+    }
+    *out = h;
+    return EVS_OK;
+}
+
+int evs_destroy(evs_handle h) {
+    if (h == nullptr) return EVS_ERR_INVALID;
+    free_all(h);
+    return EVS_OK;
+}
+
+int evs_lookup_batch(evs_handle h, const int64_t *idx_dev, int32_t B, float *out_dev, int64_t out_stride,
+                     uint8_t *hit_dev, const uint8_t *agg_in, void *stream) {
+    if (h == nullptr || B < 0 || B > h->cfg.max_batch || (B > 0 && (idx_dev == nullptr || out_dev == nullptr))) {
+        set_error("evs_lookup_batch: bad handle / B / pointers");
+        return EVS_ERR_INVALID;
+    }
+    if (B == 0) return EVS_OK;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    LookupArgs a{};
+    a.idx = reinterpret_cast<const long long *>(idx_dev);
+    a.rows = h->d_rows;
+    a.out = out_dev;
+    a.out_stride = out_stride > 0 ? out_stride : static_cast<long long>(h->cfg.n_tables) * h->cfg.dim;
+    a.hit = hit_dev;
+    a.agg_in = agg_in;
+    a.agg_out = h->d_agg;
+    a.B = B;
+    a.T = h->cfg.n_tables;
+    a.D = h->cfg.dim;
+    a.table_base = h->cfg.table_base;
+    a.n_perfect_agg = h->cfg.n_tables_total;
+    a.approx_thres = h->cfg.approx_emb_thres;
+    a.g = h->g;
+    int rc = EVS_OK;
+    if (h->n_tiers == 1) {
+        Tier &tr = h->tier[0];
+        switch (tr.prec) {
+            case 32: launch_single_tier<32>(h, tr, a, st); break;
+            case 16: launch_single_tier<16>(h, tr, a, st); break;
+            case 8: launch_single_tier<8>(h, tr, a, st); break;
+            default: launch_single_tier<4>(h, tr, a, st); break;
+        }
+    } else {
+        rc = launch_multi_tier(h, a, st);
+        if (rc) return rc;
+    }
+    EVS_CUDA(cudaGetLastError());
+    h->batches++;
+    for (int i = 0; i < h->n_tiers; ++i) {
+        h->tier[i].ub_used += static_cast<unsigned long long>(B) * a.T;
+        if ((rc = maintain_rings(h, h->tier[i], st))) return rc;
+    }
+    return EVS_OK;
+}
+
+int evs_probe_batch(evs_handle h, const int64_t *idx_dev, int32_t B, uint8_t *agg_out_dev, void *stream) {
+    if (h == nullptr || B < 0 || B > h->cfg.max_batch || idx_dev == nullptr || agg_out_dev == nullptr) return EVS_ERR_INVALID;
+    if (h->n_tiers != 1) {
+        set_error("evs_probe_batch: single-tier caches only");
+        return EVS_ERR_INVALID;
+    }
+    if (B == 0) return EVS_OK;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    LookupArgs a{};
+    a.idx = reinterpret_cast<const long long *>(idx_dev);
+    a.rows = h->d_rows;
+    a.agg_out = agg_out_dev;
+    a.B = B;
+    a.T = h->cfg.n_tables;
+    a.D = h->cfg.dim;
+    a.table_base = h->cfg.table_base;
+    a.g = h->g;
+    k_probe<<<(B + kSamplesPerCta - 1) / kSamplesPerCta, kLookupThreads, 0, st>>>(h->tier[0].dev, a);
+    EVS_CUDA(cudaGetLastError());
+    return EVS_OK;
+}
+
+int evs_lookup_batch_host(evs_handle h, const int64_t *idx_host, int32_t B, float *out_host, uint8_t *hit_host) {
+    if (h == nullptr || B < 0 || B > h->cfg.max_batch || (B > 0 && (idx_host == nullptr || out_host == nullptr))) {
+        set_error("evs_lookup_batch_host: bad handle / B / pointers");
+        return EVS_ERR_INVALID;
+    }
+    if (B == 0) return EVS_OK;
+    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t n = static_cast<size_t>(B) * h->cfg.n_tables;
+    EVS_CUDA(cudaMemcpyAsync(h->d_idx, idx_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    int rc = evs_lookup_batch(h, reinterpret_cast<const int64_t *>(h->d_idx), B, h->d_out, 0, h->d_hit, nullptr, h->stream);
+    if (rc) return rc;
+    EVS_CUDA(cudaMemcpyAsync(out_host, h->d_out, n * h->cfg.dim * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (hit_host != nullptr) EVS_CUDA(cudaMemcpyAsync(hit_host, h->d_hit, n, cudaMemcpyDeviceToHost, h->stream));
+    EVS_CUDA(cudaStreamSynchronize(h->stream));
+    return EVS_OK;
+}
+
+int evs_sync(evs_handle h) {
+    if (h == nullptr) return EVS_ERR_INVALID;
+    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    EVS_CUDA(cudaDeviceSynchronize());
+    return check_device_errors(h);
+}
+
+int evs_stats(evs_handle h, evs_stats_t *out, int reset) {
+    if (h == nullptr || out == nullptr) return EVS_ERR_INVALID;
+    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    EVS_CUDA(cudaDeviceSynchronize());
+    GlobalCtl g;
+    EVS_CUDA(cudaMemcpy(&g, h->g, sizeof(g), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->lookups = g.lookups;
+    out->samples = g.samples;
+    out->hits[0] = g.hits[0];
+    out->hits[1] = g.hits[1];
+    out->c3_hits = g.c3_hits;
+    out->approx_subst = g.approx_subst;
+    out->misses = g.misses;
+    out->perfect_hits = g.perfect_hits;
+    out->batches = g.batches;
+    for (int i = 0; i < h->n_tiers; ++i) {
+        TierCtl c;
+        EVS_CUDA(cudaMemcpy(&c, h->tier[i].dev.ctl, sizeof(c), cudaMemcpyDeviceToHost));
+        out->inserts[i] = c.stat_inserts;
+        out->evictions[i] = c.stat_evictions;
+        out->flushed[i] = c.stat_flushed;
+        uint64_t sz = 0;
+        for (int b = 0; b < h->tier[i].dev.n_buckets; ++b) sz += c.count[b];
+        out->size[i] = sz;
+        out->capacity[i] = h->tier[i].dev.cap;
+        if (reset) {
+            c.stat_inserts = c.stat_evictions = c.stat_flushed = 0;
+            EVS_CUDA(cudaMemcpy(h->tier[i].dev.ctl, &c, sizeof(c), cudaMemcpyHostToDevice));
+        }
+    }
+    if (h->c3_active) c3_stats(h, &out->c3_size, &out->c3_capacity);
+    if (reset) {
+        const unsigned err = g.error;
+        memset(&g, 0, sizeof(g));
+        g.error = err;
+        EVS_CUDA(cudaMemcpy(h->g, &g, sizeof(g), cudaMemcpyHostToDevice));
+    }
+    return EVS_OK;
+}
+
+int evs_last_events(evs_handle h, int tier, int64_t *evicted, int64_t *n_evicted, int64_t *flushed, int64_t *n_flushed) {
+    if (h == nullptr || tier < 0 || tier >= h->n_tiers || n_evicted == nullptr || n_flushed == nullptr) return EVS_ERR_INVALID;
+    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    EVS_CUDA(cudaDeviceSynchronize());
+    TierCtl c;
+    const TierDev &d = h->tier[tier].dev;
+    EVS_CUDA(cudaMemcpy(&c, d.ctl, sizeof(c), cudaMemcpyDeviceToHost));
+    if (c.n_evicted_last > *n_evicted || c.n_flushed_last > *n_flushed) {
+        set_error("evs_last_events: arrays too small");
+        return EVS_ERR_INVALID;
+    }
+    *n_evicted = c.n_evicted_last;
+    if (c.n_evicted_last) EVS_CUDA(cudaMemcpy(evicted, d.evicted, sizeof(int64_t) * c.n_evicted_last, cudaMemcpyDeviceToHost));
+    if (c.n_flushed_last && d.flushed == nullptr) {
+        set_error("evs_last_events: create the handle with record_events to read flushed keys");
+        return EVS_ERR_INVALID;
+    }
+    *n_flushed = c.n_flushed_last;
+    if (c.n_flushed_last) EVS_CUDA(cudaMemcpy(flushed, d.flushed, sizeof(int64_t) * c.n_flushed_last, cudaMemcpyDeviceToHost));
+    return EVS_OK;
+}
+
+int evs_dump_state(evs_handle h, int tier, int64_t *keys, int64_t *n_keys, int64_t *bucket_off, int64_t *n_perfect) {
+    if (h == nullptr || tier < 0 || tier >= h->n_tiers || keys == nullptr || n_keys == nullptr || bucket_off == nullptr)
+        return EVS_ERR_INVALID;
+    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    EVS_CUDA(cudaDeviceSynchronize());
+    const TierDev &d = h->tier[tier].dev;
+    TierCtl c;
+    EVS_CUDA(cudaMemcpy(&c, d.ctl, sizeof(c), cudaMemcpyDeviceToHost));
+    std::vector<unsigned long long> meta(d.rows_total), rkey(d.rows_total);
+    EVS_CUDA(cudaMemcpy(meta.data(), d.row_meta, sizeof(unsigned long long) * d.rows_total, cudaMemcpyDeviceToHost));
+    EVS_CUDA(cudaMemcpy(rkey.data(), d.row_key, sizeof(unsigned long long) * d.rows_total, cudaMemcpyDeviceToHost));
+    int64_t n = 0;
+    std::vector<unsigned> rec;
+    for (int b = 0; b < d.n_buckets; ++b) {
+        bucket_off[b] = n;
+        const unsigned long long len = c.tail[b] - c.head[b];
+        rec.resize(len);
+        for (unsigned long long done = 0; done < len;) {        // the live window may wrap the ring
+            const unsigned long long pos = (c.head[b] + done) & (d.ring_cap - 1);
+            const unsigned long long run = std::min<unsigned long long>(len - done, d.ring_cap - pos);
+            EVS_CUDA(cudaMemcpy(rec.data() + done, d.ring + static_cast<size_t>(b) * d.ring_cap + pos, sizeof(unsigned) * run,
+                                cudaMemcpyDeviceToHost));
+            done += run;
+        }
+        unsigned live = 0;
+        for (unsigned long long i = 0; i < len; ++i) {
+            const unsigned row = rec[i];
+            if (row < d.rows_total && meta[row] == pack_meta(b, c.head[b] + i)) {
+                if (n >= *n_keys) {
+                    set_error("evs_dump_state: keys array too small");
+                    return EVS_ERR_INVALID;
+                }
+                keys[n++] = static_cast<int64_t>(rkey[row]);
+                ++live;
+            }
+        }
+        if (live != c.count[b]) {
+            set_error("evs_dump_state: bucket " + std::to_string(b) + " live records " + std::to_string(live) +
+                      " != count " + std::to_string(c.count[b]));
+            return EVS_ERR_CAPACITY;
+        }
+    }
+    bucket_off[d.n_buckets] = n;
+    *n_keys = n;
+    if (n_perfect) *n_perfect = c.n_perfect;
+    return EVS_OK;
+}
+
+int evs_dump_c3(evs_handle h, int64_t *keys, uint32_t *alt, uint8_t *recency, int64_t *n) {
+    if (h == nullptr || n == nullptr) return EVS_ERR_INVALID;
+    if (!h->c3_active) {
+        *n = 0;
+        return EVS_OK;
+    }
+    return c3_dump(h, keys, alt, recency, n);
+}
+
+int evs_interact(const float *x_dev, const float *ly_dev, float *r_dev, int32_t B, int32_t n_f, int32_t dim, void *stream) {
+    return launch_interact(x_dev, ly_dev, r_dev, B, n_f, dim, static_cast<cudaStream_t>(stream));
+}
+
+// ---- legacy libcachemanager.so surface ----------------------------------------------------
+static evs_handle g_legacy = nullptr;
+static std::vector<float> g_legacy_out;       // emb_weights_in_1d_floats (cache_manager.hpp:51)
+static std::vector<int64_t> g_legacy_idx;
+static uint64_t g_legacy_perfect_base = 0, g_legacy_c3_base = 0;
+
+int evs_legacy_configure(const evs_config *cfg) {
+    if (g_legacy) {
+        evs_destroy(g_legacy);
+        g_legacy = nullptr;
+    }
+    int rc = evs_create(cfg, &g_legacy);
+    if (rc) return rc;
+    g_legacy_out.assign(static_cast<size_t>(cfg->n_tables) * cfg->dim, 0.0f);
+    g_legacy_idx.assign(cfg->n_tables, 0);
+    g_legacy_perfect_base = g_legacy_c3_base = 0;
+    return EVS_OK;
+}
+
+evs_handle evs_legacy_handle(void) { return g_legacy; }
+
+float *ev_lookup(int *arr) {
+    if (g_legacy == nullptr) {
+        fprintf(stderr, "evstore_b200: ev_lookup before evs_legacy_configure\n");
+        return nullptr;
+    }
+    for (size_t t = 0; t < g_legacy_idx.size(); ++t) g_legacy_idx[t] = arr[t];
+    int rc = evs_lookup_batch_host(g_legacy, g_legacy_idx.data(), 1, g_legacy_out.data(), nullptr);
+    if (rc) {
+        fprintf(stderr, "evstore_b200: ev_lookup failed (%d): %s\n", rc, evs_last_error());
+        return nullptr;
+    }
+    return g_legacy_out.data();
+}
+
+float *get_ev_values(int *arr) {
+    (void)arr;
+    return g_legacy_out.empty() ? nullptr : g_legacy_out.data();
+}
+
+void print_perfect_hit(void) {
+    if (g_legacy == nullptr) {
+        fprintf(stderr, "evstore_b200: print_perfect_hit before evs_legacy_configure\n");
+        return;
+    }
+    evs_stats_t s;
+    if (evs_stats(g_legacy, &s, 0)) return;
+    const evs_config &c = g_legacy->cfg;
+    printf("\n[epoll worker] C1_PRECISION    = %d\n", c.main_precision);
+    if (c.n_layers >= 2) printf("[epoll worker] C2_PRECISION    = %d\n", c.secondary_precision);
+    if (c.n_layers == 3) {
+        printf("[epoll worker] C3 APRX_EV      = ACTIVE\n");
+        printf("[epoll worker] SIZE_PROPORTION = %d-%d-%d\n", c.prop_c1, c.prop_c2, c.prop_c3);
+        // the reference never resets aprx_ev_hit; keep it cumulative too
+        printf("[epoll worker] C3 Indiv-Hit    = %llu\n", static_cast<unsigned long long>(s.c3_hits));
+    }
+    printf("[epoll worker] TOTAL_SIZE      = %lld\n", static_cast<long long>(c.total_size));
+    printf("[epoll worker] Perfect hit     = %llu\n", static_cast<unsigned long long>(s.perfect_hits - g_legacy_perfect_base));
+    fflush(stdout);
+    g_legacy_perfect_base = s.perfect_hits;   // cache_manager.cpp:289 resets the counter
+}
+
+void test_arr(int *arr) {
+    for (int i = 0; i < 5; i++) printf("key %d, ", arr[i]);
+    printf("\n");
+    for (int i = 0; i < 5; i++) printf("vec %d, ", arr[i]);
+    printf("\n");
+    fflush(stdout);
+}
+
+int ev_lookup_based_on_list_keys(int *arr) {
+    (void)arr;
+    fprintf(stderr, "ERROR: This ev_lookup_based_on_list_keys() is outdated, use ev_lookup() instead!\n");
+    return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+"""Synthetic Criteo-shaped tables and Zipf index traces.
+
+Tables follow DLRM's create_emb initialisation (dlrm_s_pytorch_C1_C2_C3.py:446-449):
+U(-1/sqrt(rows), 1/sqrt(rows)), clipped into the dense range of the 16-bit codec.
+Indices: per table, rank r drawn with p ~ r^-alpha, mapped to a row by a fixed permutation;
+layout lS_i[n_tables, B] int64 (collate_wrapper_criteo_offset, dlrm_data_pytorch.py:397).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# logs/sample-inference-criteo_kaggle_all.txt:31
+KAGGLE_ROWS = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27, 14992,
+               5461306, 10, 5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572]
+# MLPerf DLRM Criteo-Terabyte cardinalities capped at 40M (not in the reference repo)
+TERABYTE_ROWS = [39884406, 39043, 17289, 7420, 20263, 3, 7120, 1543, 63, 38532951, 2953546, 403346, 10, 2208,
+                 11938, 155, 4, 976, 14, 39979771, 25641295, 39664984, 585935, 12972, 108, 36]
+
+
+def scaled_rows(rows, scale: float, floor: int = 3):
+    """Shrink a cardinality list for tests / small hosts, keeping the skew."""
+    return [max(floor, int(r * scale)) if r > 1000 else r for r in rows]
+
+
+def make_table(t: int, rows: int, dim: int, seed: int = 1234) -> np.ndarray:
+    rng = np.random.default_rng(seed + t)
+    bound = 1.0 / np.sqrt(rows)
+    w = rng.uniform(-bound, bound, size=(rows, dim)).astype(np.float32)
+    return np.clip(w, -0.6499, 0.6499)
+
+
+def make_tables(rows, dim: int, seed: int = 1234):
+    return [make_table(t, r, dim, seed) for t, r in enumerate(rows)]
+
+
+class ZipfTrace:
+    """Reproducible stream of index batches lS_i[n_tables, B]."""
+
+    def __init__(self, rows, alpha: float = 1.05, seed: int = 42, perm_seed: int = 7):
+        self.rows = list(rows)
+        self.rng = np.random.default_rng(seed)
+        self.cdfs, self.perms = [], []
+        for t, n in enumerate(self.rows):
+            w = np.arange(1, n + 1, dtype=np.float64) ** (-alpha)
+            c = np.cumsum(w)
+            self.cdfs.append(c / c[-1])
+            self.perms.append(np.random.default_rng(perm_seed + t).permutation(n).astype(np.int64))
+
+    def batch(self, B: int) -> np.ndarray:
+        out = np.empty((len(self.rows), B), dtype=np.int64)
+        for t, n in enumerate(self.rows):
+            r = np.searchsorted(self.cdfs[t], self.rng.random(B), side="left")
+            out[t] = self.perms[t][np.minimum(r, n - 1)]
+        return out
+
+
+def make_alt_keys(rows, seed: int = 11):
+    """A stand-in for the offline kNN alt-key tables (script/approximate_embedding/...):
+    alt_key = alt_row*100 + alt_table(1-based) (convert_altkeys_to_binary.py:50).  Each row's
+    alternative is a more popular row (lower Zipf rank) of the same table under ZipfTrace's
+    permutation -- the property the reference's "most popular neighbour" pick provides."""
+    out = []
+    for t, n in enumerate(rows):
+        perm = np.random.default_rng(7 + t).permutation(n).astype(np.int64)
+        rank_of_row = np.empty(n, dtype=np.int64)
+        rank_of_row[perm] = np.arange(n)
+        alt_rank = rank_of_row // 2
+        alt_row = perm[alt_rank]
+        out.append((alt_row * 100 + (t + 1)).astype(np.uint32))
+    return out

@@ -1,0 +1,169 @@
+/*
+ * evstore_b200 -- C-ABI of the B200-native EVStore embedding-lookup hot path.
+ *
+ * This header is the drop-in boundary.  It has two parts:
+ *
+ *  (1) the LEGACY entry points of the reference's libcachemanager.so
+ *      (/root/reference/mixed_precs_caching/cache_manager.cpp), same names, same
+ *      signatures, same "process-global cache + library-owned float buffer"
+ *      contract, so cache_algo/cpp_socket_client.py:63-83 binds them unchanged;
+ *
+ *  (2) a runtime-configured, batched API that replaces the reference's
+ *      compile-time #defines (cache_manager.cpp:13-20) and its one-sample-per-call
+ *      limit.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions
+ *  - table ids are 0-based here; the reference's keys are "<table+1>-<row>"
+ *    (evlfu_32.cpp:477).  A key is (table << 40) | row in every key stream.
+ *  - every call returns EVS_OK (0) or a negative evs_status; nothing calls exit()
+ *    (the reference's error path is printf + exit(-1), cache_manager.cpp:213-217).
+ *  - one handle == one stream-ordered, single-writer cache (the reference is
+ *    not thread safe either: globals, no locks).
+ *  - "dev" pointers are CUDA device pointers on cfg.device; "host" pointers are
+ *    ordinary host memory (pinned memory makes the copies asynchronous).
+ */
+#ifndef EVSTORE_B200_H
+#define EVSTORE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVS_MAX_TABLES 32      /* keys of one sample are handled by one warp */
+#define EVS_MAX_TIERS 2        /* C1 and C2 (C3 holds alternative keys, not rows) */
+
+typedef enum {
+    EVS_OK = 0,
+    EVS_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+    EVS_ERR_CUDA = -2,         /* a CUDA runtime call failed (see evs_last_error) */
+    EVS_ERR_INDEX = -3,        /* an index was outside [0, rows[table]) */
+    EVS_ERR_CAPACITY = -4,     /* internal structure overflow (should not happen) */
+    EVS_ERR_NOT_CONFIGURED = -5
+} evs_status;
+
+typedef struct evs_handle_s *evs_handle;
+
+/* Replaces cache_manager.cpp:13-20 (N_CACHING_LAYER, MAIN_PRECISION,
+ * SECONDARY_PRECISION, TOTAL_SIZE, SIZE_PROPORTION) plus the hard-coded
+ * EV_DIMENSION / N_EV_TABLE (cache_manager.hpp:30-31) and file roots
+ * (evlfu_32.hpp:61, evlfu_8.hpp:58, evlfu_4.hpp:61, aprx_embedding.hpp:39). */
+typedef struct {
+    int32_t device;              /* CUDA device ordinal */
+    int32_t n_tables;            /* tables served by this cache (<= EVS_MAX_TABLES) */
+    int32_t n_tables_total;      /* agg_hit range: buckets 0..n_tables_total (26 in the reference) */
+    int32_t table_base;          /* global id of local table 0 (table-wise sharding), else 0 */
+    int32_t dim;                 /* embedding dimension (reference: 36) */
+    int32_t n_layers;            /* 1, 2 or 3  (N_CACHING_LAYER) */
+    int32_t main_precision;      /* 32, 16, 8 or 4  (MAIN_PRECISION) */
+    int32_t secondary_precision; /* 16, 8 or 4, lower than main (SECONDARY_PRECISION); 0 if n_layers == 1 */
+    int64_t total_size;          /* TOTAL_SIZE, in fp32-row units */
+    int32_t prop_c1, prop_c2, prop_c3; /* SIZE_PROPORTION "c1-c2-c3" in percent; all 0 = even split */
+    int32_t max_batch;           /* largest B passed to evs_lookup_batch */
+    int32_t approx_emb_thres;    /* EvLFU_C1.request_to_ev_lfu approx_emb_thres; <= 0 disables */
+    int32_t high_agghit_threshold; /* evlfu_32.hpp:74; 0 = default 23 */
+    float flush_rate;            /* 0 = default 0.3  (evlfu_32.hpp:53) */
+    float perfect_item_cap;      /* 0 = default 0.95 (evlfu_32.hpp:54) */
+    const int64_t *rows;         /* [n_tables] table cardinalities */
+    /* Backing store (stands in for emb_storage/* and EVLFU_*::get_from_file): per table a
+     * host pointer to rows*dim*precision/8 bytes, row-major, the layout of
+     * binary/ev-table-N.bin (script/convert_ev_to_binary.py).  The library page-locks and
+     * maps the memory (zero-copy); it must stay valid until evs_destroy. */
+    const void *const *store_main;       /* [n_tables] rows at main_precision */
+    const void *const *store_secondary;  /* [n_tables] rows at secondary_precision, or NULL */
+    /* Alternative keys for C3 (aprx_embedding.cpp): per table a host pointer to rows uint32
+     * alt_key = alt_row*100 + (alt_table+1), host byte order (the file is big-endian,
+     * convert_altkeys_to_binary.py:35); NULL unless n_layers == 3. */
+    const uint32_t *const *alt_keys;
+    int32_t store_in_hbm;        /* testing aid: copy the backing store into HBM instead of mapping it */
+    int32_t record_events;       /* keep per-batch eviction / flush key streams for evs_last_events */
+} evs_config;
+
+typedef struct {
+    uint64_t lookups;            /* keys looked up */
+    uint64_t samples;
+    uint64_t hits[EVS_MAX_TIERS];       /* served from C1 / C2 */
+    uint64_t c3_hits;            /* "C3 Indiv-Hit" (evlfu_8.cpp:539) */
+    uint64_t approx_subst;       /* EvLFU_C1 approximate substitutions (EvLFU_C1.py:150) */
+    uint64_t misses;             /* fetched from the backing store */
+    uint64_t perfect_hits;       /* samples whose every key hit ("Perfect hit", cache_manager.cpp:288) */
+    uint64_t inserts[EVS_MAX_TIERS];
+    uint64_t evictions[EVS_MAX_TIERS];
+    uint64_t flushed[EVS_MAX_TIERS];
+    uint64_t size[EVS_MAX_TIERS];       /* resident entries now */
+    uint64_t capacity[EVS_MAX_TIERS];
+    uint64_t c3_size, c3_capacity;
+    uint64_t batches;
+} evs_stats_t;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+int evs_create(const evs_config *cfg, evs_handle *out);
+int evs_destroy(evs_handle h);
+const char *evs_last_error(void);       /* text of the last failure on this thread */
+int evs_version(void);
+
+/* ---- the hot path ---------------------------------------------------------------- *
+ * One batch: probe -> EvLFU promote -> fetch misses -> insert/evict -> dequantise ->
+ * fp32 rows.  Replaces B calls of ev_lookup (cache_manager.cpp:231) /
+ * EvLFU_C1.request_to_ev_lfu (EvLFU_C1.py:97).
+ *   idx_dev   int64 [n_tables][B]          (the reference's lS_i, table-major)
+ *   out_dev   fp32  B rows of n_tables*dim, consecutive samples out_stride floats apart
+ *             (out_stride 0 == n_tables*dim)
+ *   hit_dev   uint8 [B][n_tables] or NULL  (aggHitMissRecord; 1 = answered from a cache tier)
+ *   agg_in    uint8 [B] or NULL: externally supplied agg_hit per sample (exact
+ *             groupability under table-wise sharding); NULL = count locally
+ *   stream    cudaStream_t (NULL = the handle's own stream)
+ * Asynchronous with respect to the host. */
+int evs_lookup_batch(evs_handle h, const int64_t *idx_dev, int32_t B, float *out_dev, int64_t out_stride,
+                     uint8_t *hit_dev, const uint8_t *agg_in, void *stream);
+
+/* Probe only: per-sample local hit counts (for the sharded exact mode the ranks
+ * all-reduce these and pass the sum back as agg_in).  Does not change state. */
+int evs_probe_batch(evs_handle h, const int64_t *idx_dev, int32_t B, uint8_t *agg_out_dev, void *stream);
+
+/* Same batch through host buffers: H2D of idx, the hot path, D2H of out (and hit),
+ * then a stream synchronise.  This is what a reference-side caller (ctypes / cgo) uses. */
+int evs_lookup_batch_host(evs_handle h, const int64_t *idx_host, int32_t B, float *out_host, uint8_t *hit_host);
+
+int evs_sync(evs_handle h);
+int evs_stats(evs_handle h, evs_stats_t *out, int reset);
+
+/* ---- parity / introspection (used by tests; cheap, off the hot path) -------------- */
+/* Keys evicted / flushed by the LAST batch of tier (0 = C1, 1 = C2), in eviction order.
+ * Needs cfg.record_events.  *n_* in: capacity of the arrays, out: count. */
+int evs_last_events(evs_handle h, int tier, int64_t *evicted, int64_t *n_evicted, int64_t *flushed,
+                    int64_t *n_flushed);
+/* Resident keys of a tier in eviction order: bucket_off[b]..bucket_off[b+1] index keys of
+ * agg_hit bucket b (FIFO).  keys capacity in *n_keys (in) -> count (out); bucket_off has
+ * n_tables_total+2 entries. */
+int evs_dump_state(evs_handle h, int tier, int64_t *keys, int64_t *n_keys, int64_t *bucket_off,
+                   int64_t *n_perfect);
+/* Resident keys of C3 in FIFO order with their alt keys and recency flags. */
+int evs_dump_c3(evs_handle h, int64_t *keys, uint32_t *alt, uint8_t *recency, int64_t *n);
+
+/* ---- feature interaction (dlrm_s_pytorch_C1_C2_C3.py:625-658, "dot") ---------------- *
+ *   x_dev  fp32 [B][dim]        bottom-MLP output
+ *   ly_dev fp32 [B][n_f][dim]   pooled embeddings (evs_lookup_batch output)
+ *   r_dev  fp32 [B][dim + (n_f+1)*n_f/2]   (arch_interaction_itself = 0)
+ */
+int evs_interact(const float *x_dev, const float *ly_dev, float *r_dev, int32_t B, int32_t n_f, int32_t dim,
+                 void *stream);
+
+/* ---- legacy libcachemanager.so surface (cache_manager.cpp) ------------------------ *
+ * A process-global cache answers one sample per call.  Where the reference fixes its
+ * configuration at compile time, call evs_legacy_configure once first (or set
+ * EVSTORE_B200_LEGACY=... and let the Python shim do it); ev_lookup before that
+ * prints an error and returns NULL instead of exiting. */
+int evs_legacy_configure(const evs_config *cfg);
+evs_handle evs_legacy_handle(void);
+float *ev_lookup(int *arr);                    /* cache_manager.cpp:231 */
+float *get_ev_values(int *arr);                /* cache_manager.cpp:257 */
+void print_perfect_hit(void);                  /* cache_manager.cpp:262 (prints, then resets) */
+void test_arr(int *arr);                       /* cache_manager.cpp:154 */
+int ev_lookup_based_on_list_keys(int *arr);    /* cache_manager.cpp:239 (deprecated there; returns -1 here) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVSTORE_B200_H */

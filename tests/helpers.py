@@ -1,0 +1,73 @@
+"""Shared helpers for the parity tests."""
+import importlib
+
+import numpy as np
+
+from oracle import codecs as ocodecs
+from oracle.evlfu import BatchEvLFU, gather_rows
+
+SMALL_ROWS = [50, 7, 400, 300, 9, 4, 60, 12, 3, 120, 30, 350, 40, 5, 45, 280, 4, 33, 21, 4, 390, 6, 5, 90, 11, 70]
+SKEW_ROWS = [3, 5, 4000, 2500, 7, 4, 60, 9, 3, 300, 50, 3500, 40, 4, 80, 3000, 5, 45, 30, 4, 3800, 6, 5, 600, 11, 400]
+TINY_ROWS = [4 + (t % 3) for t in range(26)]
+
+
+def pkg():
+    return importlib.import_module("ev-store-dlrm_b200")
+
+
+def decoded_tables(tables, prec):
+    """What a tier of precision `prec` returns for every row (oracle codecs)."""
+    if prec == 32:
+        return tables
+    return [ocodecs.dequantize_rows(ocodecs.quantize_table(t, prec), prec) for t in tables]
+
+
+def run_single_tier_parity(rows, dim, prec, total_size, B_list, n_batches, seed=42, approx=-1,
+                           store_in_hbm=False, host_path=False, check_state_every=1, alpha=1.05):
+    """Drive the CUDA path and BatchEvLFU with the same batches; compare everything, every batch."""
+    import torch
+    p = pkg()
+    tables = p.workload.make_tables(rows, dim)
+    dec = decoded_tables(tables, prec)
+    trace = p.workload.ZipfTrace(rows, alpha=alpha, seed=seed)
+    cap = total_size * (32 // prec)
+    cfg = p.CacheConfig(n_layers=1, main_precision=prec, total_size=total_size, max_batch=max(B_list),
+                        approx_emb_thres=approx, record_events=True, store_in_hbm=store_in_hbm)
+    store = p.EvStore(tables, cfg)
+    oracle = BatchEvLFU(cap, n_tables=len(rows))
+    T = len(rows)
+    totals = dict(hits=0, lookups=0, evicted=0, flushed=0)
+    try:
+        for it in range(n_batches):
+            B = B_list[it % len(B_list)]
+            idx = trace.batch(B)
+            if host_path:
+                out, hit = store.lookup_host(idx)
+            else:
+                o, h = store.lookup(torch.from_numpy(idx).cuda())
+                torch.cuda.synchronize()
+                out, hit = o.cpu().numpy(), h.cpu().numpy()
+            o_hit, st, sr, agg = oracle.lookup_batch(idx, approx_emb_thres=approx)
+            want = gather_rows(dec, st, sr)
+            assert (hit.astype(bool) == o_hit).all(), f"hit stream, batch {it} (B={B})"
+            ok = st >= 0
+            assert (out[ok] == want[ok]).all(), f"rows, batch {it} (B={B})"
+            ev, fl = store.last_events()
+            assert ev.tolist() == oracle.evicted, f"eviction stream, batch {it}: {ev.tolist()[:8]} vs {oracle.evicted[:8]}"
+            assert fl.tolist() == oracle.flushed, f"flush stream, batch {it}"
+            if it % check_state_every == 0 or it == n_batches - 1:
+                state, n_perfect = store.dump_state()
+                assert state == oracle.state(), f"resident state / FIFO order, batch {it}"
+                assert n_perfect == oracle.n_perfect, f"n_perfect, batch {it}"
+            totals["hits"] += int(o_hit.sum())
+            totals["lookups"] += B * T
+            totals["evicted"] += len(oracle.evicted)
+            totals["flushed"] += len(oracle.flushed)
+        store.sync()
+        s = store.stats()
+        assert s["lookups"] == totals["lookups"]
+        assert s["evictions"][0] == totals["evicted"] and s["flushed"][0] == totals["flushed"]
+        assert s["size"][0] == len(oracle.entries)
+    finally:
+        store.close()
+    return totals

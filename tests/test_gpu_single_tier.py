@@ -1,0 +1,93 @@
+"""CUDA path vs the batch-granular oracle, through the C-ABI: hit stream, fp32 rows,
+eviction / flush streams and the resident FIFO state must be bit-exact, every batch."""
+import numpy as np
+import pytest
+
+from helpers import SKEW_ROWS, SMALL_ROWS, TINY_ROWS, pkg, run_single_tier_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fp32_small_batches():
+    t = run_single_tier_parity(SMALL_ROWS, 16, 32, 600, [64], 30)
+    assert t["evicted"] > 0
+
+
+def test_fp32_batch_of_one_and_ragged_sizes():
+    run_single_tier_parity(SMALL_ROWS, 16, 32, 500, [1, 3, 8, 9, 31, 64, 2, 100], 64)
+
+
+def test_fp32_dim36_reference_dimension():
+    run_single_tier_parity(SMALL_ROWS, 36, 32, 700, [48], 25)
+
+
+def test_fp32_dim64_skewed_tables_large_batch():
+    t = run_single_tier_parity(SKEW_ROWS, 64, 32, 6000, [512], 24, check_state_every=4)
+    assert t["evicted"] > 0
+
+
+def test_fp32_flush_rule():
+    """Tiny tables: most samples are perfect hits, bucket 26 fills and gets flushed."""
+    t = run_single_tier_parity(TINY_ROWS, 16, 32, 110, [4, 16], 220, check_state_every=5)
+    assert t["flushed"] > 0
+
+
+@pytest.mark.parametrize("prec", [16, 8, 4])
+def test_quantised_single_tier(prec):
+    run_single_tier_parity(SMALL_ROWS, 16, prec, 150, [64, 17], 30, check_state_every=3)
+
+
+@pytest.mark.parametrize("prec", [16, 8, 4])
+def test_quantised_dim36(prec):
+    run_single_tier_parity(SMALL_ROWS, 36, prec, 150, [33], 16, check_state_every=3)
+
+
+def test_approximate_embedding_threshold():
+    run_single_tier_parity(SMALL_ROWS, 16, 32, 900, [64], 40, approx=20, check_state_every=4)
+
+
+def test_host_buffer_path_and_hbm_store():
+    run_single_tier_parity(SMALL_ROWS, 16, 32, 600, [64, 5], 20, host_path=True)
+    run_single_tier_parity(SMALL_ROWS, 16, 8, 200, [64], 10, store_in_hbm=True)
+
+
+def test_empty_batch_and_bad_index():
+    import torch
+    p = pkg()
+    tables = p.workload.make_tables(SMALL_ROWS, 16)
+    store = p.EvStore(tables, p.CacheConfig(total_size=300, max_batch=32))
+    out, hit = store.lookup(torch.zeros((26, 0), dtype=torch.int64, device="cuda"))
+    assert out.shape == (0, 26, 16)
+    bad = torch.zeros((26, 4), dtype=torch.int64, device="cuda")
+    bad[3, 2] = 10 ** 9
+    store.lookup(bad)
+    with pytest.raises(p.EvsError):
+        store.sync()
+    with pytest.raises(p.EvsError):
+        store.lookup(torch.zeros((26, 33), dtype=torch.int64, device="cuda"))
+    store.close()
+
+
+def test_ring_compaction_keeps_order():
+    """Many small batches on a tiny cache: the bucket rings wrap and get compacted."""
+    run_single_tier_parity(SMALL_ROWS, 16, 32, 64, [8], 700, check_state_every=50)
+
+
+def test_interaction_matches_torch_bmm():
+    import torch
+    p = pkg()
+    tables = p.workload.make_tables(SMALL_ROWS, 16)
+    store = p.EvStore(tables, p.CacheConfig(total_size=300, max_batch=32))
+    for B, nf, d in [(1, 26, 16), (37, 26, 36), (256, 26, 64), (5, 3, 8)]:
+        g = torch.Generator(device="cuda").manual_seed(B)
+        x = torch.randn((B, d), device="cuda", generator=g)
+        ly = torch.randn((B, nf, d), device="cuda", generator=g)
+        r = store.interact(x, ly)
+        T = torch.cat([x.unsqueeze(1), ly], dim=1)
+        Z = torch.bmm(T, T.transpose(1, 2))
+        li = torch.tensor([i for i in range(nf + 1) for j in range(i)])
+        lj = torch.tensor([j for i in range(nf + 1) for j in range(i)])
+        want = torch.cat([x, Z[:, li, lj]], dim=1)
+        # fp32 dot products, different summation order than cuBLAS: tolerance 1e-4 abs on O(d) sums
+        assert torch.allclose(r, want, rtol=1e-5, atol=1e-4), (B, nf, d)
+    store.close()
