@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- EV lookups/s of the embedding-lookup hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference's CPU path
+
+A *step* is one pass of the hot path over one batch of synthetic Zipf(1.05) indices
+(26 tables x B samples): probe -> EvLFU promote -> miss fetch from the host-pinned backing
+store -> insert/evict -> dequantise -> fp32 rows [B, 26, dim].
+
+N = 1  : BASELINE configs[1] -- C1 EvLFU cache in HBM, Kaggle-shape tables, batch 2048, fp32 tier.
+N > 1  : BASELINE configs[4] -- Terabyte-shape tables, table-wise sharded, exact groupability
+         (all-reduce of per-sample hit counts) and an NCCL all-to-all of the pooled rows.
+
+One JSON line on stdout (rank 0); everything else goes to stderr.
+  value     lookups/s with the index batches already resident in HBM (CUDA events, max over ranks)
+  e2e       the same through the host-buffer C-ABI call (pinned host indices in, fp32 rows out)
+  roofline  dominant kernel: algorithmic bytes per launch / its CUDA-event time, vs measured HBM peak
+  cpu_baseline  the reference's own libcachemanager.so (oracle/_ref) on this box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="samples per step (default 2048)")
+    ap.add_argument("--dim", type=int, default=0)
+    ap.add_argument("--precision", type=int, default=32)
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink table cardinalities (debug only; invalidates the number)")
+    ap.add_argument("--cache-warm", type=int, default=-1, help="untimed batches that fill the cache before warm-up")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
+    ap.add_argument("--no-clocks", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed regions run (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception as e:                      # no nvidia-smi: report it, do not fail the bench
+            log("clock sampler unavailable:", e)
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def bytes_per_lookup(dim: int, prec: int) -> int:
+    """int64 index + one 16 B index slot + stored row + fp32 output row (P = 1)."""
+    return 8 + 16 + dim * prec // 8 + 4 * dim
+
+
+def build_workload(args, n_batches: int, rows, dim: int, B: int, seed: int = 42):
+    pkg = importlib.import_module("ev-store-dlrm_b200")
+    t0 = time.time()
+    tables = pkg.workload.make_tables(rows, dim)
+    t1 = time.time()
+    trace = pkg.workload.ZipfTrace(rows, alpha=1.05, seed=seed)
+    idx = trace.batches(n_batches, B)
+    log(f"workload: tables {sum(t.nbytes for t in tables) / 1e9:.2f} GB in {t1 - t0:.1f}s, "
+        f"{n_batches} index batches in {time.time() - t1:.1f}s")
+    return pkg, tables, idx
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def run_cpu_reference(variant, tables_raw, idx, B, warm_batches, timed_batches, budget_s=None):
+    """Times the reference's libcachemanager.so (oracle/_ref) through ev_lookup, one sample per
+    call, 1 caller thread + the library's 3 reader threads.  idx: int64 [n, 26, B]."""
+    from oracle import ref_driver
+    v = ref_driver.VARIANTS[variant]
+    t0 = time.time()
+    ref_driver.write_fixture(variant, {v["main"]: tables_raw})
+    log(f"reference fixture written to {ref_driver.fixture_dir(variant)} in {time.time() - t0:.1f}s")
+    ref = ref_driver.RefCache(variant)
+    perfect = __import__("ctypes").c_int.in_dll(ref.lib, "perfectHit")
+
+    def as_trace(k0, k1):
+        # [n, 26, B] -> sample-major int32 [n*B, 26]
+        return np.ascontiguousarray(idx[k0:k1].transpose(0, 2, 1).reshape(-1, idx.shape[1]).astype(np.int32))
+
+    warm_s = 0.0
+    done = 0
+    while done < warm_batches:
+        step = min(16, warm_batches - done)
+        s, _ = ref.drive(as_trace(done, done + step))
+        warm_s += s
+        done += step
+        if budget_s is not None and warm_s > budget_s:
+            break
+    warm_done = done
+    perfect.value = 0
+    per_step = []
+    for k in range(timed_batches):
+        kk = warm_done + k
+        if kk >= idx.shape[0]:
+            break
+        s, _ = ref.drive(as_trace(kk, kk + 1))
+        per_step.append(s)
+    total = float(sum(per_step))
+    n_samples = len(per_step) * B
+    return {
+        "seconds": total, "steps": len(per_step), "samples": n_samples, "samples_per_s": n_samples / total,
+        "lookups_per_s": n_samples * idx.shape[1] / total, "warm_batches": warm_done, "warm_seconds": warm_s,
+        "perfect_hits": int(perfect.value), "ms_per_step": 1e3 * total / max(1, len(per_step)),
+    }
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import ref_driver
+    from oracle.ref_variants import KAGGLE_CACHE_13PCT
+    pkg = importlib.import_module("ev-store-dlrm_b200")
+    B = args.batch or 2048
+    dim = args.dim or 16
+    variant = "bench_c1_fp32_d16"
+    if not ref_driver.available(variant) or dim != 16 or args.scale != 1.0:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/lib%s.so not built for this config" % variant}))
+        return 0
+    rows = pkg.workload.KAGGLE_ROWS
+    warm = args.cache_warm if args.cache_warm >= 0 else 600
+    n_batches = warm + args.warmup + args.steps
+    _, tables, idx = build_workload(args, n_batches, rows, dim, B)
+    r = run_cpu_reference(variant, tables, idx, B, warm + args.warmup, args.steps)
+    line = {
+        "impl": "reference", "metric": "ev_lookups_per_s", "value": r["lookups_per_s"], "unit": "lookups/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "samples_per_s": r["samples_per_s"],
+        "config": {"workload": "configs[1]: C1 EvLFU fp32, Kaggle-shape 26 tables (33.76M rows), dim 16, Zipf(1.05), batch %d, "
+                               "cache %d rows (13%%)" % (B, KAGGLE_CACHE_13PCT),
+                   "batch": B, "dim": dim, "cache_rows": KAGGLE_CACHE_13PCT, "cache_warm_batches": r["warm_batches"]},
+        "cpu_baseline": {"value": r["lookups_per_s"], "unit": "lookups/s", "cores": 4, "kind": "reference",
+                         "sample": "%d full batches of %d samples after %d warm batches; reference libcachemanager.so "
+                                   "(1 caller + 3 reader threads), tables in /dev/shm" % (r["steps"], B, r["warm_batches"]),
+                         "perfect_hits": r["perfect_hits"], "host_cpus": os.cpu_count()},
+        "e2e": {"value": r["lookups_per_s"], "unit": "lookups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------ our arm
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from bench_sharded import main_sharded          # Terabyte-shape, table-wise sharded
+        return main_sharded(args)
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product path has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch or 2048
+    dim = args.dim or 16
+    prec = args.precision
+    K, W = args.steps, max(args.warmup, 3)
+    pkg = importlib.import_module("ev-store-dlrm_b200")
+    rows = pkg.workload.KAGGLE_ROWS if args.scale == 1.0 else pkg.workload.scaled_rows(pkg.workload.KAGGLE_ROWS, args.scale)
+    T = len(rows)
+    cache_rows = pkg.workload.KAGGLE_CACHE_ROWS if args.scale == 1.0 else int(sum(rows) * 0.13)
+    warm = args.cache_warm if args.cache_warm >= 0 else 1200
+    n_batches = warm + 3 * (W + K)
+    _, tables, idx = build_workload(args, n_batches, rows, dim, B)
+
+    cfg = pkg.CacheConfig(n_layers=1, main_precision=prec, total_size=cache_rows * prec // 32, max_batch=B, device=local_rank)
+    t0 = time.time()
+    store = pkg.EvStore(tables, cfg)
+    log(f"EvStore created in {time.time() - t0:.1f}s (cache {cache_rows} rows, backing store host-pinned zero-copy)")
+
+    idx_host = torch.from_numpy(idx).pin_memory()                    # [n, T, B] int64
+    idx_dev = idx_host.to(dev, non_blocking=True)
+    out = torch.empty((B, T, dim), dtype=torch.float32, device=dev)
+    hit = torch.empty((B, T), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    # ---- fill the cache (mirrors the reference's --cache-warmup pass) ------------------------
+    t0 = time.time()
+    for k in range(warm):
+        store.lookup(idx_dev[k], out=out, hit=hit)
+    store.sync()
+    st = store.stats(reset=True)
+    log(f"cache warm: {warm} batches in {time.time() - t0:.2f}s, resident {st['size'][0]}/{st['capacity'][0]}, "
+        f"hit rate so far {st['hits'][0] / max(1, st['lookups']):.3f}")
+    fill = st["size"][0] / max(1, st["capacity"][0])
+
+    sampler = ClockSampler(local_rank)
+    if not args.no_clocks:
+        sampler.start()
+        time.sleep(0.3)
+
+    # ---- value: indices resident in HBM ------------------------------------------------------
+    base = warm
+    for k in range(W):
+        store.lookup(idx_dev[base + k], out=out, hit=hit)
+    torch.cuda.synchronize()
+    l0 = store.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        store.lookup(idx_dev[base + W + k], out=out, hit=hit)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_dev = e0.elapsed_time(e1)
+    launches = store.launch_count() - l0
+    st = store.stats(reset=True)
+    hit_rate = st["hits"][0] / max(1, st["lookups"])
+    perfect_rate = st["perfect_hits"] / max(1, st["samples"])
+    lookups = K * B * T
+    value = lookups / (ms_dev * 1e-3)
+
+    # ---- e2e: host buffers through evs_lookup_batch_host -------------------------------------
+    base += W + K
+    out_host = torch.empty((B, T, dim), dtype=torch.float32).pin_memory()
+    hit_host = torch.empty((B, T), dtype=torch.uint8).pin_memory()
+    ih = idx_host
+    for k in range(W):
+        store.lookup_host_ptr(ih[base + k].data_ptr(), B, out_host.data_ptr(), hit_host.data_ptr())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(K):
+        store.lookup_host_ptr(ih[base + W + k].data_ptr(), B, out_host.data_ptr(), hit_host.data_ptr())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_value = lookups / e2e_s
+    h2d = B * T * 8
+    d2h = B * T * dim * 4 + B * T
+
+    clocks = sampler.stop() if not args.no_clocks else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+
+    # ---- roofline: per-kernel CUDA-event times over K more steps ------------------------------
+    base += W + K
+    store.kernel_times(reset=True)
+    store.set_profiling(True)
+    for k in range(K):
+        store.lookup(idx_dev[base + k], out=out, hit=hit)
+    torch.cuda.synchronize()
+    kt = store.kernel_times(reset=True)
+    store.set_profiling(False)
+    per_kernel = {n: {"avg_us": 1e3 * ms / max(1, timed), "launches": timed} for n, (ms, timed, _l) in kt.items() if timed}
+    tot_us = sum(v["avg_us"] * v["launches"] for v in per_kernel.values())
+    for v in per_kernel.values():
+        v["share"] = v["avg_us"] * v["launches"] / max(tot_us, 1e-9)
+    dom = max(per_kernel, key=lambda n: per_kernel[n]["share"])
+    peak, peak_src = measured_peak_hbm()
+    bpl = bytes_per_lookup(dim, prec)
+    alg_bytes = B * T * bpl
+    dom_us = per_kernel[dom]["avg_us"]
+    look_us = per_kernel.get("k_lookup", {"avg_us": float("nan")})["avg_us"]
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": alg_bytes / (dom_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": alg_bytes / (dom_us * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_lookup": bpl, "kernel_avg_us": dom_us,
+        "k_lookup_avg_us": look_us, "k_lookup_frac": alg_bytes / (look_us * 1e-6) / 1e9 / peak,
+        "step_frac": lookups * bpl / (ms_dev * 1e-3) / 1e9 / peak, "per_kernel": per_kernel,
+    }
+
+    # ---- CPU baseline: the reference's own library on this host -------------------------------
+    cpu = None
+    if not args.no_cpu_baseline and args.scale == 1.0 and dim == 16 and prec == 32:
+        try:
+            from oracle import ref_driver
+            variant = "bench_c1_fp32_d16"
+            if ref_driver.available(variant):
+                # ~10-30 s of CPU work: the reference does ~25 k samples/s => 12 batches/s
+                warm_b = int(args.cpu_baseline_seconds * 8)
+                r = run_cpu_reference(variant, tables, idx, B, warm_b, 40, budget_s=args.cpu_baseline_seconds)
+                cpu = {"value": r["lookups_per_s"], "unit": "lookups/s", "cores": 4, "kind": "reference",
+                       "sample": "%d batches of %d samples timed after %d warm batches (cache only partly full); reference "
+                                 "libcachemanager.so, 1 caller + 3 reader threads, tables in /dev/shm"
+                                 % (r["steps"], B, r["warm_batches"]),
+                       "samples_per_s": r["samples_per_s"], "host_cpus": os.cpu_count()}
+            else:
+                log("cpu_baseline: oracle/_ref not built")
+        except Exception as e:                          # the baseline must not take the GPU number down
+            log("cpu_baseline failed:", repr(e))
+    if cpu is None:
+        cpu = {"value": None, "unit": "lookups/s", "cores": 0, "kind": "reference", "sample": "not run"}
+
+    line = {
+        "metric": "ev_lookups_per_s", "value": value, "unit": "lookups/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if prec == 32 else f"u{prec}->f32", "data": "synthetic",
+        "samples_per_s": value / T, "hit_rate": hit_rate, "perfect_hit_rate": perfect_rate,
+        "config": {"workload": "configs[1]: C1 EvLFU fp%d tier, Kaggle-shape 26 tables (%.2fM rows), dim %d, Zipf(1.05), "
+                               "batch %d, cache %d rows, host-pinned backing store" % (prec, sum(rows) / 1e6, dim, B, cache_rows),
+                   "batch": B, "dim": dim, "precision": prec, "cache_rows": cache_rows, "cache_fill": fill,
+                   "cache_warm_batches": warm,
+                   "l2": "no flush: index+slab working set (%.2f GB) exceeds the 126 MB L2 and every step reads a distinct index batch"
+                         % ((cache_rows * (dim * prec // 8 + 32)) / 1e9)},
+        "e2e": {"value": e2e_value, "unit": "lookups/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / K},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    store.close()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

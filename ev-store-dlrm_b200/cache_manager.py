@@ -169,6 +169,24 @@ class EvStore:
         _native.check(self.lib.evs_stats(self.handle, C.byref(s), int(reset)), "evs_stats")
         return s.as_dict()
 
+    def set_profiling(self, on: bool):
+        _native.check(self.lib.evs_set_profiling(self.handle, int(on)), "evs_set_profiling")
+
+    def kernel_times(self, reset: bool = False) -> dict:
+        """{kernel name: (summed device ms over timed launches, timed launches, launches)}."""
+        cap = 32
+        n = C.c_int32(cap)
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        timed = (C.c_uint64 * cap)()
+        launches = (C.c_uint64 * cap)()
+        _native.check(self.lib.evs_kernel_times(self.handle, C.byref(n), names, ms, timed, launches, int(reset)),
+                      "evs_kernel_times")
+        return {names[i].decode(): (ms[i], int(timed[i]), int(launches[i])) for i in range(n.value)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.evs_launch_count(self.handle))
+
     def last_events(self, tier: int = 0):
         cap_e = self.cfg.max_batch * self.n_tables
         cap_f = int(self.stats()["capacity"][tier] * 0.35) + 8

@@ -196,6 +196,7 @@ static void free_all(evs_handle h) {
     for (void *p : h->dev_allocs) cudaFree(p);
     for (void *p : h->registered) cudaHostUnregister(p);
     delete h->c3;
+    h->prof.destroy();
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -212,6 +213,7 @@ static int maintain_rings(evs_handle h, Tier &tr, cudaStream_t st) {
     bool any = false;
     for (int b = 0; b < tr.dev.n_buckets; ++b) {
         if (ctl.tail[b] - ctl.head[b] + 2 * n_max > tr.dev.ring_cap) {
+            LaunchScope ls(h->prof, K_COMPACT, st);
             k_compact<<<1, 1024, 0, st>>>(tr.dev, b);
             any = true;
         }
@@ -230,12 +232,13 @@ static int maintain_rings(evs_handle h, Tier &tr, cudaStream_t st) {
 template <int PREC>
 static void launch_single_tier(evs_handle h, Tier &tr, const LookupArgs &a, cudaStream_t st) {
     const int n_chunks = (a.B + kSamplesPerCta - 1) / kSamplesPerCta;
-    k_lookup<PREC><<<n_chunks, kLookupThreads, 0, st>>>(tr.dev, a);
+    Profiler &pf = h->prof;
+    { LaunchScope ls(pf, K_LOOKUP, st); k_lookup<PREC><<<n_chunks, kLookupThreads, 0, st>>>(tr.dev, a); }
     const int miss_ctas = std::min(n_chunks, 592);
-    k_miss<PREC><<<miss_ctas, 256, 8 * tr.dev.row_stride, st>>>(tr.dev, a);
-    k_hist_scan<<<1, 1024, 0, st>>>(tr.dev, n_chunks);
-    k_append<<<n_chunks, kLookupThreads, 0, st>>>(tr.dev, a.B, a.T);
-    k_evict<<<1, 1024, 0, st>>>(tr.dev, a.g);
+    { LaunchScope ls(pf, K_MISS, st); k_miss<PREC><<<miss_ctas, 256, 8 * tr.dev.row_stride, st>>>(tr.dev, a); }
+    { LaunchScope ls(pf, K_HIST_SCAN, st); k_hist_scan<<<1, 1024, 0, st>>>(tr.dev, n_chunks); }
+    { LaunchScope ls(pf, K_APPEND, st); k_append<<<n_chunks, kLookupThreads, 0, st>>>(tr.dev, a.B, a.T); }
+    { LaunchScope ls(pf, K_EVICT, st); k_evict<<<1, 1024, 0, st>>>(tr.dev, a.g); }
 }
 
 static int check_device_errors(evs_handle h) {
@@ -409,7 +412,10 @@ int evs_probe_batch(evs_handle h, const int64_t *idx_dev, int32_t B, uint8_t *ag
     a.D = h->cfg.dim;
     a.table_base = h->cfg.table_base;
     a.g = h->g;
-    k_probe<<<(B + kSamplesPerCta - 1) / kSamplesPerCta, kLookupThreads, 0, st>>>(h->tier[0].dev, a);
+    {
+        LaunchScope ls(h->prof, K_PROBE, st);
+        k_probe<<<(B + kSamplesPerCta - 1) / kSamplesPerCta, kLookupThreads, 0, st>>>(h->tier[0].dev, a);
+    }
     EVS_CUDA(cudaGetLastError());
     return EVS_OK;
 }
@@ -477,6 +483,38 @@ int evs_stats(evs_handle h, evs_stats_t *out, int reset) {
         EVS_CUDA(cudaMemcpy(h->g, &g, sizeof(g), cudaMemcpyHostToDevice));
     }
     return EVS_OK;
+}
+
+int evs_set_profiling(evs_handle h, int enable) {
+    if (h == nullptr) return EVS_ERR_INVALID;
+    h->prof.drain();
+    h->prof.on = enable != 0;
+    return EVS_OK;
+}
+
+int evs_kernel_times(evs_handle h, int32_t *n, const char **names, double *total_ms, uint64_t *timed,
+                     uint64_t *launches, int reset) {
+    if (h == nullptr || n == nullptr) return EVS_ERR_INVALID;
+    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    h->prof.drain();
+    const int cap = *n;
+    *n = K_COUNT;
+    for (int i = 0; i < K_COUNT && i < cap; ++i) {
+        if (names) names[i] = kKernelNames[i];
+        if (total_ms) total_ms[i] = h->prof.ms[i];
+        if (timed) timed[i] = h->prof.timed[i];
+        if (launches) launches[i] = h->prof.launches[i];
+    }
+    if (reset)
+        for (int i = 0; i < K_COUNT; ++i) h->prof.ms[i] = 0.0, h->prof.timed[i] = 0, h->prof.launches[i] = 0;
+    return EVS_OK;
+}
+
+uint64_t evs_launch_count(evs_handle h) {
+    if (h == nullptr) return 0;
+    uint64_t t = 0;
+    for (int i = 0; i < K_COUNT; ++i) t += h->prof.launches[i];
+    return t;
 }
 
 int evs_last_events(evs_handle h, int tier, int64_t *evicted, int64_t *n_evicted, int64_t *flushed, int64_t *n_flushed) {

@@ -39,6 +39,58 @@ struct Tier {
 
 struct C3Dev;                                // evs_tiers.cuh
 
+// Kernel ids for the launch counter / per-kernel CUDA-event timing (evs_set_profiling).
+enum KernelId { K_LOOKUP = 0, K_MISS, K_HIST_SCAN, K_APPEND, K_EVICT, K_COMPACT, K_PROBE, K_INTERACT, K_MT_LOOKUP,
+                K_MT_ROUTE, K_C3, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_lookup", "k_miss", "k_hist_scan", "k_append", "k_evict", "k_compact",
+                                                  "k_probe", "k_interact", "k_mt_lookup", "k_mt_route", "k_c3"};
+
+struct Profiler {
+    bool on = false;
+    unsigned long long launches[K_COUNT] = {};
+    double ms[K_COUNT] = {};
+    unsigned long long timed[K_COUNT] = {};
+    struct Rec { int id; cudaEvent_t a, b; };
+    std::vector<Rec> pending;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void drain() {
+        for (auto &r : pending) {
+            cudaEventSynchronize(r.b);
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.id] += t; timed[r.id]++; }
+            pool.push_back(r.a); pool.push_back(r.b);
+        }
+        pending.clear();
+    }
+    void destroy() {
+        drain();
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+        pool.clear();
+    }
+};
+
+// Brackets one kernel launch: counts it and, when profiling is on, times it with CUDA events on
+// the launching stream.
+struct LaunchScope {
+    Profiler &p; int id; cudaStream_t st; cudaEvent_t a = nullptr;
+    LaunchScope(Profiler &p_, int id_, cudaStream_t st_) : p(p_), id(id_), st(st_) {
+        p.launches[id]++;
+        if (p.on) { a = p.get(); cudaEventRecord(a, st); }
+    }
+    ~LaunchScope() {
+        if (a) {
+            cudaEvent_t b = p.get();
+            cudaEventRecord(b, st);
+            p.pending.push_back({id, a, b});
+            if (p.pending.size() >= 8192) p.drain();
+        }
+    }
+};
+
 }  // namespace evs
 
 struct evs_handle_s {
@@ -62,4 +114,5 @@ struct evs_handle_s {
     std::vector<void *> dev_allocs;
     const uint32_t **d_alt = nullptr;        // [n_tables] device-visible alt-key tables
     uint64_t batches = 0;
+    evs::Profiler prof;
 };

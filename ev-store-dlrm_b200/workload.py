@@ -12,6 +12,8 @@ import numpy as np
 # logs/sample-inference-criteo_kaggle_all.txt:31
 KAGGLE_ROWS = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27, 14992,
                5461306, 10, 5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572]
+# the reference's "13 %" operating point (cache_manager.cpp:16) applied to all Kaggle rows
+KAGGLE_CACHE_ROWS = int(sum(KAGGLE_ROWS) * 0.13)
 # MLPerf DLRM Criteo-Terabyte cardinalities capped at 40M (not in the reference repo)
 TERABYTE_ROWS = [39884406, 39043, 17289, 7420, 20263, 3, 7120, 1543, 63, 38532951, 2953546, 403346, 10, 2208,
                  11938, 155, 4, 976, 14, 39979771, 25641295, 39664984, 585935, 12972, 108, 36]
@@ -24,9 +26,11 @@ def scaled_rows(rows, scale: float, floor: int = 3):
 
 def make_table(t: int, rows: int, dim: int, seed: int = 1234) -> np.ndarray:
     rng = np.random.default_rng(seed + t)
-    bound = 1.0 / np.sqrt(rows)
-    w = rng.uniform(-bound, bound, size=(rows, dim)).astype(np.float32)
-    return np.clip(w, -0.6499, 0.6499)
+    bound = np.float32(min(1.0 / np.sqrt(rows), 0.6499))
+    w = rng.random(size=(rows, dim), dtype=np.float32)
+    w *= np.float32(2) * bound
+    w -= bound
+    return w
 
 
 def make_tables(rows, dim: int, seed: int = 1234):
@@ -45,6 +49,14 @@ class ZipfTrace:
             c = np.cumsum(w)
             self.cdfs.append(c / c[-1])
             self.perms.append(np.random.default_rng(perm_seed + t).permutation(n).astype(np.int64))
+
+    def batches(self, n: int, B: int) -> np.ndarray:
+        """n consecutive batches at once: int64 [n, n_tables, B]."""
+        out = np.empty((n, len(self.rows), B), dtype=np.int64)
+        for t, rows in enumerate(self.rows):
+            r = np.searchsorted(self.cdfs[t], self.rng.random(n * B), side="left")
+            out[:, t, :] = self.perms[t][np.minimum(r, rows - 1)].reshape(n, B)
+        return out
 
     def batch(self, B: int) -> np.ndarray:
         out = np.empty((len(self.rows), B), dtype=np.int64)

@@ -129,6 +129,16 @@ int evs_lookup_batch_host(evs_handle h, const int64_t *idx_host, int32_t B, floa
 int evs_sync(evs_handle h);
 int evs_stats(evs_handle h, evs_stats_t *out, int reset);
 
+/* ---- measurement ------------------------------------------------------------------- *
+ * Every kernel launch of a handle is counted.  With profiling on, each launch is also bracketed
+ * by CUDA events on its launching stream; evs_kernel_times synchronises and returns, per kernel
+ * name, the summed device time, the number of timed launches and the number of launches.
+ * *n in: capacity of the arrays, out: number of kernel kinds. */
+int evs_set_profiling(evs_handle h, int enable);
+int evs_kernel_times(evs_handle h, int32_t *n, const char **names, double *total_ms, uint64_t *timed,
+                     uint64_t *launches, int reset);
+uint64_t evs_launch_count(evs_handle h);
+
 /* ---- parity / introspection (used by tests; cheap, off the hot path) -------------- */
 /* Keys evicted / flushed by the LAST batch of tier (0 = C1, 1 = C2), in eviction order.
  * Needs cfg.record_events.  *n_* in: capacity of the arrays, out: count. */
