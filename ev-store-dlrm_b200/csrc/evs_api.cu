@@ -10,7 +10,7 @@
 #include "evs_host.h"
 #include "evs_interact.cuh"
 #include "evs_kernels.cuh"
-#include "evs_tiers.cuh"
+#include "evs_c3.cuh"
 
 namespace evs {
 
@@ -131,16 +131,16 @@ static int build_tier(evs_handle h, Tier &tr, int prec, long long cap, const voi
         set_error("tier capacity below 32 entries");
         return EVS_ERR_INVALID;
     }
-    const long long rows_total = cap + n_max;
-    if (rows_total >= static_cast<long long>(kRowMask)) {
-        set_error("tier too large: rows must fit 27 bits");
+    // the index holds cap entries between batches and up to cap + n_max while a batch is in flight
+    const unsigned long long want_slots = static_cast<unsigned long long>(cap + n_max) * 3ull / 2ull;
+    if (want_slots >= (1ull << 31)) {
+        set_error("tier too large: the index must stay below 2^31 slots");
         return EVS_ERR_INVALID;
     }
     TierDev &d = tr.dev;
     tr.prec = prec;
     d.prec = prec;
     d.cap = static_cast<unsigned>(cap);
-    d.rows_total = static_cast<unsigned>(rows_total);
     d.row_bytes = static_cast<unsigned>(c.dim * prec / 8);
     d.row_stride = (d.row_bytes + 15u) & ~15u;
     const float pic = c.perfect_item_cap > 0 ? c.perfect_item_cap : 0.95f;
@@ -148,23 +148,14 @@ static int build_tier(evs_handle h, Tier &tr, int prec, long long cap, const voi
     d.max_perfect = static_cast<unsigned>(static_cast<int>(static_cast<double>(cap) * static_cast<double>(pic)));
     d.flush_n = static_cast<unsigned>(static_cast<int>(static_cast<double>(fr) * static_cast<double>(cap))) + 1u;
     d.n_buckets = c.n_tables_total + 1;
-    const unsigned hash_cap = next_pow2(static_cast<unsigned long long>(rows_total) * 2);
+    const unsigned hash_cap = next_pow2(want_slots);
     d.hash_mask = hash_cap - 1;
-    d.ring_cap = next_pow2(static_cast<unsigned long long>(std::max(2 * rows_total, rows_total + 4 * n_max)));
+    d.ring_cap = next_pow2(static_cast<unsigned long long>(std::max(2 * (cap + n_max), cap + 5 * n_max)));
     int rc;
     if ((rc = dev_alloc(tr.allocs, &d.slots, hash_cap, false))) return rc;
-    if ((rc = dev_alloc(tr.allocs, &d.slab, static_cast<size_t>(rows_total) * d.row_stride, true))) return rc;
-    if ((rc = dev_alloc(tr.allocs, &d.row_meta, rows_total, false))) return rc;
-    if ((rc = dev_alloc(tr.allocs, &d.row_key, rows_total, false))) return rc;
-    if ((rc = dev_alloc(tr.allocs, &d.row_slot, rows_total, false))) return rc;
-    if ((rc = dev_alloc(tr.allocs, &d.free_rows, rows_total, false))) return rc;
+    if ((rc = dev_alloc(tr.allocs, &d.slab, static_cast<size_t>(hash_cap) * d.row_stride, true))) return rc;
     if ((rc = dev_alloc(tr.allocs, &d.ring, static_cast<size_t>(d.n_buckets) * d.ring_cap, false))) return rc;
     if ((rc = dev_alloc(tr.allocs, &d.ctl, 1, true))) return rc;
-    const long long n_chunks = (c.max_batch + kSamplesPerCta - 1) / kSamplesPerCta;
-    if ((rc = dev_alloc(tr.allocs, &d.flags, n_max, true))) return rc;
-    if ((rc = dev_alloc(tr.allocs, &d.pos_slot, n_max, true))) return rc;
-    if ((rc = dev_alloc(tr.allocs, &d.miss_list, n_max, true))) return rc;
-    if ((rc = dev_alloc(tr.allocs, &d.hist, n_chunks * kMaxBuckets, true))) return rc;
     if ((rc = dev_alloc(tr.allocs, &d.evicted, n_max, true))) return rc;
     d.flushed = nullptr;
     if (c.record_events)
@@ -178,25 +169,82 @@ static int build_tier(evs_handle h, Tier &tr, int prec, long long cap, const voi
 
     k_init_tier<<<592, 256, 0, h->stream>>>(d);
     EVS_CUDA(cudaGetLastError());
-    TierCtl init{};
-    init.free_top = d.rows_total;
-    EVS_CUDA(cudaMemcpyAsync(d.ctl, &init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
     EVS_CUDA(cudaStreamSynchronize(h->stream));
     tr.ub_used = 0;
+    return EVS_OK;
+}
+
+static int build_c3(evs_handle h) {
+    const evs_config &c = h->cfg;
+    C3Dev &d = h->params.c3;
+    const long long n_max = static_cast<long long>(c.max_batch) * c.n_tables;
+    const long long cap = h->caps.c3;
+    if (c.alt_keys == nullptr) {
+        set_error("n_layers == 3 needs alt_keys");
+        return EVS_ERR_INVALID;
+    }
+    d.cap = static_cast<unsigned>(cap);
+    const unsigned hash_cap = next_pow2(static_cast<unsigned long long>(cap + 2 * n_max) * 3ull / 2ull);
+    d.hash_mask = hash_cap - 1;
+    d.ring_cap = next_pow2(static_cast<unsigned long long>(4 * cap + 8 * n_max));
+    int rc;
+    if ((rc = dev_alloc(h->c3_allocs, &d.slots, hash_cap, false))) return rc;
+    if ((rc = dev_alloc(h->c3_allocs, &d.scratch, hash_cap, false))) return rc;
+    if ((rc = dev_alloc(h->c3_allocs, &d.ring, d.ring_cap, true))) return rc;
+    if ((rc = dev_alloc(h->c3_allocs, &d.ctl, 1, true))) return rc;
+    // alt-key tables: device-visible like the backing store
+    std::vector<const unsigned int *> ptrs;
+    for (int t = 0; t < c.n_tables; ++t) {
+        const size_t bytes = static_cast<size_t>(h->rows[t]) * sizeof(uint32_t);
+        if (c.alt_keys[t] == nullptr) {
+            set_error("alt_keys pointer missing for table " + std::to_string(t));
+            return EVS_ERR_INVALID;
+        }
+        if (c.store_in_hbm) {
+            unsigned int *dp = nullptr;
+            if ((rc = dev_alloc(h->c3_allocs, &dp, h->rows[t], false))) return rc;
+            EVS_CUDA(cudaMemcpy(dp, c.alt_keys[t], bytes, cudaMemcpyHostToDevice));
+            ptrs.push_back(dp);
+        } else {
+            void *hp = const_cast<uint32_t *>(c.alt_keys[t]);
+            cudaError_t e = cudaHostRegister(hp, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+            if (e == cudaSuccess) h->registered.push_back(hp);
+            else if (e == cudaErrorHostMemoryAlreadyRegistered) cudaGetLastError();
+            else {
+                set_error(std::string("cudaHostRegister(alt keys) -> ") + cudaGetErrorString(e));
+                cudaGetLastError();
+                return EVS_ERR_CUDA;
+            }
+            void *dp = nullptr;
+            EVS_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+            ptrs.push_back(static_cast<const unsigned int *>(dp));
+        }
+    }
+    const unsigned int **dalt = nullptr;
+    if ((rc = dev_alloc(h->c3_allocs, &dalt, c.n_tables, false))) return rc;
+    EVS_CUDA(cudaMemcpy(dalt, ptrs.data(), sizeof(void *) * c.n_tables, cudaMemcpyHostToDevice));
+    d.alt = dalt;
+    d.active = 1;
+    k_init_c3<<<592, 256, 0, h->stream>>>(d);
+    EVS_CUDA(cudaGetLastError());
+    EVS_CUDA(cudaStreamSynchronize(h->stream));
     return EVS_OK;
 }
 
 static void free_all(evs_handle h) {
     if (h == nullptr) return;
     cudaSetDevice(h->cfg.device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaDeviceSynchronize();
+    if (h->graph) cudaGraphExecDestroy(h->graph);
     for (int i = 0; i < EVS_MAX_TIERS; ++i)
         for (void *p : h->tier[i].allocs) cudaFree(p);
     for (void *p : h->c3_allocs) cudaFree(p);
     for (void *p : h->dev_allocs) cudaFree(p);
     for (void *p : h->registered) cudaHostUnregister(p);
-    delete h->c3;
     h->prof.destroy();
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side) cudaStreamDestroy(h->side);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -204,7 +252,8 @@ static void free_all(evs_handle h) {
 
 // Keep every bucket ring from overflowing: the host only tracks an upper bound of the
 // occupancy and looks at the real head/tail when that bound gets close to the ring size.
-static int maintain_rings(evs_handle h, Tier &tr, cudaStream_t st) {
+static int maintain_rings(evs_handle h, int ti, cudaStream_t st) {
+    Tier &tr = h->tier[ti];
     const unsigned long long n_max = static_cast<unsigned long long>(h->cfg.max_batch) * h->cfg.n_tables;
     if (tr.ub_used + 2 * n_max <= tr.dev.ring_cap) return EVS_OK;
     TierCtl ctl;
@@ -229,16 +278,85 @@ static int maintain_rings(evs_handle h, Tier &tr, cudaStream_t st) {
     return EVS_OK;
 }
 
-template <int PREC>
-static void launch_single_tier(evs_handle h, Tier &tr, const LookupArgs &a, cudaStream_t st) {
-    const int n_chunks = (a.B + kSamplesPerCta - 1) / kSamplesPerCta;
+// ---- kernel selection by (main precision, secondary precision) -----------------------------
+using KernelFn = void (*)(const Params);
+struct KernelSet {
+    KernelFn serve = nullptr, fetch = nullptr;
+};
+template <int P0, int P1>
+static KernelSet kernels_of() {
+    KernelSet k;
+    k.serve = k_serve<P0, P1>;
+    k.fetch = k_fetch<P0, P1>;
+    return k;
+}
+static KernelSet pick_kernels(int p0, int p1) {
+    switch (p0 * 100 + p1) {
+        case 3200: return kernels_of<32, 0>();
+        case 1600: return kernels_of<16, 0>();
+        case 800: return kernels_of<8, 0>();
+        case 400: return kernels_of<4, 0>();
+        case 3216: return kernels_of<32, 16>();
+        case 3208: return kernels_of<32, 8>();
+        case 3204: return kernels_of<32, 4>();
+        case 1608: return kernels_of<16, 8>();
+        case 1604: return kernels_of<16, 4>();
+        case 804: return kernels_of<8, 4>();
+        default: return KernelSet();
+    }
+}
+
+static cudaError_t launch(KernelFn fn, int grid, int block, size_t smem, cudaStream_t st, const Params &p) {
+    void *args[] = {const_cast<Params *>(&p)};
+    return cudaLaunchKernel(reinterpret_cast<const void *>(fn), dim3(grid), dim3(block), args, smem, st);
+}
+
+static int fetch_grid(evs_handle h) {
+    const long long n_max = static_cast<long long>(h->cfg.max_batch) * h->cfg.n_tables;
+    return static_cast<int>(std::max<long long>(1, std::min<long long>((n_max + 255) / 256, 148 * 4)));
+}
+static size_t fetch_smem(evs_handle h) {
+    unsigned s = h->tier[0].dev.row_stride;
+    if (h->n_tiers == 2) s = std::max(s, h->tier[1].dev.row_stride);
+    return static_cast<size_t>(8) * s;
+}
+
+// The per-batch kernel sequence.  `n_chunks` CTAs of k_serve / k_update (CTAs past the batch end
+// exit at once, so a captured graph uses the maximum).  The miss fetch runs on the side stream
+// next to the eviction and the C3 update.
+static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks) {
+    const Params &p = h->params;
+    const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
     Profiler &pf = h->prof;
-    { LaunchScope ls(pf, K_LOOKUP, st); k_lookup<PREC><<<n_chunks, kLookupThreads, 0, st>>>(tr.dev, a); }
-    const int miss_ctas = std::min(n_chunks, 592);
-    { LaunchScope ls(pf, K_MISS, st); k_miss<PREC><<<miss_ctas, 256, 8 * tr.dev.row_stride, st>>>(tr.dev, a); }
-    { LaunchScope ls(pf, K_HIST_SCAN, st); k_hist_scan<<<1, 1024, 0, st>>>(tr.dev, n_chunks); }
-    { LaunchScope ls(pf, K_APPEND, st); k_append<<<n_chunks, kLookupThreads, 0, st>>>(tr.dev, a.B, a.T); }
-    { LaunchScope ls(pf, K_EVICT, st); k_evict<<<1, 1024, 0, st>>>(tr.dev, a.g); }
+    { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch(ks.serve, n_chunks, kLookupThreads, 0, st, p)); }
+    { LaunchScope ls(pf, K_SCAN, st); EVS_CUDA(launch(k_scan, h->n_tiers * h->tier[0].dev.n_buckets, 256, 0, st, p)); }
+    { LaunchScope ls(pf, K_UPDATE, st); EVS_CUDA(launch(k_update, n_chunks, kLookupThreads, 0, st, p)); }
+    EVS_CUDA(cudaEventRecord(h->ev_fork, st));
+    EVS_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    { LaunchScope ls(pf, K_FETCH, h->side); EVS_CUDA(launch(ks.fetch, fetch_grid(h), 256, fetch_smem(h), h->side, p)); }
+    EVS_CUDA(cudaEventRecord(h->ev_join, h->side));
+    { LaunchScope ls(pf, K_EVICT, st); EVS_CUDA(launch(k_evict, h->n_tiers, kEvictThreads, 0, st, p)); }
+    if (h->c3_active) { LaunchScope ls(pf, K_C3, st); EVS_CUDA(launch(k_c3_update, 1, kC3Threads, 0, st, p)); }
+    EVS_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+    return EVS_OK;
+}
+
+static int build_graph(evs_handle h) {
+    cudaGraph_t g = nullptr;
+    const bool was_on = h->prof.on;
+    h->prof.on = false;                                   // no event records inside the capture
+    unsigned long long saved[K_COUNT];
+    memcpy(saved, h->prof.launches, sizeof(saved));
+    EVS_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_batch(h, h->stream, h->params.n_chunks_max);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    memcpy(h->prof.launches, saved, sizeof(saved));
+    h->prof.on = was_on;
+    if (rc) return rc;
+    EVS_CUDA(e);
+    EVS_CUDA(cudaGraphInstantiate(&h->graph, g, 0));
+    EVS_CUDA(cudaGraphDestroy(g));
+    return EVS_OK;
 }
 
 static int check_device_errors(evs_handle h) {
@@ -255,6 +373,14 @@ static int check_device_errors(evs_handle h) {
         EVS_CUDA(cudaMemcpy(&c, h->tier[i].dev.ctl, sizeof(c), cudaMemcpyDeviceToHost));
         if (c.error) {
             set_error("tier " + std::to_string(i) + ": internal capacity error " + std::to_string(c.error));
+            return EVS_ERR_CAPACITY;
+        }
+    }
+    if (h->c3_active) {
+        C3Ctl c;
+        EVS_CUDA(cudaMemcpy(&c, h->params.c3.ctl, sizeof(c), cudaMemcpyDeviceToHost));
+        if (c.error) {
+            set_error("C3: internal capacity error " + std::to_string(c.error));
             return EVS_ERR_CAPACITY;
         }
     }
@@ -318,12 +444,27 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         free_all(h);
         return code;
     };
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        set_error("cudaStreamCreate failed");
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("cudaStreamCreate / cudaEventCreate failed");
         return fail(EVS_ERR_CUDA);
     }
+    h->n_tiers = cfg->n_layers >= 2 ? 2 : 1;
+    if (pick_kernels(cfg->main_precision, h->n_tiers == 2 ? cfg->secondary_precision : 0).serve == nullptr) {
+        set_error("evs_create: no kernel for this precision pair");
+        return fail(EVS_ERR_INVALID);
+    }
+    if (h->n_tiers == 2 && (static_cast<long long>(cfg->dim) * cfg->secondary_precision) % 8 != 0) {
+        set_error("evs_create: dim*secondary_precision must be a whole number of bytes");
+        return fail(EVS_ERR_INVALID);
+    }
     const long long n_max = static_cast<long long>(cfg->max_batch) * cfg->n_tables;
+    const int n_chunks_max = (cfg->max_batch + kSamplesPerCta - 1) / kSamplesPerCta;
+    Params &P = h->params;
     if ((rc = dev_alloc(h->dev_allocs, &h->g, 1))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &h->d_args, 1))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &h->d_rows, cfg->n_tables))) return fail(rc);
     if (cudaMemcpy(h->d_rows, h->rows.data(), sizeof(int64_t) * cfg->n_tables, cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(EVS_ERR_CUDA);
@@ -331,15 +472,42 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     if ((rc = dev_alloc(h->dev_allocs, &h->d_idx, n_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &h->d_out, n_max * cfg->dim))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &h->d_hit, n_max))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &P.flags, n_max))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &P.pos_slot, n_max))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &P.hist, static_cast<size_t>(kSeqs) * n_chunks_max))) return fail(rc);
 
-    h->n_tiers = cfg->n_layers >= 2 ? 2 : 1;
     if ((rc = build_tier(h, h->tier[0], cfg->main_precision, h->caps.c1, cfg->store_main))) return fail(rc);
     if (h->n_tiers == 2)
         if ((rc = build_tier(h, h->tier[1], cfg->secondary_precision, h->caps.c2, cfg->store_secondary))) return fail(rc);
     if (cfg->n_layers == 3 && h->caps.c3 > 0) {
-        if ((rc = c3_build(h))) return fail(rc);
+        if ((rc = build_c3(h))) return fail(rc);
         h->c3_active = true;
     }
+    P.tier[0] = h->tier[0].dev;
+    if (h->n_tiers == 2) P.tier[1] = h->tier[1].dev;
+    P.n_tiers = h->n_tiers;
+    P.T = cfg->n_tables;
+    P.D = cfg->dim;
+    P.table_base = cfg->table_base;
+    P.n_perfect_agg = h->cfg.n_tables_total;
+    P.approx_thres = (h->n_tiers == 1) ? cfg->approx_emb_thres : 0;
+    P.high_thres = h->cfg.high_agghit_threshold;
+    P.n_chunks_max = n_chunks_max;
+    P.rows = h->d_rows;
+    P.args = h->d_args;
+    P.g = h->g;
+    const size_t fs = fetch_smem(h);
+    if (fs > 48 * 1024) {
+        const KernelSet ks = pick_kernels(cfg->main_precision, h->n_tiers == 2 ? cfg->secondary_precision : 0);
+        if (cudaFuncSetAttribute(reinterpret_cast<const void *>(ks.fetch), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(fs)) != cudaSuccess) {
+            set_error("row too large for the fetch kernel's staging buffer");
+            return fail(EVS_ERR_INVALID);
+        }
+    }
+    const char *ng = getenv("EVSTORE_B200_NO_GRAPH");
+    h->use_graph = !(ng && ng[0] == '1');
+    if (h->use_graph && (rc = build_graph(h))) return fail(rc);
     *out = h;
     return EVS_OK;
 }
@@ -347,6 +515,33 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
 int evs_destroy(evs_handle h) {
     if (h == nullptr) return EVS_ERR_INVALID;
     free_all(h);
+    return EVS_OK;
+}
+
+static int run_batch(evs_handle h, const BatchArgs &a, cudaStream_t st) {
+    // the 64-byte argument block is staged by the runtime before this returns (pageable source)
+    EVS_CUDA(cudaMemcpyAsync(h->d_args, &a, sizeof(a), cudaMemcpyHostToDevice, st));
+    if (a.probe_only) {
+        const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
+        LaunchScope ls(h->prof, K_PROBE, st);
+        EVS_CUDA(launch(ks.serve, (a.B + kSamplesPerCta - 1) / kSamplesPerCta, kLookupThreads, 0, st, h->params));
+        return EVS_OK;
+    }
+    if (h->use_graph && !h->prof.on) {
+        EVS_CUDA(cudaGraphLaunch(h->graph, st));
+        h->prof.launches[K_SERVE]++, h->prof.launches[K_SCAN]++, h->prof.launches[K_UPDATE]++;
+        h->prof.launches[K_FETCH]++, h->prof.launches[K_EVICT]++;
+        if (h->c3_active) h->prof.launches[K_C3]++;
+    } else {
+        int rc = enqueue_batch(h, st, (a.B + kSamplesPerCta - 1) / kSamplesPerCta);
+        if (rc) return rc;
+    }
+    h->batches++;
+    for (int i = 0; i < h->n_tiers; ++i) {
+        h->tier[i].ub_used += static_cast<unsigned long long>(a.B) * h->cfg.n_tables;
+        int rc = maintain_rings(h, i, st);
+        if (rc) return rc;
+    }
     return EVS_OK;
 }
 
@@ -358,66 +553,28 @@ int evs_lookup_batch(evs_handle h, const int64_t *idx_dev, int32_t B, float *out
     }
     if (B == 0) return EVS_OK;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
-    LookupArgs a{};
+    BatchArgs a{};
     a.idx = reinterpret_cast<const long long *>(idx_dev);
-    a.rows = h->d_rows;
     a.out = out_dev;
     a.out_stride = out_stride > 0 ? out_stride : static_cast<long long>(h->cfg.n_tables) * h->cfg.dim;
     a.hit = hit_dev;
     a.agg_in = agg_in;
     a.agg_out = h->d_agg;
     a.B = B;
-    a.T = h->cfg.n_tables;
-    a.D = h->cfg.dim;
-    a.table_base = h->cfg.table_base;
-    a.n_perfect_agg = h->cfg.n_tables_total;
-    a.approx_thres = h->cfg.approx_emb_thres;
-    a.g = h->g;
-    int rc = EVS_OK;
-    if (h->n_tiers == 1) {
-        Tier &tr = h->tier[0];
-        switch (tr.prec) {
-            case 32: launch_single_tier<32>(h, tr, a, st); break;
-            case 16: launch_single_tier<16>(h, tr, a, st); break;
-            case 8: launch_single_tier<8>(h, tr, a, st); break;
-            default: launch_single_tier<4>(h, tr, a, st); break;
-        }
-    } else {
-        rc = launch_multi_tier(h, a, st);
-        if (rc) return rc;
-    }
-    EVS_CUDA(cudaGetLastError());
-    h->batches++;
-    for (int i = 0; i < h->n_tiers; ++i) {
-        h->tier[i].ub_used += static_cast<unsigned long long>(B) * a.T;
-        if ((rc = maintain_rings(h, h->tier[i], st))) return rc;
-    }
-    return EVS_OK;
+    a.probe_only = 0;
+    return run_batch(h, a, st);
 }
 
 int evs_probe_batch(evs_handle h, const int64_t *idx_dev, int32_t B, uint8_t *agg_out_dev, void *stream) {
     if (h == nullptr || B < 0 || B > h->cfg.max_batch || idx_dev == nullptr || agg_out_dev == nullptr) return EVS_ERR_INVALID;
-    if (h->n_tiers != 1) {
-        set_error("evs_probe_batch: single-tier caches only");
-        return EVS_ERR_INVALID;
-    }
     if (B == 0) return EVS_OK;
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
-    LookupArgs a{};
+    BatchArgs a{};
     a.idx = reinterpret_cast<const long long *>(idx_dev);
-    a.rows = h->d_rows;
     a.agg_out = agg_out_dev;
     a.B = B;
-    a.T = h->cfg.n_tables;
-    a.D = h->cfg.dim;
-    a.table_base = h->cfg.table_base;
-    a.g = h->g;
-    {
-        LaunchScope ls(h->prof, K_PROBE, st);
-        k_probe<<<(B + kSamplesPerCta - 1) / kSamplesPerCta, kLookupThreads, 0, st>>>(h->tier[0].dev, a);
-    }
-    EVS_CUDA(cudaGetLastError());
-    return EVS_OK;
+    a.probe_only = 1;
+    return run_batch(h, a, st);
 }
 
 int evs_lookup_batch_host(evs_handle h, const int64_t *idx_host, int32_t B, float *out_host, uint8_t *hit_host) {
@@ -475,7 +632,12 @@ int evs_stats(evs_handle h, evs_stats_t *out, int reset) {
             EVS_CUDA(cudaMemcpy(h->tier[i].dev.ctl, &c, sizeof(c), cudaMemcpyHostToDevice));
         }
     }
-    if (h->c3_active) c3_stats(h, &out->c3_size, &out->c3_capacity);
+    if (h->c3_active) {
+        C3Ctl c3;
+        EVS_CUDA(cudaMemcpy(&c3, h->params.c3.ctl, sizeof(c3), cudaMemcpyDeviceToHost));
+        out->c3_size = c3.size;
+        out->c3_capacity = h->params.c3.cap;
+    }
     if (reset) {
         const unsigned err = g.error;
         memset(&g, 0, sizeof(g));
@@ -547,9 +709,8 @@ int evs_dump_state(evs_handle h, int tier, int64_t *keys, int64_t *n_keys, int64
     const TierDev &d = h->tier[tier].dev;
     TierCtl c;
     EVS_CUDA(cudaMemcpy(&c, d.ctl, sizeof(c), cudaMemcpyDeviceToHost));
-    std::vector<unsigned long long> meta(d.rows_total), rkey(d.rows_total);
-    EVS_CUDA(cudaMemcpy(meta.data(), d.row_meta, sizeof(unsigned long long) * d.rows_total, cudaMemcpyDeviceToHost));
-    EVS_CUDA(cudaMemcpy(rkey.data(), d.row_key, sizeof(unsigned long long) * d.rows_total, cudaMemcpyDeviceToHost));
+    std::vector<Slot> slots(static_cast<size_t>(d.hash_mask) + 1);
+    EVS_CUDA(cudaMemcpy(slots.data(), d.slots, sizeof(Slot) * slots.size(), cudaMemcpyDeviceToHost));
     int64_t n = 0;
     std::vector<unsigned> rec;
     for (int b = 0; b < d.n_buckets; ++b) {
@@ -565,13 +726,13 @@ int evs_dump_state(evs_handle h, int tier, int64_t *keys, int64_t *n_keys, int64
         }
         unsigned live = 0;
         for (unsigned long long i = 0; i < len; ++i) {
-            const unsigned row = rec[i];
-            if (row < d.rows_total && meta[row] == pack_meta(b, c.head[b] + i)) {
+            const unsigned sl = rec[i];
+            if (sl <= d.hash_mask && slots[sl].meta == pack_meta(b, c.head[b] + i)) {
                 if (n >= *n_keys) {
                     set_error("evs_dump_state: keys array too small");
                     return EVS_ERR_INVALID;
                 }
-                keys[n++] = static_cast<int64_t>(rkey[row]);
+                keys[n++] = static_cast<int64_t>(slots[sl].kw & kKeyMask);
                 ++live;
             }
         }
@@ -587,13 +748,49 @@ int evs_dump_state(evs_handle h, int tier, int64_t *keys, int64_t *n_keys, int64
     return EVS_OK;
 }
 
+// C3 in FIFO order: one entry per queue record whose key is still mapped (stale records of
+// evicted keys are skipped, duplicates of a mapped key are reported as they sit in the queue).
 int evs_dump_c3(evs_handle h, int64_t *keys, uint32_t *alt, uint8_t *recency, int64_t *n) {
     if (h == nullptr || n == nullptr) return EVS_ERR_INVALID;
     if (!h->c3_active) {
         *n = 0;
         return EVS_OK;
     }
-    return c3_dump(h, keys, alt, recency, n);
+    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    EVS_CUDA(cudaDeviceSynchronize());
+    const C3Dev &d = h->params.c3;
+    C3Ctl c;
+    EVS_CUDA(cudaMemcpy(&c, d.ctl, sizeof(c), cudaMemcpyDeviceToHost));
+    std::vector<C3Slot> slots(static_cast<size_t>(d.hash_mask) + 1);
+    EVS_CUDA(cudaMemcpy(slots.data(), d.slots, sizeof(C3Slot) * slots.size(), cudaMemcpyDeviceToHost));
+    std::vector<unsigned long long> ring(d.ring_cap);
+    EVS_CUDA(cudaMemcpy(ring.data(), d.ring, sizeof(unsigned long long) * d.ring_cap, cudaMemcpyDeviceToHost));
+    int64_t cnt = 0;
+    for (unsigned long long q = c.head; q < c.tail; ++q) {
+        const unsigned long long key = ring[q & (d.ring_cap - 1)];
+        unsigned i = hash_key(key, d.hash_mask);
+        bool found = false;
+        while (true) {
+            const unsigned long long kw = slots[i].kw;
+            if ((kw & kKeyMask) == key) {
+                found = true;
+                break;
+            }
+            if ((kw >> 48) == 0ull) break;
+            i = (i + 1) & d.hash_mask;
+        }
+        if (!found) continue;
+        if (cnt >= *n) {
+            set_error("evs_dump_c3: arrays too small");
+            return EVS_ERR_INVALID;
+        }
+        if (keys) keys[cnt] = static_cast<int64_t>(key);
+        if (alt) alt[cnt] = slots[i].alt;
+        if (recency) recency[cnt] = static_cast<uint8_t>(slots[i].flag & 1u);
+        ++cnt;
+    }
+    *n = cnt;
+    return EVS_OK;
 }
 
 int evs_interact(const float *x_dev, const float *ly_dev, float *r_dev, int32_t B, int32_t n_f, int32_t dim, void *stream) {

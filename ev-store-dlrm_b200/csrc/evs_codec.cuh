@@ -43,11 +43,13 @@ struct CodecLut {
     float lut4[16];
 };
 
-template <int PREC>
+// Fills the tables the two precisions of a tier pair need (P1 == 0: single tier).
+template <int P0, int P1>
 __device__ __forceinline__ void codec_lut_init(CodecLut *l) {
-    if (PREC == 8) {
+    if (P0 == 8 || P1 == 8) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) l->lut8[i] = dec8(i);
-    } else if (PREC == 4) {
+    }
+    if (P0 == 4 || P1 == 4) {
         if (threadIdx.x < 16) l->lut4[threadIdx.x] = dec4(threadIdx.x);
     }
 }

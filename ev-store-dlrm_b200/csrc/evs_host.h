@@ -37,13 +37,11 @@ struct Tier {
     std::vector<const unsigned char *> store_dev;   // per table, device-visible backing rows
 };
 
-struct C3Dev;                                // evs_tiers.cuh
 
 // Kernel ids for the launch counter / per-kernel CUDA-event timing (evs_set_profiling).
-enum KernelId { K_LOOKUP = 0, K_MISS, K_HIST_SCAN, K_APPEND, K_EVICT, K_COMPACT, K_PROBE, K_INTERACT, K_MT_LOOKUP,
-                K_MT_ROUTE, K_C3, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_lookup", "k_miss", "k_hist_scan", "k_append", "k_evict", "k_compact",
-                                                  "k_probe", "k_interact", "k_mt_lookup", "k_mt_route", "k_c3"};
+enum KernelId { K_SERVE = 0, K_SCAN, K_UPDATE, K_FETCH, K_EVICT, K_C3, K_COMPACT, K_PROBE, K_INTERACT, K_GATHER, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_serve", "k_scan", "k_update", "k_fetch", "k_evict", "k_c3_update",
+                                                  "k_compact", "k_probe", "k_interact", "k_gather"};
 
 struct Profiler {
     bool on = false;
@@ -100,10 +98,15 @@ struct evs_handle_s {
     bool c3_active = false;
     evs::Caps caps;
     evs::Tier tier[EVS_MAX_TIERS];
-    evs::C3Dev *c3 = nullptr;                // host copy of the device view
+    evs::Params params{};                    // kernel parameter block (device pointers inside)
     std::vector<void *> c3_allocs;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;           // the handle's own stream
+    cudaStream_t side = nullptr;             // miss fetch runs here, next to the eviction
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaGraphExec_t graph = nullptr;         // serve -> scan -> update -> {evict || fetch} [-> c3]
+    bool use_graph = true;
     evs::GlobalCtl *g = nullptr;             // device
+    evs::BatchArgs *d_args = nullptr;        // device copy of the per-batch arguments
     long long *d_rows = nullptr;
     uint8_t *d_agg = nullptr;                // [max_batch]
     // staging for the host-buffer path
@@ -112,7 +115,6 @@ struct evs_handle_s {
     uint8_t *d_hit = nullptr;
     std::vector<void *> registered;          // host ranges we page-locked
     std::vector<void *> dev_allocs;
-    const uint32_t **d_alt = nullptr;        // [n_tables] device-visible alt-key tables
     uint64_t batches = 0;
     evs::Profiler prof;
 };

@@ -1,16 +1,19 @@
-// Device-side data layout of one EvLFU cache tier (C1 or C2) in HBM.
+// Device-side data layout of the EvLFU cache tiers (C1, C2) and the alternative-key map (C3).
 //
 // What the reference keeps in std::unordered_map<string, Cache_data> vals_C1 plus
-// vector<unordered_set<string>> lists_C1 (evlfu_32.hpp:47-49) is here:
+// vector<unordered_set<string>> lists_C1 (evlfu_32.hpp:47-49) is, per tier, in HBM:
 //
-//   slots[]     open-addressing index, 16 B per slot {key, rowword, pass}
-//               rowword = (bucket+1) << 27 | slab row;  pass = number of resident keys whose
-//               probe path crosses this slot (lets a probe stop without tombstones)
-//   slab[]      the rows themselves, row_stride bytes each (precision dependent)
-//   row_meta[]  per slab row: (bucket+1) << 56 | position of its live record in the bucket ring
-//   ring[b][]   per agg_hit bucket b a FIFO log of slab rows (lists_C1[b]); a record is live
-//               iff row_meta[row] still points at it, so promotion/eviction never edits a log
-//   free_rows[] stack of unused slab rows
+//   slots[]   open-addressing index (linear probing), 16 B per slot {kw, meta}
+//             kw   = pass << 48 | key   (key 48 bits, all ones = empty).  pass counts the resident
+//                    keys whose probe path crosses the slot, so a probe stops at the first slot
+//                    nobody crosses and deletions need no tombstones; one 128-bit load answers
+//                    "is it my key / may I stop / which bucket".
+//             meta = (bucket+1) << 56 | position of the entry's live record in its bucket ring;
+//                    0 on an occupied slot = claimed by the batch in flight, not in a bucket yet
+//   slab[]    the rows themselves, indexed BY SLOT (row_stride bytes each, precision dependent):
+//             no row indirection and no free list -- claiming a slot is one CAS
+//   ring[b][] per agg_hit bucket b a FIFO log of slot ids (lists_C1[b]); a record is live iff
+//             slots[slot].meta still points at it, so promotion / eviction never edit a log
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -19,40 +22,45 @@ namespace evs {
 
 constexpr int kMaxTables = 32;
 constexpr int kMaxBuckets = 32;              // agg_hit 0..n_tables_total (<= 31)
+constexpr int kMaxTiers = 2;
+constexpr int kSeqs = kMaxTiers * kMaxBuckets;   // (tier, bucket) append sequences
 constexpr int kSamplesPerCta = 8;            // one warp per sample
 constexpr int kLookupThreads = kSamplesPerCta * 32;
-constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
-constexpr unsigned kRowBits = 27;
-constexpr unsigned kRowMask = (1u << kRowBits) - 1u;
 constexpr int kKeyShift = 40;
-constexpr unsigned kNoRow = 0xFFFFFFFFu;
+constexpr unsigned long long kKeyMask = 0x0000FFFFFFFFFFFFull;
+constexpr unsigned long long kEmptyKey = kKeyMask;           // 48 one bits
+constexpr unsigned long long kPassOne = 1ull << 48;
+constexpr unsigned kNoSlot = 0xFFFFFFFFu;
+constexpr unsigned kClaimedBit = 0x80000000u;     // pos_slot: this position claimed the slot (it fills the slab row)
 
-// flags[p]: 0 = nothing to do; low 6 bits = bucket+1 of the append this position asks for;
-// bit 7 = the position missed and needs a row
+// flags[p]: 0 = nothing to do; bits 0-5 = bucket+1 of the append this position asks for;
+// bit 6 = tier of the append; bit 7 = the position missed: claim a slot and fetch the row
 constexpr uint8_t kFlagMiss = 0x80;
+constexpr uint8_t kFlagTier = 0x40;
+
+// hit[p] codes (nonzero == answered without touching the backing store)
+constexpr uint8_t kHitMiss = 0, kHitC1 = 1, kHitC2 = 2, kHitC3 = 3, kHitApprox = 4;
 
 struct __align__(16) Slot {
-    unsigned long long key;
-    unsigned int rowword;
-    unsigned int pass;
+    unsigned long long kw;
+    unsigned long long meta;
 };
 
 struct TierCtl {
     unsigned long long head[kMaxBuckets];
     unsigned long long tail[kMaxBuckets];
-    unsigned long long tail_prev[kMaxBuckets];   // tail before this batch's appends (k_hist_scan)
+    unsigned long long tail_prev[kMaxBuckets];   // tail before this batch's appends (k_scan)
     unsigned int count[kMaxBuckets];       // live entries per bucket
-    unsigned int free_top;
     unsigned int n_perfect;                // n_perfect_item_C1 (evlfu_32.hpp:51)
+    unsigned int full_at_start;            // size >= cap when the batch began (two-tier routing, evlfu_32.cpp:373)
     // per batch (reset by the evict kernel)
-    unsigned int miss_count;
     unsigned int n_new;
-    unsigned long long prot;               // max over new keys of (bucket+1) << 32 | position
     unsigned int any_perfect;
+    unsigned long long prot;               // max over new keys of (bucket+1) << 32 | position
     unsigned int n_evicted_last;
     unsigned int n_flushed_last;
     unsigned int error;
-    unsigned int full_at_start;            // size >= cap when the batch began (two-tier routing)
+    unsigned int pad;
     // cumulative
     unsigned long long stat_inserts, stat_evictions, stat_flushed;
 };
@@ -60,30 +68,44 @@ struct TierCtl {
 struct TierDev {
     Slot *slots;
     unsigned int hash_mask;
-    unsigned char *slab;
     unsigned int row_stride;               // bytes, multiple of 16
+    unsigned char *slab;                   // [hash_cap][row_stride]
     unsigned int row_bytes;                // dim*prec/8 (bytes of one backing-store row)
     int prec;                              // 32/16/8/4
-    unsigned long long *row_meta;
-    unsigned long long *row_key;
-    unsigned int *row_slot;
-    unsigned int *free_rows;
-    unsigned int *ring;                    // [n_buckets][ring_cap]
+    unsigned int *ring;                    // [n_buckets][ring_cap] slot ids
     unsigned int ring_cap;                 // power of two
     unsigned int cap;                      // policy capacity (entries)
-    unsigned int rows_total;               // cap + spare rows for one batch of inserts
     unsigned int max_perfect;              // int(cap * 0.95)
     unsigned int flush_n;                  // int(0.3 * cap) + 1
     int n_buckets;                         // n_tables_total + 1
     TierCtl *ctl;
     const unsigned char *const *store;     // [n_tables] device-visible backing rows at this precision
-    // per-batch scratch
-    uint8_t *flags;                        // [N]
-    unsigned int *pos_slot;                // [N]
-    unsigned int *miss_list;               // [N]
-    unsigned int *hist;                    // [n_chunks][kMaxBuckets]
     unsigned long long *evicted;           // [N] keys evicted by the last batch (rank order)
     unsigned long long *flushed;           // [flush_n] keys flushed by the last batch (or null)
+};
+
+// C3 (aprx_embedding.cpp): key -> alternative key, FIFO with second-chance eviction.
+struct C3Ctl {
+    unsigned long long head, tail;         // FIFO ring window (lists_C3)
+    unsigned int size;                     // vals_C3.size()
+    unsigned int error;
+    unsigned long long stat_inserts, stat_evictions;
+};
+struct __align__(16) C3Slot {
+    unsigned long long kw;                 // pass << 48 | key, as in Slot
+    unsigned int alt;                      // alt_row*100 + alt_table(1-based)   (convert_altkeys_to_binary.py:50)
+    unsigned int flag;                     // recency flag (aprx_embedding.cpp:402)
+};
+struct C3Dev {
+    C3Slot *slots;
+    unsigned int hash_mask;
+    unsigned int ring_cap;
+    unsigned long long *ring;              // FIFO of keys; may hold stale duplicates like the reference's queue
+    unsigned int cap;
+    int active;
+    C3Ctl *ctl;
+    const unsigned int *const *alt;        // [n_tables] device-visible alt-key tables
+    unsigned int *scratch;                 // [window] duplicate detection
 };
 
 struct GlobalCtl {
@@ -92,19 +114,37 @@ struct GlobalCtl {
     unsigned int pad;
 };
 
-struct LookupArgs {
+// Arguments that change from batch to batch live in device memory so that the kernel sequence
+// can be captured once in a CUDA graph; a 64-byte H2D copy precedes each launch.
+struct BatchArgs {
     const long long *idx;                  // [T][B]
-    const long long *rows;                 // [T] cardinalities (device)
     float *out;
     long long out_stride;                  // floats between samples
     uint8_t *hit;                          // [B][T] or null
     const uint8_t *agg_in;                 // [B] or null
-    uint8_t *agg_out;                      // [B] (scratch; always written)
-    int B, T, D;
+    uint8_t *agg_out;                      // [B]
+    int B;
+    int probe_only;
+};
+
+// Everything a kernel of the batch pipeline needs; constant for the life of a handle.
+struct Params {
+    TierDev tier[kMaxTiers];
+    C3Dev c3;
+    int n_tiers;
+    int T, D;
     int table_base;
     int n_perfect_agg;                     // agg value that counts as a perfect hit (n_tables_total)
     int approx_thres;
+    int high_thres;                        // high_agghit_threshold (evlfu_32.hpp:74)
+    int n_chunks_max;
+    const long long *rows;                 // [T] cardinalities
+    const BatchArgs *args;
     GlobalCtl *g;
+    // per-batch scratch
+    uint8_t *flags;                        // [N]
+    unsigned int *pos_slot;                // [N] slot (in the flag's tier) of a promoted / inserted key
+    unsigned int *hist;                    // [kSeqs][n_chunks_max]: counts, then absolute ring positions
 };
 
 __host__ __device__ inline unsigned long long pack_meta(int bucket, unsigned long long q) {
