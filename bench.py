@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--store-in-hbm", action="store_true", help="debug: backing store copied into HBM (not the BASELINE config)")
     return ap.parse_args()
 
 
@@ -237,13 +238,21 @@ def main_ours(args):
     rows = pkg.workload.KAGGLE_ROWS if args.scale == 1.0 else pkg.workload.scaled_rows(pkg.workload.KAGGLE_ROWS, args.scale)
     T = len(rows)
     cache_rows = pkg.workload.KAGGLE_CACHE_ROWS if args.scale == 1.0 else int(sum(rows) * 0.13)
-    warm = args.cache_warm if args.cache_warm >= 0 else 1200
+    warm = args.cache_warm if args.cache_warm >= 0 else 3200
     n_batches = warm + 3 * (W + K)
     _, tables, idx = build_workload(args, n_batches, rows, dim, B)
 
-    cfg = pkg.CacheConfig(n_layers=1, main_precision=prec, total_size=cache_rows * prec // 32, max_batch=B, device=local_rank)
+    cfg = pkg.CacheConfig(n_layers=1, main_precision=prec, total_size=cache_rows * prec // 32, max_batch=B, device=local_rank,
+                          store_in_hbm=args.store_in_hbm)
     t0 = time.time()
-    store = pkg.EvStore(tables, cfg)
+    stores = None
+    if os.environ.get("EVS_BENCH_PINNED_ALLOC", "1") == "1":
+        # backing store in cudaHostAlloc memory (torch's pinned allocator) instead of page-locking numpy's pages
+        raw = [pkg.codecs.encode_table(t, prec) for t in tables]
+        pinned = [torch.from_numpy(r).pin_memory() for r in raw]
+        stores = {prec: [q.numpy() for q in pinned]}
+        log(f"backing store copied to pinned allocations in {time.time() - t0:.1f}s")
+    store = pkg.EvStore(tables, cfg, stores=stores)
     log(f"EvStore created in {time.time() - t0:.1f}s (cache {cache_rows} rows, backing store host-pinned zero-copy)")
 
     idx_host = torch.from_numpy(idx).pin_memory()                    # [n, T, B] int64
@@ -267,6 +276,7 @@ def main_ours(args):
         sampler.start()
         time.sleep(0.3)
 
+    store.phase_times()                           # clears the debug accumulators
     # ---- value: indices resident in HBM ------------------------------------------------------
     base = warm
     for k in range(W):
@@ -281,7 +291,11 @@ def main_ours(args):
     torch.cuda.synchronize()
     ms_dev = e0.elapsed_time(e1)
     launches = store.launch_count() - l0
+    phases = store.phase_times()
+    log("device phases of the last timed batch (us):", phases)
     st = store.stats(reset=True)
+    log("per step: misses %.0f evictions %.0f flushed %.0f inserts %.0f" % (st["misses"] / K, st["evictions"][0] / K,
+        st["flushed"][0] / K, st["inserts"][0] / K))
     hit_rate = st["hits"][0] / max(1, st["lookups"])
     perfect_rate = st["perfect_hits"] / max(1, st["samples"])
     lookups = K * B * T
@@ -330,7 +344,7 @@ def main_ours(args):
         "frac": alg_bytes / (dom_us * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_lookup": bpl, "kernel_avg_us": dom_us,
         "k_lookup_avg_us": look_us, "k_lookup_frac": alg_bytes / (look_us * 1e-6) / 1e9 / peak,
-        "step_frac": lookups * bpl / (ms_dev * 1e-3) / 1e9 / peak, "per_kernel": per_kernel,
+        "step_frac": lookups * bpl / (ms_dev * 1e-3) / 1e9 / peak, "per_kernel": per_kernel, "phases_us": phases,
     }
 
     # ---- CPU baseline: the reference's own library on this host -------------------------------

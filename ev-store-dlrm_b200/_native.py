@@ -52,7 +52,7 @@ class EvsStats(C.Structure):
 SYMBOLS = [
     "evs_create", "evs_destroy", "evs_last_error", "evs_version", "evs_lookup_batch", "evs_probe_batch",
     "evs_lookup_batch_host", "evs_sync", "evs_stats", "evs_last_events", "evs_dump_state", "evs_dump_c3",
-    "evs_interact", "evs_set_profiling", "evs_kernel_times", "evs_launch_count", "evs_legacy_configure", "evs_legacy_handle", "ev_lookup", "get_ev_values", "print_perfect_hit",
+    "evs_interact", "evs_set_profiling", "evs_kernel_times", "evs_launch_count", "evs_phase_times", "evs_legacy_configure", "evs_legacy_handle", "ev_lookup", "get_ev_values", "print_perfect_hit",
     "test_arr", "ev_lookup_based_on_list_keys",
 ]
 
@@ -100,6 +100,8 @@ def load_library(path: str | None = None):
     lib.evs_kernel_times.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
     lib.evs_kernel_times.restype = C.c_int
+    lib.evs_phase_times.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.evs_phase_times.restype = C.c_int
     lib.evs_launch_count.argtypes = [vp]
     lib.evs_launch_count.restype = C.c_uint64
     lib.evs_legacy_configure.argtypes = [C.POINTER(EvsConfig)]

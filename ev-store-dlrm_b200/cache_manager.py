@@ -184,6 +184,19 @@ class EvStore:
                       "evs_kernel_times")
         return {names[i].decode(): (ms[i], int(timed[i]), int(launches[i])) for i in range(n.value)}
 
+    def phase_times(self) -> dict:
+        """Device-side phase durations (us) of the last batch, from %globaltimer stamps."""
+        t = (C.c_uint64 * 16)()
+        _native.check(self.lib.evs_phase_times(self.handle, t), "evs_phase_times")
+        v = [int(x) for x in t]
+        us = lambda a, b: (v[b] - v[a]) / 1e3
+        n = max(1, v[8])
+        return {"upd_warps": v[8], "upd_prefix_avg": v[9] / n / 1e3, "upd_append_avg": v[10] / n / 1e3,
+                "upd_fetch_avg": v[11] / n / 1e3, "evict_scanned_total": v[15], "appends_total": v[1],
+                "upd_prefix_max": v[12] / 1e3, "upd_append_max": v[13] / 1e3, "upd_fetch_max": v[14] / 1e3,
+                "serve": us(0, 7), "serve_to_update_gap": us(7, 2), "update": us(2, 3), "update_to_evict_gap": us(3, 4),
+                "evict": us(4, 5), "c3": us(5, 6), "total": us(0, 6)}
+
     def launch_count(self) -> int:
         return int(self.lib.evs_launch_count(self.handle))
 

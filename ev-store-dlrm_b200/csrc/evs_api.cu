@@ -11,6 +11,7 @@
 #include "evs_interact.cuh"
 #include "evs_kernels.cuh"
 #include "evs_c3.cuh"
+#include "evs_update.cuh"
 
 namespace evs {
 
@@ -88,6 +89,29 @@ static int dev_alloc(std::vector<void *> &owner, T **p, size_t n, bool zero = tr
     return EVS_OK;
 }
 
+// Device-visible alias of a host range: ranges that are already page-locked (cudaHostAlloc /
+// an earlier cudaHostRegister, e.g. a framework's pinned allocator) are used as they are,
+// anything else is page-locked and mapped here (and released in free_all).
+static int map_host_range(evs_handle h, void *hp, size_t bytes, void **dp, const std::string &what) {
+    cudaPointerAttributes attr{};
+    cudaError_t e = cudaPointerGetAttributes(&attr, hp);
+    if (e != cudaSuccess) cudaGetLastError();
+    if (e != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+        e = cudaHostRegister(hp, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+        if (e == cudaSuccess) {
+            h->registered.push_back(hp);
+        } else if (e == cudaErrorHostMemoryAlreadyRegistered) {
+            cudaGetLastError();
+        } else {
+            set_error("cudaHostRegister(" + what + ", " + std::to_string(bytes) + " B) -> " + cudaGetErrorString(e));
+            cudaGetLastError();
+            return EVS_ERR_CUDA;
+        }
+    }
+    EVS_CUDA(cudaHostGetDevicePointer(dp, hp, 0));
+    return EVS_OK;
+}
+
 static int make_store(evs_handle h, const void *const *ptrs, int prec, std::vector<const unsigned char *> &out) {
     const evs_config &c = h->cfg;
     out.clear();
@@ -105,19 +129,9 @@ static int make_store(evs_handle h, const void *const *ptrs, int prec, std::vect
             out.push_back(d);
         } else {
             void *hp = const_cast<void *>(ptrs[t]);
-            cudaError_t e = cudaHostRegister(hp, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
-            if (e == cudaSuccess) {
-                h->registered.push_back(hp);
-            } else if (e == cudaErrorHostMemoryAlreadyRegistered) {
-                cudaGetLastError();
-            } else {
-                set_error(std::string("cudaHostRegister(table ") + std::to_string(t) + ", " + std::to_string(bytes) +
-                          " B) -> " + cudaGetErrorString(e));
-                cudaGetLastError();
-                return EVS_ERR_CUDA;
-            }
             void *dp = nullptr;
-            EVS_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+            int rc2 = map_host_range(h, hp, bytes, &dp, "table " + std::to_string(t));
+            if (rc2) return rc2;
             out.push_back(static_cast<const unsigned char *>(dp));
         }
     }
@@ -132,7 +146,9 @@ static int build_tier(evs_handle h, Tier &tr, int prec, long long cap, const voi
         return EVS_ERR_INVALID;
     }
     // the index holds cap entries between batches and up to cap + n_max while a batch is in flight
-    const unsigned long long want_slots = static_cast<unsigned long long>(cap + n_max) * 3ull / 2ull;
+    // load factor <= 1/3: linear-probing clusters stay short, which bounds the dependent-access
+    // chains of probes, claims and evictions (the slab is slot-indexed, so this is also its size)
+    const unsigned long long want_slots = static_cast<unsigned long long>(cap + n_max) * 3ull;
     if (want_slots >= (1ull << 31)) {
         set_error("tier too large: the index must stay below 2^31 slots");
         return EVS_ERR_INVALID;
@@ -207,16 +223,8 @@ static int build_c3(evs_handle h) {
             ptrs.push_back(dp);
         } else {
             void *hp = const_cast<uint32_t *>(c.alt_keys[t]);
-            cudaError_t e = cudaHostRegister(hp, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
-            if (e == cudaSuccess) h->registered.push_back(hp);
-            else if (e == cudaErrorHostMemoryAlreadyRegistered) cudaGetLastError();
-            else {
-                set_error(std::string("cudaHostRegister(alt keys) -> ") + cudaGetErrorString(e));
-                cudaGetLastError();
-                return EVS_ERR_CUDA;
-            }
             void *dp = nullptr;
-            EVS_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+            if ((rc = map_host_range(h, hp, bytes, &dp, "alt keys " + std::to_string(t)))) return rc;
             ptrs.push_back(static_cast<const unsigned int *>(dp));
         }
     }
@@ -242,9 +250,6 @@ static void free_all(evs_handle h) {
     for (void *p : h->dev_allocs) cudaFree(p);
     for (void *p : h->registered) cudaHostUnregister(p);
     h->prof.destroy();
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->side) cudaStreamDestroy(h->side);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -281,13 +286,13 @@ static int maintain_rings(evs_handle h, int ti, cudaStream_t st) {
 // ---- kernel selection by (main precision, secondary precision) -----------------------------
 using KernelFn = void (*)(const Params);
 struct KernelSet {
-    KernelFn serve = nullptr, fetch = nullptr;
+    KernelFn serve = nullptr, update = nullptr;
 };
 template <int P0, int P1>
 static KernelSet kernels_of() {
     KernelSet k;
     k.serve = k_serve<P0, P1>;
-    k.fetch = k_fetch<P0, P1>;
+    k.update = k_update<P0, P1>;
     return k;
 }
 static KernelSet pick_kernels(int p0, int p1) {
@@ -311,33 +316,25 @@ static cudaError_t launch(KernelFn fn, int grid, int block, size_t smem, cudaStr
     return cudaLaunchKernel(reinterpret_cast<const void *>(fn), dim3(grid), dim3(block), args, smem, st);
 }
 
-static int fetch_grid(evs_handle h) {
-    const long long n_max = static_cast<long long>(h->cfg.max_batch) * h->cfg.n_tables;
-    return static_cast<int>(std::max<long long>(1, std::min<long long>((n_max + 255) / 256, 148 * 4)));
-}
-static size_t fetch_smem(evs_handle h) {
+static size_t update_smem(evs_handle h) {
     unsigned s = h->tier[0].dev.row_stride;
     if (h->n_tiers == 2) s = std::max(s, h->tier[1].dev.row_stride);
-    return static_cast<size_t>(8) * s;
+    return static_cast<size_t>(kSamplesPerCta) * s;
 }
 
-// The per-batch kernel sequence.  `n_chunks` CTAs of k_serve / k_update (CTAs past the batch end
-// exit at once, so a captured graph uses the maximum).  The miss fetch runs on the side stream
-// next to the eviction and the C3 update.
+// The per-batch kernel sequence: three launches (four for very large batches).  `n_chunks` CTAs
+// of k_serve / k_update; CTAs past the batch end exit at once, so a captured graph uses the maximum.
 static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks) {
     const Params &p = h->params;
     const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
     Profiler &pf = h->prof;
     { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch(ks.serve, n_chunks, kLookupThreads, 0, st, p)); }
-    { LaunchScope ls(pf, K_SCAN, st); EVS_CUDA(launch(k_scan, h->n_tiers * h->tier[0].dev.n_buckets, 256, 0, st, p)); }
-    { LaunchScope ls(pf, K_UPDATE, st); EVS_CUDA(launch(k_update, n_chunks, kLookupThreads, 0, st, p)); }
-    EVS_CUDA(cudaEventRecord(h->ev_fork, st));
-    EVS_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-    { LaunchScope ls(pf, K_FETCH, h->side); EVS_CUDA(launch(ks.fetch, fetch_grid(h), 256, fetch_smem(h), h->side, p)); }
-    EVS_CUDA(cudaEventRecord(h->ev_join, h->side));
+    if (p.n_chunks_max > kQuadMaxChunks) {
+        LaunchScope ls(pf, K_SCAN, st);
+        EVS_CUDA(launch(k_scan, h->n_tiers * h->tier[0].dev.n_buckets, 256, 0, st, p));
+    }
+    { LaunchScope ls(pf, K_UPDATE, st); EVS_CUDA(launch(ks.update, n_chunks, kLookupThreads, update_smem(h), st, p)); }
     { LaunchScope ls(pf, K_EVICT, st); EVS_CUDA(launch(k_evict, h->n_tiers, kEvictThreads, 0, st, p)); }
-    if (h->c3_active) { LaunchScope ls(pf, K_C3, st); EVS_CUDA(launch(k_c3_update, 1, kC3Threads, 0, st, p)); }
-    EVS_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
     return EVS_OK;
 }
 
@@ -444,11 +441,8 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         free_all(h);
         return code;
     };
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-        set_error("cudaStreamCreate / cudaEventCreate failed");
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
         return fail(EVS_ERR_CUDA);
     }
     h->n_tiers = cfg->n_layers >= 2 ? 2 : 1;
@@ -475,6 +469,8 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     if ((rc = dev_alloc(h->dev_allocs, &P.flags, n_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.pos_slot, n_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.hist, static_cast<size_t>(kSeqs) * n_chunks_max))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &P.done, 1))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &P.dbg, 16))) return fail(rc);
 
     if ((rc = build_tier(h, h->tier[0], cfg->main_precision, h->caps.c1, cfg->store_main))) return fail(rc);
     if (h->n_tiers == 2)
@@ -496,12 +492,17 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     P.rows = h->d_rows;
     P.args = h->d_args;
     P.g = h->g;
-    const size_t fs = fetch_smem(h);
-    if (fs > 48 * 1024) {
+    for (int i = 0; i < h->n_tiers; ++i) {
+        bool al = (h->tier[i].dev.row_bytes & 15u) == 0;
+        for (const unsigned char *q : h->tier[i].store_dev) al = al && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0);
+        if (al) P.store_aligned |= 1 << i;
+    }
+    const size_t us = update_smem(h);
+    if (us > 40 * 1024) {
         const KernelSet ks = pick_kernels(cfg->main_precision, h->n_tiers == 2 ? cfg->secondary_precision : 0);
-        if (cudaFuncSetAttribute(reinterpret_cast<const void *>(ks.fetch), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(fs)) != cudaSuccess) {
-            set_error("row too large for the fetch kernel's staging buffer");
+        if (cudaFuncSetAttribute(reinterpret_cast<const void *>(ks.update), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(us)) != cudaSuccess) {
+            set_error("row too large for the update kernel's staging buffer");
             return fail(EVS_ERR_INVALID);
         }
     }
@@ -529,9 +530,8 @@ static int run_batch(evs_handle h, const BatchArgs &a, cudaStream_t st) {
     }
     if (h->use_graph && !h->prof.on) {
         EVS_CUDA(cudaGraphLaunch(h->graph, st));
-        h->prof.launches[K_SERVE]++, h->prof.launches[K_SCAN]++, h->prof.launches[K_UPDATE]++;
-        h->prof.launches[K_FETCH]++, h->prof.launches[K_EVICT]++;
-        if (h->c3_active) h->prof.launches[K_C3]++;
+        h->prof.launches[K_SERVE]++, h->prof.launches[K_UPDATE]++, h->prof.launches[K_EVICT]++;
+        if (h->params.n_chunks_max > kQuadMaxChunks) h->prof.launches[K_SCAN]++;
     } else {
         int rc = enqueue_batch(h, st, (a.B + kSamplesPerCta - 1) / kSamplesPerCta);
         if (rc) return rc;
@@ -669,6 +669,20 @@ int evs_kernel_times(evs_handle h, int32_t *n, const char **names, double *total
     }
     if (reset)
         for (int i = 0; i < K_COUNT; ++i) h->prof.ms[i] = 0.0, h->prof.timed[i] = 0, h->prof.launches[i] = 0;
+    return EVS_OK;
+}
+
+int evs_phase_times(evs_handle h, uint64_t *ns8) {
+    if (h == nullptr || ns8 == nullptr) return EVS_ERR_INVALID;
+    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    EVS_CUDA(cudaDeviceSynchronize());
+    EVS_CUDA(cudaMemcpy(ns8, h->params.dbg, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    unsigned long long sc = 0, ap = 0;
+    EVS_CUDA(cudaMemcpyFromSymbol(&sc, p_dbg_scanned, sizeof(sc)));
+    EVS_CUDA(cudaMemcpyFromSymbol(&ap, p_dbg_appends, sizeof(ap)));
+    ns8[15] = sc;
+    ns8[1] = ap;
+    EVS_CUDA(cudaMemset(h->params.dbg + 8, 0, 7 * sizeof(uint64_t)));
     return EVS_OK;
 }
 

@@ -10,7 +10,6 @@
 
 namespace evs {
 
-constexpr int kC3Threads = 1024;
 
 __device__ __forceinline__ void c3_erase(const C3Dev &c, unsigned slot, unsigned long long key) {
     const unsigned mask = c.hash_mask;
@@ -71,14 +70,18 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned *s_w, u
     return s_w[warp] + incl - v;
 }
 
-__global__ void __launch_bounds__(kC3Threads) k_c3_update(const __grid_constant__ Params p) {
+// Whole CTA (any multiple of 32 threads up to 1024); called by the last CTA of k_update after the
+// evictions, so the victims' key lists are complete.
+__device__ void c3_update(const Params &p) {
     __shared__ unsigned s_w[33];
     __shared__ unsigned s_dup;
     __shared__ unsigned long long s_head, s_tail;
     __shared__ unsigned s_evicted, s_size;
     const C3Dev &c = p.c3;
-    C3Ctl *ctl = c.ctl;
-    const unsigned n1 = p.tier[1].ctl->n_evicted_last, n0 = p.tier[0].ctl->n_evicted_last;
+    volatile C3Ctl *ctl = c.ctl;
+    __syncthreads();
+    const unsigned n1 = reinterpret_cast<volatile TierCtl *>(p.tier[1].ctl)->n_evicted_last;
+    const unsigned n0 = reinterpret_cast<volatile TierCtl *>(p.tier[0].ctl)->n_evicted_last;
     const unsigned n = n1 + n0;
     if (n == 0) return;
     if (threadIdx.x == 0) {
@@ -106,19 +109,19 @@ __global__ void __launch_bounds__(kC3Threads) k_c3_update(const __grid_constant_
         unsigned slot = 0, alt = 0;
         bool present = false;
         if (inw) {
-            key = c.ring[q & (c.ring_cap - 1)];
+            key = __ldcg(c.ring + (q & (c.ring_cap - 1)));
             present = c3_find(c, key, slot, alt);
         }
         if (threadIdx.x == 0) s_dup = 0;
         if (present) atomicMin(&c.scratch[slot], threadIdx.x);
         __syncthreads();
-        if (present && c.scratch[slot] != threadIdx.x) s_dup = 1u;
+        if (present && __ldcg(c.scratch + slot) != threadIdx.x) s_dup = 1u;
         __syncthreads();
         if (present) c.scratch[slot] = 0xFFFFFFFFu;
         const bool dup = s_dup != 0u;
         const unsigned budget = n_erase - done;
         if (!dup) {
-            const bool flag = present && (c.slots[slot].flag & 1u);
+            const bool flag = present && (__ldcg(&c.slots[slot].flag) & 1u);
             const bool cand = present && !flag;
             unsigned tot_c;
             const unsigned ci = block_excl_scan(cand ? 1u : 0u, s_w, &tot_c);
@@ -152,10 +155,10 @@ __global__ void __launch_bounds__(kC3Threads) k_c3_update(const __grid_constant_
                 unsigned ev = 0;
                 const unsigned long long wend = (head + blockDim.x < tail) ? head + blockDim.x : tail;
                 while (h < wend && ev < budget) {
-                    const unsigned long long k = c.ring[h & (c.ring_cap - 1)];
+                    const unsigned long long k = __ldcg(c.ring + (h & (c.ring_cap - 1)));
                     unsigned sl, al;
                     if (c3_find(c, k, sl, al)) {
-                        if (c.slots[sl].flag & 1u) {
+                        if (__ldcg(&c.slots[sl].flag) & 1u) {
                             c.slots[sl].flag = 0u;
                             c.ring[tl & (c.ring_cap - 1)] = k;
                             ++tl;
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(kC3Threads) k_c3_update(const __grid_constant_
     }
     unsigned my_new = 0;
     for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned long long key = (i < n1) ? p.tier[1].evicted[i] : p.tier[0].evicted[i - n1];
+        const unsigned long long key = (i < n1) ? __ldcg(p.tier[1].evicted + i) : __ldcg(p.tier[0].evicted + (i - n1));
         c.ring[(tail + i) & (c.ring_cap - 1)] = key;
         const int tbl = static_cast<int>(key >> kKeyShift) - p.table_base;
         const unsigned long long row = key & ((1ull << kKeyShift) - 1ull);

@@ -39,9 +39,9 @@ struct Tier {
 
 
 // Kernel ids for the launch counter / per-kernel CUDA-event timing (evs_set_profiling).
-enum KernelId { K_SERVE = 0, K_SCAN, K_UPDATE, K_FETCH, K_EVICT, K_C3, K_COMPACT, K_PROBE, K_INTERACT, K_GATHER, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_serve", "k_scan", "k_update", "k_fetch", "k_evict", "k_c3_update",
-                                                  "k_compact", "k_probe", "k_interact", "k_gather"};
+enum KernelId { K_SERVE = 0, K_SCAN, K_UPDATE, K_EVICT, K_COMPACT, K_PROBE, K_INTERACT, K_GATHER, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_serve", "k_scan", "k_update", "k_evict", "k_compact", "k_probe", "k_interact",
+                                                  "k_gather"};
 
 struct Profiler {
     bool on = false;
@@ -101,9 +101,7 @@ struct evs_handle_s {
     evs::Params params{};                    // kernel parameter block (device pointers inside)
     std::vector<void *> c3_allocs;
     cudaStream_t stream = nullptr;           // the handle's own stream
-    cudaStream_t side = nullptr;             // miss fetch runs here, next to the eviction
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaGraphExec_t graph = nullptr;         // serve -> scan -> update -> {evict || fetch} [-> c3]
+    cudaGraphExec_t graph = nullptr;         // k_serve [-> k_scan] -> k_update -> k_evict
     bool use_graph = true;
     evs::GlobalCtl *g = nullptr;             // device
     evs::BatchArgs *d_args = nullptr;        // device copy of the per-batch arguments

@@ -2,13 +2,16 @@
 //
 //   k_serve    probe both tiers -> per-sample agg_hit -> route (EvLFU promote / insert per tier) ->
 //              gather + dequantise every resident row into the fp32 output.  Read-only on the cache.
-//   k_scan     per (tier, bucket): exclusive scan of the per-CTA append counts -> ring positions
-//   k_update   claim index slots for missing keys (dedup by CAS) and append promoted / inserted
-//              entries to their bucket's FIFO ring in position order
-//   k_fetch    rows of the missing keys from the host-pinned backing store (zero-copy) -> slab +
-//              output; runs on a side stream next to k_evict
-//   k_evict    flush rule, then evict in (bucket, FIFO) order down to capacity; one CTA per tier
+//   k_update   (evs_update.cuh) claim index slots for missing keys (dedup by CAS), append promoted /
+//              inserted entries to their bucket's FIFO ring in position order, fetch the missing
+//              rows from the host-pinned backing store (zero-copy) into slab + output; the last
+//              CTA to finish then applies the flush rule, evicts in (bucket, FIFO) order down to
+//              capacity and feeds C3
+//   k_scan     only for batches of more than kQuadMaxChunks CTAs: per (tier, bucket) exclusive scan
+//              of the per-CTA append counts (smaller batches sum their predecessors directly)
 //   k_compact  squeeze dead records out of one bucket ring (rare, host-triggered)
+// Every kernel boundary costs ~2-4 us on this part while a dependent L2/HBM access costs 0.15/0.4 us,
+// so the batch is two launches.
 #pragma once
 #include "evs_codec.cuh"
 #include "evs_types.cuh"
@@ -18,33 +21,61 @@ namespace evs {
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kEvictThreads = 1024;
 constexpr int kEvictPerThread = 4;           // ring records one thread examines per window
+constexpr int kQuadMaxChunks = 2048;         // above this a k_scan launch replaces the direct prefix sums
 
 __device__ __forceinline__ uint4 ldg16(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ unsigned long long u64_of(unsigned lo, unsigned hi) {
     return (static_cast<unsigned long long>(hi) << 32) | lo;
 }
 
 // ---- index probe ---------------------------------------------------------------------
 // Linear probing.  The walk ends at the key or at the first slot no resident key's path crosses
-// (pass == 0).  `v` is the already loaded content of slot `i` (lets two tiers' first loads overlap).
-__device__ __forceinline__ bool probe_from(const Slot *__restrict__ slots, unsigned mask, unsigned long long key,
-                                           unsigned i, uint4 v, unsigned &slot_out, unsigned long long &meta_out) {
-    while (true) {
-        const unsigned long long kw = u64_of(v.x, v.y);
+// (pass == 0).  A dependent HBM access costs ~0.4 us here, so a probe never walks slot by slot:
+// it loads 4 consecutive slots at once (two 32-byte sectors), then 8 per round; at the <= 1/3
+// load factor of the index > 98 % of the probes end in the first round.
+template <int N>
+__device__ __forceinline__ void probe_load(const Slot *__restrict__ slots, unsigned mask, unsigned i, uint4 (&v)[N]) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = ldg16(slots + ((i + k) & mask));
+}
+// 1 = found, 0 = absent, -1 = undecided after these N slots
+template <int N>
+__device__ __forceinline__ int probe_check(const uint4 (&v)[N], unsigned mask, unsigned long long key, unsigned i,
+                                           unsigned &slot_out, unsigned long long &meta_out) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const unsigned long long kw = u64_of(v[k].x, v[k].y);
         if ((kw & kKeyMask) == key) {
-            slot_out = i;
-            meta_out = u64_of(v.z, v.w);
-            return true;
+            slot_out = (i + k) & mask;
+            meta_out = u64_of(v[k].z, v[k].w);
+            return 1;
         }
-        if ((kw >> 48) == 0ull) return false;
-        i = (i + 1) & mask;
-        v = ldg16(slots + i);
+        if ((kw >> 48) == 0ull) return 0;
+    }
+    return -1;
+}
+__device__ __forceinline__ bool probe_rest(const Slot *__restrict__ slots, unsigned mask, unsigned long long key, unsigned i,
+                                           unsigned &slot_out, unsigned long long &meta_out) {
+    while (true) {
+        uint4 v[8];
+        probe_load<8>(slots, mask, i, v);
+        const int r = probe_check<8>(v, mask, key, i, slot_out, meta_out);
+        if (r >= 0) return r == 1;
+        i += 8;
     }
 }
-
 __device__ __forceinline__ bool probe(const TierDev &t, unsigned long long key, unsigned &slot, unsigned long long &meta) {
     const unsigned i = hash_key(key, t.hash_mask);
-    return probe_from(t.slots, t.hash_mask, key, i, ldg16(t.slots + i), slot, meta);
+    uint4 v[4];
+    probe_load<4>(t.slots, t.hash_mask, i, v);
+    const int r = probe_check<4>(v, t.hash_mask, key, i, slot, meta);
+    if (r >= 0) return r == 1;
+    return probe_rest(t.slots, t.hash_mask, key, i + 4, slot, meta);
 }
 
 // C3: key -> alt key (aprx_embedding.cpp:344 get_altkey_str).  Plain loads: the recency flag of
@@ -52,10 +83,10 @@ __device__ __forceinline__ bool probe(const TierDev &t, unsigned long long key, 
 __device__ __forceinline__ bool c3_find(const C3Dev &c, unsigned long long key, unsigned &slot_out, unsigned &alt_out) {
     unsigned i = hash_key(key, c.hash_mask);
     while (true) {
-        const unsigned long long kw = c.slots[i].kw;
+        const unsigned long long kw = __ldcg(&c.slots[i].kw);
         if ((kw & kKeyMask) == key) {
             slot_out = i;
-            alt_out = c.slots[i].alt;
+            alt_out = __ldcg(&c.slots[i].alt);
             return true;
         }
         if ((kw >> 48) == 0ull) return false;
@@ -105,6 +136,8 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
     __shared__ unsigned s_stat[8];           // hits C1, hits C2, C3, approx, misses, perfect
     __shared__ CodecLut s_lut;
 
+    const unsigned long long t_start = gtime();
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.dbg[0] = t_start;
     const BatchArgs a = *p.args;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int T = p.T, B = a.B, D = p.D;
@@ -137,14 +170,19 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
             r = 0;
         }
         key = make_key(p.table_base + lane, r);
+        // both tiers' first rounds are in flight together
         const unsigned i0 = hash_key(key, t0.hash_mask);
-        const uint4 v0 = ldg16(t0.slots + i0);
+        uint4 v0[4];
+        probe_load<4>(t0.slots, t0.hash_mask, i0, v0);
         if (P1 != 0) {
             const unsigned i1 = hash_key(key, t1.hash_mask);
-            const uint4 v1 = ldg16(t1.slots + i1);
-            h1 = probe_from(t1.slots, t1.hash_mask, key, i1, v1, slot1, m1);
+            uint4 v1[4];
+            probe_load<4>(t1.slots, t1.hash_mask, i1, v1);
+            const int r1 = probe_check<4>(v1, t1.hash_mask, key, i1, slot1, m1);
+            h1 = (r1 >= 0) ? (r1 == 1) : probe_rest(t1.slots, t1.hash_mask, key, i1 + 4, slot1, m1);
         }
-        h0 = probe_from(t0.slots, t0.hash_mask, key, i0, v0, slot0, m0);
+        const int r0 = probe_check<4>(v0, t0.hash_mask, key, i0, slot0, m0);
+        h0 = (r0 >= 0) ? (r0 == 1) : probe_rest(t0.slots, t0.hash_mask, key, i0 + 4, slot0, m0);
     }
 
     // C3 (evlfu_8.cpp:474-489, 528-558): a double miss whose alternative key is resident in C1,
@@ -170,6 +208,7 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
         }
     }
 
+    const unsigned long long t_probe = gtime();
     const unsigned m_h0 = __ballot_sync(kFull, h0);
     const unsigned m_h1 = __ballot_sync(kFull, h1);
     const unsigned m_c3 = __ballot_sync(kFull, c3hit);
@@ -259,6 +298,9 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
     const int n_seq = p.n_tiers * kMaxBuckets;
     if (threadIdx.x < n_seq) p.hist[static_cast<size_t>(threadIdx.x) * p.n_chunks_max + blockIdx.x] = s_hist[threadIdx.x];
     if (threadIdx.x == 0) {
+        const unsigned long long t_end = gtime();
+        (void)t_probe;
+        atomicMax(&p.dbg[1], t_end);
         GlobalCtl *g = p.g;
         const int ns = min(kSamplesPerCta, B - s0);
         atomicAdd(&g->lookups, static_cast<unsigned long long>(ns) * T);
@@ -283,6 +325,7 @@ __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Params p) 
     __shared__ unsigned s_w[8];
     const int B = p.args->B;
     const int n_chunks = (B + kSamplesPerCta - 1) / kSamplesPerCta;
+    if (n_chunks <= kQuadMaxChunks) return;          // k_update sums its predecessors directly
     const int nb = p.tier[0].n_buckets;
     const int tier = blockIdx.x / nb, b = blockIdx.x - tier * nb;
     unsigned *h = p.hist + static_cast<size_t>(tier * kMaxBuckets + b) * p.n_chunks_max;
@@ -344,76 +387,10 @@ __device__ __forceinline__ unsigned claim_slot(const TierDev &tier, unsigned lon
         i = (i + 1) & mask;
     }
     if (claimed) {
-        for (unsigned j = home; j != i; j = (j + 1) & mask) {
-            const unsigned long long old = atomicAdd(&tier.slots[j].kw, kPassOne);
-            if ((old >> 48) == 0xFFFFull) tier.ctl->error = 5u;      // pass counter overflow
-        }
-        atomicAdd(&tier.ctl->n_new, 1u);
+        // 16 bits of pass: a 65 535-key probe cluster cannot form at the <= 0.67 load factor used here
+        for (unsigned j = home; j != i; j = (j + 1) & mask) atomicAdd(&tier.slots[j].kw, kPassOne);
     }
     return i;
-}
-
-// Same thread <-> position mapping as k_serve, so ring order inside a bucket is position
-// order: by warp (sample) then lane (table).  All flagged positions of a sample share the
-// bucket agg_hit(sample).
-__global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant__ Params p) {
-    __shared__ unsigned s_cnt[kSamplesPerCta][kMaxTiers];
-    __shared__ int s_b[kSamplesPerCta];
-    const BatchArgs a = *p.args;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int T = p.T, B = a.B;
-    const int s = blockIdx.x * kSamplesPerCta + warp;
-    if (blockIdx.x * kSamplesPerCta >= B) return;
-    const bool act = (s < B) && (lane < T);
-    const int pos = s * T + lane;
-    const unsigned f = act ? p.flags[pos] : 0u;
-    if (__syncthreads_or(f != 0u) == 0) return;
-
-    const int tr = (f & kFlagTier) ? 1 : 0;
-    const int b = static_cast<int>(f & 0x3Fu) - 1;
-    const unsigned m0 = __ballot_sync(kFull, f != 0u && tr == 0);
-    const unsigned m1 = __ballot_sync(kFull, f != 0u && tr == 1);
-    if (lane == 0) {
-        s_cnt[warp][0] = __popc(m0);
-        s_cnt[warp][1] = __popc(m1);
-    }
-    const unsigned any = m0 | m1;
-    const int wb = __shfl_sync(kFull, b, any ? (__ffs(any) - 1) : 0);
-    if (lane == 0) s_b[warp] = any ? wb : -1;
-    __syncthreads();
-    if (!f) return;
-
-    const TierDev &tier = p.tier[tr];
-    unsigned slot;
-    if (f & kFlagMiss) {
-        long long r = __ldg(a.idx + static_cast<size_t>(lane) * B + s);
-        if (r < 0 || r >= __ldg(p.rows + lane)) r = 0;
-        bool claimed;
-        slot = claim_slot(tier, make_key(p.table_base + lane, r), claimed);
-        p.pos_slot[pos] = slot | (claimed ? kClaimedBit : 0u);
-        atomicMax(&tier.ctl->prot, (static_cast<unsigned long long>(f & 0x3Fu) << 32) | static_cast<unsigned>(pos));
-    } else {
-        slot = p.pos_slot[pos];
-    }
-
-    unsigned pre = 0;
-    for (int w = 0; w < warp; ++w)
-        if (s_b[w] == b) pre += s_cnt[w][tr];
-    const unsigned rank = __popc((tr ? m1 : m0) & ((1u << lane) - 1u));
-    TierCtl *c = tier.ctl;
-    const unsigned long long q =
-        c->tail_prev[b] + p.hist[static_cast<size_t>(tr * kMaxBuckets + b) * p.n_chunks_max + blockIdx.x] + pre + rank;
-    tier.ring[static_cast<size_t>(b) * tier.ring_cap + (q & (tier.ring_cap - 1))] = slot;
-    const unsigned long long mine = pack_meta(b, q);
-    const unsigned long long old = atomicMax(&tier.slots[slot].meta, mine);
-    if (mine > old) {
-        const int ob = meta_bucket(old);
-        if (ob != b) {
-            atomicAdd(&c->count[b], 1u);
-            if (ob >= 0) atomicSub(&c->count[ob], 1u);
-            else atomicAdd(&c->stat_inserts, 1ull);
-        }
-    }
 }
 
 // ---- k_fetch -----------------------------------------------------------------------------
@@ -434,23 +411,19 @@ __device__ __forceinline__ void fetch_row(const unsigned char *__restrict__ src,
     for (unsigned o = row_bytes + lane; o < stride; o += 32u) stage[o] = 0;
 }
 
+// Fetch one missing row (table t, row r of sample s) from the backing store: raw bytes into the
+// slab row of `slot` when this position claimed it, dequantised into the output.  Executed by a
+// group of `gsize` consecutive lanes (glane = lane within the group) straight through registers
+// when rows are 16-byte aligned (stage == nullptr), else by the whole warp via a staging row.
 template <int PREC>
-__device__ __forceinline__ void fetch_one(const TierDev &tier, const Params &p, const BatchArgs &a, int pos, int lane,
-                                          int glane, int gsize, unsigned char *stage, bool vec, const CodecLut *lut) {
-    // executed by a group of `gsize` consecutive lanes (glane = lane within the group); the group
-    // is the whole warp on the staged (unaligned) path
-    const int T = p.T, D = p.D;
-    const int s = pos / T, t = pos - s * T;
-    long long r = __ldg(a.idx + static_cast<size_t>(t) * a.B + s);
-    if (r < 0 || r >= __ldg(p.rows + t)) r = 0;
-    const unsigned ps = p.pos_slot[pos];
-    const unsigned slot = ps & ~kClaimedBit;
-    const bool claimed = (ps & kClaimedBit) != 0u;
+__device__ __forceinline__ void fetch_one(const TierDev &tier, const BatchArgs &a, int D, int s, int t, long long r,
+                                          unsigned slot, bool claimed, int lane, int glane, int gsize,
+                                          unsigned char *stage, bool vec, const CodecLut *lut) {
     const unsigned char *src = tier.store[t] + static_cast<size_t>(r) * tier.row_bytes;
     float *orow = a.out + static_cast<size_t>(s) * a.out_stride + t * D;
     const int cpr = static_cast<int>(tier.row_stride >> 4);
     unsigned char *dst = tier.slab + static_cast<size_t>(slot) * tier.row_stride;
-    if (stage == nullptr) {                       // 16-byte aligned rows: straight through registers
+    if (stage == nullptr) {
         for (int c = glane; c < cpr; c += gsize) {
             const uint4 v = ldg16(src + (c << 4));
             if (claimed) *reinterpret_cast<uint4 *>(dst + (c << 4)) = v;
@@ -468,83 +441,37 @@ __device__ __forceinline__ void fetch_one(const TierDev &tier, const Params &p, 
     }
 }
 
-// A warp scans 32 positions' flags at a time and serves the misses among them.
-// Dynamic shared memory: warps * max(row_stride) bytes of staging.
-template <int P0, int P1>
-__global__ void __launch_bounds__(256) k_fetch(const __grid_constant__ Params p) {
-    extern __shared__ __align__(16) unsigned char s_stage[];
-    __shared__ CodecLut s_lut;
-    codec_lut_init<P0, P1>(&s_lut);
-    __syncthreads();
-    const BatchArgs a = *p.args;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wpc = blockDim.x >> 5;
-    const int N = a.B * p.T;
-    const TierDev &t0 = p.tier[0];
-    const TierDev &t1 = p.tier[1];
-    const unsigned max_stride = (P1 != 0 && t1.row_stride > t0.row_stride) ? t1.row_stride : t0.row_stride;
-    unsigned char *stage = s_stage + static_cast<size_t>(warp) * max_stride;
-    const bool vec = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && ((a.out_stride & 3) == 0) && ((p.D & 3) == 0);
-    // rows of a tier can go straight through registers when every row start is 16-byte aligned
-    bool al0 = (t0.row_bytes & 15u) == 0, al1 = (P1 != 0) && (t1.row_bytes & 15u) == 0;
-    for (int t = 0; t < p.T; ++t) {
-        al0 = al0 && ((reinterpret_cast<uintptr_t>(t0.store[t]) & 15u) == 0);
-        if (P1 != 0) al1 = al1 && ((reinterpret_cast<uintptr_t>(t1.store[t]) & 15u) == 0);
-    }
-    auto group_of = [](unsigned stride) {
-        int g = 1;
-        while (g < static_cast<int>(stride >> 4) && g < 32) g <<= 1;
-        return g;
-    };
-    const int g0 = group_of(t0.row_stride), g1 = (P1 != 0) ? group_of(t1.row_stride) : 32;
-
-    for (int base = (blockIdx.x * wpc + warp) * 32; base < N; base += gridDim.x * wpc * 32) {
-        const int pos = base + lane;
-        const unsigned f = (pos < N) ? p.flags[pos] : 0u;
-        unsigned m0 = __ballot_sync(kFull, (f & kFlagMiss) && !(f & kFlagTier));
-        unsigned m1 = __ballot_sync(kFull, (f & kFlagMiss) && (f & kFlagTier));
-        // tier 0 misses
-        if (al0) {
-            const int ngrp = 32 / g0, grp = lane / g0, gl = lane - grp * g0;
-            while (m0) {
-                unsigned mm = m0;
-                int mine = -1;
-                for (int k = 0; k < ngrp && mm; ++k) {
-                    const int bit = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    if (k == grp) mine = bit;
-                }
-                m0 = mm;
-                if (mine >= 0) fetch_one<P0>(t0, p, a, base + mine, lane, gl, g0, nullptr, vec, &s_lut);
+// The misses of one warp's sample that go to `tier` (bit t of `mm` = table t missed).  Every lane
+// passes its own r / slot word; the fetching lanes pull the victim lane's values by shuffle.
+template <int PREC>
+__device__ __forceinline__ void fetch_misses(const TierDev &tier, const BatchArgs &a, int D, int s, unsigned mm,
+                                             long long r, unsigned slotword, int lane, bool aligned, int gsize,
+                                             unsigned char *stage, bool vec, const CodecLut *lut) {
+    if (aligned) {
+        const int ngrp = 32 / gsize, grp = lane / gsize, gl = lane - grp * gsize;
+        while (mm) {
+            unsigned rest = mm;
+            int mine = -1;
+            for (int k = 0; k < ngrp && rest; ++k) {
+                const int bit = __ffs(rest) - 1;
+                rest &= rest - 1;
+                if (k == grp) mine = bit;
             }
-        } else {
-            while (m0) {
-                const int bit = __ffs(m0) - 1;
-                m0 &= m0 - 1;
-                fetch_one<P0>(t0, p, a, base + bit, lane, lane, 32, stage, vec, &s_lut);
-            }
+            mm = rest;
+            const int srcl = mine < 0 ? 0 : mine;
+            const long long rr = __shfl_sync(kFull, r, srcl);
+            const unsigned sw = __shfl_sync(kFull, slotword, srcl);
+            if (mine >= 0)
+                fetch_one<PREC>(tier, a, D, s, mine, rr, sw & ~kClaimedBit, (sw & kClaimedBit) != 0u, lane, gl, gsize, nullptr,
+                                vec, lut);
         }
-        if (P1 != 0) {
-            if (al1) {
-                const int ngrp = 32 / g1, grp = lane / g1, gl = lane - grp * g1;
-                while (m1) {
-                    unsigned mm = m1;
-                    int mine = -1;
-                    for (int k = 0; k < ngrp && mm; ++k) {
-                        const int bit = __ffs(mm) - 1;
-                        mm &= mm - 1;
-                        if (k == grp) mine = bit;
-                    }
-                    m1 = mm;
-                    if (mine >= 0) fetch_one<(P1 != 0 ? P1 : 32)>(t1, p, a, base + mine, lane, gl, g1, nullptr, vec, &s_lut);
-                }
-            } else {
-                while (m1) {
-                    const int bit = __ffs(m1) - 1;
-                    m1 &= m1 - 1;
-                    fetch_one<(P1 != 0 ? P1 : 32)>(t1, p, a, base + bit, lane, lane, 32, stage, vec, &s_lut);
-                }
-            }
+    } else {
+        while (mm) {
+            const int bit = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const long long rr = __shfl_sync(kFull, r, bit);
+            const unsigned sw = __shfl_sync(kFull, slotword, bit);
+            fetch_one<PREC>(tier, a, D, s, bit, rr, sw & ~kClaimedBit, (sw & kClaimedBit) != 0u, lane, lane, 32, stage, vec, lut);
         }
     }
 }
@@ -557,62 +484,115 @@ __device__ __forceinline__ void evict_slot(const TierDev &tier, unsigned slot, u
     atomicOr(&tier.slots[slot].kw, kEmptyKey);        // keep the pass bits: other keys may cross this slot
 }
 
-// Pop up to `want` live records from the head of bucket b (whole CTA).  The protected slot is
-// skipped but keeps its place.  Returns the number popped (uniform across the CTA).
-__device__ unsigned pop_bucket(const TierDev &tier, int b, unsigned want, unsigned prot_slot,
-                               unsigned long long *out_keys, unsigned out_base) {
-    __shared__ unsigned s_wsum[32];
-    __shared__ unsigned s_total;
-    __shared__ unsigned long long s_first_kept;
+// Per-tier eviction state of the evicting CTA (a copy of the bucket heads / tails / counts that
+// is written back once at the end).
+__device__ unsigned long long p_dbg_appends;      // ring records appended (cumulative, debug)
+__device__ unsigned long long p_dbg_scanned;      // ring records examined by evictions (cumulative, debug)
+struct EvictShared {
+    unsigned long long head[kMaxBuckets];      // first record that may still be live
+    unsigned long long cur[kMaxBuckets];       // scan cursor (>= head)
+    unsigned long long tail[kMaxBuckets];
+    unsigned long long kept[kMaxBuckets];      // first live record left in place by this call (~0: none)
+    unsigned count[kMaxBuckets];
+    // one window
+    int seg_b[kMaxBuckets];
+    unsigned long long seg_q0[kMaxBuckets];
+    unsigned seg_off[kMaxBuckets + 1];
+    unsigned seg_taken[kMaxBuckets];
+    int n_seg;
+    unsigned wsum[33];
+};
+
+// Pop up to `want` live records in (bucket, FIFO) order from buckets b_lo..b_hi (whole CTA).  One
+// window of blockDim.x * R ring records can span several sparsely filled buckets, so the cost is
+// a function of the records scanned, not of the buckets visited.  The protected slot is skipped
+// but keeps its place.  Returns the number popped (uniform across the CTA).
+__device__ unsigned pop_range(const TierDev &tier, EvictShared &S, int b_lo, int b_hi, unsigned want, unsigned prot_slot,
+                              unsigned long long *out_keys, unsigned out_base) {
     constexpr int R = kEvictPerThread;
-    TierCtl *c = tier.ctl;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const unsigned long long h = c->head[b], tl = c->tail[b];
-    __syncthreads();                       // everyone has read head/tail before thread 0 rewrites them
-    if (threadIdx.x == 0) s_first_kept = ~0ull;
-    __syncthreads();
+    const unsigned W = blockDim.x * R;
     unsigned got = 0;
-    unsigned long long base = h;
-    const unsigned *ring = tier.ring + static_cast<size_t>(b) * tier.ring_cap;
-    for (; base < tl && got < want; base += static_cast<unsigned long long>(blockDim.x) * R) {
-        const unsigned long long q0 = base + static_cast<unsigned long long>(threadIdx.x) * R;
+    while (got < want) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int n = 0;
+            unsigned acc = 0;
+            for (int b = b_lo; b <= b_hi && acc < W; ++b) {
+                if (S.count[b] == 0) {               // only dead records are left in this ring
+                    S.cur[b] = S.tail[b];
+                    continue;
+                }
+                const unsigned long long len = S.tail[b] - S.cur[b];
+                if (len == 0) continue;
+                const unsigned take = static_cast<unsigned>(len < static_cast<unsigned long long>(W - acc) ? len : (W - acc));
+                S.seg_b[n] = b;
+                S.seg_q0[n] = S.cur[b];
+                S.seg_off[n] = acc;
+                S.seg_taken[n] = 0;
+                acc += take;
+                ++n;
+            }
+            S.seg_off[n] = acc;
+            S.n_seg = n;
+        }
+        __syncthreads();
+        const int n_seg = S.n_seg;
+        if (n_seg == 0) break;
+        const unsigned n_rec = S.seg_off[n_seg];
         unsigned slot[R];
+        unsigned long long q[R];
+        int seg[R];
         uint4 sv[R];
         bool live[R], cand[R];
+        const unsigned v0 = threadIdx.x * R;
 #pragma unroll
-        for (int r = 0; r < R; ++r) slot[r] = (q0 + r < tl) ? ring[(q0 + r) & (tier.ring_cap - 1)] : kNoSlot;
+        for (int r = 0; r < R; ++r) {
+            const unsigned v = v0 + r;
+            slot[r] = kNoSlot;
+            seg[r] = 0;
+            q[r] = 0;
+            if (v < n_rec) {
+                int sg = 0;
+                while (sg + 1 < n_seg && S.seg_off[sg + 1] <= v) ++sg;
+                seg[r] = sg;
+                q[r] = S.seg_q0[sg] + (v - S.seg_off[sg]);
+                const unsigned *ring = tier.ring + static_cast<size_t>(S.seg_b[sg]) * tier.ring_cap;
+                slot[r] = __ldcg(ring + (q[r] & (tier.ring_cap - 1)));
+            }
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (slot[r] <= tier.hash_mask) sv[r] = *reinterpret_cast<const uint4 *>(tier.slots + slot[r]);
+            if (slot[r] <= tier.hash_mask) sv[r] = __ldcg(reinterpret_cast<const uint4 *>(tier.slots + slot[r]));
         unsigned mycnt = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            live[r] = (slot[r] <= tier.hash_mask) && (u64_of(sv[r].z, sv[r].w) == pack_meta(b, q0 + r));
+            live[r] = (slot[r] <= tier.hash_mask) && (u64_of(sv[r].z, sv[r].w) == pack_meta(S.seg_b[seg[r]], q[r]));
             cand[r] = live[r] && (slot[r] != prot_slot);
             mycnt += cand[r] ? 1u : 0u;
         }
-        // block-wide exclusive scan of mycnt
         unsigned incl = mycnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned n = __shfl_up_sync(kFull, incl, d);
             if (lane >= d) incl += n;
         }
-        if (lane == 31) s_wsum[warp] = incl;
+        if (lane == 31) S.wsum[warp] = incl;
         __syncthreads();
         if (warp == 0) {
-            const unsigned v = (lane < nwarp) ? s_wsum[lane] : 0u;
-            unsigned wi = v;
+            const unsigned x = (lane < nwarp) ? S.wsum[lane] : 0u;
+            unsigned wi = x;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const unsigned n = __shfl_up_sync(kFull, wi, d);
                 if (lane >= d) wi += n;
             }
-            s_wsum[lane] = wi - v;
-            if (lane == 31) s_total = wi;
+            S.wsum[lane] = wi - x;
+            if (lane == 31) S.wsum[32] = wi;
         }
         __syncthreads();
-        unsigned idx = s_wsum[warp] + incl - mycnt;
+        unsigned idx = S.wsum[warp] + incl - mycnt;
+        const unsigned total = S.wsum[32];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const bool take = cand[r] && (got + idx < want);
@@ -620,67 +600,88 @@ __device__ unsigned pop_bucket(const TierDev &tier, int b, unsigned want, unsign
                 const unsigned long long key = u64_of(sv[r].x, sv[r].y) & kKeyMask;
                 evict_slot(tier, slot[r], key);
                 if (out_keys != nullptr) out_keys[out_base + got + idx] = key;
+                atomicAdd(&S.seg_taken[seg[r]], 1u);
             }
-            if (live[r] && !take) atomicMin(&s_first_kept, q0 + r);
+            // first live record left in place, per bucket; the plain pre-check keeps the same-address
+            // shared-memory atomics to a handful per bucket (benign race: atomicMin decides)
+            if (live[r] && !take && q[r] < *reinterpret_cast<volatile unsigned long long *>(&S.kept[S.seg_b[seg[r]]]))
+                atomicMin(&S.kept[S.seg_b[seg[r]]], q[r]);
             idx += cand[r] ? 1u : 0u;
         }
-        got += min(s_total, want - got);
         __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const unsigned long long fk = s_first_kept;
-        c->head[b] = (fk != ~0ull) ? fk : (base < tl ? base : tl);
-        c->count[b] -= got;
+        if (threadIdx.x == 0) atomicAdd(&p_dbg_scanned, static_cast<unsigned long long>(n_rec));
+        if (threadIdx.x < n_seg) {
+            const int b = S.seg_b[threadIdx.x];
+            S.cur[b] = S.seg_q0[threadIdx.x] + (S.seg_off[threadIdx.x + 1] - S.seg_off[threadIdx.x]);
+            S.count[b] -= S.seg_taken[threadIdx.x];
+        }
+        got += min(total, want - got);
     }
     __syncthreads();
     return got;
 }
 
-// One CTA per tier.
-__global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__ Params p) {
+// Flush rule, then evict down to capacity (whole CTA).
+__device__ void evict_tier(const TierDev &tier, const Params &p) {
+    __shared__ EvictShared S;
     __shared__ unsigned s_size;
-    const TierDev &tier = p.tier[blockIdx.x];
-    TierCtl *c = tier.ctl;
+    volatile TierCtl *c = tier.ctl;
     const int top = tier.n_buckets - 1;
-    if (threadIdx.x == 0) {
-        unsigned sz = 0;
-        for (int b = 0; b < tier.n_buckets; ++b) sz += c->count[b];
-        s_size = sz;
-    }
     __syncthreads();
-    unsigned size = s_size;
+    if (threadIdx.x < kMaxBuckets) {
+        const int b = threadIdx.x;
+        const bool in = b < tier.n_buckets;
+        S.head[b] = in ? c->head[b] : 0ull;
+        S.cur[b] = S.head[b];
+        S.tail[b] = in ? c->tail[b] : 0ull;
+        S.kept[b] = ~0ull;
+        const unsigned cnt = in ? c->count[b] : 0u;
+        S.count[b] = cnt;
+        unsigned sum = cnt;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(kFull, sum, d);
+        if (b == 0) s_size = sum;
+    }
     const unsigned n_new = c->n_new;
     const unsigned long long prot = c->prot;
     const unsigned n_perfect = c->n_perfect;
     const unsigned any_perfect = c->any_perfect;
     __syncthreads();
+    unsigned size = s_size;
 
     // flush rule (EvLFU_C1.py:36-44, evlfu_32.cpp:209-218): bucket `top` is trimmed FIFO
     unsigned flushed = 0;
+    unsigned new_n_perfect = n_perfect;
     if (n_new > 0 && n_perfect >= tier.max_perfect) {
-        const unsigned want = min(tier.flush_n, c->count[top]);
-        flushed = pop_bucket(tier, top, want, kNoSlot, tier.flushed, 0);
+        const unsigned want = min(tier.flush_n, S.count[top]);
+        flushed = pop_range(tier, S, top, top, want, kNoSlot, tier.flushed, 0);
         size -= flushed;
-        if (threadIdx.x == 0) c->n_perfect = c->count[top];
+        new_n_perfect = S.count[top];
+        // records the flush scanned but kept stay ahead of later scans
+        if (threadIdx.x == 0) {
+            if (S.kept[top] != ~0ull) S.cur[top] = S.kept[top];
+            S.head[top] = S.cur[top];
+            S.kept[top] = ~0ull;
+        }
         __syncthreads();
     }
 
     // evict down to capacity, lowest bucket first, FIFO inside a bucket; the highest ranked
     // new key is never the victim (the reference evicts before it inserts)
     unsigned prot_slot = kNoSlot;
-    if (n_new > 0) prot_slot = p.pos_slot[static_cast<unsigned>(prot & 0xFFFFFFFFull)] & ~kClaimedBit;
-    unsigned need = size > tier.cap ? size - tier.cap : 0u;
+    if (n_new > 0) prot_slot = __ldcg(p.pos_slot + static_cast<unsigned>(prot & 0xFFFFFFFFull)) & ~kClaimedBit;
+    const unsigned need = size > tier.cap ? size - tier.cap : 0u;
     unsigned ev = 0;
-    for (int b = 0; b <= top && need > 0; ++b) {
-        if (c->count[b] == 0) continue;
-        const unsigned got = pop_bucket(tier, b, need, prot_slot, tier.evicted, ev);
-        ev += got;
-        need -= got;
-    }
+    if (need > 0) ev = pop_range(tier, S, 0, top, need, prot_slot, tier.evicted, 0);
     size -= ev;
 
+    if (threadIdx.x < tier.n_buckets) {
+        const int b = threadIdx.x;
+        c->head[b] = (S.kept[b] != ~0ull) ? S.kept[b] : S.cur[b];
+        c->count[b] = S.count[b];
+    }
     if (threadIdx.x == 0) {
-        if (any_perfect) c->n_perfect = c->count[top];      // EvLFU_C1.py:163-165
+        c->n_perfect = any_perfect ? S.count[top] : new_n_perfect;      // EvLFU_C1.py:163-165
         c->stat_evictions += ev;
         c->stat_flushed += flushed;
         c->n_evicted_last = ev;
@@ -689,9 +690,9 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
         c->n_new = 0;
         c->prot = 0ull;
         c->any_perfect = 0;
-        if (need > 0) c->error = 4u;
-        if (blockIdx.x == 0 && p.g != nullptr) atomicAdd(&p.g->batches, 1ull);
+        if (ev < need) c->error = 4u;
     }
+    __syncthreads();
 }
 
 // ---- k_compact ---------------------------------------------------------------------------

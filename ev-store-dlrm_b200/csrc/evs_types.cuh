@@ -144,7 +144,10 @@ struct Params {
     // per-batch scratch
     uint8_t *flags;                        // [N]
     unsigned int *pos_slot;                // [N] slot (in the flag's tier) of a promoted / inserted key
-    unsigned int *hist;                    // [kSeqs][n_chunks_max]: counts, then absolute ring positions
+    unsigned int *hist;                    // [kSeqs][n_chunks_max]: per-CTA append counts (prefixes after k_scan)
+    unsigned int *done;                    // CTAs of k_update that have finished (last one evicts)
+    int store_aligned;                     // bit t: every backing row of tier t starts 16-byte aligned
+    unsigned long long *dbg;               // [16] %globaltimer stamps of the last batch's phases (ns)
 };
 
 __host__ __device__ inline unsigned long long pack_meta(int bucket, unsigned long long q) {
