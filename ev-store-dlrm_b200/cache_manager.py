@@ -50,6 +50,17 @@ def _ptr_array(arrays):
     return arr
 
 
+CUDA_STREAM_LEGACY = 1     # cudaStreamLegacy: the C-ABI treats a NULL stream as "the handle's own stream"
+
+
+def _stream_handle(stream, device):
+    """The cudaStream_t the work is ordered on: an explicit handle, else torch's current stream."""
+    if stream is not None:
+        return stream
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream or CUDA_STREAM_LEGACY
+
+
 class EvStore:
     def __init__(self, tables_fp32, cfg: CacheConfig, stores: dict | None = None, alt_keys=None):
         """tables_fp32: list of [rows, dim] float32 arrays (the trained embedding tables).
@@ -116,7 +127,7 @@ class EvStore:
             out = torch.empty((B, T, self.dim), dtype=torch.float32, device=lS_i.device)
         if hit is None:
             hit = torch.empty((B, T), dtype=torch.uint8, device=lS_i.device)
-        st = stream if stream is not None else torch.cuda.current_stream(lS_i.device).cuda_stream
+        st = _stream_handle(stream, lS_i.device)
         stride = out.stride(0)
         rc = self.lib.evs_lookup_batch(self.handle, lS_i.data_ptr(), B, out.data_ptr(), stride, hit.data_ptr(),
                                        agg_in.data_ptr() if agg_in is not None else None, st)
@@ -128,7 +139,7 @@ class EvStore:
         T, B = lS_i.shape
         if agg_out is None:
             agg_out = torch.empty((B,), dtype=torch.uint8, device=lS_i.device)
-        st = stream if stream is not None else torch.cuda.current_stream(lS_i.device).cuda_stream
+        st = _stream_handle(stream, lS_i.device)
         _native.check(self.lib.evs_probe_batch(self.handle, lS_i.data_ptr(), B, agg_out.data_ptr(), st), "evs_probe_batch")
         return agg_out
 
@@ -156,7 +167,7 @@ class EvStore:
         n_f = ly.shape[1]
         if out is None:
             out = torch.empty((B, d + (n_f + 1) * n_f // 2), dtype=torch.float32, device=x.device)
-        st = stream if stream is not None else torch.cuda.current_stream(x.device).cuda_stream
+        st = _stream_handle(stream, x.device)
         _native.check(self.lib.evs_interact(x.data_ptr(), ly.data_ptr(), out.data_ptr(), B, n_f, d, st), "evs_interact")
         return out
 
@@ -190,10 +201,10 @@ class EvStore:
         _native.check(self.lib.evs_phase_times(self.handle, t), "evs_phase_times")
         v = [int(x) for x in t]
         us = lambda a, b: (v[b] - v[a]) / 1e3
-        n = max(1, v[8])
-        return {"upd_warps": v[8], "upd_prefix_avg": v[9] / n / 1e3, "upd_append_avg": v[10] / n / 1e3,
-                "upd_fetch_avg": v[11] / n / 1e3, "evict_scanned_total": v[15], "appends_total": v[1],
-                "upd_prefix_max": v[12] / 1e3, "upd_append_max": v[13] / 1e3, "upd_fetch_max": v[14] / 1e3,
+        n = max(1, v[13])
+        return {"avg_over_batches": n, "avg_serve": v[8] / n / 1e3, "avg_gap1": v[9] / n / 1e3, "avg_update": v[10] / n / 1e3,
+                "avg_gap2": v[11] / n / 1e3, "avg_evict": v[12] / n / 1e3,
+                "overlapped_batches": v[14], "evict_scanned_total": v[15], "appends_total": v[1],
                 "serve": us(0, 7), "serve_to_update_gap": us(7, 2), "update": us(2, 3), "update_to_evict_gap": us(3, 4),
                 "evict": us(4, 5), "c3": us(5, 6), "total": us(0, 6)}
 

@@ -244,12 +244,17 @@ static void free_all(evs_handle h) {
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     if (h->graph) cudaGraphExecDestroy(h->graph);
+    if (h->graph_src) cudaGraphDestroy(h->graph_src);
     for (int i = 0; i < EVS_MAX_TIERS; ++i)
         for (void *p : h->tier[i].allocs) cudaFree(p);
     for (void *p : h->c3_allocs) cudaFree(p);
     for (void *p : h->dev_allocs) cudaFree(p);
     for (void *p : h->registered) cudaHostUnregister(p);
     h->prof.destroy();
+    if (h->ev_served) cudaEventDestroy(h->ev_served);
+    if (h->ev_updated) cudaEventDestroy(h->ev_updated);
+    if (h->ev_filled) cudaEventDestroy(h->ev_filled);
+    if (h->side) cudaStreamDestroy(h->side);
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -285,14 +290,16 @@ static int maintain_rings(evs_handle h, int ti, cudaStream_t st) {
 
 // ---- kernel selection by (main precision, secondary precision) -----------------------------
 using KernelFn = void (*)(const Params);
+using ServeFn = void (*)(const Params, const BatchArgs);
 struct KernelSet {
-    KernelFn serve = nullptr, update = nullptr;
+    ServeFn serve = nullptr;
+    KernelFn fetch = nullptr;
 };
 template <int P0, int P1>
 static KernelSet kernels_of() {
     KernelSet k;
     k.serve = k_serve<P0, P1>;
-    k.update = k_update<P0, P1>;
+    k.fetch = k_fetch<P0, P1>;
     return k;
 }
 static KernelSet pick_kernels(int p0, int p1) {
@@ -311,30 +318,52 @@ static KernelSet pick_kernels(int p0, int p1) {
     }
 }
 
+static cudaError_t launch_serve(ServeFn fn, int grid, cudaStream_t st, const Params &p, const BatchArgs &a) {
+    void *args[] = {const_cast<Params *>(&p), const_cast<BatchArgs *>(&a)};
+    return cudaLaunchKernel(reinterpret_cast<const void *>(fn), dim3(grid), dim3(kLookupThreads), args, 0, st);
+}
+
 static cudaError_t launch(KernelFn fn, int grid, int block, size_t smem, cudaStream_t st, const Params &p) {
     void *args[] = {const_cast<Params *>(&p)};
     return cudaLaunchKernel(reinterpret_cast<const void *>(fn), dim3(grid), dim3(block), args, smem, st);
 }
 
-static size_t update_smem(evs_handle h) {
+static size_t fetch_smem(evs_handle h) {
     unsigned s = h->tier[0].dev.row_stride;
     if (h->n_tiers == 2) s = std::max(s, h->tier[1].dev.row_stride);
     return static_cast<size_t>(kSamplesPerCta) * s;
 }
 
-// The per-batch kernel sequence: three launches (four for very large batches).  `n_chunks` CTAs
-// of k_serve / k_update; CTAs past the batch end exit at once, so a captured graph uses the maximum.
-static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks) {
+static int side_grid(evs_handle h, int n_chunks) {
+    const long long n = static_cast<long long>(n_chunks) * kSamplesPerCta * h->cfg.n_tables;
+    return static_cast<int>(std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 4)));
+}
+
+// The per-batch kernel sequence.  Critical path: k_serve -> [k_scan ->] k_update -> k_evict.  The
+// zero-copy miss fetch (PCIe round trips) and the slab fill run on the side stream next to it:
+//     k_serve --> k_update --+--> k_evict ------------+--> (next batch)
+//                            +--> k_fetch --> k_fill --+
+// (fetching next to k_update instead slowed k_update from 9 to 17 us: the SMs' outstanding
+// PCIe reads get in the way of its atomics)
+// `n_chunks` CTAs of k_serve / k_update; CTAs past the batch end exit at once, so a captured graph
+// uses the maximum.
+static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const BatchArgs &a) {
     const Params &p = h->params;
     const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
     Profiler &pf = h->prof;
-    { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch(ks.serve, n_chunks, kLookupThreads, 0, st, p)); }
+    { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch_serve(ks.serve, n_chunks, st, p, a)); }
     if (p.n_chunks_max > kQuadMaxChunks) {
         LaunchScope ls(pf, K_SCAN, st);
         EVS_CUDA(launch(k_scan, h->n_tiers * h->tier[0].dev.n_buckets, 256, 0, st, p));
     }
-    { LaunchScope ls(pf, K_UPDATE, st); EVS_CUDA(launch(ks.update, n_chunks, kLookupThreads, update_smem(h), st, p)); }
+    { LaunchScope ls(pf, K_UPDATE, st); EVS_CUDA(launch(k_update, n_chunks, kLookupThreads, 0, st, p)); }
+    EVS_CUDA(cudaEventRecord(h->ev_updated, st));
+    EVS_CUDA(cudaStreamWaitEvent(h->side, h->ev_updated, 0));
     { LaunchScope ls(pf, K_EVICT, st); EVS_CUDA(launch(k_evict, h->n_tiers, kEvictThreads, 0, st, p)); }
+    { LaunchScope ls(pf, K_FETCH, h->side); EVS_CUDA(launch(ks.fetch, side_grid(h, n_chunks), 256, fetch_smem(h), h->side, p)); }
+    { LaunchScope ls(pf, K_FILL, h->side); EVS_CUDA(launch(k_fill, side_grid(h, n_chunks), 256, 0, h->side, p)); }
+    EVS_CUDA(cudaEventRecord(h->ev_filled, h->side));
+    EVS_CUDA(cudaStreamWaitEvent(st, h->ev_filled, 0));
     return EVS_OK;
 }
 
@@ -345,14 +374,34 @@ static int build_graph(evs_handle h) {
     unsigned long long saved[K_COUNT];
     memcpy(saved, h->prof.launches, sizeof(saved));
     EVS_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_batch(h, h->stream, h->params.n_chunks_max);
+    BatchArgs none{};
+    int rc = enqueue_batch(h, h->stream, h->params.n_chunks_max, none);
     cudaError_t e = cudaStreamEndCapture(h->stream, &g);
     memcpy(h->prof.launches, saved, sizeof(saved));
     h->prof.on = was_on;
     if (rc) return rc;
     EVS_CUDA(e);
+    // find the k_serve node: its BatchArgs parameter is the only thing that changes between launches
+    size_t n_nodes = 0;
+    EVS_CUDA(cudaGraphGetNodes(g, nullptr, &n_nodes));
+    std::vector<cudaGraphNode_t> nodes(n_nodes);
+    EVS_CUDA(cudaGraphGetNodes(g, nodes.data(), &n_nodes));
+    const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
+    h->serve_node = nullptr;
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType ty;
+        EVS_CUDA(cudaGraphNodeGetType(nd, &ty));
+        if (ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp{};
+        EVS_CUDA(cudaGraphKernelNodeGetParams(nd, &kp));
+        if (kp.func == reinterpret_cast<void *>(ks.serve)) h->serve_node = nd;
+    }
+    if (h->serve_node == nullptr) {
+        set_error("graph capture: k_serve node not found");
+        return EVS_ERR_CUDA;
+    }
     EVS_CUDA(cudaGraphInstantiate(&h->graph, g, 0));
-    EVS_CUDA(cudaGraphDestroy(g));
+    h->graph_src = g;                                     // kept: the node handle belongs to it
     return EVS_OK;
 }
 
@@ -441,8 +490,12 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         free_all(h);
         return code;
     };
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        set_error("cudaStreamCreate failed");
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_served, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_updated, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_filled, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("cudaStreamCreate / cudaEventCreate failed");
         return fail(EVS_ERR_CUDA);
     }
     h->n_tiers = cfg->n_layers >= 2 ? 2 : 1;
@@ -497,12 +550,14 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         for (const unsigned char *q : h->tier[i].store_dev) al = al && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0);
         if (al) P.store_aligned |= 1 << i;
     }
-    const size_t us = update_smem(h);
+    P.stage_stride = std::max(h->tier[0].dev.row_stride, h->n_tiers == 2 ? h->tier[1].dev.row_stride : 0u);
+    if ((rc = dev_alloc(h->dev_allocs, &P.miss_stage, static_cast<size_t>(n_max) * P.stage_stride, false))) return fail(rc);
+    const size_t us = fetch_smem(h);
     if (us > 40 * 1024) {
         const KernelSet ks = pick_kernels(cfg->main_precision, h->n_tiers == 2 ? cfg->secondary_precision : 0);
-        if (cudaFuncSetAttribute(reinterpret_cast<const void *>(ks.update), cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(reinterpret_cast<const void *>(ks.fetch), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(us)) != cudaSuccess) {
-            set_error("row too large for the update kernel's staging buffer");
+            set_error("row too large for the fetch kernel's staging buffer");
             return fail(EVS_ERR_INVALID);
         }
     }
@@ -520,20 +575,27 @@ int evs_destroy(evs_handle h) {
 }
 
 static int run_batch(evs_handle h, const BatchArgs &a, cudaStream_t st) {
-    // the 64-byte argument block is staged by the runtime before this returns (pageable source)
-    EVS_CUDA(cudaMemcpyAsync(h->d_args, &a, sizeof(a), cudaMemcpyHostToDevice, st));
+    const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
     if (a.probe_only) {
-        const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
         LaunchScope ls(h->prof, K_PROBE, st);
-        EVS_CUDA(launch(ks.serve, (a.B + kSamplesPerCta - 1) / kSamplesPerCta, kLookupThreads, 0, st, h->params));
+        EVS_CUDA(launch_serve(ks.serve, (a.B + kSamplesPerCta - 1) / kSamplesPerCta, st, h->params, a));
         return EVS_OK;
     }
     if (h->use_graph && !h->prof.on) {
+        void *kargs[] = {&h->params, const_cast<BatchArgs *>(&a)};
+        cudaKernelNodeParams kp{};
+        kp.func = reinterpret_cast<void *>(ks.serve);
+        kp.gridDim = dim3(h->params.n_chunks_max);
+        kp.blockDim = dim3(kLookupThreads);
+        kp.sharedMemBytes = 0;
+        kp.kernelParams = kargs;
+        EVS_CUDA(cudaGraphExecKernelNodeSetParams(h->graph, h->serve_node, &kp));
         EVS_CUDA(cudaGraphLaunch(h->graph, st));
         h->prof.launches[K_SERVE]++, h->prof.launches[K_UPDATE]++, h->prof.launches[K_EVICT]++;
+        h->prof.launches[K_FETCH]++, h->prof.launches[K_FILL]++;
         if (h->params.n_chunks_max > kQuadMaxChunks) h->prof.launches[K_SCAN]++;
     } else {
-        int rc = enqueue_batch(h, st, (a.B + kSamplesPerCta - 1) / kSamplesPerCta);
+        int rc = enqueue_batch(h, st, (a.B + kSamplesPerCta - 1) / kSamplesPerCta, a);
         if (rc) return rc;
     }
     h->batches++;

@@ -94,6 +94,161 @@ __device__ __forceinline__ bool c3_find(const C3Dev &c, unsigned long long key, 
     }
 }
 
+// ---- miss fetch ---------------------------------------------------------------------------
+// Copy one backing-store row (row_bytes, arbitrary alignment) into a 16-byte aligned staging
+// row of `stride` bytes, zero padded.  Zero-copy reads when the store lives in pinned host memory.
+__device__ __forceinline__ void fetch_row(const unsigned char *__restrict__ src, unsigned row_bytes,
+                                          unsigned char *stage, unsigned stride, int lane) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+    if (((a | row_bytes) & 3u) == 0) {
+        for (unsigned o = lane * 4u; o < row_bytes; o += 128u)
+            *reinterpret_cast<unsigned *>(stage + o) = __ldg(reinterpret_cast<const unsigned *>(src + o));
+    } else if (((a | row_bytes) & 1u) == 0) {
+        for (unsigned o = lane * 2u; o < row_bytes; o += 64u)
+            *reinterpret_cast<unsigned short *>(stage + o) = __ldg(reinterpret_cast<const unsigned short *>(src + o));
+    } else {
+        for (unsigned o = lane; o < row_bytes; o += 32u) stage[o] = __ldg(src + o);
+    }
+    for (unsigned o = row_bytes + lane; o < stride; o += 32u) stage[o] = 0;
+}
+
+// Fetch one missing row (table t, row r of sample s) from the backing store: dequantised into the
+// output and, raw, into the position's row of the miss staging buffer in HBM, from where k_update
+// moves it into the slab row the key claims.  Executed by a group of `gsize` consecutive lanes
+// (glane = lane within the group) straight through registers when rows are 16-byte aligned
+// (stage == nullptr), else by the whole warp via a shared-memory staging row.
+template <int PREC>
+__device__ __forceinline__ void fetch_one(const TierDev &tier, const BatchArgs &a, int D, int s, int t, long long r,
+                                          unsigned char *dst, int lane, int glane, int gsize, unsigned char *stage,
+                                          bool vec, const CodecLut *lut) {
+    const unsigned char *src = tier.store[t] + static_cast<size_t>(r) * tier.row_bytes;
+    float *orow = a.out + static_cast<size_t>(s) * a.out_stride + t * D;
+    const int cpr = static_cast<int>(tier.row_stride >> 4);
+    if (stage == nullptr) {
+        for (int c = glane; c < cpr; c += gsize) {
+            const uint4 v = ldg16(src + (c << 4));
+            *reinterpret_cast<uint4 *>(dst + (c << 4)) = v;
+            decode_store<PREC>(v, orow, c, D, vec, lut);
+        }
+    } else {
+        fetch_row(src, tier.row_bytes, stage, tier.row_stride, lane);
+        __syncwarp();
+        for (int c = lane; c < cpr; c += 32) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(stage + (c << 4));
+            *reinterpret_cast<uint4 *>(dst + (c << 4)) = v;
+            decode_store<PREC>(v, orow, c, D, vec, lut);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- k_fetch -----------------------------------------------------------------------------
+// Runs on a side stream next to k_update: a warp scans 32 positions' flags at a time and fetches
+// the rows of the misses among them (groups of lanes share a row when rows are 16-byte aligned).
+template <int PREC>
+__device__ __forceinline__ void fetch_group(const TierDev &tier, const Params &p, const BatchArgs &a, int base, unsigned mm,
+                                            int lane, bool aligned, unsigned char *stage, bool vec, const CodecLut *lut) {
+    const int T = p.T, D = p.D;
+    auto row_of = [&](int pos, int &s, int &t) {
+        s = pos / T;
+        t = pos - s * T;
+        long long r = __ldg(a.idx + static_cast<size_t>(t) * a.B + s);
+        if (r < 0 || r >= __ldg(p.rows + t)) r = 0;
+        return r;
+    };
+    if (aligned) {
+        int gsize = 1;
+        while (gsize < static_cast<int>(tier.row_stride >> 4) && gsize < 32) gsize <<= 1;
+        const int ngrp = 32 / gsize, grp = lane / gsize, gl = lane - grp * gsize;
+        while (mm) {
+            unsigned rest = mm;
+            int mine = -1;
+            for (int k = 0; k < ngrp && rest; ++k) {
+                const int bit = __ffs(rest) - 1;
+                rest &= rest - 1;
+                if (k == grp) mine = bit;
+            }
+            mm = rest;
+            if (mine >= 0) {
+                int s, t;
+                const long long r = row_of(base + mine, s, t);
+                fetch_one<PREC>(tier, a, D, s, t, r, p.miss_stage + static_cast<size_t>(base + mine) * p.stage_stride, lane, gl,
+                                gsize, nullptr, vec, lut);
+            }
+        }
+    } else {
+        while (mm) {
+            const int bit = __ffs(mm) - 1;
+            mm &= mm - 1;
+            int s, t;
+            const long long r = row_of(base + bit, s, t);
+            fetch_one<PREC>(tier, a, D, s, t, r, p.miss_stage + static_cast<size_t>(base + bit) * p.stage_stride, lane, lane, 32,
+                            stage, vec, lut);
+        }
+    }
+}
+
+template <int P0, int P1>
+__global__ void __launch_bounds__(256) k_fetch(const __grid_constant__ Params p) {
+    extern __shared__ __align__(16) unsigned char s_stage[];    // warps * max(row_stride); unaligned rows only
+    __shared__ CodecLut s_lut;
+    codec_lut_init<P0, P1>(&s_lut);
+    __syncthreads();
+    const BatchArgs a = *p.args;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpc = blockDim.x >> 5;
+    const int N = a.B * p.T;
+    const TierDev &t0 = p.tier[0];
+    const TierDev &t1 = p.tier[1];
+    unsigned char *stage = s_stage + static_cast<size_t>(warp) * p.stage_stride;
+    const bool vec = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && ((a.out_stride & 3) == 0) && ((p.D & 3) == 0);
+    for (int base = (blockIdx.x * wpc + warp) * 32; base < N; base += gridDim.x * wpc * 32) {
+        const int pos = base + lane;
+        const unsigned f = (pos < N) ? p.flags[pos] : 0u;
+        const unsigned m0 = __ballot_sync(kFull, (f & kFlagMiss) && !(f & kFlagTier));
+        const unsigned m1 = __ballot_sync(kFull, (f & kFlagMiss) && (f & kFlagTier));
+        if (m0) fetch_group<P0>(t0, p, a, base, m0, lane, (p.store_aligned & 1) != 0, stage, vec, &s_lut);
+        if (P1 != 0 && m1)
+            fetch_group<(P1 != 0 ? P1 : 32)>(t1, p, a, base, m1, lane, (p.store_aligned & 2) != 0, stage, vec, &s_lut);
+    }
+}
+
+// ---- k_fill ------------------------------------------------------------------------------
+// After k_update (slots claimed) and k_fetch (rows staged): the claiming position's row moves
+// into the slab row of its slot.  Groups of 4 lanes copy one row.
+__global__ void __launch_bounds__(256) k_fill(const __grid_constant__ Params p) {
+    const BatchArgs a = *p.args;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpc = blockDim.x >> 5;
+    const int N = a.B * p.T;
+    for (int base = (blockIdx.x * wpc + warp) * 32; base < N; base += gridDim.x * wpc * 32) {
+        const int pos = base + lane;
+        const unsigned f = (pos < N) ? p.flags[pos] : 0u;
+        const unsigned sw = (f & kFlagMiss) ? p.pos_slot[pos] : 0u;
+        unsigned mm = __ballot_sync(kFull, (f & kFlagMiss) && (sw & kClaimedBit));
+        const int grp = lane >> 2, gl = lane & 3;
+        while (mm) {
+            unsigned rest = mm;
+            int mine = -1;
+            for (int k = 0; k < 8 && rest; ++k) {
+                const int bit = __ffs(rest) - 1;
+                rest &= rest - 1;
+                if (k == grp) mine = bit;
+            }
+            mm = rest;
+            const unsigned msw = __shfl_sync(kFull, sw, mine < 0 ? 0 : mine);
+            const unsigned mf = __shfl_sync(kFull, f, mine < 0 ? 0 : mine);
+            if (mine >= 0) {
+                const TierDev &tier = p.tier[(mf & kFlagTier) ? 1 : 0];
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.miss_stage + static_cast<size_t>(base + mine) * p.stage_stride);
+                uint4 *dst = reinterpret_cast<uint4 *>(tier.slab + static_cast<size_t>(msw & ~kClaimedBit) * tier.row_stride);
+                const int cpr = static_cast<int>(tier.row_stride >> 4);
+                for (int c = gl; c < cpr; c += 4) dst[c] = src[c];
+            }
+        }
+    }
+}
+
 // ---- k_serve ---------------------------------------------------------------------------
 // Gather the rows tier `k` serves for this warp's sample: lanes walk the sample's T*CPR 16-byte
 // chunks so consecutive lanes read consecutive 16 B of a row and write consecutive floats of
@@ -130,15 +285,18 @@ __device__ __forceinline__ void gather_tier(const TierDev &t, int k, int src_t, 
 // consecutive samples so the int64 index tile is read as T runs of 64 contiguous bytes.
 // P1 == 0: single tier.  The cache state is only read here (C3 recency flags excepted).
 template <int P0, int P1>
-__global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant__ Params p, const __grid_constant__ BatchArgs a) {
     __shared__ long long s_idx[kSamplesPerCta][kMaxTables];
     __shared__ unsigned s_hist[kSeqs];
     __shared__ unsigned s_stat[8];           // hits C1, hits C2, C3, approx, misses, perfect
     __shared__ CodecLut s_lut;
 
     const unsigned long long t_start = gtime();
-    if (blockIdx.x == 0 && threadIdx.x == 0) p.dbg[0] = t_start;
-    const BatchArgs a = *p.args;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.dbg[0] = t_start;
+        if (p.dbg[4] > p.dbg[6]) p.dbg[14] += 1ull;       // previous batch's k_evict has not finished (must stay 0)
+        *p.args = a;                                       // the later kernels of this batch read the arguments here
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int T = p.T, B = a.B, D = p.D;
     const int s0 = blockIdx.x * kSamplesPerCta;
@@ -373,107 +531,43 @@ __device__ __forceinline__ unsigned claim_slot(const TierDev &tier, unsigned lon
     unsigned i = home;
     claimed = false;
     while (true) {
-        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&tier.slots[i].kw);
-        const unsigned long long k = cur & kKeyMask;
-        if (k == key) break;
-        if (k == kEmptyKey) {
-            const unsigned long long old = atomicCAS(&tier.slots[i].kw, cur, (cur & ~kKeyMask) | key);
-            if (old == cur) {
-                claimed = true;
+        // look at 4 slots per round trip (L2-coherent loads: other claimers write these words)
+        unsigned long long kw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) kw[k] = __ldcg(&tier.slots[(i + k) & mask].kw);
+        int k = 0;
+        for (; k < 4; ++k) {
+            unsigned long long cur = kw[k];
+            const unsigned j = (i + k) & mask;
+            bool done = false;
+            while (true) {
+                const unsigned long long kk = cur & kKeyMask;
+                if (kk == key) {
+                    done = true;
+                    break;
+                }
+                if (kk != kEmptyKey) break;                       // someone else's key: next slot
+                const unsigned long long old = atomicCAS(&tier.slots[j].kw, cur, (cur & ~kKeyMask) | key);
+                if (old == cur) {
+                    claimed = true;
+                    done = true;
+                    break;
+                }
+                cur = old;                                          // pass bits moved or the slot got taken: re-examine
+            }
+            if (done) {
+                i = j;
                 break;
             }
-            continue;                            // look at the same slot again
         }
-        i = (i + 1) & mask;
+        if (k < 4) break;
+        i = (i + 4) & mask;
     }
     if (claimed) {
-        // 16 bits of pass: a 65 535-key probe cluster cannot form at the <= 0.67 load factor used here
+        // 16 bits of pass: a 65 535-key probe cluster cannot form at the <= 1/3 load factor used here
         for (unsigned j = home; j != i; j = (j + 1) & mask) atomicAdd(&tier.slots[j].kw, kPassOne);
     }
     return i;
-}
-
-// ---- k_fetch -----------------------------------------------------------------------------
-// Copy one backing-store row (row_bytes, arbitrary alignment) into a 16-byte aligned staging
-// row of `stride` bytes, zero padded.  Zero-copy reads when the store lives in pinned host memory.
-__device__ __forceinline__ void fetch_row(const unsigned char *__restrict__ src, unsigned row_bytes,
-                                          unsigned char *stage, unsigned stride, int lane) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-    if (((a | row_bytes) & 3u) == 0) {
-        for (unsigned o = lane * 4u; o < row_bytes; o += 128u)
-            *reinterpret_cast<unsigned *>(stage + o) = __ldg(reinterpret_cast<const unsigned *>(src + o));
-    } else if (((a | row_bytes) & 1u) == 0) {
-        for (unsigned o = lane * 2u; o < row_bytes; o += 64u)
-            *reinterpret_cast<unsigned short *>(stage + o) = __ldg(reinterpret_cast<const unsigned short *>(src + o));
-    } else {
-        for (unsigned o = lane; o < row_bytes; o += 32u) stage[o] = __ldg(src + o);
-    }
-    for (unsigned o = row_bytes + lane; o < stride; o += 32u) stage[o] = 0;
-}
-
-// Fetch one missing row (table t, row r of sample s) from the backing store: raw bytes into the
-// slab row of `slot` when this position claimed it, dequantised into the output.  Executed by a
-// group of `gsize` consecutive lanes (glane = lane within the group) straight through registers
-// when rows are 16-byte aligned (stage == nullptr), else by the whole warp via a staging row.
-template <int PREC>
-__device__ __forceinline__ void fetch_one(const TierDev &tier, const BatchArgs &a, int D, int s, int t, long long r,
-                                          unsigned slot, bool claimed, int lane, int glane, int gsize,
-                                          unsigned char *stage, bool vec, const CodecLut *lut) {
-    const unsigned char *src = tier.store[t] + static_cast<size_t>(r) * tier.row_bytes;
-    float *orow = a.out + static_cast<size_t>(s) * a.out_stride + t * D;
-    const int cpr = static_cast<int>(tier.row_stride >> 4);
-    unsigned char *dst = tier.slab + static_cast<size_t>(slot) * tier.row_stride;
-    if (stage == nullptr) {
-        for (int c = glane; c < cpr; c += gsize) {
-            const uint4 v = ldg16(src + (c << 4));
-            if (claimed) *reinterpret_cast<uint4 *>(dst + (c << 4)) = v;
-            decode_store<PREC>(v, orow, c, D, vec, lut);
-        }
-    } else {
-        fetch_row(src, tier.row_bytes, stage, tier.row_stride, lane);
-        __syncwarp();
-        for (int c = lane; c < cpr; c += 32) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(stage + (c << 4));
-            if (claimed) *reinterpret_cast<uint4 *>(dst + (c << 4)) = v;
-            decode_store<PREC>(v, orow, c, D, vec, lut);
-        }
-        __syncwarp();
-    }
-}
-
-// The misses of one warp's sample that go to `tier` (bit t of `mm` = table t missed).  Every lane
-// passes its own r / slot word; the fetching lanes pull the victim lane's values by shuffle.
-template <int PREC>
-__device__ __forceinline__ void fetch_misses(const TierDev &tier, const BatchArgs &a, int D, int s, unsigned mm,
-                                             long long r, unsigned slotword, int lane, bool aligned, int gsize,
-                                             unsigned char *stage, bool vec, const CodecLut *lut) {
-    if (aligned) {
-        const int ngrp = 32 / gsize, grp = lane / gsize, gl = lane - grp * gsize;
-        while (mm) {
-            unsigned rest = mm;
-            int mine = -1;
-            for (int k = 0; k < ngrp && rest; ++k) {
-                const int bit = __ffs(rest) - 1;
-                rest &= rest - 1;
-                if (k == grp) mine = bit;
-            }
-            mm = rest;
-            const int srcl = mine < 0 ? 0 : mine;
-            const long long rr = __shfl_sync(kFull, r, srcl);
-            const unsigned sw = __shfl_sync(kFull, slotword, srcl);
-            if (mine >= 0)
-                fetch_one<PREC>(tier, a, D, s, mine, rr, sw & ~kClaimedBit, (sw & kClaimedBit) != 0u, lane, gl, gsize, nullptr,
-                                vec, lut);
-        }
-    } else {
-        while (mm) {
-            const int bit = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const long long rr = __shfl_sync(kFull, r, bit);
-            const unsigned sw = __shfl_sync(kFull, slotword, bit);
-            fetch_one<PREC>(tier, a, D, s, bit, rr, sw & ~kClaimedBit, (sw & kClaimedBit) != 0u, lane, lane, 32, stage, vec, lut);
-        }
-    }
 }
 
 // ---- k_evict ---------------------------------------------------------------------------
@@ -515,26 +609,39 @@ __device__ unsigned pop_range(const TierDev &tier, EvictShared &S, int b_lo, int
     unsigned got = 0;
     while (got < want) {
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int n = 0;
-            unsigned acc = 0;
-            for (int b = b_lo; b <= b_hi && acc < W; ++b) {
-                if (S.count[b] == 0) {               // only dead records are left in this ring
-                    S.cur[b] = S.tail[b];
-                    continue;
-                }
-                const unsigned long long len = S.tail[b] - S.cur[b];
-                if (len == 0) continue;
-                const unsigned take = static_cast<unsigned>(len < static_cast<unsigned long long>(W - acc) ? len : (W - acc));
-                S.seg_b[n] = b;
-                S.seg_q0[n] = S.cur[b];
-                S.seg_off[n] = acc;
-                S.seg_taken[n] = 0;
-                acc += take;
-                ++n;
+        if (warp == 0) {
+            // lane = bucket: unscanned ring length of every bucket in range, clipped so that the
+            // window holds at most W records; buckets without live entries are skipped for good
+            const int b = lane;
+            const bool in = b >= b_lo && b <= b_hi;
+            unsigned long long len = 0;
+            if (in) {
+                if (S.count[b] == 0) S.cur[b] = S.tail[b];
+                len = S.tail[b] - S.cur[b];
             }
-            S.seg_off[n] = acc;
-            S.n_seg = n;
+            const unsigned l32 = len > W ? W : static_cast<unsigned>(len);
+            unsigned incl = l32;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned n = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += n;
+            }
+            const unsigned excl = incl - l32;
+            const unsigned take = excl >= W ? 0u : (l32 < W - excl ? l32 : W - excl);
+            const unsigned has = __ballot_sync(kFull, take > 0);
+            const int si = __popc(has & ((1u << lane) - 1u));
+            if (take > 0) {
+                S.seg_b[si] = b;
+                S.seg_q0[si] = S.cur[b];
+                S.seg_off[si] = excl;
+                S.seg_taken[si] = 0;
+            }
+            const unsigned total_take = __shfl_sync(kFull, incl < W ? incl : W, 31);
+            if (lane == 0) {
+                const int n = __popc(has);
+                S.seg_off[n] = total_take;
+                S.n_seg = n;
+            }
         }
         __syncthreads();
         const int n_seg = S.n_seg;
@@ -600,7 +707,15 @@ __device__ unsigned pop_range(const TierDev &tier, EvictShared &S, int b_lo, int
                 const unsigned long long key = u64_of(sv[r].x, sv[r].y) & kKeyMask;
                 evict_slot(tier, slot[r], key);
                 if (out_keys != nullptr) out_keys[out_base + got + idx] = key;
-                atomicAdd(&S.seg_taken[seg[r]], 1u);
+            }
+            // victims per segment, one shared-memory atomic per warp and segment
+            unsigned pending = __ballot_sync(kFull, take);
+            while (pending) {
+                const int leader = __ffs(pending) - 1;
+                const int sg = __shfl_sync(kFull, seg[r], leader);
+                const unsigned same = __ballot_sync(kFull, take && seg[r] == sg);
+                if (lane == leader) atomicAdd(&S.seg_taken[sg], static_cast<unsigned>(__popc(same)));
+                pending &= ~same;
             }
             // first live record left in place, per bucket; the plain pre-check keeps the same-address
             // shared-memory atomics to a handful per bucket (benign race: atomicMin decides)

@@ -114,8 +114,9 @@ struct GlobalCtl {
     unsigned int pad;
 };
 
-// Arguments that change from batch to batch live in device memory so that the kernel sequence
-// can be captured once in a CUDA graph; a 64-byte H2D copy precedes each launch.
+// Arguments that change from batch to batch.  k_serve receives them as a kernel parameter (the
+// only graph node whose parameters are updated per batch) and stores them in device memory for
+// the kernels that follow it.
 struct BatchArgs {
     const long long *idx;                  // [T][B]
     float *out;
@@ -139,13 +140,15 @@ struct Params {
     int high_thres;                        // high_agghit_threshold (evlfu_32.hpp:74)
     int n_chunks_max;
     const long long *rows;                 // [T] cardinalities
-    const BatchArgs *args;
+    BatchArgs *args;
     GlobalCtl *g;
     // per-batch scratch
     uint8_t *flags;                        // [N]
     unsigned int *pos_slot;                // [N] slot (in the flag's tier) of a promoted / inserted key
     unsigned int *hist;                    // [kSeqs][n_chunks_max]: per-CTA append counts (prefixes after k_scan)
-    unsigned int *done;                    // CTAs of k_update that have finished (last one evicts)
+    unsigned char *miss_stage;             // [N][stage_stride] raw rows fetched for the missing positions
+    unsigned int stage_stride;             // max row_stride of the tiers
+    unsigned int *done;                    // k_evict: tier 1 finished (C3 needs both tiers' victims)
     int store_aligned;                     // bit t: every backing row of tier t starts 16-byte aligned
     unsigned long long *dbg;               // [16] %globaltimer stamps of the last batch's phases (ns)
 };

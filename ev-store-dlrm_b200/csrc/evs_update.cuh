@@ -7,8 +7,8 @@
 //                  the order EvLFU_C1.py processes them), computed from k_serve's per-CTA counts,
 //              (c) atomicMax on the slot's meta picks the winning occurrence of a key (highest
 //                  (agg_hit, position)), bucket counters follow,
-//              (d) if it missed, fetches its row from the host-pinned backing store (zero-copy) into
-//                  the slab row it claimed and, dequantised, into the output.
+// The rows of the missing keys are fetched meanwhile by k_fetch on a side stream (output + miss
+// staging buffer); k_fill then moves the claimers' rows into their slab rows, next to k_evict.
 // k_evict (one 1024-thread CTA per tier) then advances the ring tails, applies the flush rule,
 // evicts down to capacity and inserts the victims into C3.
 #pragma once
@@ -17,23 +17,17 @@
 
 namespace evs {
 
-template <int P0, int P1>
 __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant__ Params p) {
-    extern __shared__ __align__(16) unsigned char s_stage[];    // warps * max(row_stride), unaligned rows only
     __shared__ unsigned s_cnt[kSamplesPerCta][kMaxTiers];
     __shared__ int s_b[kSamplesPerCta];
     __shared__ int s_delta[kSeqs];
     __shared__ unsigned s_new[kMaxTiers], s_ins[kMaxTiers];
     __shared__ unsigned long long s_prot[kMaxTiers];
-    __shared__ CodecLut s_lut;
-    __shared__ int s_first_any;
 
-    const unsigned long long t_start = gtime();
-    unsigned long long t_pre = t_start, t_app = t_start;
-    if (blockIdx.x == 0 && threadIdx.x == 0) p.dbg[2] = t_start;
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.dbg[2] = gtime();
     const BatchArgs a = *p.args;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int T = p.T, B = a.B, D = p.D;
+    const int T = p.T, B = a.B;
     const int n_chunks = (B + kSamplesPerCta - 1) / kSamplesPerCta;
     if (static_cast<int>(blockIdx.x) >= n_chunks) return;
     const int s = blockIdx.x * kSamplesPerCta + warp;
@@ -51,7 +45,6 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
         s_ins[threadIdx.x] = 0;
         s_prot[threadIdx.x] = 0ull;
     }
-    codec_lut_init<P0, P1>(&s_lut);
 
     const int tr = (f & kFlagTier) ? 1 : 0;
     const int b = static_cast<int>(f & 0x3Fu) - 1;
@@ -59,18 +52,26 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
     const unsigned m1 = __ballot_sync(kFull, f != 0u && tr == 1);
     const unsigned any = m0 | m1;
     const int wb = __shfl_sync(kFull, b, any ? (__ffs(any) - 1) : 0);    // all flagged lanes share it
-    if (threadIdx.x == 0) s_first_any = 99;
-    __syncwarp();
     if (lane == 0) {
         s_cnt[warp][0] = __popc(m0);
         s_cnt[warp][1] = __popc(m1);
         s_b[warp] = any ? wb : -1;
     }
     __syncthreads();
-    if (lane == 0 && any) atomicMin(&s_first_any, warp);
-    __syncthreads();
 
     if (any) {
+        // the claim (a chain of dependent accesses) goes first so that it overlaps the prefix sums
+        unsigned slot = 0;
+        bool claimed = false;
+        if (f & kFlagMiss) {
+            slot = claim_slot(p.tier[tr], make_key(p.table_base + lane, r), claimed);
+            p.pos_slot[pos] = slot | (claimed ? kClaimedBit : 0u);
+            if (claimed) atomicAdd(&s_new[tr], 1u);
+            atomicMax(&s_prot[tr], (static_cast<unsigned long long>(f & 0x3Fu) << 32) | static_cast<unsigned>(pos));
+        } else if (f) {
+            slot = p.pos_slot[pos];
+        }
+
         // records of earlier chunks in my bucket's sequences (k_scan already made them prefixes for
         // very large batches), then of earlier samples of this chunk
         unsigned base0 = 0, base1 = 0;
@@ -81,9 +82,19 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
             if (m1) base1 = __ldcg(h1 + blockIdx.x);
         } else {
             unsigned p0 = 0, p1 = 0;
-            for (int c = lane; c < static_cast<int>(blockIdx.x); c += 32) {
-                if (m0) p0 += __ldcg(h0 + c);
-                if (m1) p1 += __ldcg(h1 + c);
+            const int nc = static_cast<int>(blockIdx.x);
+            for (int c0 = 0; c0 < nc; c0 += 128) {             // 4 independent loads per lane and round
+                unsigned x0[4] = {0, 0, 0, 0}, x1[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = c0 + u * 32 + lane;
+                    if (c < nc) {
+                        if (m0) x0[u] = __ldcg(h0 + c);
+                        if (m1) x1[u] = __ldcg(h1 + c);
+                    }
+                }
+                p0 += x0[0] + x0[1] + x0[2] + x0[3];
+                p1 += x1[0] + x1[1] + x1[2] + x1[3];
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
@@ -93,27 +104,14 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
             base0 = p0;
             base1 = p1;
         }
-        t_pre = gtime();
         for (int w = 0; w < warp; ++w)
             if (s_b[w] == wb) {
                 base0 += s_cnt[w][0];
                 base1 += s_cnt[w][1];
             }
 
-        unsigned slotword = 0;
         if (f) {
             const TierDev &tier = p.tier[tr];
-            unsigned slot;
-            if (f & kFlagMiss) {
-                bool claimed;
-                slot = claim_slot(tier, make_key(p.table_base + lane, r), claimed);
-                slotword = slot | (claimed ? kClaimedBit : 0u);
-                p.pos_slot[pos] = slotword;
-                if (claimed) atomicAdd(&s_new[tr], 1u);
-                atomicMax(&s_prot[tr], (static_cast<unsigned long long>(f & 0x3Fu) << 32) | static_cast<unsigned>(pos));
-            } else {
-                slot = p.pos_slot[pos];
-            }
             const unsigned rank = __popc((tr ? m1 : m0) & ((1u << lane) - 1u));
             const volatile TierCtl *c = tier.ctl;
             const unsigned long long tbase = (n_chunks > kQuadMaxChunks) ? c->tail_prev[b] : c->tail[b];
@@ -130,41 +128,9 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
                 }
             }
         }
-
-        t_app = gtime();
-        // miss fetch: host-pinned rows -> slab (claimer) + output
-        const unsigned mm0 = __ballot_sync(kFull, (f & kFlagMiss) && tr == 0);
-        const unsigned mm1 = __ballot_sync(kFull, (f & kFlagMiss) && tr == 1);
-        if (mm0 | mm1) {
-            const bool vec = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && ((a.out_stride & 3) == 0) && ((D & 3) == 0);
-            const TierDev &t0 = p.tier[0];
-            const TierDev &t1 = p.tier[1];
-            const unsigned max_stride = (P1 != 0 && t1.row_stride > t0.row_stride) ? t1.row_stride : t0.row_stride;
-            unsigned char *stage = s_stage + static_cast<size_t>(warp) * max_stride;
-            auto group_of = [](unsigned stride) {
-                int g = 1;
-                while (g < static_cast<int>(stride >> 4) && g < 32) g <<= 1;
-                return g;
-            };
-            if (mm0) fetch_misses<P0>(t0, a, D, s, mm0, r, slotword, lane, (p.store_aligned & 1) != 0, group_of(t0.row_stride), stage, vec, &s_lut);
-            if (P1 != 0 && mm1)
-                fetch_misses<(P1 != 0 ? P1 : 32)>(t1, a, D, s, mm1, r, slotword, lane, (p.store_aligned & 2) != 0, group_of(t1.row_stride), stage, vec, &s_lut);
-        }
     }
 
     // ---- publish this CTA's counter deltas ----------------------------------------------------
-    const unsigned long long t_fetch = gtime();
-    if (any && lane == 0 && warp == s_first_any) {
-        atomicAdd(&p.dbg[9], t_pre - t_start);
-        atomicAdd(&p.dbg[10], t_app - t_start);
-        atomicAdd(&p.dbg[11], t_fetch - t_start);
-        atomicAdd(&p.dbg[8], 1ull);
-    }
-    if (any && lane == 0) {
-        atomicMax(&p.dbg[12], t_pre - t_start);
-        atomicMax(&p.dbg[13], t_app - t_pre);
-        atomicMax(&p.dbg[14], t_fetch - t_app);
-    }
     __syncthreads();
     if (threadIdx.x < kSeqs) {
         const int d = s_delta[threadIdx.x];
@@ -191,7 +157,10 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int B = p.args->B;
     const int n_chunks = (B + kSamplesPerCta - 1) / kSamplesPerCta;
-    if (t == 0 && threadIdx.x == 0) p.dbg[4] = gtime();
+    if (t == 0 && threadIdx.x == 0) {
+        p.dbg[4] = gtime();
+        if (p.dbg[0] > p.dbg[2]) p.dbg[14] += 1000ull;      // the next batch's k_serve already started (must not happen)
+    }
     if (n_chunks <= kQuadMaxChunks) {
         for (int bb = warp; bb < p.tier[t].n_buckets; bb += kEvictThreads / 32) {
             const unsigned *h = p.hist + static_cast<size_t>(t * kMaxBuckets + bb) * p.n_chunks_max;
@@ -231,6 +200,13 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
         p.dbg[6] = gtime();
         p.dbg[7] = p.dbg[1];
         p.dbg[1] = 0ull;
+        // running sums over batches (ns): serve, gap, update, gap, evict(+c3), count
+        p.dbg[8] += p.dbg[7] - p.dbg[0];
+        p.dbg[9] += p.dbg[2] - p.dbg[7];
+        p.dbg[10] += p.dbg[3] - p.dbg[2];
+        p.dbg[11] += p.dbg[4] - p.dbg[3];
+        p.dbg[12] += p.dbg[6] - p.dbg[4];
+        p.dbg[13] += 1ull;
         atomicAdd(&p.g->batches, 1ull);
     }
 }

@@ -91,3 +91,32 @@ def test_interaction_matches_torch_bmm():
         # fp32 dot products, different summation order than cuBLAS: tolerance 1e-4 abs on O(d) sums
         assert torch.allclose(r, want, rtol=1e-5, atol=1e-4), (B, nf, d)
     store.close()
+
+
+def test_back_to_back_batches_without_host_sync():
+    """Batches queued back to back (no host synchronisation in between, as bench.py does): every
+    batch must still see the state its predecessor left (stream order of the whole kernel graph)."""
+    import torch
+    from oracle.evlfu import BatchEvLFU, gather_rows
+    p = pkg()
+    rows, dim, B, cap, n = SKEW_ROWS, 16, 256, 3000, 60
+    tables = p.workload.make_tables(rows, dim)
+    trace = p.workload.ZipfTrace(rows, seed=5)
+    idx = trace.batches(n, B)
+    store = p.EvStore(tables, p.CacheConfig(total_size=cap, max_batch=B))
+    oracle = BatchEvLFU(cap, n_tables=len(rows))
+    d_idx = torch.from_numpy(idx).cuda()
+    outs = torch.empty((n, B, len(rows), dim), dtype=torch.float32, device="cuda")
+    hits = torch.empty((n, B, len(rows)), dtype=torch.uint8, device="cuda")
+    for k in range(n):
+        store.lookup(d_idx[k], out=outs[k], hit=hits[k])
+    torch.cuda.synchronize()
+    store.sync()
+    outs, hits = outs.cpu().numpy(), hits.cpu().numpy()
+    for k in range(n):
+        o_hit, st, sr, _ = oracle.lookup_batch(idx[k])
+        assert (hits[k].astype(bool) == o_hit).all(), f"hit stream, batch {k}"
+        assert (outs[k] == gather_rows(tables, st, sr)).all(), f"rows, batch {k}"
+    state, n_perfect = store.dump_state()
+    assert state == oracle.state() and n_perfect == oracle.n_perfect
+    store.close()
