@@ -239,7 +239,7 @@ def main_ours(args):
     T = len(rows)
     cache_rows = pkg.workload.KAGGLE_CACHE_ROWS if args.scale == 1.0 else int(sum(rows) * 0.13)
     warm = args.cache_warm if args.cache_warm >= 0 else 4800
-    n_batches = warm + 3 * (W + K)
+    n_batches = warm + 4 * (W + K)
     _, tables, idx = build_workload(args, n_batches, rows, dim, B)
 
     cfg = pkg.CacheConfig(n_layers=1, main_precision=prec, total_size=cache_rows * prec // 32, max_batch=B, device=local_rank,
@@ -305,18 +305,33 @@ def main_ours(args):
     lookups = K * B * T
     value = lookups / (ms_dev * 1e-3)
 
-    # ---- e2e: host buffers through evs_lookup_batch_host -------------------------------------
+    # ---- e2e: host buffers through the C-ABI -------------------------------------------------
+    # (a) evs_lookup_batch_host: one synchronous call per batch, like the reference's ev_lookup;
+    # (b) evs_submit_host / evs_wait_host: the same batches, at most 4 in flight, so the copies of
+    #     neighbouring batches overlap the kernels.  Both read pinned host indices and deliver the
+    #     fp32 rows (and the hit map) into pinned host buffers inside the timed region.
     base += W + K
-    out_host = torch.empty((B, T, dim), dtype=torch.float32).pin_memory()
-    hit_host = torch.empty((B, T), dtype=torch.uint8).pin_memory()
+    out_host = [torch.empty((B, T, dim), dtype=torch.float32).pin_memory() for _ in range(4)]
+    hit_host = [torch.empty((B, T), dtype=torch.uint8).pin_memory() for _ in range(4)]
     ih = idx_host
     for k in range(W):
-        store.lookup_host_ptr(ih[base + k].data_ptr(), B, out_host.data_ptr(), hit_host.data_ptr())
+        store.lookup_host_ptr(ih[base + k].data_ptr(), B, out_host[0].data_ptr(), hit_host[0].data_ptr())
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for k in range(K):
-        store.lookup_host_ptr(ih[base + W + k].data_ptr(), B, out_host.data_ptr(), hit_host.data_ptr())
+        store.lookup_host_ptr(ih[base + W + k].data_ptr(), B, out_host[0].data_ptr(), hit_host[0].data_ptr())
     torch.cuda.synchronize()
+    e2e_sync_s = time.perf_counter() - t0
+    base += W + K
+    tickets = []
+    for k in range(W):
+        tickets.append(store.submit_host_ptr(ih[base + k].data_ptr(), B, out_host[k % 4].data_ptr(), hit_host[k % 4].data_ptr()))
+    store.wait_host(tickets[-1])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(K):
+        tk = store.submit_host_ptr(ih[base + W + k].data_ptr(), B, out_host[k % 4].data_ptr(), hit_host[k % 4].data_ptr())
+    store.wait_host(tk)
     e2e_s = time.perf_counter() - t0
     e2e_value = lookups / e2e_s
     h2d = B * T * 8
@@ -385,7 +400,8 @@ def main_ours(args):
                    "l2": "no flush: index+slab working set (%.2f GB) exceeds the 126 MB L2 and every step reads a distinct index batch"
                          % ((cache_rows * (dim * prec // 8 + 32)) / 1e9)},
         "e2e": {"value": e2e_value, "unit": "lookups/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s / K},
+                "ms_per_step": 1e3 * e2e_s / K, "api": "evs_submit_host/evs_wait_host (4 batches in flight)",
+                "sync_call_value": lookups / e2e_sync_s, "sync_call_ms_per_step": 1e3 * e2e_sync_s / K},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -51,7 +51,7 @@ class EvsStats(C.Structure):
 # every symbol include/evstore_b200.h declares
 SYMBOLS = [
     "evs_create", "evs_destroy", "evs_last_error", "evs_version", "evs_lookup_batch", "evs_probe_batch",
-    "evs_lookup_batch_host", "evs_sync", "evs_stats", "evs_last_events", "evs_dump_state", "evs_dump_c3",
+    "evs_lookup_batch_host", "evs_submit_host", "evs_wait_host", "evs_sync", "evs_stats", "evs_last_events", "evs_dump_state", "evs_dump_c3",
     "evs_interact", "evs_set_profiling", "evs_kernel_times", "evs_launch_count", "evs_phase_times", "evs_legacy_configure", "evs_legacy_handle", "ev_lookup", "get_ev_values", "print_perfect_hit",
     "test_arr", "ev_lookup_based_on_list_keys",
 ]
@@ -83,6 +83,10 @@ def load_library(path: str | None = None):
     lib.evs_probe_batch.restype = C.c_int
     lib.evs_lookup_batch_host.argtypes = [vp, vp, i32, vp, vp]
     lib.evs_lookup_batch_host.restype = C.c_int
+    lib.evs_submit_host.argtypes = [vp, vp, i32, vp, vp, C.POINTER(i64)]
+    lib.evs_submit_host.restype = C.c_int
+    lib.evs_wait_host.argtypes = [vp, i64]
+    lib.evs_wait_host.restype = C.c_int
     lib.evs_sync.argtypes = [vp]
     lib.evs_sync.restype = C.c_int
     lib.evs_stats.argtypes = [vp, C.POINTER(EvsStats), C.c_int]

@@ -160,6 +160,15 @@ class EvStore:
         _native.check(self.lib.evs_lookup_batch_host(self.handle, idx_ptr, B, out_ptr, hit_ptr or None),
                       "evs_lookup_batch_host")
 
+    def submit_host_ptr(self, idx_ptr: int, B: int, out_ptr: int, hit_ptr: int = 0) -> int:
+        """Pipelined host-buffer lookup (evs_submit_host); returns the ticket for wait_host."""
+        t = C.c_int64(0)
+        _native.check(self.lib.evs_submit_host(self.handle, idx_ptr, B, out_ptr, hit_ptr or None, C.byref(t)), "evs_submit_host")
+        return t.value
+
+    def wait_host(self, ticket: int):
+        _native.check(self.lib.evs_wait_host(self.handle, ticket), "evs_wait_host")
+
     def interact(self, x, ly, out=None, stream=None):
         """dlrm interact_features (dot): x [B, d], ly [B, n_f, d] -> [B, d + (n_f+1) n_f / 2]."""
         import torch

@@ -255,6 +255,13 @@ static void free_all(evs_handle h) {
     if (h->ev_updated) cudaEventDestroy(h->ev_updated);
     if (h->ev_filled) cudaEventDestroy(h->ev_filled);
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    for (int i = 0; i < evs_handle_s::kPipeSlots; ++i) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     cudaGetLastError();
     delete h;
@@ -516,9 +523,9 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     if (cudaMemcpy(h->d_rows, h->rows.data(), sizeof(int64_t) * cfg->n_tables, cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(EVS_ERR_CUDA);
     if ((rc = dev_alloc(h->dev_allocs, &h->d_agg, cfg->max_batch))) return fail(rc);
-    if ((rc = dev_alloc(h->dev_allocs, &h->d_idx, n_max))) return fail(rc);
-    if ((rc = dev_alloc(h->dev_allocs, &h->d_out, n_max * cfg->dim))) return fail(rc);
-    if ((rc = dev_alloc(h->dev_allocs, &h->d_hit, n_max))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &h->d_idx[0], n_max))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &h->d_out[0], n_max * cfg->dim))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &h->d_hit[0], n_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.flags, n_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.pos_slot, n_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.hist, static_cast<size_t>(kSeqs) * n_chunks_max))) return fail(rc);
@@ -647,12 +654,69 @@ int evs_lookup_batch_host(evs_handle h, const int64_t *idx_host, int32_t B, floa
     if (B == 0) return EVS_OK;
     EVS_CUDA(cudaSetDevice(h->cfg.device));
     const size_t n = static_cast<size_t>(B) * h->cfg.n_tables;
-    EVS_CUDA(cudaMemcpyAsync(h->d_idx, idx_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-    int rc = evs_lookup_batch(h, reinterpret_cast<const int64_t *>(h->d_idx), B, h->d_out, 0, h->d_hit, nullptr, h->stream);
+    EVS_CUDA(cudaMemcpyAsync(h->d_idx[0], idx_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    int rc = evs_lookup_batch(h, reinterpret_cast<const int64_t *>(h->d_idx[0]), B, h->d_out[0], 0, h->d_hit[0], nullptr, h->stream);
     if (rc) return rc;
-    EVS_CUDA(cudaMemcpyAsync(out_host, h->d_out, n * h->cfg.dim * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    if (hit_host != nullptr) EVS_CUDA(cudaMemcpyAsync(hit_host, h->d_hit, n, cudaMemcpyDeviceToHost, h->stream));
+    EVS_CUDA(cudaMemcpyAsync(out_host, h->d_out[0], n * h->cfg.dim * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (hit_host != nullptr) EVS_CUDA(cudaMemcpyAsync(hit_host, h->d_hit[0], n, cudaMemcpyDeviceToHost, h->stream));
     EVS_CUDA(cudaStreamSynchronize(h->stream));
+    return EVS_OK;
+}
+
+// Pipelined host-buffer path.  evs_submit_host returns at once with a ticket; at most kPipeSlots
+// batches are in flight (the call blocks on the oldest one when all slots are taken).  The copies
+// run on their own streams, so the H2D of batch n+1 and the D2H of batch n-1 overlap the kernels
+// of batch n; the batches themselves stay strictly ordered.
+static int pipe_init(evs_handle h) {
+    if (h->s_in != nullptr) return EVS_OK;
+    const long long n_max = static_cast<long long>(h->cfg.max_batch) * h->cfg.n_tables;
+    EVS_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    EVS_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    int rc;
+    for (int i = 0; i < evs_handle_s::kPipeSlots; ++i) {
+        if (i > 0) {
+            if ((rc = dev_alloc(h->dev_allocs, &h->d_idx[i], n_max))) return rc;
+            if ((rc = dev_alloc(h->dev_allocs, &h->d_out[i], n_max * h->cfg.dim))) return rc;
+            if ((rc = dev_alloc(h->dev_allocs, &h->d_hit[i], n_max))) return rc;
+        }
+        EVS_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        EVS_CUDA(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+        EVS_CUDA(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
+    return EVS_OK;
+}
+
+int evs_submit_host(evs_handle h, const int64_t *idx_host, int32_t B, float *out_host, uint8_t *hit_host, int64_t *ticket) {
+    if (h == nullptr || B < 1 || B > h->cfg.max_batch || idx_host == nullptr || out_host == nullptr) {
+        set_error("evs_submit_host: bad handle / B / pointers");
+        return EVS_ERR_INVALID;
+    }
+    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    int rc = pipe_init(h);
+    if (rc) return rc;
+    const int slot = static_cast<int>(h->submitted % evs_handle_s::kPipeSlots);
+    if (h->submitted >= evs_handle_s::kPipeSlots) EVS_CUDA(cudaEventSynchronize(h->ev_out[slot]));   // slot free again
+    const size_t n = static_cast<size_t>(B) * h->cfg.n_tables;
+    EVS_CUDA(cudaMemcpyAsync(h->d_idx[slot], idx_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->s_in));
+    EVS_CUDA(cudaEventRecord(h->ev_in[slot], h->s_in));
+    EVS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
+    rc = evs_lookup_batch(h, reinterpret_cast<const int64_t *>(h->d_idx[slot]), B, h->d_out[slot], 0, h->d_hit[slot], nullptr,
+                          h->stream);
+    if (rc) return rc;
+    EVS_CUDA(cudaEventRecord(h->ev_comp[slot], h->stream));
+    EVS_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0));
+    EVS_CUDA(cudaMemcpyAsync(out_host, h->d_out[slot], n * h->cfg.dim * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+    if (hit_host != nullptr) EVS_CUDA(cudaMemcpyAsync(hit_host, h->d_hit[slot], n, cudaMemcpyDeviceToHost, h->s_out));
+    EVS_CUDA(cudaEventRecord(h->ev_out[slot], h->s_out));
+    if (ticket) *ticket = h->submitted;
+    h->submitted++;
+    return EVS_OK;
+}
+
+int evs_wait_host(evs_handle h, int64_t ticket) {
+    if (h == nullptr || ticket < 0 || ticket >= h->submitted) return EVS_ERR_INVALID;
+    if (ticket + evs_handle_s::kPipeSlots < h->submitted) return EVS_OK;         // its slot was already recycled => done
+    EVS_CUDA(cudaEventSynchronize(h->ev_out[ticket % evs_handle_s::kPipeSlots]));
     return EVS_OK;
 }
 

@@ -111,10 +111,15 @@ struct evs_handle_s {
     evs::BatchArgs *d_args = nullptr;        // device copy of the per-batch arguments
     long long *d_rows = nullptr;
     uint8_t *d_agg = nullptr;                // [max_batch]
-    // staging for the host-buffer path
-    long long *d_idx = nullptr;
-    float *d_out = nullptr;
-    uint8_t *d_hit = nullptr;
+    // staging for the host-buffer paths: slot 0 serves the synchronous call, all kPipeSlots the
+    // pipelined one (H2D of batch n+1 and D2H of batch n-1 overlap the kernels of batch n)
+    static constexpr int kPipeSlots = 4;
+    long long *d_idx[kPipeSlots] = {};
+    float *d_out[kPipeSlots] = {};
+    uint8_t *d_hit[kPipeSlots] = {};
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[kPipeSlots] = {}, ev_comp[kPipeSlots] = {}, ev_out[kPipeSlots] = {};
+    int64_t submitted = 0;
     std::vector<void *> registered;          // host ranges we page-locked
     std::vector<void *> dev_allocs;
     uint64_t batches = 0;

@@ -126,6 +126,13 @@ int evs_probe_batch(evs_handle h, const int64_t *idx_dev, int32_t B, uint8_t *ag
  * then a stream synchronise.  This is what a reference-side caller (ctypes / cgo) uses. */
 int evs_lookup_batch_host(evs_handle h, const int64_t *idx_host, int32_t B, float *out_host, uint8_t *hit_host);
 
+/* Pipelined variant of the same: returns at once with a ticket, at most 4 batches in flight (the
+ * call blocks on the oldest when all staging slots are taken).  H2D of the next batch and D2H of
+ * the previous one overlap the kernels of the current one; batches stay strictly ordered.  The
+ * host buffers must stay valid (and should be page-locked) until evs_wait_host(ticket) returns. */
+int evs_submit_host(evs_handle h, const int64_t *idx_host, int32_t B, float *out_host, uint8_t *hit_host, int64_t *ticket);
+int evs_wait_host(evs_handle h, int64_t ticket);
+
 int evs_sync(evs_handle h);
 int evs_stats(evs_handle h, evs_stats_t *out, int reset);
 

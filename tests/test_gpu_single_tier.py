@@ -120,3 +120,27 @@ def test_back_to_back_batches_without_host_sync():
     state, n_perfect = store.dump_state()
     assert state == oracle.state() and n_perfect == oracle.n_perfect
     store.close()
+
+
+def test_pipelined_host_buffer_path():
+    """evs_submit_host / evs_wait_host: 4 batches in flight, results identical to the oracle."""
+    import torch
+    from oracle.evlfu import BatchEvLFU, gather_rows
+    p = pkg()
+    rows, dim, B, cap, n = SMALL_ROWS, 16, 128, 700, 24
+    tables = p.workload.make_tables(rows, dim)
+    idx = p.workload.ZipfTrace(rows, seed=9).batches(n, B)
+    store = p.EvStore(tables, p.CacheConfig(total_size=cap, max_batch=B))
+    oracle = BatchEvLFU(cap, n_tables=len(rows))
+    ih = torch.from_numpy(idx).pin_memory()
+    outs = torch.empty((n, B, len(rows), dim), dtype=torch.float32).pin_memory()
+    hits = torch.empty((n, B, len(rows)), dtype=torch.uint8).pin_memory()
+    tickets = [store.submit_host_ptr(ih[k].data_ptr(), B, outs[k].data_ptr(), hits[k].data_ptr()) for k in range(n)]
+    for t in tickets:
+        store.wait_host(t)
+    store.sync()
+    for k in range(n):
+        o_hit, st, sr, _ = oracle.lookup_batch(idx[k])
+        assert (hits[k].numpy().astype(bool) == o_hit).all(), f"hit stream, batch {k}"
+        assert (outs[k].numpy() == gather_rows(tables, st, sr)).all(), f"rows, batch {k}"
+    store.close()
