@@ -81,8 +81,19 @@ def build_driver(force: bool = False) -> str:
     return target
 
 
+def build_shim(force: bool = False) -> str:
+    """oracle/stdset_shim.cpp (libstdc++ unordered_set<string> behind a C ABI) -> oracle/_ref/libstdset_shim.so."""
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(HERE, "stdset_shim.cpp")
+    target = os.path.join(OUT, "libstdset_shim.so")
+    if force or not os.path.exists(target) or os.path.getmtime(src) > os.path.getmtime(target):
+        subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", target, src], check=True)
+    return target
+
+
 def main(argv):
     build_driver(force="--force" in argv)
+    build_shim(force="--force" in argv)
     if not os.path.isdir(REF_SRC):
         print("oracle/build_ref.py: /root/reference is absent; using prebuilt oracle/_ref/*.so")
         return 0

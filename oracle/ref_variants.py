@@ -21,9 +21,11 @@ VARIANTS = {
     # small fixtures for the CPU tests (dim 36 = the reference's own EV_DIMENSION)
     "test_c1_fp32_d36": dict(layers=1, main=32, sec=4, total=600, prop="", dim=36, fixture="test_d36"),
     "test_c1_8_d36": dict(layers=1, main=8, sec=4, total=150, prop="", dim=36, fixture="test_d36"),
-    "test_c2_32_8_d36": dict(layers=2, main=32, sec=8, total=100000, prop="", dim=36, fixture="test_d36"),
+    "test_c2_32_8_small_d36": dict(layers=2, main=32, sec=8, total=100, prop="", dim=36, fixture="test_d36"),
+    "test_c1_flush_d36": dict(layers=1, main=32, sec=4, total=100, prop="", dim=36, fixture="test_d36"),
+    "test_c2_16_4_small_d36": dict(layers=2, main=16, sec=4, total=200, prop="", dim=36, fixture="test_d36"),
     "test_c2_8_4_d36": dict(layers=2, main=8, sec=4, total=100000, prop="", dim=36, fixture="test_d36"),
-    "test_c2_8_4_small_d36": dict(layers=2, main=8, sec=4, total=400, prop="", dim=36, fixture="test_d36"),
+    "test_c2_8_4_small_d36": dict(layers=2, main=8, sec=4, total=200, prop="", dim=36, fixture="test_d36"),
 }
 
 PRECISION_DIRS = {32: "ev-table", 16: "ev-table-16", 8: "ev-table-8", 4: "ev-table-4"}
