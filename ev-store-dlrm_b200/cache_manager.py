@@ -245,7 +245,8 @@ class EvStore:
 
     def dump_c3(self):
         st = self.stats()
-        cap = int(st["c3_capacity"]) + 8
+        # the queue may hold several records of one key (aprx_embedding.cpp:322), so size for the ring
+        cap = 8 * int(st["c3_capacity"]) + 16 * self.cfg.max_batch * self.n_tables + 8
         keys = np.empty(cap, dtype=np.int64)
         alt = np.empty(cap, dtype=np.uint32)
         rec = np.empty(cap, dtype=np.uint8)

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "evs_host.h"
+#include "evs_gather.cuh"
 #include "evs_interact.cuh"
 #include "evs_kernels.cuh"
 #include "evs_c3.cuh"
@@ -159,10 +160,12 @@ static int build_tier(evs_handle h, Tier &tr, int prec, long long cap, const voi
     d.cap = static_cast<unsigned>(cap);
     d.row_bytes = static_cast<unsigned>(c.dim * prec / 8);
     d.row_stride = (d.row_bytes + 15u) & ~15u;
-    const float pic = c.perfect_item_cap > 0 ? c.perfect_item_cap : 0.95f;
-    const float fr = c.flush_rate > 0 ? c.flush_rate : 0.3f;
-    d.max_perfect = static_cast<unsigned>(static_cast<int>(static_cast<double>(cap) * static_cast<double>(pic)));
-    d.flush_n = static_cast<unsigned>(static_cast<int>(static_cast<double>(fr) * static_cast<double>(cap))) + 1u;
+    // the defaults are the reference's *double* constants (evlfu_32.hpp:53-54): int(cap * 0.95) with 0.95f
+    // widened to double is one less for cap = 60
+    const double pic = c.perfect_item_cap > 0 ? static_cast<double>(c.perfect_item_cap) : 0.95;
+    const double fr = c.flush_rate > 0 ? static_cast<double>(c.flush_rate) : 0.3;
+    d.max_perfect = static_cast<unsigned>(static_cast<int>(static_cast<double>(cap) * pic));
+    d.flush_n = static_cast<unsigned>(static_cast<int>(fr * static_cast<double>(cap))) + 1u;
     d.n_buckets = c.n_tables_total + 1;
     const unsigned hash_cap = next_pow2(want_slots);
     d.hash_mask = hash_cap - 1;
@@ -173,6 +176,9 @@ static int build_tier(evs_handle h, Tier &tr, int prec, long long cap, const voi
     if ((rc = dev_alloc(tr.allocs, &d.ring, static_cast<size_t>(d.n_buckets) * d.ring_cap, false))) return rc;
     if ((rc = dev_alloc(tr.allocs, &d.ctl, 1, true))) return rc;
     if ((rc = dev_alloc(tr.allocs, &d.evicted, n_max, true))) return rc;
+    // one look-back entry per eviction chunk; the records of all rings bound the number of chunks
+    d.lb_cap = static_cast<unsigned>(static_cast<unsigned long long>(d.n_buckets) * d.ring_cap / kEvictWindow + d.n_buckets + 64);
+    if ((rc = dev_alloc(tr.allocs, &d.lookback, d.lb_cap, true))) return rc;
     d.flushed = nullptr;
     if (c.record_events)
         if ((rc = dev_alloc(tr.allocs, &d.flushed, d.flush_n, true))) return rc;
@@ -330,9 +336,9 @@ static cudaError_t launch_serve(ServeFn fn, int grid, cudaStream_t st, const Par
     return cudaLaunchKernel(reinterpret_cast<const void *>(fn), dim3(grid), dim3(kLookupThreads), args, 0, st);
 }
 
-static cudaError_t launch(KernelFn fn, int grid, int block, size_t smem, cudaStream_t st, const Params &p) {
+static cudaError_t launch(KernelFn fn, dim3 grid, int block, size_t smem, cudaStream_t st, const Params &p) {
     void *args[] = {const_cast<Params *>(&p)};
-    return cudaLaunchKernel(reinterpret_cast<const void *>(fn), dim3(grid), dim3(block), args, smem, st);
+    return cudaLaunchKernel(reinterpret_cast<const void *>(fn), grid, dim3(block), args, smem, st);
 }
 
 static size_t fetch_smem(evs_handle h) {
@@ -361,12 +367,12 @@ static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const Batc
     { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch_serve(ks.serve, n_chunks, st, p, a)); }
     if (p.n_chunks_max > kQuadMaxChunks) {
         LaunchScope ls(pf, K_SCAN, st);
-        EVS_CUDA(launch(k_scan, h->n_tiers * h->tier[0].dev.n_buckets, 256, 0, st, p));
+        EVS_CUDA(launch(k_scan, (h->n_tiers == 1 ? 1 : kSeqGroups) * h->tier[0].dev.n_buckets, 256, 0, st, p));
     }
     { LaunchScope ls(pf, K_UPDATE, st); EVS_CUDA(launch(k_update, n_chunks, kLookupThreads, 0, st, p)); }
     EVS_CUDA(cudaEventRecord(h->ev_updated, st));
     EVS_CUDA(cudaStreamWaitEvent(h->side, h->ev_updated, 0));
-    { LaunchScope ls(pf, K_EVICT, st); EVS_CUDA(launch(k_evict, h->n_tiers, kEvictThreads, 0, st, p)); }
+    { LaunchScope ls(pf, K_EVICT, st); EVS_CUDA(launch(k_evict, dim3(kTierCtas, h->n_tiers), kEvictThreads, 0, st, p)); }
     { LaunchScope ls(pf, K_FETCH, h->side); EVS_CUDA(launch(ks.fetch, side_grid(h, n_chunks), 256, fetch_smem(h), h->side, p)); }
     { LaunchScope ls(pf, K_FILL, h->side); EVS_CUDA(launch(k_fill, side_grid(h, n_chunks), 256, 0, h->side, p)); }
     EVS_CUDA(cudaEventRecord(h->ev_filled, h->side));
@@ -529,6 +535,7 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     if ((rc = dev_alloc(h->dev_allocs, &P.flags, n_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.pos_slot, n_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.hist, static_cast<size_t>(kSeqs) * n_chunks_max))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &P.tot, kSeqs))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.done, 1))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.dbg, 16))) return fail(rc);
 
@@ -935,6 +942,49 @@ int evs_dump_c3(evs_handle h, int64_t *keys, uint32_t *alt, uint8_t *recency, in
 
 int evs_interact(const float *x_dev, const float *ly_dev, float *r_dev, int32_t B, int32_t n_f, int32_t dim, void *stream) {
     return launch_interact(x_dev, ly_dev, r_dev, B, n_f, dim, static_cast<cudaStream_t>(stream));
+}
+
+// ---- sum-pooling gather (nn.EmbeddingBag(mode="sum")) ----------------------------------------
+static unsigned *g_gather_err[64] = {};       // per device: an index was out of range
+
+int evs_embedding_bag(const void *table_dev, int64_t rows, int32_t dim, int32_t precision, const int64_t *idx_dev,
+                      const int64_t *off_dev, int64_t nnz, int32_t B, const float *per_sample_weights, float *out_dev,
+                      int64_t out_stride, void *stream) {
+    int dev = 0;
+    EVS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return EVS_ERR_INVALID;
+    if (g_gather_err[dev] == nullptr) {
+        EVS_CUDA(cudaMalloc(&g_gather_err[dev], sizeof(unsigned)));
+        EVS_CUDA(cudaMemset(g_gather_err[dev], 0, sizeof(unsigned)));
+    }
+    int rc = launch_gather(table_dev, rows, dim, precision, reinterpret_cast<const long long *>(idx_dev),
+                           reinterpret_cast<const long long *>(off_dev), nnz, B, per_sample_weights, out_dev, out_stride,
+                           g_gather_err[dev], static_cast<cudaStream_t>(stream));
+    if (rc == EVS_ERR_INVALID) set_error("evs_embedding_bag: bad table / rows / dim / precision / pointers");
+    return rc;
+}
+
+int evs_embedding_bag_status(void) {
+    int dev = 0;
+    EVS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || g_gather_err[dev] == nullptr) return EVS_OK;
+    EVS_CUDA(cudaDeviceSynchronize());
+    unsigned e = 0;
+    EVS_CUDA(cudaMemcpy(&e, g_gather_err[dev], sizeof(e), cudaMemcpyDeviceToHost));
+    if (e) {
+        EVS_CUDA(cudaMemset(g_gather_err[dev], 0, sizeof(unsigned)));
+        set_error("evs_embedding_bag: an index was outside [0, rows)");
+        return EVS_ERR_INDEX;
+    }
+    return EVS_OK;
+}
+
+int evs_store_ptr(evs_handle h, int tier, int table, const void **dev_ptr, int32_t *precision) {
+    if (h == nullptr || tier < 0 || tier >= h->n_tiers || table < 0 || table >= h->cfg.n_tables || dev_ptr == nullptr)
+        return EVS_ERR_INVALID;
+    *dev_ptr = h->tier[tier].store_dev[table];
+    if (precision) *precision = h->tier[tier].prec;
+    return EVS_OK;
 }
 
 // ---- legacy libcachemanager.so surface ----------------------------------------------------

@@ -429,14 +429,16 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
     }
 
     const unsigned m_f0 = __ballot_sync(kFull, f != 0 && !(f & kFlagTier));
-    const unsigned m_f1 = __ballot_sync(kFull, (f & kFlagTier) != 0);
+    const unsigned m_p1 = __ballot_sync(kFull, (f & kFlagTier) != 0 && !(f & kFlagMiss));
+    const unsigned m_i1 = __ballot_sync(kFull, (f & kFlagTier) != 0 && (f & kFlagMiss) != 0);
     const unsigned m_miss = __ballot_sync(kFull, (f & kFlagMiss) != 0);
     const unsigned m_c2 = __ballot_sync(kFull, hc == kHitC2);
     const unsigned m_ap = __ballot_sync(kFull, hc == kHitApprox);
     if (lane == 0 && wact) {
         a.agg_out[s] = static_cast<uint8_t>(agg);
         if (m_f0) atomicAdd(&s_hist[agg], static_cast<unsigned>(__popc(m_f0)));
-        if (m_f1) atomicAdd(&s_hist[kMaxBuckets + agg], static_cast<unsigned>(__popc(m_f1)));
+        if (m_p1) atomicAdd(&s_hist[kMaxBuckets + agg], static_cast<unsigned>(__popc(m_p1)));
+        if (m_i1) atomicAdd(&s_hist[2 * kMaxBuckets + agg], static_cast<unsigned>(__popc(m_i1)));
         if (m_h0) atomicAdd(&s_stat[0], static_cast<unsigned>(__popc(m_h0)));
         if (m_c2) atomicAdd(&s_stat[1], static_cast<unsigned>(__popc(m_c2)));
         if (m_c3) atomicAdd(&s_stat[2], static_cast<unsigned>(__popc(m_c3)));
@@ -453,8 +455,12 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
     }
 
     __syncthreads();
-    const int n_seq = p.n_tiers * kMaxBuckets;
-    if (threadIdx.x < n_seq) p.hist[static_cast<size_t>(threadIdx.x) * p.n_chunks_max + blockIdx.x] = s_hist[threadIdx.x];
+    const int n_seq = (p.n_tiers == 1) ? kMaxBuckets : kSeqs;
+    if (threadIdx.x < n_seq) {
+        const unsigned v = s_hist[threadIdx.x];
+        p.hist[static_cast<size_t>(threadIdx.x) * p.n_chunks_max + blockIdx.x] = v;
+        if (v) atomicAdd(&p.tot[threadIdx.x], v);
+    }
     if (threadIdx.x == 0) {
         const unsigned long long t_end = gtime();
         (void)t_probe;
@@ -477,17 +483,16 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
 }
 
 // ---- k_scan ------------------------------------------------------------------------------
-// hist[seq][chunk] (append requests of serve-CTA `chunk` for (tier, bucket) = seq) -> offset of
-// that chunk's first record past the old tail; tails advance by the totals.  One CTA per seq.
+// hist[seq][chunk] (append requests of serve-CTA `chunk` for sequence seq) -> offset of that
+// chunk's first record inside the sequence.  One CTA per (group, bucket).
 __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Params p) {
     __shared__ unsigned s_w[8];
     const int B = p.args->B;
     const int n_chunks = (B + kSamplesPerCta - 1) / kSamplesPerCta;
     if (n_chunks <= kQuadMaxChunks) return;          // k_update sums its predecessors directly
     const int nb = p.tier[0].n_buckets;
-    const int tier = blockIdx.x / nb, b = blockIdx.x - tier * nb;
-    unsigned *h = p.hist + static_cast<size_t>(tier * kMaxBuckets + b) * p.n_chunks_max;
-    TierCtl *c = p.tier[tier].ctl;
+    const int grp = blockIdx.x / nb, b = blockIdx.x - grp * nb;
+    unsigned *h = p.hist + static_cast<size_t>(grp * kMaxBuckets + b) * p.n_chunks_max;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned running = 0;
     for (int base = 0; base < n_chunks; base += 256) {
@@ -511,12 +516,6 @@ __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Params p) 
         if (i < n_chunks) h[i] = running + woff + incl - v;
         running += tot;
         __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const unsigned long long tl = c->tail[b];
-        if (tl + running - c->head[b] > p.tier[tier].ring_cap) c->error = 4u;
-        c->tail_prev[b] = tl;
-        c->tail[b] = tl + running;
     }
 }
 
@@ -862,6 +861,7 @@ __global__ void k_init_tier(TierDev tier) {
         tier.slots[j].kw = kEmptyKey;
         tier.slots[j].meta = 0ull;
     }
+    if (i < kMaxBuckets) tier.ctl->kept[i] = ~0ull;
 }
 
 }  // namespace evs

@@ -23,7 +23,13 @@ namespace evs {
 constexpr int kMaxTables = 32;
 constexpr int kMaxBuckets = 32;              // agg_hit 0..n_tables_total (<= 31)
 constexpr int kMaxTiers = 2;
-constexpr int kSeqs = kMaxTiers * kMaxBuckets;   // (tier, bucket) append sequences
+// append sequences: group 0 = C1 (promotions and inserts interleaved in position order, as the
+// reference's C1 loop does, evlfu_8.cpp:629-652), group 1 = C2 promotions, group 2 = C2 inserts
+// (phase_2 updates every hit before it inserts any miss, evlfu_8.cpp:416-442)
+constexpr int kSeqGroups = 3;
+constexpr int kSeqs = kSeqGroups * kMaxBuckets;
+constexpr int kTierCtas = 64;                // CTAs of k_evict per tier
+constexpr int kEvictWindow = 1024;           // ring records per eviction chunk (one per thread)
 constexpr int kSamplesPerCta = 8;            // one warp per sample
 constexpr int kLookupThreads = kSamplesPerCta * 32;
 constexpr int kKeyShift = 40;
@@ -49,8 +55,13 @@ struct __align__(16) Slot {
 struct TierCtl {
     unsigned long long head[kMaxBuckets];
     unsigned long long tail[kMaxBuckets];
-    unsigned long long tail_prev[kMaxBuckets];   // tail before this batch's appends (k_scan)
+    unsigned long long kept[kMaxBuckets];        // k_evict: first live record left in place (~0: none)
+    unsigned long long scan_end[kMaxBuckets];    // k_evict: end of the scanned part of the ring
     unsigned int count[kMaxBuckets];       // live entries per bucket
+    unsigned int ticket;                   // k_evict: next eviction chunk
+    unsigned int done_ctas;                // k_evict: CTAs of this tier that finished
+    unsigned int stop;                     // k_evict: the victims are complete, take no more chunks
+    unsigned int n_taken;                  // k_evict: victims evicted by this batch
     unsigned int n_perfect;                // n_perfect_item_C1 (evlfu_32.hpp:51)
     unsigned int full_at_start;            // size >= cap when the batch began (two-tier routing, evlfu_32.cpp:373)
     // per batch (reset by the evict kernel)
@@ -82,6 +93,8 @@ struct TierDev {
     const unsigned char *const *store;     // [n_tables] device-visible backing rows at this precision
     unsigned long long *evicted;           // [N] keys evicted by the last batch (rank order)
     unsigned long long *flushed;           // [flush_n] keys flushed by the last batch (or null)
+    unsigned long long *lookback;          // [lb_cap] k_evict chunk states: status << 32 | count
+    unsigned int lb_cap;
 };
 
 // C3 (aprx_embedding.cpp): key -> alternative key, FIFO with second-chance eviction.
@@ -146,9 +159,10 @@ struct Params {
     uint8_t *flags;                        // [N]
     unsigned int *pos_slot;                // [N] slot (in the flag's tier) of a promoted / inserted key
     unsigned int *hist;                    // [kSeqs][n_chunks_max]: per-CTA append counts (prefixes after k_scan)
+    unsigned int *tot;                     // [kSeqs] batch totals of the same (k_serve adds, k_evict clears)
     unsigned char *miss_stage;             // [N][stage_stride] raw rows fetched for the missing positions
     unsigned int stage_stride;             // max row_stride of the tiers
-    unsigned int *done;                    // k_evict: tier 1 finished (C3 needs both tiers' victims)
+    unsigned int *done;                    // k_evict: tiers finished (C3 needs both tiers' victims)
     int store_aligned;                     // bit t: every backing row of tier t starts 16-byte aligned
     unsigned long long *dbg;               // [16] %globaltimer stamps of the last batch's phases (ns)
 };

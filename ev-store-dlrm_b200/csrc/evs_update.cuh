@@ -1,16 +1,21 @@
-// k_update: everything of a batch that changes the cache, in one launch.
+// k_update and k_evict: everything of a batch that changes the cache.
 //
-//   all CTAs   same warp <-> sample, lane <-> table mapping as k_serve.  A flagged position
+//   k_update   same warp <-> sample, lane <-> table mapping as k_serve.  A flagged position
 //              (a) claims an index slot if it missed (CAS; same-batch duplicates converge on one slot),
 //              (b) appends a record to the FIFO ring of bucket agg_hit(sample) at the position its
-//                  rank among ALL flagged positions of the batch dictates (sample-major, table-minor:
-//                  the order EvLFU_C1.py processes them), computed from k_serve's per-CTA counts,
+//                  rank among the flagged positions of the batch dictates (sample-major, table-minor:
+//                  the order EvLFU_C1.py processes them; in C2 all promotions come before all
+//                  inserts, as phase_2 does, evlfu_8.cpp:416-442), computed from k_serve's per-CTA counts,
 //              (c) atomicMax on the slot's meta picks the winning occurrence of a key (highest
-//                  (agg_hit, position)), bucket counters follow,
+//                  (agg_hit, position)), bucket counters follow.
+//   k_evict    advances the ring tails, then evicts down to capacity in (bucket, FIFO) order with
+//              kTierCtas CTAs per tier: the candidate records form one virtual sequence that is cut
+//              into chunks of kEvictWindow records, chunks are handed out by ticket, and a chunk
+//              learns how many victims precede it by a decoupled look-back over its predecessors'
+//              counts.  A batch that triggers the flush rule (rare) takes the single-CTA path of
+//              evs_kernels.cuh instead.  The last CTA of the last tier inserts the victims into C3.
 // The rows of the missing keys are fetched meanwhile by k_fetch on a side stream (output + miss
-// staging buffer); k_fill then moves the claimers' rows into their slab rows, next to k_evict.
-// k_evict (one 1024-thread CTA per tier) then advances the ring tails, applies the flush rule,
-// evicts down to capacity and inserts the victims into C3.
+// staging buffer); k_fill then moves the claimers' rows into their slab rows.
 #pragma once
 #include "evs_c3.cuh"
 #include "evs_kernels.cuh"
@@ -18,9 +23,9 @@
 namespace evs {
 
 __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant__ Params p) {
-    __shared__ unsigned s_cnt[kSamplesPerCta][kMaxTiers];
+    __shared__ unsigned s_cnt[kSamplesPerCta][kSeqGroups];
     __shared__ int s_b[kSamplesPerCta];
-    __shared__ int s_delta[kSeqs];
+    __shared__ int s_delta[kMaxTiers * kMaxBuckets];
     __shared__ unsigned s_new[kMaxTiers], s_ins[kMaxTiers];
     __shared__ unsigned long long s_prot[kMaxTiers];
 
@@ -39,7 +44,7 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
         r = __ldg(a.idx + static_cast<size_t>(lane) * B + s);
         if (r < 0 || r >= __ldg(p.rows + lane)) r = 0;
     }
-    if (threadIdx.x < kSeqs) s_delta[threadIdx.x] = 0;
+    if (threadIdx.x < kMaxTiers * kMaxBuckets) s_delta[threadIdx.x] = 0;
     if (threadIdx.x < kMaxTiers) {
         s_new[threadIdx.x] = 0;
         s_ins[threadIdx.x] = 0;
@@ -48,13 +53,17 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
 
     const int tr = (f & kFlagTier) ? 1 : 0;
     const int b = static_cast<int>(f & 0x3Fu) - 1;
-    const unsigned m0 = __ballot_sync(kFull, f != 0u && tr == 0);
-    const unsigned m1 = __ballot_sync(kFull, f != 0u && tr == 1);
-    const unsigned any = m0 | m1;
+    // sequence group of this position: 0 = C1, 1 = C2 promotion, 2 = C2 insert
+    const int grp = (f == 0u) ? -1 : (tr == 0 ? 0 : ((f & kFlagMiss) ? 2 : 1));
+    const unsigned m0 = __ballot_sync(kFull, grp == 0);
+    const unsigned m1 = __ballot_sync(kFull, grp == 1);
+    const unsigned m2 = __ballot_sync(kFull, grp == 2);
+    const unsigned any = m0 | m1 | m2;
     const int wb = __shfl_sync(kFull, b, any ? (__ffs(any) - 1) : 0);    // all flagged lanes share it
     if (lane == 0) {
         s_cnt[warp][0] = __popc(m0);
         s_cnt[warp][1] = __popc(m1);
+        s_cnt[warp][2] = __popc(m2);
         s_b[warp] = any ? wb : -1;
     }
     __syncthreads();
@@ -74,48 +83,52 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
 
         // records of earlier chunks in my bucket's sequences (k_scan already made them prefixes for
         // very large batches), then of earlier samples of this chunk
-        unsigned base0 = 0, base1 = 0;
-        const unsigned *h0 = p.hist + static_cast<size_t>(wb) * p.n_chunks_max;
-        const unsigned *h1 = p.hist + static_cast<size_t>(kMaxBuckets + wb) * p.n_chunks_max;
+        unsigned base[kSeqGroups] = {0, 0, 0};
+        const unsigned msk[kSeqGroups] = {m0, m1, m2};
+        const unsigned *h[kSeqGroups];
+#pragma unroll
+        for (int g = 0; g < kSeqGroups; ++g) h[g] = p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max;
         if (n_chunks > kQuadMaxChunks) {
-            if (m0) base0 = __ldcg(h0 + blockIdx.x);
-            if (m1) base1 = __ldcg(h1 + blockIdx.x);
+#pragma unroll
+            for (int g = 0; g < kSeqGroups; ++g)
+                if (msk[g]) base[g] = __ldcg(h[g] + blockIdx.x);
         } else {
-            unsigned p0 = 0, p1 = 0;
+            unsigned acc[kSeqGroups] = {0, 0, 0};
             const int nc = static_cast<int>(blockIdx.x);
-            for (int c0 = 0; c0 < nc; c0 += 128) {             // 4 independent loads per lane and round
-                unsigned x0[4] = {0, 0, 0, 0}, x1[4] = {0, 0, 0, 0};
+            for (int c0 = 0; c0 < nc; c0 += 128) {             // 4 independent loads per lane, group and round
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int c = c0 + u * 32 + lane;
-                    if (c < nc) {
-                        if (m0) x0[u] = __ldcg(h0 + c);
-                        if (m1) x1[u] = __ldcg(h1 + c);
+                for (int g = 0; g < kSeqGroups; ++g) {
+                    if (!msk[g]) continue;
+                    unsigned x[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = c0 + u * 32 + lane;
+                        if (c < nc) x[u] = __ldcg(h[g] + c);
                     }
+                    acc[g] += x[0] + x[1] + x[2] + x[3];
                 }
-                p0 += x0[0] + x0[1] + x0[2] + x0[3];
-                p1 += x1[0] + x1[1] + x1[2] + x1[3];
             }
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                p0 += __shfl_xor_sync(kFull, p0, d);
-                p1 += __shfl_xor_sync(kFull, p1, d);
+            for (int g = 0; g < kSeqGroups; ++g) {
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) acc[g] += __shfl_xor_sync(kFull, acc[g], d);
+                base[g] = acc[g];
             }
-            base0 = p0;
-            base1 = p1;
         }
         for (int w = 0; w < warp; ++w)
             if (s_b[w] == wb) {
-                base0 += s_cnt[w][0];
-                base1 += s_cnt[w][1];
+#pragma unroll
+                for (int g = 0; g < kSeqGroups; ++g) base[g] += s_cnt[w][g];
             }
+        // C2 inserts start after ALL of the batch's C2 promotions in this bucket
+        if (m2) base[2] += __ldcg(p.tot + kMaxBuckets + wb);
 
         if (f) {
             const TierDev &tier = p.tier[tr];
-            const unsigned rank = __popc((tr ? m1 : m0) & ((1u << lane) - 1u));
+            const unsigned mine_mask = grp == 0 ? m0 : (grp == 1 ? m1 : m2);
+            const unsigned rank = __popc(mine_mask & ((1u << lane) - 1u));
             const volatile TierCtl *c = tier.ctl;
-            const unsigned long long tbase = (n_chunks > kQuadMaxChunks) ? c->tail_prev[b] : c->tail[b];
-            const unsigned long long q = tbase + (tr ? base1 : base0) + rank;
+            const unsigned long long q = c->tail[b] + (grp == 0 ? base[0] : (grp == 1 ? base[1] : base[2])) + rank;
             tier.ring[static_cast<size_t>(b) * tier.ring_cap + (q & (tier.ring_cap - 1))] = slot;
             const unsigned long long mine = pack_meta(b, q);
             const unsigned long long old = atomicMax(&tier.slots[slot].meta, mine);
@@ -132,14 +145,14 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
 
     // ---- publish this CTA's counter deltas ----------------------------------------------------
     __syncthreads();
-    if (threadIdx.x < kSeqs) {
+    if (threadIdx.x < kMaxTiers * kMaxBuckets) {
         const int d = s_delta[threadIdx.x];
         if (d != 0) {
             const int t = threadIdx.x / kMaxBuckets, bb = threadIdx.x - t * kMaxBuckets;
             atomicAdd(&p.tier[t].ctl->count[bb], static_cast<unsigned>(d));
         }
-    } else if (threadIdx.x < kSeqs + kMaxTiers) {
-        const int t = threadIdx.x - kSeqs;
+    } else if (threadIdx.x < kMaxTiers * kMaxBuckets + kMaxTiers) {
+        const int t = threadIdx.x - kMaxTiers * kMaxBuckets;
         if (t < p.n_tiers) {
             if (s_new[t]) atomicAdd(&p.tier[t].ctl->n_new, s_new[t]);
             if (s_ins[t]) atomicAdd(&p.tier[t].ctl->stat_inserts, static_cast<unsigned long long>(s_ins[t]));
@@ -150,53 +163,296 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
 }
 
 // ---- k_evict -------------------------------------------------------------------------------
-// One CTA per tier: advance the ring tails by the batch totals, flush rule, evict down to
-// capacity; the CTA of tier 0 then inserts the victims of both tiers into C3.
+// What every CTA of a tier derives from the tier's counters (identically): the new ring tails,
+// how many victims each bucket gives up, and the virtual record sequence V the chunks index.
+struct EvictPlan {
+    unsigned long long head[kMaxBuckets];
+    unsigned long long tail[kMaxBuckets];      // after this batch's appends
+    unsigned count[kMaxBuckets];
+    unsigned take[kMaxBuckets];                // victims this bucket gives up
+    int seg_b[kMaxBuckets];                    // buckets that give up victims, ascending
+    unsigned long long seg_off[kMaxBuckets + 1];   // their offsets in V
+    int n_seg;
+    unsigned size, need, n_new, n_perfect, any_perfect, flush, prot_slot, appended;
+    int prot_b;
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+// Warp 0 of a chunk: publish this chunk's victim-candidate count, sum the counts of all earlier
+// chunks (decoupled look-back: an entry is  1 << 32 | count  once the chunk knows its own count
+// and  2 << 32 | inclusive prefix  once it knows its predecessors'), publish the inclusive prefix.
+__device__ __forceinline__ unsigned lookback_excl(unsigned long long *lb, unsigned ch, unsigned total, int lane) {
+    if (ch == 0) {
+        if (lane == 0) atomicExch(&lb[0], (2ull << 32) | total);
+        return 0u;
+    }
+    if (lane == 0) atomicExch(&lb[ch], (1ull << 32) | total);
+    unsigned excl = 0;
+    long long j = static_cast<long long>(ch) - 1;
+    while (true) {
+        const long long k = j - lane;
+        unsigned long long e = 2ull << 32;                   // before chunk 0: inclusive prefix 0
+        if (k >= 0) {
+            do {
+                e = ld_volatile_u64(lb + k);
+            } while ((e >> 32) == 0ull);
+        }
+        const unsigned incl = __ballot_sync(kFull, (e >> 32) == 2ull);
+        unsigned v = static_cast<unsigned>(e & 0xFFFFFFFFull);
+        if (incl) {
+            const int first = __ffs(incl) - 1;               // nearest predecessor with a full prefix
+            if (lane > first) v = 0;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+        excl += v;
+        if (incl) break;
+        j -= 32;
+    }
+    if (lane == 0) atomicExch(&lb[ch], (2ull << 32) | (excl + total));
+    return excl;
+}
+
 __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__ Params p) {
-    const int t = blockIdx.x;
+    __shared__ EvictPlan P;
+    __shared__ unsigned s_w[33];
+    __shared__ unsigned s_chunk, s_excl, s_last, s_taken;
+    const int t = blockIdx.y;
+    const TierDev &tier = p.tier[t];
+    TierCtl *ctl = tier.ctl;
+    volatile TierCtl *c = ctl;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int B = p.args->B;
-    const int n_chunks = (B + kSamplesPerCta - 1) / kSamplesPerCta;
-    if (t == 0 && threadIdx.x == 0) {
+    const int top = tier.n_buckets - 1;
+    constexpr unsigned W = kEvictWindow;
+    static_assert(kEvictWindow == kEvictThreads, "one ring record per thread");
+    if (t == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
         p.dbg[4] = gtime();
         if (p.dbg[0] > p.dbg[2]) p.dbg[14] += 1000ull;      // the next batch's k_serve already started (must not happen)
     }
-    if (n_chunks <= kQuadMaxChunks) {
-        for (int bb = warp; bb < p.tier[t].n_buckets; bb += kEvictThreads / 32) {
-            const unsigned *h = p.hist + static_cast<size_t>(t * kMaxBuckets + bb) * p.n_chunks_max;
-            unsigned tot = 0;
-            for (int c = lane; c < n_chunks; c += 32) tot += __ldcg(h + c);
+
+    // ---- plan: lane = bucket --------------------------------------------------------------
+    if (warp == 0) {
+        const int b = lane;
+        const bool in = b < tier.n_buckets;
+        unsigned app = 0;
+        if (in) app = (t == 0) ? __ldcg(p.tot + b) : __ldcg(p.tot + kMaxBuckets + b) + __ldcg(p.tot + 2 * kMaxBuckets + b);
+        const unsigned long long head = in ? c->head[b] : 0ull;
+        const unsigned long long tail = in ? c->tail[b] + app : 0ull;
+        const unsigned cnt = in ? c->count[b] : 0u;
+        const unsigned n_new = c->n_new;
+        const unsigned long long prot = c->prot;
+        unsigned size = cnt, appended = app;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(kFull, tot, d);
-            if (lane == 0 && tot) {
-                atomicAdd(&p_dbg_appends, static_cast<unsigned long long>(tot));
-                volatile TierCtl *c = p.tier[t].ctl;
-                const unsigned long long tl = c->tail[bb] + tot;
-                if (tl - c->head[bb] > p.tier[t].ring_cap) c->error = 4u;
-                c->tail[bb] = tl;
+        for (int d = 16; d > 0; d >>= 1) {
+            size += __shfl_xor_sync(kFull, size, d);
+            appended += __shfl_xor_sync(kFull, appended, d);
+        }
+        const int prot_b = n_new ? static_cast<int>(prot >> 32) - 1 : -1;
+        const unsigned need = size > tier.cap ? size - tier.cap : 0u;
+        const unsigned avail = cnt - ((b == prot_b && cnt > 0) ? 1u : 0u);
+        unsigned incl = avail;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned n = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += n;
+        }
+        const unsigned excl = incl - avail;
+        const unsigned take = need > excl ? min(avail, need - excl) : 0u;
+        const unsigned long long len = take > 0 ? tail - head : 0ull;
+        unsigned long long lincl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long n = __shfl_up_sync(kFull, lincl, d);
+            if (lane >= d) lincl += n;
+        }
+        const unsigned has = __ballot_sync(kFull, take > 0);
+        const int si = __popc(has & ((1u << lane) - 1u));
+        P.head[b] = head;
+        P.tail[b] = tail;
+        P.count[b] = cnt;
+        P.take[b] = take;
+        if (take > 0) {
+            P.seg_b[si] = b;
+            P.seg_off[si] = lincl - len;
+        }
+        const unsigned long long total_v = __shfl_sync(kFull, lincl, 31);
+        if (lane == 0) {
+            const int n = __popc(has);
+            P.n_seg = n;
+            P.seg_off[n] = total_v;
+            P.size = size;
+            P.need = need;
+            if (total_v > static_cast<unsigned long long>(tier.lb_cap) * W) {     // cannot happen unless a ring overflowed
+                c->error = 5u;
+                P.need = 0;
             }
+            P.n_new = n_new;
+            P.n_perfect = c->n_perfect;
+            P.any_perfect = c->any_perfect;
+            P.flush = (n_new > 0 && c->n_perfect >= tier.max_perfect) ? 1u : 0u;
+            P.prot_b = prot_b;
+            P.prot_slot = n_new ? (__ldcg(p.pos_slot + static_cast<unsigned>(prot & 0xFFFFFFFFull)) & ~kClaimedBit) : kNoSlot;
+            P.appended = appended;
+            s_taken = 0;
         }
     }
     __syncthreads();
-    evict_tier(p.tier[t], p);
-    if (t == 0 && threadIdx.x == 0) p.dbg[5] = gtime();
-    if (p.c3.active) {
-        // C3 needs the victims of both tiers: the tier-1 CTA publishes completion, tier 0 waits for it
-        if (t == 1) {
-            __threadfence();
+
+    if (P.flush) {
+        // flush rule (EvLFU_C1.py:36-44): rare; CTA 0 does flush + eviction alone
+        if (blockIdx.x == 0) {
+            // the tier's counters may change only after every other CTA has derived its plan from them
+            // (they do nothing else in this case and are not waiting for anything)
+            if (threadIdx.x == 0)
+                while (c->done_ctas < gridDim.x - 1) {}
             __syncthreads();
-            if (threadIdx.x == 0) atomicExch(p.done, 1u);
-            return;
+            if (threadIdx.x < tier.n_buckets) c->tail[threadIdx.x] = P.tail[threadIdx.x];
+            __syncthreads();
+            evict_tier(tier, p);
+        }
+    } else if (P.need > 0) {
+        const unsigned need = P.need;
+        const int n_seg = P.n_seg;
+        const unsigned long long total_v = P.seg_off[n_seg];
+        while (true) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_chunk = c->stop ? kNoSlot : atomicAdd(&ctl->ticket, 1u);
+            __syncthreads();
+            const unsigned ch = s_chunk;
+            if (ch == kNoSlot || static_cast<unsigned long long>(ch) * W >= total_v) break;
+            if (ch >= tier.lb_cap) {
+                if (threadIdx.x == 0) c->error = 5u;
+                break;
+            }
+            // my record of the chunk
+            const unsigned long long v = static_cast<unsigned long long>(ch) * W + threadIdx.x;
+            const bool inr = v < total_v;
+            int sg = 0, b = 0;
+            unsigned long long q = 0;
+            unsigned slot = kNoSlot;
+            if (inr) {
+                while (sg + 1 < n_seg && P.seg_off[sg + 1] <= v) ++sg;
+                b = P.seg_b[sg];
+                q = P.head[b] + (v - P.seg_off[sg]);
+                slot = __ldcg(tier.ring + static_cast<size_t>(b) * tier.ring_cap + (q & (tier.ring_cap - 1)));
+            }
+            uint4 sv = make_uint4(0, 0, 0, 0);
+            const bool okslot = inr && slot <= tier.hash_mask;
+            if (okslot) sv = __ldcg(reinterpret_cast<const uint4 *>(tier.slots + slot));
+            const bool live = okslot && (u64_of(sv.z, sv.w) == pack_meta(b, q));
+            const bool cand = live && slot != P.prot_slot;
+            unsigned total;
+            const unsigned idx = block_excl_scan(cand ? 1u : 0u, s_w, &total);
+            if (warp == 0) {
+                const unsigned e = lookback_excl(tier.lookback, ch, total, lane);
+                if (lane == 0) s_excl = e;
+            }
+            __syncthreads();
+            const unsigned before = s_excl;
+            const bool takeit = cand && (before + idx < need);
+            if (takeit) {
+                const unsigned long long key = u64_of(sv.x, sv.y) & kKeyMask;
+                evict_slot(tier, slot, key);
+                tier.evicted[before + idx] = key;
+            }
+            // first live record left in place, per bucket: within a warp q grows with the lane
+            const bool stays = live && !takeit;
+            unsigned pending = __ballot_sync(kFull, stays);
+            while (pending) {
+                const int leader = __ffs(pending) - 1;
+                const int lb_ = __shfl_sync(kFull, b, leader);
+                const unsigned same = __ballot_sync(kFull, stays && b == lb_);
+                if (lane == leader && q < ld_volatile_u64(&ctl->kept[b])) atomicMin(&ctl->kept[b], q);
+                pending &= ~same;
+            }
+            if (before < need) {
+                // everything of these buckets up to here has been examined
+                const bool seg_end = inr && (threadIdx.x == W - 1 || v + 1 == total_v || v + 1 == P.seg_off[sg + 1]);
+                if (seg_end) atomicMax(&ctl->scan_end[b], q + 1);
+                const unsigned nt = __popc(__ballot_sync(kFull, takeit));
+                if (lane == 0 && nt) atomicAdd(&s_taken, nt);
+                if (threadIdx.x == 0 && before + total >= need) c->stop = 1u;
+            }
+        }
+    }
+
+    // ---- the last CTA of the tier writes the tier's counters back ---------------------------
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_taken) atomicAdd(&ctl->n_taken, s_taken);
+        __threadfence();
+        s_last = (atomicAdd(&ctl->done_ctas, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (!P.flush) {
+        const unsigned taken = c->n_taken;
+        if (threadIdx.x < tier.n_buckets) {
+            const int b = threadIdx.x;
+            const unsigned cnt = P.count[b] - P.take[b];
+            unsigned long long head = P.head[b];
+            if (P.take[b] > 0) {
+                const unsigned long long kept = c->kept[b], se = c->scan_end[b];
+                head = (kept != ~0ull) ? kept : (se > head ? se : head);
+            }
+            if (cnt == 0) head = P.tail[b];
+            if (P.tail[b] - head > tier.ring_cap) c->error = 4u;
+            c->head[b] = head;
+            c->tail[b] = P.tail[b];
+            c->count[b] = cnt;
         }
         if (threadIdx.x == 0) {
-            while (atomicAdd(p.done, 0u) == 0u) {}
-            *p.done = 0u;
-            __threadfence();
+            const unsigned size = P.size - taken;
+            if (P.any_perfect) c->n_perfect = P.count[top] - P.take[top];       // EvLFU_C1.py:163-165
+            c->stat_evictions += taken;
+            c->n_evicted_last = taken;
+            c->n_flushed_last = 0;
+            c->full_at_start = (size >= tier.cap) ? 1u : 0u;
+            c->n_new = 0;
+            c->prot = 0ull;
+            c->any_perfect = 0;
+            if (taken != P.need) c->error = 4u;
+            atomicAdd(&p_dbg_appends, static_cast<unsigned long long>(P.appended));
         }
-        __syncthreads();
-        c3_update(p);
     }
-    if (t == 0 && threadIdx.x == 0) {
+    // per-batch scratch of the tier
+    const unsigned n_tk = min(c->ticket, tier.lb_cap);
+    for (unsigned i = threadIdx.x; i < n_tk; i += blockDim.x) tier.lookback[i] = 0ull;
+    if (threadIdx.x < kMaxBuckets) {
+        c->kept[threadIdx.x] = ~0ull;
+        c->scan_end[threadIdx.x] = 0ull;
+        if (t == 0) {
+            p.tot[threadIdx.x] = 0u;
+        } else {
+            p.tot[kMaxBuckets + threadIdx.x] = 0u;
+            p.tot[2 * kMaxBuckets + threadIdx.x] = 0u;
+        }
+    }
+    if (threadIdx.x == 0) {
+        c->ticket = 0;
+        c->done_ctas = 0;
+        c->stop = 0;
+        c->n_taken = 0;
+    }
+
+    // ---- the last tier to finish feeds C3 and closes the batch ---------------------------------
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned prev = atomicAdd(p.done, 1u);
+        s_last = (prev == static_cast<unsigned>(p.n_tiers) - 1u) ? 1u : 0u;
+        if (s_last) *p.done = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) p.dbg[5] = gtime();
+    if (p.c3.active) c3_update(p);
+    if (threadIdx.x == 0) {
         p.dbg[6] = gtime();
         p.dbg[7] = p.dbg[1];
         p.dbg[1] = 0ull;

@@ -171,6 +171,21 @@ int evs_dump_c3(evs_handle h, int64_t *keys, uint32_t *alt, uint8_t *recency, in
 int evs_interact(const float *x_dev, const float *ly_dev, float *r_dev, int32_t B, int32_t n_f, int32_t dim,
                  void *stream);
 
+/* ---- sum pooling: nn.EmbeddingBag(mode="sum") of apply_emb_ori_dlrm ------------------- *
+ * (dlrm_s_pytorch_C1_C2_C3.py:191-223)   out[b] = sum_{j = off[b] .. off[b+1]-1} w[j] * W[idx[j]], j ascending.
+ *   table_dev  device-visible rows of ONE table, rows*dim*precision/8 bytes, the binary/ev-table-N.bin
+ *              layout at 32 / 16 / 8 / 4 bits (HBM, or mapped pinned host memory: evs_store_ptr)
+ *   idx_dev    int64 [nnz], off_dev int64 [B] (bag b ends where bag b+1 starts, the last at nnz)
+ *   per_sample_weights fp32 [nnz] or NULL; out_dev fp32 [B] rows of dim, out_stride floats apart (0 = dim)
+ * Out-of-range indices read row 0 and make evs_embedding_bag_status() (synchronising) return EVS_ERR_INDEX. */
+int evs_embedding_bag(const void *table_dev, int64_t rows, int32_t dim, int32_t precision, const int64_t *idx_dev,
+                      const int64_t *off_dev, int64_t nnz, int32_t B, const float *per_sample_weights, float *out_dev,
+                      int64_t out_stride, void *stream);
+int evs_embedding_bag_status(void);
+/* Device-visible alias of the handle's backing rows of (tier, table): the storage_manager no-cache
+ * path (request_to_emb_storage, emb_storage/storage_manager.py:125) reads it with evs_embedding_bag. */
+int evs_store_ptr(evs_handle h, int tier, int table, const void **dev_ptr, int32_t *precision);
+
 /* ---- legacy libcachemanager.so surface (cache_manager.cpp) ------------------------ *
  * A process-global cache answers one sample per call.  Where the reference fixes its
  * configuration at compile time, call evs_legacy_configure once first (or set

@@ -71,3 +71,65 @@ def run_single_tier_parity(rows, dim, prec, total_size, B_list, n_batches, seed=
     finally:
         store.close()
     return totals
+
+
+def run_tier_parity(rows, dim, layers, main, sec, total, B_list, n_batches, prop="", seed=42, check_state_every=1,
+                    alpha=1.05, store_in_hbm=False, high_thres=0):
+    """Two / three layer CUDA path vs oracle.tiers.BatchTiers: hit codes, fp32 rows (dequantised at the
+    answering tier's precision), eviction / flush streams and FIFO state of both tiers, C3 contents."""
+    import torch
+    from oracle import tiers as otiers
+    p = pkg()
+    tables = p.workload.make_tables(rows, dim)
+    dec = [decoded_tables(tables, main), decoded_tables(tables, sec)]
+    alt = p.workload.make_alt_keys(rows) if layers == 3 else None
+    trace = p.workload.ZipfTrace(rows, alpha=alpha, seed=seed)
+    caps = otiers.capacities(layers, main, sec, total, prop, dim)
+    cfg = p.CacheConfig(n_layers=layers, main_precision=main, secondary_precision=sec, total_size=total,
+                        size_proportion=prop, max_batch=max(B_list), record_events=True, store_in_hbm=store_in_hbm,
+                        high_agghit_threshold=high_thres)
+    store = p.EvStore(tables, cfg, alt_keys=alt)
+    oracle = otiers.BatchTiers(caps, n_layers=layers, T=len(rows), alt_keys=alt, high_thres=high_thres or 23)
+    tot = dict(c1=0, c2=0, c3=0, miss=0, ev1=0, ev2=0, fl1=0, fl2=0)
+    try:
+        st0 = store.stats()
+        assert tuple(st0["capacity"]) == caps[:2] and st0["c3_capacity"] == (caps[2] if layers == 3 else 0), (st0, caps)
+        for it in range(n_batches):
+            B = B_list[it % len(B_list)]
+            idx = trace.batch(B)
+            o, h = store.lookup(torch.from_numpy(idx).cuda())
+            torch.cuda.synchronize()
+            out, hit = o.cpu().numpy(), h.cpu().numpy()
+            code, val_tier, st, sr, agg = oracle.lookup_batch(idx)
+            assert (hit == code).all(), f"hit codes, batch {it} (B={B}): {np.argwhere(hit != code)[:4].tolist()}"
+            want = otiers.gather_tier_rows(dec, val_tier, st, sr)
+            assert (out == want).all(), f"rows, batch {it} (B={B})"
+            for ti, ot in ((0, oracle.c1), (1, oracle.c2)):
+                ev, fl = store.last_events(ti)
+                assert ev.tolist() == ot.evicted, f"eviction stream of C{ti + 1}, batch {it}: {ev.tolist()[:6]} vs {ot.evicted[:6]}"
+                assert fl.tolist() == ot.flushed, f"flush stream of C{ti + 1}, batch {it}"
+            if it % check_state_every == 0 or it == n_batches - 1:
+                for ti, ot in ((0, oracle.c1), (1, oracle.c2)):
+                    state, n_perfect = store.dump_state(ti)
+                    assert state == ot.state(), f"FIFO state of C{ti + 1}, batch {it}"
+                    assert n_perfect == ot.n_perfect, f"n_perfect of C{ti + 1}, batch {it}"
+                if layers == 3:
+                    k, a, r = store.dump_c3()
+                    ok, oa, orr = oracle.c3.dump()
+                    assert k.tolist() == ok and a.tolist() == oa and r.tolist() == orr, f"C3 contents, batch {it}"
+            tot["c1"] += int((code == 1).sum())
+            tot["c2"] += int((code == 2).sum())
+            tot["c3"] += int((code == 3).sum())
+            tot["miss"] += int((code == 0).sum())
+            tot["ev1"] += len(oracle.c1.evicted)
+            tot["ev2"] += len(oracle.c2.evicted)
+            tot["fl1"] += len(oracle.c1.flushed)
+            tot["fl2"] += len(oracle.c2.flushed)
+        store.sync()
+        s = store.stats()
+        assert s["hits"] == [tot["c1"], tot["c2"]] and s["c3_hits"] == tot["c3"] and s["misses"] == tot["miss"], (s, tot)
+        assert s["evictions"] == [tot["ev1"], tot["ev2"]]
+        assert s["size"] == [len(oracle.c1.entries), len(oracle.c2.entries)]
+    finally:
+        store.close()
+    return tot

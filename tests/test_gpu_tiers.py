@@ -1,0 +1,52 @@
+"""C1+C2 mixed-precision tiers and C3 approximate embeddings: CUDA path vs the batch-granular
+oracle (oracle/tiers.py, whose sequential form is pinned to the compiled reference by
+tests/test_oracle_tiers.py).  Integer streams are bit-exact; the fp32 rows are bit-exact with the
+reference's own dequantisers (evlfu_16.cpp:332, evlfu_8.cpp:370, evlfu_4.cpp:319)."""
+import pytest
+
+from helpers import SKEW_ROWS, SMALL_ROWS, TINY_ROWS, run_tier_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_tier_8_4_reference_dimension():
+    t = run_tier_parity(SMALL_ROWS, 36, 2, 8, 4, 200, [64, 17], 40)
+    assert t["c2"] > 0 and t["ev1"] > 0 and t["ev2"] > 0, t
+
+
+@pytest.mark.parametrize("main,sec,total", [(32, 16, 300), (32, 8, 100), (32, 4, 200), (16, 8, 100), (16, 4, 200)])
+def test_two_tier_precision_pairs(main, sec, total):
+    t = run_tier_parity(SMALL_ROWS, 16, 2, main, sec, total, [48, 5, 64], 36, check_state_every=3)
+    assert t["c2"] > 0 and t["ev1"] > 0, t
+
+
+def test_two_tier_batch_of_one_and_ragged():
+    run_tier_parity(SMALL_ROWS, 16, 2, 8, 4, 160, [1, 2, 31, 64, 7, 100], 90, check_state_every=5)
+
+
+def test_two_tier_larger_batches_skewed_tables():
+    t = run_tier_parity(SKEW_ROWS, 64, 2, 32, 8, 3000, [512], 20, check_state_every=4)
+    assert t["ev1"] > 0, t
+
+
+def test_two_tier_flush_rule():
+    """A hot trace fills bucket 26 of C1 to 95 % of its capacity; with high_agghit_threshold above 26
+    odd tables keep inserting into C1, so the flush rule fires there.  C1 then falls below capacity
+    and the not-full routing (everything to C1, C2 untouched) resumes until it is full again."""
+    t = run_tier_parity(SMALL_ROWS, 16, 2, 8, 4, 30, [4, 16], 260, check_state_every=5, alpha=2.5, high_thres=27)
+    assert t["fl1"] > 0 and t["ev1"] > 0 and t["ev2"] > 0, t
+
+
+def test_three_tier_c3_substitution():
+    t = run_tier_parity(SMALL_ROWS, 16, 3, 8, 4, 200, [64, 9], 60, prop="45-45-10", check_state_every=2)
+    assert t["c3"] > 0 and t["ev1"] > 0 and t["ev2"] > 0, t
+
+
+def test_three_tier_even_split_dim36():
+    t = run_tier_parity(SMALL_ROWS, 36, 3, 8, 4, 150, [32], 50, check_state_every=5)
+    assert t["c3"] > 0, t
+
+
+def test_three_tier_zero_c3_share_is_two_tier():
+    """SIZE_PROPORTION with 0 % for C3 disables the third layer (evlfu_8.cpp:81-84)."""
+    run_tier_parity(SMALL_ROWS, 16, 3, 8, 4, 200, [64], 20, prop="50-50-0", check_state_every=4)
