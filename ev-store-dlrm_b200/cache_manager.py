@@ -66,6 +66,13 @@ class EvStore:
         """tables_fp32: list of [rows, dim] float32 arrays (the trained embedding tables).
         stores: optional {precision: [raw rows per table]} if the quantised files already exist;
         otherwise they are derived from the fp32 tables with the reference's quantisers."""
+        self._init_config(tables_fp32, cfg, stores, alt_keys)
+        self.handle = C.c_void_p()
+        self._owns_handle = True
+        _native.check(self.lib.evs_create(C.byref(self._c), C.byref(self.handle)), "evs_create")
+
+    def _init_config(self, tables_fp32, cfg: CacheConfig, stores=None, alt_keys=None):
+        """Marshal the tables and the configuration into an evs_config (kept alive in self._c)."""
         self.lib = _native.load_library()
         self.cfg = cfg
         self.n_tables = len(tables_fp32)
@@ -113,8 +120,6 @@ class EvStore:
         c.store_in_hbm = int(cfg.store_in_hbm)
         c.record_events = int(cfg.record_events)
         self._c = c
-        self.handle = C.c_void_p()
-        _native.check(self.lib.evs_create(C.byref(c), C.byref(self.handle)), "evs_create")
 
     # ---- hot path ------------------------------------------------------------------------
     def lookup(self, lS_i, out=None, hit=None, agg_in=None, stream=None):
@@ -178,6 +183,30 @@ class EvStore:
             out = torch.empty((B, d + (n_f + 1) * n_f // 2), dtype=torch.float32, device=x.device)
         st = _stream_handle(stream, x.device)
         _native.check(self.lib.evs_interact(x.data_ptr(), ly.data_ptr(), out.data_ptr(), B, n_f, d, st), "evs_interact")
+        return out
+
+    def store_ptr(self, table: int, tier: int = 0):
+        """(device-visible pointer, precision) of the backing rows of a table (evs_store_ptr)."""
+        p = C.c_void_p()
+        prec = C.c_int32(0)
+        _native.check(self.lib.evs_store_ptr(self.handle, tier, table, C.byref(p), C.byref(prec)), "evs_store_ptr")
+        return p.value, prec.value
+
+    def storage_lookup(self, lS_i, out=None, stream=None):
+        """The no-cache path (apply_emb_evstore with use_emb_cache=False -> request_to_emb_storage,
+        emb_storage/storage_manager.py:125): every row straight from the pinned backing store,
+        pooling factor 1.  lS_i int64 CUDA [n_tables, B] -> fp32 [B, n_tables, dim]."""
+        import torch
+        T, B = lS_i.shape
+        if out is None:
+            out = torch.empty((B, T, self.dim), dtype=torch.float32, device=lS_i.device)
+        off = torch.arange(B, dtype=torch.int64, device=lS_i.device)
+        st = _stream_handle(stream, lS_i.device)
+        for t in range(T):
+            ptr, prec = self.store_ptr(t)
+            rc = self.lib.evs_embedding_bag(ptr, int(self.rows[t]), self.dim, prec, lS_i[t].data_ptr(), off.data_ptr(), B, B,
+                                            None, out[:, t, :].data_ptr(), out.stride(0), st)
+            _native.check(rc, "evs_embedding_bag")
         return out
 
     # ---- bookkeeping ---------------------------------------------------------------------
@@ -257,7 +286,8 @@ class EvStore:
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle:
-            self.lib.evs_destroy(self.handle)
+            if getattr(self, "_owns_handle", True):
+                self.lib.evs_destroy(self.handle)
             self.handle = C.c_void_p()
 
     def __del__(self):

@@ -1,0 +1,105 @@
+"""The DLRM operators either side of the cache, behind the reference's own names
+(dlrm_s_pytorch_C1_C2_C3.py): ``apply_emb_evstore`` (:226-267), ``apply_emb_ori_dlrm`` (:191-223),
+``interact_features`` (:625-658, op "dot").  All of them run hand-written CUDA kernels through the
+C-ABI; inputs and outputs are CUDA tensors.
+
+Differences from the reference, on purpose:
+* the reference's apply_emb_evstore serves batch element 0 only (``sparse_index[0]``, :236-239;
+  its drivers force --test-mini-batch-size=1); here the whole ``lS_i [n_tables, B]`` batch is
+  served in one call and every returned tensor is ``[B, dim]`` (a view of one ``[B, n_tables, dim]``
+  buffer) instead of ``[1, dim]``;
+* ``cache_algo`` selects between the GPU cache ("cpp_algo", "evlfu", "lfu" -- the reference's
+  EvLFU branch is keyed "lfu", :249) and nothing else; LRU / LFU are out of scope.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _native
+from .cache_manager import EvStore, _stream_handle
+
+cache_algo = "cpp_algo"        # --cache-algo (dlrm_s_pytorch_C1_C2_C3.py:1229)
+evstore_gpu_id = 0             # --evstore-gpu-id
+_store: EvStore | None = None  # the cache the module-level operator uses (set_store)
+last_hit = None                # aggHitMissRecord of the last call: uint8 [B, n_tables]
+
+
+def set_store(store: EvStore):
+    global _store
+    _store = store
+
+
+def apply_emb_evstore(lS_o, lS_i, emb_l=None, v_W_l=None, use_gpu=True, use_emb_cache=True, approx_emb_threshold=-1,
+                      store: EvStore | None = None, out=None):
+    """lS_i: int64 CUDA tensor [n_tables, B] (or a list of n_tables [B] tensors); lS_o is ignored, as
+    in the reference (pooling factor 1).  Returns ly: list of n_tables tensors [B, dim]."""
+    global last_hit
+    import torch
+    st = store or _store
+    if st is None:
+        raise RuntimeError("apply_emb_evstore: no EvStore (call dlrm_ops.set_store)")
+    if isinstance(lS_i, (list, tuple)):
+        lS_i = torch.stack(list(lS_i))
+    if not lS_i.is_cuda:
+        raise RuntimeError("apply_emb_evstore runs on the GPU cache: pass CUDA indices (there is no CPU fallback)")
+    lS_i = lS_i.contiguous()
+    if use_emb_cache:
+        if cache_algo not in ("cpp_algo", "evlfu", "lfu"):
+            raise ValueError("ERROR: This algorithm is not yet supported! " + str(cache_algo))
+        if approx_emb_threshold > 0 and st.cfg.approx_emb_thres != approx_emb_threshold:
+            raise ValueError("approx_emb_threshold is a property of the cache: set CacheConfig.approx_emb_thres")
+        buf, last_hit = st.lookup(lS_i, out=out)
+    else:
+        buf = st.storage_lookup(lS_i, out=out)          # storage_manager.request_to_emb_storage (:264)
+    return [buf[:, k, :] for k in range(buf.shape[1])]
+
+
+def embedding_bag(table, indices, offsets, per_sample_weights=None, precision=32, dim=None, out=None, stream=None):
+    """nn.EmbeddingBag(mode="sum") on one table.  table: CUDA tensor [rows, dim] fp32, or raw rows
+    (uint16 / uint8) at `precision` bits with `dim` given."""
+    import torch
+    lib = _native.load_library()
+    rows = table.shape[0]
+    d = dim or table.shape[1]
+    B = offsets.numel()
+    if out is None:
+        out = torch.empty((B, d), dtype=torch.float32, device=indices.device)
+    st = _stream_handle(stream, indices.device)
+    rc = lib.evs_embedding_bag(table.data_ptr(), rows, d, precision, indices.data_ptr(), offsets.data_ptr(),
+                               indices.numel(), B, per_sample_weights.data_ptr() if per_sample_weights is not None else None,
+                               out.data_ptr(), out.stride(0), st)
+    _native.check(rc, "evs_embedding_bag")
+    return out
+
+
+def apply_emb_ori_dlrm(lS_o, lS_i, emb_l, v_W_l=None):
+    """emb_l: list of fp32 CUDA weight tensors [rows_k, dim] (nn.EmbeddingBag.weight).  Returns ly."""
+    ly = []
+    for k, idx in enumerate(lS_i):
+        w = None
+        if v_W_l is not None and v_W_l[k] is not None:
+            w = v_W_l[k].gather(0, idx)                 # dlrm_s_pytorch_C1_C2_C3.py:208
+        E = emb_l[k].weight if hasattr(emb_l[k], "weight") else emb_l[k]
+        ly.append(embedding_bag(E, idx, lS_o[k], w))
+    return ly
+
+
+def interact_features(x, ly, out=None, stream=None):
+    """x [B, d], ly: list of n_f tensors [B, d] (or one [B, n_f, d] tensor) -> [B, d + (n_f+1) n_f / 2]."""
+    import torch
+    lib = _native.load_library()
+    if isinstance(ly, (list, tuple)):
+        base = ly[0]._base if ly[0]._base is not None else None
+        n_f = len(ly)
+        same = base is not None and base.dim() == 3 and base.shape[1] == n_f and base.is_contiguous() and all(
+            t._base is base and t.data_ptr() == base.data_ptr() + k * base.shape[2] * 4 for k, t in enumerate(ly))
+        lyt = base if same else torch.stack(list(ly), dim=1).contiguous()
+    else:
+        lyt = ly.contiguous()
+    B, d = x.shape
+    n_f = lyt.shape[1]
+    if out is None:
+        out = torch.empty((B, d + (n_f + 1) * n_f // 2), dtype=torch.float32, device=x.device)
+    st = _stream_handle(stream, x.device)
+    _native.check(lib.evs_interact(x.contiguous().data_ptr(), lyt.data_ptr(), out.data_ptr(), B, n_f, d, st), "evs_interact")
+    return out

@@ -115,7 +115,7 @@ def run_tier_parity(rows, dim, layers, main, sec, total, B_list, n_batches, prop
                     assert n_perfect == ot.n_perfect, f"n_perfect of C{ti + 1}, batch {it}"
                 if layers == 3:
                     k, a, r = store.dump_c3()
-                    ok, oa, orr = oracle.c3.dump()
+                    ok, oa, orr = oracle.c3.dump() if oracle.c3 is not None else ([], [], [])
                     assert k.tolist() == ok and a.tolist() == oa and r.tolist() == orr, f"C3 contents, batch {it}"
             tot["c1"] += int((code == 1).sum())
             tot["c2"] += int((code == 2).sum())

@@ -1,0 +1,81 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares (no compute
+calls without a GPU), storage_manager keeps the reference's API and file layout, table split."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import SMALL_ROWS, pkg
+from oracle import codecs as ocodecs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    p = pkg()
+    lib = p.load_library()
+    text = open(os.path.join(ROOT, "include", "evstore_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b([a-z_][a-z0-9_]*)\s*\([^;{]*\)\s*;", text)
+    names = [n for n in names if n not in ("defined",)]
+    assert len(names) >= 25, names
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/evstore_b200.h but not exported"
+    assert sorted(set(names)) == sorted(set(p.SYMBOLS)), set(names) ^ set(p.SYMBOLS)
+    assert lib.evs_version() >= 100
+
+
+def test_product_path_refuses_to_run_without_its_library(tmp_path):
+    p = pkg()
+    with pytest.raises(RuntimeError):
+        p.load_library(str(tmp_path / "missing.so"))
+
+
+def test_no_product_module_imports_the_oracle():
+    pk = os.path.join(ROOT, "ev-store-dlrm_b200")
+    for dirpath, _d, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+@pytest.mark.parametrize("prec", [32, 16, 8, 4])
+def test_storage_manager_api_and_file_layout(tmp_path, prec):
+    p = pkg()
+    sm = p.storage_manager
+    tables = p.workload.make_tables(SMALL_ROWS, 36)
+    sm.ev_precs, sm.ev_dimension, sm.n_tables = prec, 36, 26
+    sm.storage_type = sm.EmbStorage.FILEPY
+    sm.load_tables(tables, precisions=(prec,))
+    sm.save_ev_tables(str(tmp_path), prec)
+    # the file is the reference's binary/ev-table-N.bin: row-major, dim*bits/8 bytes per row
+    raw = ocodecs.quantize_table(tables[2], prec)
+    assert open(tmp_path / "binary" / "ev-table-3.bin", "rb").read() == np.ascontiguousarray(raw).tobytes()
+    sm.close_any_db_conn()
+    sm.load_ev_table_into_emb_stor(str(tmp_path), rows=SMALL_ROWS)
+    want = ocodecs.dequantize_rows(raw, prec)
+    v = sm.get_val_from_storage(3, 17)                   # tableId is 1-based
+    assert len(v) == 36 and np.array_equal(np.float32(v), want[17])
+    vals = sm.get_arr_val_from_storage([(3, 0), (1, 5)])
+    assert np.array_equal(np.float32(vals[0]), want[0])
+    _, ly = sm.request_to_emb_storage([0] * 26)
+    assert len(ly) == 26 and tuple(ly[0].shape) == (1, 36)
+    with pytest.raises(sm.StorageError):
+        sm.get_val_from_storage(27, 0)
+    sm.close_any_db_conn()
+
+
+def test_table_split_matches_extend_distributed():
+    s = pkg().sharded
+    assert s.get_split_lengths(26, 2) == [13, 13]
+    assert s.get_split_lengths(26, 4) == [7, 7, 6, 6]
+    assert s.get_split_lengths(26, 8) == [4, 4, 3, 3, 3, 3, 3, 3]
+    for size in (1, 2, 4, 8):
+        got = []
+        for r in range(size):
+            sl = s.get_my_slice(26, r, size)
+            got += list(range(26))[sl]
+            assert sl.stop - sl.start == s.get_split_lengths(26, size)[r]
+        assert got == list(range(26))
