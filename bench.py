@@ -9,8 +9,9 @@ A *step* is one pass of the hot path over one batch of synthetic Zipf(1.05) indi
 store -> insert/evict -> dequantise -> fp32 rows [B, 26, dim].
 
 N = 1  : BASELINE configs[1] -- C1 EvLFU cache in HBM, Kaggle-shape tables, batch 2048, fp32 tier.
-N > 1  : BASELINE configs[4] -- Terabyte-shape tables, table-wise sharded, exact groupability
-         (all-reduce of per-sample hit counts) and an NCCL all-to-all of the pooled rows.
+N > 1  : the same tables table-wise sharded over N GPUs (bench_sharded.py), global batch 2048*N (weak
+         scaling), exact groupability (all-reduce of per-sample hit counts) and an NCCL all-to-all of
+         the pooled rows; --shape terabyte selects BASELINE configs[4] (dim 64, 40 M-row tables).
 
 One JSON line on stdout (rank 0); everything else goes to stderr.
   value     lookups/s with the index batches already resident in HBM (CUDA events, max over ranks)
@@ -55,6 +56,7 @@ def parse_args():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--store-in-hbm", action="store_true", help="debug: backing store copied into HBM (not the BASELINE config)")
+    ap.add_argument("--shape", default="kaggle", choices=["kaggle", "terabyte"], help="N > 1 only: table shape of the sharded run")
     return ap.parse_args()
 
 
@@ -185,7 +187,7 @@ def main_reference(args):
     from oracle import ref_driver
     from oracle.ref_variants import KAGGLE_CACHE_13PCT
     pkg = importlib.import_module("ev-store-dlrm_b200")
-    B = args.batch or 2048
+    B = (args.batch or 2048) * max(1, args.gpus)          # the N-GPU arm's global batch (weak scaling)
     dim = args.dim or 16
     variant = "bench_c1_fp32_d16"
     if not ref_driver.available(variant) or dim != 16 or args.scale != 1.0:

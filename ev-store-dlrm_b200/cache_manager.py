@@ -235,14 +235,16 @@ class EvStore:
 
     def phase_times(self) -> dict:
         """Device-side phase durations (us) of the last batch, from %globaltimer stamps."""
-        t = (C.c_uint64 * 16)()
+        t = (C.c_uint64 * 32)()
         _native.check(self.lib.evs_phase_times(self.handle, t), "evs_phase_times")
         v = [int(x) for x in t]
         us = lambda a, b: (v[b] - v[a]) / 1e3
         n = max(1, v[13])
         return {"avg_over_batches": n, "avg_serve": v[8] / n / 1e3, "avg_gap1": v[9] / n / 1e3, "avg_update": v[10] / n / 1e3,
                 "avg_gap2": v[11] / n / 1e3, "avg_evict": v[12] / n / 1e3,
-                "overlapped_batches": v[14], "evict_scanned_total": v[15], "appends_total": v[1],
+                "overlapped_batches": v[14], "evict_plan": v[22] / n / 1e3, "evict_chunks": v[23] / n / 1e3,
+                "evict_wait_last": v[24] / n / 1e3, "evict_writeback": v[25] / n / 1e3, "evict_chunks_per_batch": v[20] / n,
+                "evict_records_per_batch": v[21] / n, "evict_scanned_total": v[15], "appends_total": v[1],
                 "serve": us(0, 7), "serve_to_update_gap": us(7, 2), "update": us(2, 3), "update_to_evict_gap": us(3, 4),
                 "evict": us(4, 5), "c3": us(5, 6), "total": us(0, 6)}
 

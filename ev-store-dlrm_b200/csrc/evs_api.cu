@@ -354,8 +354,8 @@ static int side_grid(evs_handle h, int n_chunks) {
 
 // The per-batch kernel sequence.  Critical path: k_serve -> [k_scan ->] k_update -> k_evict.  The
 // zero-copy miss fetch (PCIe round trips) and the slab fill run on the side stream next to it:
-//     k_serve --> k_update --+--> k_evict ------------+--> (next batch)
-//                            +--> k_fetch --> k_fill --+
+//     k_serve --> k_update --+--> k_evict --+--> (next batch)
+//                            +--> k_fetch --+
 // (fetching next to k_update instead slowed k_update from 9 to 17 us: the SMs' outstanding
 // PCIe reads get in the way of its atomics)
 // `n_chunks` CTAs of k_serve / k_update; CTAs past the batch end exit at once, so a captured graph
@@ -374,7 +374,6 @@ static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const Batc
     EVS_CUDA(cudaStreamWaitEvent(h->side, h->ev_updated, 0));
     { LaunchScope ls(pf, K_EVICT, st); EVS_CUDA(launch(k_evict, dim3(kTierCtas, h->n_tiers), kEvictThreads, 0, st, p)); }
     { LaunchScope ls(pf, K_FETCH, h->side); EVS_CUDA(launch(ks.fetch, side_grid(h, n_chunks), 256, fetch_smem(h), h->side, p)); }
-    { LaunchScope ls(pf, K_FILL, h->side); EVS_CUDA(launch(k_fill, side_grid(h, n_chunks), 256, 0, h->side, p)); }
     EVS_CUDA(cudaEventRecord(h->ev_filled, h->side));
     EVS_CUDA(cudaStreamWaitEvent(st, h->ev_filled, 0));
     return EVS_OK;
@@ -537,7 +536,7 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     if ((rc = dev_alloc(h->dev_allocs, &P.hist, static_cast<size_t>(kSeqs) * n_chunks_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.tot, kSeqs))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.done, 1))) return fail(rc);
-    if ((rc = dev_alloc(h->dev_allocs, &P.dbg, 16))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &P.dbg, 32))) return fail(rc);
 
     if ((rc = build_tier(h, h->tier[0], cfg->main_precision, h->caps.c1, cfg->store_main))) return fail(rc);
     if (h->n_tiers == 2)
@@ -565,7 +564,6 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         if (al) P.store_aligned |= 1 << i;
     }
     P.stage_stride = std::max(h->tier[0].dev.row_stride, h->n_tiers == 2 ? h->tier[1].dev.row_stride : 0u);
-    if ((rc = dev_alloc(h->dev_allocs, &P.miss_stage, static_cast<size_t>(n_max) * P.stage_stride, false))) return fail(rc);
     const size_t us = fetch_smem(h);
     if (us > 40 * 1024) {
         const KernelSet ks = pick_kernels(cfg->main_precision, h->n_tiers == 2 ? cfg->secondary_precision : 0);
@@ -606,7 +604,7 @@ static int run_batch(evs_handle h, const BatchArgs &a, cudaStream_t st) {
         EVS_CUDA(cudaGraphExecKernelNodeSetParams(h->graph, h->serve_node, &kp));
         EVS_CUDA(cudaGraphLaunch(h->graph, st));
         h->prof.launches[K_SERVE]++, h->prof.launches[K_UPDATE]++, h->prof.launches[K_EVICT]++;
-        h->prof.launches[K_FETCH]++, h->prof.launches[K_FILL]++;
+        h->prof.launches[K_FETCH]++;
         if (h->params.n_chunks_max > kQuadMaxChunks) h->prof.launches[K_SCAN]++;
     } else {
         int rc = enqueue_batch(h, st, (a.B + kSamplesPerCta - 1) / kSamplesPerCta, a);
@@ -809,13 +807,14 @@ int evs_phase_times(evs_handle h, uint64_t *ns8) {
     if (h == nullptr || ns8 == nullptr) return EVS_ERR_INVALID;
     EVS_CUDA(cudaSetDevice(h->cfg.device));
     EVS_CUDA(cudaDeviceSynchronize());
-    EVS_CUDA(cudaMemcpy(ns8, h->params.dbg, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    EVS_CUDA(cudaMemcpy(ns8, h->params.dbg, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     unsigned long long sc = 0, ap = 0;
     EVS_CUDA(cudaMemcpyFromSymbol(&sc, p_dbg_scanned, sizeof(sc)));
     EVS_CUDA(cudaMemcpyFromSymbol(&ap, p_dbg_appends, sizeof(ap)));
     ns8[15] = sc;
     ns8[1] = ap;
     EVS_CUDA(cudaMemset(h->params.dbg + 8, 0, 7 * sizeof(uint64_t)));
+    EVS_CUDA(cudaMemset(h->params.dbg + 20, 0, 6 * sizeof(uint64_t)));
     return EVS_OK;
 }
 

@@ -39,8 +39,8 @@ struct Tier {
 
 
 // Kernel ids for the launch counter / per-kernel CUDA-event timing (evs_set_profiling).
-enum KernelId { K_SERVE = 0, K_SCAN, K_UPDATE, K_EVICT, K_FETCH, K_FILL, K_COMPACT, K_PROBE, K_INTERACT, K_GATHER, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_serve", "k_scan", "k_update", "k_evict", "k_fetch", "k_fill", "k_compact", "k_probe", "k_interact",
+enum KernelId { K_SERVE = 0, K_SCAN, K_UPDATE, K_EVICT, K_FETCH, K_COMPACT, K_PROBE, K_INTERACT, K_GATHER, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_serve", "k_scan", "k_update", "k_evict", "k_fetch", "k_compact", "k_probe", "k_interact",
                                                   "k_gather"};
 
 struct Profiler {
@@ -101,11 +101,11 @@ struct evs_handle_s {
     evs::Params params{};                    // kernel parameter block (device pointers inside)
     std::vector<void *> c3_allocs;
     cudaStream_t stream = nullptr;           // the handle's own stream
-    cudaStream_t side = nullptr;             // miss fetch + slab fill, next to update + evict
+    cudaStream_t side = nullptr;             // miss fetch (+ slab fill), next to the eviction
     cudaEvent_t ev_served = nullptr, ev_updated = nullptr, ev_filled = nullptr;
     cudaGraphNode_t serve_node = nullptr;    // its BatchArgs parameter is rewritten before every graph launch
     cudaGraph_t graph_src = nullptr;
-    cudaGraphExec_t graph = nullptr;         // k_serve -> {[k_scan ->] k_update -> k_evict || k_fetch -> k_fill}
+    cudaGraphExec_t graph = nullptr;         // k_serve -> [k_scan ->] k_update -> {k_evict || k_fetch}
     bool use_graph = true;
     evs::GlobalCtl *g = nullptr;             // device
     evs::BatchArgs *d_args = nullptr;        // device copy of the per-batch arguments

@@ -19,7 +19,7 @@
 namespace evs {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr int kEvictThreads = 1024;
+constexpr int kEvictThreads = 256;         // small CTAs: they must fit on SMs that k_fetch occupies
 constexpr int kEvictPerThread = 4;           // ring records one thread examines per window
 constexpr int kQuadMaxChunks = 2048;         // above this a k_scan launch replaces the direct prefix sums
 
@@ -113,8 +113,8 @@ __device__ __forceinline__ void fetch_row(const unsigned char *__restrict__ src,
 }
 
 // Fetch one missing row (table t, row r of sample s) from the backing store: dequantised into the
-// output and, raw, into the position's row of the miss staging buffer in HBM, from where k_update
-// moves it into the slab row the key claims.  Executed by a group of `gsize` consecutive lanes
+// output and, raw, into the slab row of the slot the position claimed (dst; null for a same-batch
+// duplicate of a key another position claimed).  Executed by a group of `gsize` consecutive lanes
 // (glane = lane within the group) straight through registers when rows are 16-byte aligned
 // (stage == nullptr), else by the whole warp via a shared-memory staging row.
 template <int PREC>
@@ -127,7 +127,7 @@ __device__ __forceinline__ void fetch_one(const TierDev &tier, const BatchArgs &
     if (stage == nullptr) {
         for (int c = glane; c < cpr; c += gsize) {
             const uint4 v = ldg16(src + (c << 4));
-            *reinterpret_cast<uint4 *>(dst + (c << 4)) = v;
+            if (dst != nullptr) *reinterpret_cast<uint4 *>(dst + (c << 4)) = v;
             decode_store<PREC>(v, orow, c, D, vec, lut);
         }
     } else {
@@ -135,7 +135,7 @@ __device__ __forceinline__ void fetch_one(const TierDev &tier, const BatchArgs &
         __syncwarp();
         for (int c = lane; c < cpr; c += 32) {
             const uint4 v = *reinterpret_cast<const uint4 *>(stage + (c << 4));
-            *reinterpret_cast<uint4 *>(dst + (c << 4)) = v;
+            if (dst != nullptr) *reinterpret_cast<uint4 *>(dst + (c << 4)) = v;
             decode_store<PREC>(v, orow, c, D, vec, lut);
         }
         __syncwarp();
@@ -143,8 +143,10 @@ __device__ __forceinline__ void fetch_one(const TierDev &tier, const BatchArgs &
 }
 
 // ---- k_fetch -----------------------------------------------------------------------------
-// Runs on a side stream next to k_update: a warp scans 32 positions' flags at a time and fetches
-// the rows of the misses among them (groups of lanes share a row when rows are 16-byte aligned).
+// Runs on a side stream after k_update (the slots are claimed), next to k_evict: a warp scans 32
+// positions' flags at a time and fetches the rows of the misses among them from the host-pinned
+// backing store into the output and the slab (groups of lanes share a row when rows are 16-byte
+// aligned).  PCIe read tags bound it: ~110 rows / us on this part, whatever the row size <= 256 B.
 template <int PREC>
 __device__ __forceinline__ void fetch_group(const TierDev &tier, const Params &p, const BatchArgs &a, int base, unsigned mm,
                                             int lane, bool aligned, unsigned char *stage, bool vec, const CodecLut *lut) {
@@ -155,6 +157,11 @@ __device__ __forceinline__ void fetch_group(const TierDev &tier, const Params &p
         long long r = __ldg(a.idx + static_cast<size_t>(t) * a.B + s);
         if (r < 0 || r >= __ldg(p.rows + t)) r = 0;
         return r;
+    };
+    // the slab row of the slot this position claimed in k_update, if it is the claimer
+    auto slab_of = [&](int pos) -> unsigned char * {
+        const unsigned sw = __ldcg(p.pos_slot + pos);
+        return (sw & kClaimedBit) ? tier.slab + static_cast<size_t>(sw & ~kClaimedBit) * tier.row_stride : nullptr;
     };
     if (aligned) {
         int gsize = 1;
@@ -172,8 +179,7 @@ __device__ __forceinline__ void fetch_group(const TierDev &tier, const Params &p
             if (mine >= 0) {
                 int s, t;
                 const long long r = row_of(base + mine, s, t);
-                fetch_one<PREC>(tier, a, D, s, t, r, p.miss_stage + static_cast<size_t>(base + mine) * p.stage_stride, lane, gl,
-                                gsize, nullptr, vec, lut);
+                fetch_one<PREC>(tier, a, D, s, t, r, slab_of(base + mine), lane, gl, gsize, nullptr, vec, lut);
             }
         }
     } else {
@@ -182,8 +188,7 @@ __device__ __forceinline__ void fetch_group(const TierDev &tier, const Params &p
             mm &= mm - 1;
             int s, t;
             const long long r = row_of(base + bit, s, t);
-            fetch_one<PREC>(tier, a, D, s, t, r, p.miss_stage + static_cast<size_t>(base + bit) * p.stage_stride, lane, lane, 32,
-                            stage, vec, lut);
+            fetch_one<PREC>(tier, a, D, s, t, r, slab_of(base + bit), lane, lane, 32, stage, vec, lut);
         }
     }
 }
@@ -210,42 +215,6 @@ __global__ void __launch_bounds__(256) k_fetch(const __grid_constant__ Params p)
         if (m0) fetch_group<P0>(t0, p, a, base, m0, lane, (p.store_aligned & 1) != 0, stage, vec, &s_lut);
         if (P1 != 0 && m1)
             fetch_group<(P1 != 0 ? P1 : 32)>(t1, p, a, base, m1, lane, (p.store_aligned & 2) != 0, stage, vec, &s_lut);
-    }
-}
-
-// ---- k_fill ------------------------------------------------------------------------------
-// After k_update (slots claimed) and k_fetch (rows staged): the claiming position's row moves
-// into the slab row of its slot.  Groups of 4 lanes copy one row.
-__global__ void __launch_bounds__(256) k_fill(const __grid_constant__ Params p) {
-    const BatchArgs a = *p.args;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wpc = blockDim.x >> 5;
-    const int N = a.B * p.T;
-    for (int base = (blockIdx.x * wpc + warp) * 32; base < N; base += gridDim.x * wpc * 32) {
-        const int pos = base + lane;
-        const unsigned f = (pos < N) ? p.flags[pos] : 0u;
-        const unsigned sw = (f & kFlagMiss) ? p.pos_slot[pos] : 0u;
-        unsigned mm = __ballot_sync(kFull, (f & kFlagMiss) && (sw & kClaimedBit));
-        const int grp = lane >> 2, gl = lane & 3;
-        while (mm) {
-            unsigned rest = mm;
-            int mine = -1;
-            for (int k = 0; k < 8 && rest; ++k) {
-                const int bit = __ffs(rest) - 1;
-                rest &= rest - 1;
-                if (k == grp) mine = bit;
-            }
-            mm = rest;
-            const unsigned msw = __shfl_sync(kFull, sw, mine < 0 ? 0 : mine);
-            const unsigned mf = __shfl_sync(kFull, f, mine < 0 ? 0 : mine);
-            if (mine >= 0) {
-                const TierDev &tier = p.tier[(mf & kFlagTier) ? 1 : 0];
-                const uint4 *src = reinterpret_cast<const uint4 *>(p.miss_stage + static_cast<size_t>(base + mine) * p.stage_stride);
-                uint4 *dst = reinterpret_cast<uint4 *>(tier.slab + static_cast<size_t>(msw & ~kClaimedBit) * tier.row_stride);
-                const int cpr = static_cast<int>(tier.row_stride >> 4);
-                for (int c = gl; c < cpr; c += 4) dst[c] = src[c];
-            }
-        }
     }
 }
 

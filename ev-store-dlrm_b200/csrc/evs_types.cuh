@@ -28,8 +28,8 @@ constexpr int kMaxTiers = 2;
 // (phase_2 updates every hit before it inserts any miss, evlfu_8.cpp:416-442)
 constexpr int kSeqGroups = 3;
 constexpr int kSeqs = kSeqGroups * kMaxBuckets;
-constexpr int kTierCtas = 64;                // CTAs of k_evict per tier
-constexpr int kEvictWindow = 1024;           // ring records per eviction chunk (one per thread)
+constexpr int kTierCtas = 192;               // CTAs of k_evict per tier
+constexpr int kEvictWindow = 256;            // ring records per eviction chunk (one per thread)
 constexpr int kSamplesPerCta = 8;            // one warp per sample
 constexpr int kLookupThreads = kSamplesPerCta * 32;
 constexpr int kKeyShift = 40;
@@ -160,8 +160,7 @@ struct Params {
     unsigned int *pos_slot;                // [N] slot (in the flag's tier) of a promoted / inserted key
     unsigned int *hist;                    // [kSeqs][n_chunks_max]: per-CTA append counts (prefixes after k_scan)
     unsigned int *tot;                     // [kSeqs] batch totals of the same (k_serve adds, k_evict clears)
-    unsigned char *miss_stage;             // [N][stage_stride] raw rows fetched for the missing positions
-    unsigned int stage_stride;             // max row_stride of the tiers
+    unsigned int stage_stride;             // max row_stride of the tiers (shared-memory staging of unaligned rows)
     unsigned int *done;                    // k_evict: tiers finished (C3 needs both tiers' victims)
     int store_aligned;                     // bit t: every backing row of tier t starts 16-byte aligned
     unsigned long long *dbg;               // [16] %globaltimer stamps of the last batch's phases (ns)

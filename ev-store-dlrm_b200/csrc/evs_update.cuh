@@ -14,8 +14,8 @@
 //              learns how many victims precede it by a decoupled look-back over its predecessors'
 //              counts.  A batch that triggers the flush rule (rare) takes the single-CTA path of
 //              evs_kernels.cuh instead.  The last CTA of the last tier inserts the victims into C3.
-// The rows of the missing keys are fetched meanwhile by k_fetch on a side stream (output + miss
-// staging buffer); k_fill then moves the claimers' rows into their slab rows.
+// The rows of the missing keys are fetched by k_fetch on a side stream next to k_evict (into the
+// output and the slab rows of the slots k_update claimed).
 #pragma once
 #include "evs_c3.cuh"
 #include "evs_kernels.cuh"
@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
         }
     }
     __syncthreads();
+    if (t == 0 && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[16] = gtime();
 
     if (P.flush) {
         // flush rule (EvLFU_C1.py:36-44): rare; CTA 0 does flush + eviction alone
@@ -317,9 +318,13 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
         const unsigned need = P.need;
         const int n_seg = P.n_seg;
         const unsigned long long total_v = P.seg_off[n_seg];
+        bool first = true;
         while (true) {
+            // the first chunk of a CTA is its block index (no round trip); further ones are handed out
+            // by ticket, so a chunk's predecessors always belong to CTAs that are already running
             __syncthreads();
-            if (threadIdx.x == 0) s_chunk = c->stop ? kNoSlot : atomicAdd(&ctl->ticket, 1u);
+            if (threadIdx.x == 0) s_chunk = first ? blockIdx.x : (c->stop ? kNoSlot : gridDim.x + atomicAdd(&ctl->ticket, 1u));
+            first = false;
             __syncthreads();
             const unsigned ch = s_chunk;
             if (ch == kNoSlot || static_cast<unsigned long long>(ch) * W >= total_v) break;
@@ -381,6 +386,7 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
 
     // ---- the last CTA of the tier writes the tier's counters back ---------------------------
     __syncthreads();
+    if (t == 0 && threadIdx.x == 0) atomicMax(&p.dbg[17], gtime());
     if (threadIdx.x == 0) {
         if (s_taken) atomicAdd(&ctl->n_taken, s_taken);
         __threadfence();
@@ -389,6 +395,11 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    if (t == 0 && threadIdx.x == 0) {
+        p.dbg[18] = gtime();
+        p.dbg[20] += c->ticket + gridDim.x;
+        p.dbg[21] += P.seg_off[P.n_seg];
+    }
     if (!P.flush) {
         const unsigned taken = c->n_taken;
         if (threadIdx.x < tier.n_buckets) {
@@ -420,7 +431,7 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
         }
     }
     // per-batch scratch of the tier
-    const unsigned n_tk = min(c->ticket, tier.lb_cap);
+    const unsigned n_tk = min(c->ticket + gridDim.x, tier.lb_cap);
     for (unsigned i = threadIdx.x; i < n_tk; i += blockDim.x) tier.lookback[i] = 0ull;
     if (threadIdx.x < kMaxBuckets) {
         c->kept[threadIdx.x] = ~0ull;
@@ -463,6 +474,12 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
         p.dbg[11] += p.dbg[4] - p.dbg[3];
         p.dbg[12] += p.dbg[6] - p.dbg[4];
         p.dbg[13] += 1ull;
+        // k_evict in detail: plan, chunk loops (slowest CTA), wait for the last CTA, write-back + C3
+        p.dbg[22] += p.dbg[16] - p.dbg[4];
+        p.dbg[23] += p.dbg[17] - p.dbg[16];
+        p.dbg[24] += p.dbg[18] - p.dbg[17];
+        p.dbg[25] += p.dbg[6] - p.dbg[18];
+        p.dbg[17] = 0ull;
         atomicAdd(&p.g->batches, 1ull);
     }
 }

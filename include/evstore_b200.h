@@ -148,7 +148,7 @@ uint64_t evs_launch_count(evs_handle h);
 /* %globaltimer stamps (ns) of the LAST batch: [0] k_serve start, [7] k_serve end (last CTA),
  * [2] k_update start, [3] all CTAs done (claims, appends, miss fetch), [4] ring tails advanced,
  * [5] evictions done, [6] C3 done.  Synchronises. */
-int evs_phase_times(evs_handle h, uint64_t *ns8);
+int evs_phase_times(evs_handle h, uint64_t *ns8);   /* ns8: 32 entries */
 
 /* ---- parity / introspection (used by tests; cheap, off the hot path) -------------- */
 /* Keys evicted / flushed by the LAST batch of tier (0 = C1, 1 = C2), in eviction order.
