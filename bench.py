@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--store-in-hbm", action="store_true", help="debug: backing store copied into HBM (not the BASELINE config)")
+    ap.add_argument("--layers", type=int, default=1, help="1 = configs[1] (C1); 2 = configs[2] (C1+C2); 3 = configs[3] (C1+C2+C3, needs 8/4)")
+    ap.add_argument("--secondary", type=int, default=0, help="SECONDARY_PRECISION of the C2 tier")
+    ap.add_argument("--prop", default="", help='SIZE_PROPORTION "c1-c2-c3" (3 layers)')
     ap.add_argument("--shape", default="kaggle", choices=["kaggle", "terabyte"], help="N > 1 only: table shape of the sharded run")
     return ap.parse_args()
 
@@ -244,17 +247,25 @@ def main_ours(args):
     n_batches = warm + 4 * (W + K)
     _, tables, idx = build_workload(args, n_batches, rows, dim, B)
 
-    cfg = pkg.CacheConfig(n_layers=1, main_precision=prec, total_size=cache_rows * prec // 32, max_batch=B, device=local_rank,
-                          store_in_hbm=args.store_in_hbm)
+    layers = args.layers
+    sec = args.secondary if layers >= 2 else 0
+    # TOTAL_SIZE is in fp32-row units (cache_manager.cpp:16): a single tier of `prec` bits holding cache_rows entries
+    # takes cache_rows * prec / 32 of them; the multi-layer configs get the same memory budget as configs[1]
+    total_size = cache_rows * prec // 32 if layers == 1 else cache_rows
+    cfg = pkg.CacheConfig(n_layers=layers, main_precision=prec, secondary_precision=sec, size_proportion=args.prop,
+                          total_size=total_size, max_batch=B, device=local_rank, store_in_hbm=args.store_in_hbm)
+    alt = pkg.workload.make_alt_keys(rows) if layers == 3 else None
     t0 = time.time()
     stores = None
     if os.environ.get("EVS_BENCH_PINNED_ALLOC", "1") == "1":
         # backing store in cudaHostAlloc memory (torch's pinned allocator) instead of page-locking numpy's pages
-        raw = [pkg.codecs.encode_table(t, prec) for t in tables]
-        pinned = [torch.from_numpy(r).pin_memory() for r in raw]
-        stores = {prec: [q.numpy() for q in pinned]}
+        stores, keep = {}, []
+        for pr in [prec] + ([sec] if layers >= 2 else []):
+            pinned = [torch.from_numpy(pkg.codecs.encode_table(t, pr)).pin_memory() for t in tables]
+            keep.append(pinned)
+            stores[pr] = [q.numpy() for q in pinned]
         log(f"backing store copied to pinned allocations in {time.time() - t0:.1f}s")
-    store = pkg.EvStore(tables, cfg, stores=stores)
+    store = pkg.EvStore(tables, cfg, stores=stores, alt_keys=alt)
     log(f"EvStore created in {time.time() - t0:.1f}s (cache {cache_rows} rows, backing store host-pinned zero-copy)")
 
     # everything below is ordered on one explicit stream: the CUDA events that bracket the timed
@@ -302,7 +313,9 @@ def main_ours(args):
     st = store.stats(reset=True)
     log("per step: misses %.0f evictions %.0f flushed %.0f inserts %.0f" % (st["misses"] / K, st["evictions"][0] / K,
         st["flushed"][0] / K, st["inserts"][0] / K))
-    hit_rate = st["hits"][0] / max(1, st["lookups"])
+    hit_rate = (st["hits"][0] + st["hits"][1] + st["c3_hits"]) / max(1, st["lookups"])
+    tier_rates = {"c1": st["hits"][0] / max(1, st["lookups"]), "c2": st["hits"][1] / max(1, st["lookups"]),
+                  "c3": st["c3_hits"] / max(1, st["lookups"])}
     perfect_rate = st["perfect_hits"] / max(1, st["samples"])
     lookups = K * B * T
     value = lookups / (ms_dev * 1e-3)
@@ -359,18 +372,30 @@ def main_ours(args):
     bpl = bytes_per_lookup(dim, prec)
     alg_bytes = B * T * bpl
     dom_us = per_kernel[dom]["avg_us"]
-    look_us = per_kernel.get("k_lookup", {"avg_us": float("nan")})["avg_us"]
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
+    # same command (profiles/r1_traffic.json, written by tools/ncu_summary.py); null when no capture is committed
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if tj.get("batch") == B and tj.get("dim") == dim and tj.get("precision") == prec:
+            traffic = tj["dram_bytes_per_launch"].get(dom)
+    except Exception:
+        pass
+    # the gather kernel the north-star's 50 % target is about: in-kernel %globaltimer span (first CTA start to
+    # last CTA end) averaged over the timed batches; the CUDA-event figure includes ~6 us of launch and drain
+    serve_us = phases["avg_serve"]
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": alg_bytes / (dom_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
-        "frac": alg_bytes / (dom_us * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+        "frac": alg_bytes / (dom_us * 1e-6) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_lookup": bpl, "kernel_avg_us": dom_us,
-        "k_lookup_avg_us": look_us, "k_lookup_frac": alg_bytes / (look_us * 1e-6) / 1e9 / peak,
+        "k_serve": {"event_avg_us": per_kernel.get("k_serve", {}).get("avg_us"), "in_kernel_avg_us": serve_us,
+                    "achieved": alg_bytes / (serve_us * 1e-6) / 1e9, "frac": alg_bytes / (serve_us * 1e-6) / 1e9 / peak},
         "step_frac": lookups * bpl / (ms_dev * 1e-3) / 1e9 / peak, "per_kernel": per_kernel, "phases_us": phases,
     }
 
     # ---- CPU baseline: the reference's own library on this host -------------------------------
     cpu = None
-    if not args.no_cpu_baseline and args.scale == 1.0 and dim == 16 and prec == 32:
+    if not args.no_cpu_baseline and args.scale == 1.0 and dim == 16 and prec == 32 and layers == 1:
         try:
             from oracle import ref_driver
             variant = "bench_c1_fp32_d16"
@@ -394,9 +419,13 @@ def main_ours(args):
         "metric": "ev_lookups_per_s", "value": value, "unit": "lookups/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if prec == 32 else f"u{prec}->f32", "data": "synthetic",
-        "samples_per_s": value / T, "hit_rate": hit_rate, "perfect_hit_rate": perfect_rate,
-        "config": {"workload": "configs[1]: C1 EvLFU fp%d tier, Kaggle-shape 26 tables (%.2fM rows), dim %d, Zipf(1.05), "
-                               "batch %d, cache %d rows, host-pinned backing store" % (prec, sum(rows) / 1e6, dim, B, cache_rows),
+        "samples_per_s": value / T, "hit_rate": hit_rate, "hit_rate_by_tier": tier_rates, "perfect_hit_rate": perfect_rate,
+        "config": {"workload": ("configs[1]: C1 EvLFU fp%d tier" % prec if layers == 1 else
+                                "configs[%d]: C1 %d-bit + C2 %d-bit%s, TOTAL_SIZE %d fp32-row units%s" % (
+                                    layers, prec, sec, " + C3" if layers == 3 else "", total_size, (" split " + args.prop) if args.prop else ""))
+                               + ", Kaggle-shape 26 tables (%.2fM rows), dim %d, Zipf(1.05), batch %d, cache %d rows, "
+                                 "host-pinned backing store" % (sum(rows) / 1e6, dim, B, cache_rows),
+                   "layers": layers, "secondary_precision": sec,
                    "batch": B, "dim": dim, "precision": prec, "cache_rows": cache_rows, "cache_fill": fill,
                    "cache_warm_batches": warm,
                    "l2": "no flush: index+slab working set (%.2f GB) exceeds the 126 MB L2 and every step reads a distinct index batch"

@@ -349,7 +349,11 @@ static size_t fetch_smem(evs_handle h) {
 
 static int side_grid(evs_handle h, int n_chunks) {
     const long long n = static_cast<long long>(n_chunks) * kSamplesPerCta * h->cfg.n_tables;
-    return static_cast<int>(std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 4)));
+    static const int cap = [] {
+        const char *e = getenv("EVSTORE_B200_FETCH_CTAS");      // tuning aid: CTAs of the miss-fetch kernel
+        return (e && atoi(e) > 0) ? atoi(e) : 148 * 4;
+    }();
+    return static_cast<int>(std::max<long long>(1, std::min<long long>((n + 255) / 256, cap)));
 }
 
 // The per-batch kernel sequence.  Critical path: k_serve -> [k_scan ->] k_update -> k_evict.  The

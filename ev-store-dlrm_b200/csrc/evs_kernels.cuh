@@ -47,17 +47,21 @@ __device__ __forceinline__ void probe_load(const Slot *__restrict__ slots, unsig
 template <int N>
 __device__ __forceinline__ int probe_check(const uint4 (&v)[N], unsigned mask, unsigned long long key, unsigned i,
                                            unsigned &slot_out, unsigned long long &meta_out) {
+    // branch-free, last slot first, so that the FIRST decisive slot wins and the loaded words stay in
+    // registers (an early return inside the loop made ptxas spill the array to local memory)
+    int res = -1;
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
+    for (int k = N - 1; k >= 0; --k) {
         const unsigned long long kw = u64_of(v[k].x, v[k].y);
-        if ((kw & kKeyMask) == key) {
+        const bool match = (kw & kKeyMask) == key;
+        const bool stop = (kw >> 48) == 0ull;
+        if (match) {
             slot_out = (i + k) & mask;
             meta_out = u64_of(v[k].z, v[k].w);
-            return 1;
         }
-        if ((kw >> 48) == 0ull) return 0;
+        res = match ? 1 : (stop ? 0 : res);
     }
-    return -1;
+    return res;
 }
 __device__ __forceinline__ bool probe_rest(const Slot *__restrict__ slots, unsigned mask, unsigned long long key, unsigned i,
                                            unsigned &slot_out, unsigned long long &meta_out) {

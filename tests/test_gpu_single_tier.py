@@ -144,3 +144,9 @@ def test_pipelined_host_buffer_path():
         assert (hits[k].numpy().astype(bool) == o_hit).all(), f"hit stream, batch {k}"
         assert (outs[k].numpy() == gather_rows(tables, st, sr)).all(), f"rows, batch {k}"
     store.close()
+
+
+def test_fp32_very_large_batch_scan_path():
+    """More than 2048 serve-CTAs (B > 16384): ring positions come from the k_scan prefix pass."""
+    t = run_single_tier_parity(SKEW_ROWS, 16, 32, 5000, [17000, 16500, 3], 5)
+    assert t["evicted"] > 0

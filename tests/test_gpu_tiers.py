@@ -50,3 +50,9 @@ def test_three_tier_even_split_dim36():
 def test_three_tier_zero_c3_share_is_two_tier():
     """SIZE_PROPORTION with 0 % for C3 disables the third layer (evlfu_8.cpp:81-84)."""
     run_tier_parity(SMALL_ROWS, 16, 3, 8, 4, 200, [64], 20, prop="50-50-0", check_state_every=4)
+
+
+def test_two_tier_very_large_batch_scan_path():
+    """More than 2048 serve-CTAs (B > 16384): ring positions come from the k_scan prefix pass."""
+    t = run_tier_parity(SKEW_ROWS, 16, 2, 8, 4, 2000, [17000, 16400], 4, check_state_every=1)
+    assert t["ev1"] > 0 and t["c2"] > 0, t
