@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--layers", type=int, default=1, help="1 = configs[1] (C1); 2 = configs[2] (C1+C2); 3 = configs[3] (C1+C2+C3, needs 8/4)")
     ap.add_argument("--secondary", type=int, default=0, help="SECONDARY_PRECISION of the C2 tier")
     ap.add_argument("--prop", default="", help='SIZE_PROPORTION "c1-c2-c3" (3 layers)')
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1 only: exchange fused into the kernels over NVLink peer memory, or NCCL all-reduce + all-to-all")
     ap.add_argument("--shape", default="kaggle", choices=["kaggle", "terabyte"], help="N > 1 only: table shape of the sharded run")
     return ap.parse_args()
 
@@ -440,6 +442,16 @@ def main_ours(args):
     return 0
 
 
+def _guard_stdout():
+    """Libraries (NCCL's version banner, the reference's printf) write to fd 1; the contract is ONE JSON
+    line on stdout.  Everything else is sent to stderr; the JSON line goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w")
+
+
 if __name__ == "__main__":
     a = parse_args()
+    _guard_stdout()
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

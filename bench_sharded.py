@@ -64,7 +64,8 @@ def main_sharded(args):
                           n_tables_total=T, table_base=sl.start)
     store = pkg.EvStore(tables, cfg, stores=stores)
     del tables
-    sh = pkg.sharded.ShardedLookup(store, T, dim, rank, world)
+    transport = getattr(args, "transport", "p2p")
+    sh = pkg.sharded.ShardedLookup(store, T, dim, rank, world, transport=transport, batch_max=B)
 
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -191,7 +192,7 @@ def main_sharded(args):
                 "frac": alg_bytes / (dom_us * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_lookup": bpl, "kernel_avg_us": dom_us,
                 "per_kernel_rank0": per_kernel,
-                "alltoall": {"bytes_sent_per_rank": a2a_bytes, "ms": a2a_ms, "achieved_GBps": a2a_bytes / (a2a_ms * 1e-3) / 1e9,
+                "alltoall_nccl_alone": {"bytes_sent_per_rank": a2a_bytes, "ms": a2a_ms, "achieved_GBps": a2a_bytes / (a2a_ms * 1e-3) / 1e9,
                              "peak_GBps": 770.0, "peak_source": "B200_PROFILING.md measured peer copy per direction",
                              "frac": a2a_bytes / (a2a_ms * 1e-3) / 1e9 / 770.0}}
 
@@ -202,14 +203,17 @@ def main_sharded(args):
             "dtype": "f32" if prec == 32 else f"u{prec}->f32", "data": "synthetic", "samples_per_s": value / T,
             "hit_rate": hit_rate,
             "config": {"workload": "%s-shape 26 tables (%.2fM rows), dim %d, C1 EvLFU fp%d tier, Zipf(1.05), table-wise sharded over %d "
-                                   "GPUs (13 %% of each rank's rows cached), global batch %d = %d per GPU, exact agg_hit all-reduce + "
-                                   "NCCL all-to-all of the pooled rows" % (shape, sum(all_rows) / 1e6, dim, prec, world, B, Bl),
+                                   "GPUs (13 %% of each rank's rows cached), global batch %d = %d per GPU, exact agg_hit; exchange: %s"
+                                   % (shape, sum(all_rows) / 1e6, dim, prec, world, B, Bl,
+                                      "fused into the kernels (peer-memory stores over NVLink + epoch flags, evs_shard_*)"
+                                      if transport == "p2p" else "NCCL all-reduce of the hit counts + all_to_all_single of the pooled rows"),
                        "batch": B, "dim": dim, "precision": prec, "parallelism": "table-wise x%d + all-to-all" % world,
+                       "transport": transport,
                        "cache_warm_batches": done,
                        "l2": "no flush: index+slab working set exceeds the 126 MB L2 and every step reads a distinct index batch"},
             "e2e": {"value": e2e_value, "unit": "lookups/s", "h2d_bytes_per_step": T_local * B * 8 * world,
                     "d2h_bytes_per_step": Bl * T * dim * 4 * world, "ms_per_step": 1e3 * e2e_s / K,
-                    "api": "ShardedLookup.lookup on pinned host indices, pooled rows copied back to pinned host memory"},
+                    "api": "ShardedLookup.lookup (%s) on pinned host indices, pooled rows copied back to pinned host memory" % transport},
             "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": {"value": None, "unit": "lookups/s", "cores": 0, "kind": "reference", "sample": "reported at N = 1 only"},
         }

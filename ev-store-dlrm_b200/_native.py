@@ -52,7 +52,8 @@ class EvsStats(C.Structure):
 SYMBOLS = [
     "evs_create", "evs_destroy", "evs_last_error", "evs_version", "evs_lookup_batch", "evs_probe_batch",
     "evs_lookup_batch_host", "evs_submit_host", "evs_wait_host", "evs_sync", "evs_stats", "evs_last_events", "evs_dump_state", "evs_dump_c3",
-    "evs_interact", "evs_embedding_bag", "evs_embedding_bag_status", "evs_store_ptr", "evs_set_profiling", "evs_kernel_times", "evs_launch_count", "evs_phase_times", "evs_legacy_configure", "evs_legacy_handle", "ev_lookup", "get_ev_values", "print_perfect_hit",
+    "evs_interact", "evs_embedding_bag", "evs_embedding_bag_status", "evs_store_ptr", "evs_shard_create", "evs_shard_export",
+    "evs_shard_connect", "evs_shard_lookup", "evs_shard_destroy", "evs_set_profiling", "evs_kernel_times", "evs_launch_count", "evs_phase_times", "evs_legacy_configure", "evs_legacy_handle", "ev_lookup", "get_ev_values", "print_perfect_hit",
     "test_arr", "ev_lookup_based_on_list_keys",
 ]
 
@@ -105,6 +106,16 @@ def load_library(path: str | None = None):
     lib.evs_embedding_bag_status.restype = C.c_int
     lib.evs_store_ptr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(i32)]
     lib.evs_store_ptr.restype = C.c_int
+    lib.evs_shard_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
+    lib.evs_shard_create.restype = C.c_int
+    lib.evs_shard_export.argtypes = [vp, vp]
+    lib.evs_shard_export.restype = C.c_int
+    lib.evs_shard_connect.argtypes = [vp, vp]
+    lib.evs_shard_connect.restype = C.c_int
+    lib.evs_shard_lookup.argtypes = [vp, vp, i32, vp, C.POINTER(vp), vp]
+    lib.evs_shard_lookup.restype = C.c_int
+    lib.evs_shard_destroy.argtypes = [vp]
+    lib.evs_shard_destroy.restype = C.c_int
     lib.evs_set_profiling.argtypes = [vp, C.c_int]
     lib.evs_set_profiling.restype = C.c_int
     lib.evs_kernel_times.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_char_p), C.POINTER(C.c_double),

@@ -61,6 +61,18 @@ def _stream_handle(stream, device):
     return torch.cuda.current_stream(device).cuda_stream or CUDA_STREAM_LEGACY
 
 
+class _DevArray:
+    """A device buffer owned by the library, exposed through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def _tensor_from_ptr(ptr, shape, device):
+    import torch
+    return torch.as_tensor(_DevArray(ptr, shape), device=device)
+
+
 class EvStore:
     def __init__(self, tables_fp32, cfg: CacheConfig, stores: dict | None = None, alt_keys=None):
         """tables_fp32: list of [rows, dim] float32 arrays (the trained embedding tables).
@@ -209,6 +221,39 @@ class EvStore:
             _native.check(rc, "evs_embedding_bag")
         return out
 
+    # ---- table-wise sharding over peer memory (evs_shard_*) -------------------------------------
+    def shard_create(self, rank: int, world: int, batch_max: int):
+        self._shard = C.c_void_p()
+        self._shard_world, self._shard_batch_max = world, batch_max
+        _native.check(self.lib.evs_shard_create(self.handle, rank, world, batch_max, C.byref(self._shard)), "evs_shard_create")
+        buf = C.create_string_buffer(64)
+        _native.check(self.lib.evs_shard_export(self._shard, buf), "evs_shard_export")
+        return buf.raw
+
+    def shard_connect(self, handles):
+        """handles: the 64-byte exports of all ranks, in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self._shard_world
+        _native.check(self.lib.evs_shard_connect(self._shard, blob), "evs_shard_connect")
+
+    def shard_lookup(self, lS_i, hit=None, stream=None):
+        """lS_i int64 CUDA [n_tables_local, B_global] -> (this rank's [B/world, n_tables_total, dim] rows, hit)."""
+        import torch
+        T, B = lS_i.shape
+        assert lS_i.is_cuda and lS_i.dtype == torch.int64 and lS_i.is_contiguous() and T == self.n_tables
+        if hit is None:
+            hit = torch.empty((B, T), dtype=torch.uint8, device=lS_i.device)
+        st = _stream_handle(stream, lS_i.device)
+        ptr = C.c_void_p()
+        _native.check(self.lib.evs_shard_lookup(self._shard, lS_i.data_ptr(), B, hit.data_ptr(), C.byref(ptr), st), "evs_shard_lookup")
+        shape = (B // self._shard_world, self.cfg.n_tables_total or self.n_tables, self.dim)
+        return _tensor_from_ptr(ptr.value, shape, lS_i.device), hit
+
+    def shard_destroy(self):
+        if getattr(self, "_shard", None):
+            self.lib.evs_shard_destroy(self._shard)
+            self._shard = None
+
     # ---- bookkeeping ---------------------------------------------------------------------
     def sync(self):
         _native.check(self.lib.evs_sync(self.handle), "evs_sync")
@@ -288,6 +333,7 @@ class EvStore:
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle:
+            self.shard_destroy()
             if getattr(self, "_owns_handle", True):
                 self.lib.evs_destroy(self.handle)
             self.handle = C.c_void_p()

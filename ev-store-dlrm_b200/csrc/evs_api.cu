@@ -380,6 +380,10 @@ static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const Batc
     { LaunchScope ls(pf, K_FETCH, h->side); EVS_CUDA(launch(ks.fetch, side_grid(h, n_chunks), 256, fetch_smem(h), h->side, p)); }
     EVS_CUDA(cudaEventRecord(h->ev_filled, h->side));
     EVS_CUDA(cudaStreamWaitEvent(st, h->ev_filled, 0));
+    if (h->sharded) {
+        { LaunchScope ls(pf, K_SIGNAL, st); EVS_CUDA(launch(k_signal, 1, 32, 0, st, p)); }
+        { LaunchScope ls(pf, K_WAIT, st); EVS_CUDA(launch(k_wait, 1, 32, 0, st, p)); }
+    }
     return EVS_OK;
 }
 
@@ -427,6 +431,10 @@ static int check_device_errors(evs_handle h) {
     if (g.error) {
         unsigned zero = 0;
         cudaMemcpy(&h->g->error, &zero, sizeof(zero), cudaMemcpyHostToDevice);
+        if (g.error == 7u) {
+            set_error("a peer rank did not deliver its hit counts / rows in time (table-wise sharding)");
+            return EVS_ERR_PEER;
+        }
         set_error("an index was outside [0, rows[table])");
         return EVS_ERR_INDEX;
     }
@@ -540,6 +548,7 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     if ((rc = dev_alloc(h->dev_allocs, &P.hist, static_cast<size_t>(kSeqs) * n_chunks_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.tot, kSeqs))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.done, 1))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &P.probe_done, 1))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.dbg, 32))) return fail(rc);
 
     if ((rc = build_tier(h, h->tier[0], cfg->main_precision, h->caps.c1, cfg->store_main))) return fail(rc);
@@ -609,6 +618,7 @@ static int run_batch(evs_handle h, const BatchArgs &a, cudaStream_t st) {
         EVS_CUDA(cudaGraphLaunch(h->graph, st));
         h->prof.launches[K_SERVE]++, h->prof.launches[K_UPDATE]++, h->prof.launches[K_EVICT]++;
         h->prof.launches[K_FETCH]++;
+        if (h->sharded) h->prof.launches[K_SIGNAL]++, h->prof.launches[K_WAIT]++;
         if (h->params.n_chunks_max > kQuadMaxChunks) h->prof.launches[K_SCAN]++;
     } else {
         int rc = enqueue_batch(h, st, (a.B + kSamplesPerCta - 1) / kSamplesPerCta, a);
@@ -945,6 +955,143 @@ int evs_dump_c3(evs_handle h, int64_t *keys, uint32_t *alt, uint8_t *recency, in
 
 int evs_interact(const float *x_dev, const float *ly_dev, float *r_dev, int32_t B, int32_t n_f, int32_t dim, void *stream) {
     return launch_interact(x_dev, ly_dev, r_dev, B, n_f, dim, static_cast<cudaStream_t>(stream));
+}
+
+// ---- table-wise sharding over NVLink peer memory -----------------------------------------------
+int evs_shard_create(evs_handle h, int32_t rank, int32_t world, int32_t batch_max, evs_shard *out) {
+    if (h == nullptr || out == nullptr || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || batch_max < world ||
+        batch_max % world != 0 || batch_max > h->cfg.max_batch) {
+        set_error("evs_shard_create: bad rank / world / batch_max (batch_max must be a multiple of world and <= max_batch)");
+        return EVS_ERR_INVALID;
+    }
+    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    evs_shard s = new evs_shard_s();
+    s->h = h;
+    s->rank = rank;
+    s->world = world;
+    s->batch_max = batch_max;
+    s->t_total = h->cfg.n_tables_total;
+    const size_t bl = static_cast<size_t>(batch_max / world);
+    s->recv_bytes = (bl * s->t_total * h->cfg.dim * sizeof(float) + 255) & ~static_cast<size_t>(255);
+    s->off_parts = 2 * s->recv_bytes;
+    s->off_pflags = (s->off_parts + 2 * static_cast<size_t>(world) * batch_max + 255) & ~static_cast<size_t>(255);
+    s->off_oflags = s->off_pflags + 256;
+    s->bytes = s->off_oflags + 256;
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, s->bytes);
+    if (e != cudaSuccess) {
+        set_error(std::string("evs_shard_create: cudaMalloc -> ") + cudaGetErrorString(e));
+        delete s;
+        return EVS_ERR_CUDA;
+    }
+    cudaMemset(q, 0, s->bytes);
+    cudaDeviceSynchronize();
+    s->block = static_cast<unsigned char *>(q);
+    s->peer[rank] = s->block;
+    *out = s;
+    return EVS_OK;
+}
+
+int evs_shard_export(evs_shard s, void *handle64) {
+    if (s == nullptr || handle64 == nullptr) return EVS_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t hd;
+    EVS_CUDA(cudaIpcGetMemHandle(&hd, s->block));
+    memcpy(handle64, &hd, sizeof(hd));
+    return EVS_OK;
+}
+
+int evs_shard_connect(evs_shard s, const void *handles) {
+    if (s == nullptr || handles == nullptr) return EVS_ERR_INVALID;
+    EVS_CUDA(cudaSetDevice(s->h->cfg.device));
+    for (int r = 0; r < s->world; ++r) {
+        if (r == s->rank) continue;
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, static_cast<const unsigned char *>(handles) + 64 * r, sizeof(hd));
+        void *q = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&q, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("evs_shard_connect: cudaIpcOpenMemHandle(rank " + std::to_string(r) + ") -> " + cudaGetErrorString(e));
+            cudaGetLastError();
+            return EVS_ERR_CUDA;
+        }
+        s->peer[r] = static_cast<unsigned char *>(q);
+        s->opened[r] = true;
+    }
+    // the batch graph gets its k_signal / k_wait tail
+    evs_handle h = s->h;
+    EVS_CUDA(cudaDeviceSynchronize());
+    h->sharded = true;
+    if (h->use_graph) {
+        if (h->graph) cudaGraphExecDestroy(h->graph);
+        if (h->graph_src) cudaGraphDestroy(h->graph_src);
+        h->graph = nullptr;
+        h->graph_src = nullptr;
+        int rc = build_graph(h);
+        if (rc) return rc;
+    }
+    return EVS_OK;
+}
+
+int evs_shard_lookup(evs_shard s, const int64_t *idx_dev, int32_t B, uint8_t *hit_dev, float **out_dev, void *stream) {
+    if (s == nullptr || idx_dev == nullptr || out_dev == nullptr || B < s->world || B > s->batch_max || B % s->world != 0) {
+        set_error("evs_shard_lookup: bad shard / pointers / B (B must be a multiple of world, <= batch_max)");
+        return EVS_ERR_INVALID;
+    }
+    evs_handle h = s->h;
+    for (int r = 0; r < s->world; ++r)
+        if (s->peer[r] == nullptr) {
+            set_error("evs_shard_lookup: evs_shard_connect has not been called");
+            return EVS_ERR_NOT_CONFIGURED;
+        }
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    const unsigned epoch = ++s->epoch;
+    const unsigned par = epoch & 1u;
+    ShardArgs sh{};
+    sh.world = s->world;
+    sh.rank = s->rank;
+    sh.Bl = B / s->world;
+    sh.T_total = s->t_total;
+    sh.epoch = epoch;
+    const size_t parts_par = s->off_parts + static_cast<size_t>(par) * s->world * s->batch_max;
+    for (int r = 0; r < s->world; ++r) {
+        sh.recv[r] = reinterpret_cast<float *>(s->peer[r] + par * s->recv_bytes);
+        sh.parts[r] = s->peer[r] + parts_par + static_cast<size_t>(s->rank) * B;
+        sh.probe_flag[r] = reinterpret_cast<unsigned *>(s->peer[r] + s->off_pflags) + s->rank;
+        sh.out_flag[r] = reinterpret_cast<unsigned *>(s->peer[r] + s->off_oflags) + s->rank;
+    }
+    sh.my_parts = s->block + parts_par;
+    sh.my_probe_flags = reinterpret_cast<const unsigned *>(s->block + s->off_pflags);
+    sh.my_out_flags = reinterpret_cast<const unsigned *>(s->block + s->off_oflags);
+
+    BatchArgs a{};
+    a.idx = reinterpret_cast<const long long *>(idx_dev);
+    a.B = B;
+    a.agg_out = h->d_agg;
+    a.sh = sh;
+    a.probe_only = 1;
+    int rc = run_batch(h, a, st);
+    if (rc) return rc;
+    a.probe_only = 0;
+    a.hit = hit_dev;
+    a.out = nullptr;
+    a.out_stride = static_cast<long long>(h->cfg.n_tables) * h->cfg.dim;
+    rc = run_batch(h, a, st);
+    if (rc) return rc;
+    *out_dev = reinterpret_cast<float *>(s->block + par * s->recv_bytes);
+    return EVS_OK;
+}
+
+int evs_shard_destroy(evs_shard s) {
+    if (s == nullptr) return EVS_ERR_INVALID;
+    cudaSetDevice(s->h->cfg.device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < s->world; ++r)
+        if (s->opened[r]) cudaIpcCloseMemHandle(s->peer[r]);
+    if (s->block) cudaFree(s->block);
+    cudaGetLastError();
+    delete s;
+    return EVS_OK;
 }
 
 // ---- sum-pooling gather (nn.EmbeddingBag(mode="sum")) ----------------------------------------

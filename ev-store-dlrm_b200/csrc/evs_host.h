@@ -39,9 +39,9 @@ struct Tier {
 
 
 // Kernel ids for the launch counter / per-kernel CUDA-event timing (evs_set_profiling).
-enum KernelId { K_SERVE = 0, K_SCAN, K_UPDATE, K_EVICT, K_FETCH, K_COMPACT, K_PROBE, K_INTERACT, K_GATHER, K_COUNT };
+enum KernelId { K_SERVE = 0, K_SCAN, K_UPDATE, K_EVICT, K_FETCH, K_COMPACT, K_PROBE, K_INTERACT, K_GATHER, K_SIGNAL, K_WAIT, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"k_serve", "k_scan", "k_update", "k_evict", "k_fetch", "k_compact", "k_probe", "k_interact",
-                                                  "k_gather"};
+                                                  "k_gather", "k_signal", "k_wait"};
 
 struct Profiler {
     bool on = false;
@@ -120,8 +120,22 @@ struct evs_handle_s {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[kPipeSlots] = {}, ev_comp[kPipeSlots] = {}, ev_out[kPipeSlots] = {};
     int64_t submitted = 0;
+    bool sharded = false;                    // an evs_shard is connected: the batch ends with k_signal + k_wait
     std::vector<void *> registered;          // host ranges we page-locked
     std::vector<void *> dev_allocs;
     uint64_t batches = 0;
     evs::Profiler prof;
+};
+
+// Table-wise sharding over peer memory (evs_shard_*).
+struct evs_shard_s {
+    evs_handle h = nullptr;
+    int rank = 0, world = 1;
+    int batch_max = 0;                       // global batch
+    int t_total = 0;
+    unsigned char *block = nullptr;          // our exchange block (cudaMalloc, exported by CUDA IPC)
+    size_t bytes = 0, off_parts = 0, off_pflags = 0, off_oflags = 0, recv_bytes = 0;
+    unsigned char *peer[evs::kMaxPeers] = {};   // peer r's block in our address space (ours at [rank])
+    bool opened[evs::kMaxPeers] = {};
+    unsigned epoch = 0;
 };

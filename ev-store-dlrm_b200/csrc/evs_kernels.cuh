@@ -33,6 +33,37 @@ __device__ __forceinline__ unsigned long long u64_of(unsigned lo, unsigned hi) {
     return (static_cast<unsigned long long>(hi) << 32) | lo;
 }
 
+// Where the fp32 rows of sample s go: the caller's buffer, or -- table-wise sharded -- the receive
+// buffer of the rank that owns the sample, at this rank's table offset (peer memory over NVLink).
+__device__ __forceinline__ float *out_row(const BatchArgs &a, const Params &p, int s) {
+    if (a.sh.world <= 1) return a.out + static_cast<size_t>(s) * a.out_stride;
+    const int dst = s / a.sh.Bl, ls = s - dst * a.sh.Bl;
+    return a.sh.recv[dst] + (static_cast<size_t>(ls) * a.sh.T_total + p.table_base) * p.D;
+}
+__device__ __forceinline__ bool out_vec_ok(const BatchArgs &a, int D) {
+    if (a.sh.world > 1) return (D & 3) == 0;              // receive buffers are cudaMalloc'ed blocks
+    return ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && ((a.out_stride & 3) == 0) && ((D & 3) == 0);
+}
+
+// Lanes 0..world-1 wait until every rank's flag word has reached `epoch` (the words live in OUR
+// memory, peers store into them).  Gives up after kPeerTimeoutNs and reports error 7.
+__device__ __forceinline__ void wait_flags(const unsigned *flags, int world, unsigned epoch, int lane, GlobalCtl *g) {
+    if (lane < world) {
+        const volatile unsigned *f = flags + lane;
+        if (static_cast<int>(*f - epoch) < 0) {
+            const unsigned long long t0 = gtime();
+            while (static_cast<int>(*f - epoch) < 0) {
+                if (gtime() - t0 > kPeerTimeoutNs) {
+                    g->error = 7u;
+                    break;
+                }
+            }
+        }
+        __threadfence();
+    }
+    __syncwarp();
+}
+
 // ---- index probe ---------------------------------------------------------------------
 // Linear probing.  The walk ends at the key or at the first slot no resident key's path crosses
 // (pass == 0).  A dependent HBM access costs ~0.4 us here, so a probe never walks slot by slot:
@@ -122,11 +153,10 @@ __device__ __forceinline__ void fetch_row(const unsigned char *__restrict__ src,
 // (glane = lane within the group) straight through registers when rows are 16-byte aligned
 // (stage == nullptr), else by the whole warp via a shared-memory staging row.
 template <int PREC>
-__device__ __forceinline__ void fetch_one(const TierDev &tier, const BatchArgs &a, int D, int s, int t, long long r,
+__device__ __forceinline__ void fetch_one(const TierDev &tier, float *orow, int D, int t, long long r,
                                           unsigned char *dst, int lane, int glane, int gsize, unsigned char *stage,
                                           bool vec, const CodecLut *lut) {
     const unsigned char *src = tier.store[t] + static_cast<size_t>(r) * tier.row_bytes;
-    float *orow = a.out + static_cast<size_t>(s) * a.out_stride + t * D;
     const int cpr = static_cast<int>(tier.row_stride >> 4);
     if (stage == nullptr) {
         for (int c = glane; c < cpr; c += gsize) {
@@ -183,7 +213,7 @@ __device__ __forceinline__ void fetch_group(const TierDev &tier, const Params &p
             if (mine >= 0) {
                 int s, t;
                 const long long r = row_of(base + mine, s, t);
-                fetch_one<PREC>(tier, a, D, s, t, r, slab_of(base + mine), lane, gl, gsize, nullptr, vec, lut);
+                fetch_one<PREC>(tier, out_row(a, p, s) + t * D, D, t, r, slab_of(base + mine), lane, gl, gsize, nullptr, vec, lut);
             }
         }
     } else {
@@ -192,7 +222,7 @@ __device__ __forceinline__ void fetch_group(const TierDev &tier, const Params &p
             mm &= mm - 1;
             int s, t;
             const long long r = row_of(base + bit, s, t);
-            fetch_one<PREC>(tier, a, D, s, t, r, slab_of(base + bit), lane, lane, 32, stage, vec, lut);
+            fetch_one<PREC>(tier, out_row(a, p, s) + t * D, D, t, r, slab_of(base + bit), lane, lane, 32, stage, vec, lut);
         }
     }
 }
@@ -210,7 +240,7 @@ __global__ void __launch_bounds__(256) k_fetch(const __grid_constant__ Params p)
     const TierDev &t0 = p.tier[0];
     const TierDev &t1 = p.tier[1];
     unsigned char *stage = s_stage + static_cast<size_t>(warp) * p.stage_stride;
-    const bool vec = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && ((a.out_stride & 3) == 0) && ((p.D & 3) == 0);
+    const bool vec = out_vec_ok(a, p.D);
     for (int base = (blockIdx.x * wpc + warp) * 32; base < N; base += gridDim.x * wpc * 32) {
         const int pos = base + lane;
         const unsigned f = (pos < N) ? p.flags[pos] : 0u;
@@ -348,10 +378,35 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
     else if (full) agg = __popc(m_h0 | m_h1) + __popc(m_c3);           // evlfu_8.cpp:512-541
     else agg = __popc(m_h0);                                           // evlfu_8.cpp:601 (C1 not full)
     const int local_agg = agg;
-    if (a.agg_in != nullptr && wact) agg = a.agg_in[s];
     if (a.probe_only) {
-        if (lane == 0 && wact) a.agg_out[s] = static_cast<uint8_t>(local_agg);
+        if (a.sh.world > 1) {
+            // sharded probe: our count of every sample goes into every rank's count table; the last
+            // CTA raises the ranks' "counts of epoch e complete" words
+            if (wact && lane < a.sh.world) a.sh.parts[lane][s] = static_cast<uint8_t>(local_agg);
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const bool last = atomicAdd(p.probe_done, 1u) == gridDim.x - 1;
+                if (last) {
+                    *p.probe_done = 0u;
+                    __threadfence_system();
+                    for (int r = 0; r < a.sh.world; ++r) *reinterpret_cast<volatile unsigned *>(a.sh.probe_flag[r]) = a.sh.epoch;
+                }
+            }
+        } else if (lane == 0 && wact) {
+            a.agg_out[s] = static_cast<uint8_t>(local_agg);
+        }
         return;
+    }
+    if (a.agg_in != nullptr) {
+        if (wact) agg = a.agg_in[s];
+    } else if (a.sh.world > 1 && wact) {
+        // exact groupability: agg_hit = sum over the ranks of their local hit counts
+        wait_flags(a.sh.my_probe_flags, a.sh.world, a.sh.epoch, lane, p.g);
+        int v = (lane < a.sh.world) ? static_cast<int>(__ldcg(a.sh.my_parts + static_cast<size_t>(lane) * a.B + s)) : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+        agg = v;
     }
     const bool approx = (P1 == 0) && (p.approx_thres > 0) && (agg >= p.approx_thres) && (m_h0 != 0u);
 
@@ -421,8 +476,8 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
     }
 
     if (wact) {
-        float *orow = a.out + static_cast<size_t>(s) * a.out_stride;
-        const bool vec = ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && ((a.out_stride & 3) == 0) && ((D & 3) == 0);
+        float *orow = out_row(a, p, s);
+        const bool vec = out_vec_ok(a, D);
         gather_tier<P0>(t0, 0, src_t, src_s, orow, T, D, vec, lane, &s_lut);
         if (P1 != 0) gather_tier<(P1 != 0 ? P1 : 32)>(t1, 1, src_t, src_s, orow, T, D, vec, lane, &s_lut);
     }
@@ -780,6 +835,19 @@ __device__ void evict_tier(const TierDev &tier, const Params &p) {
         if (ev < need) c->error = 4u;
     }
     __syncthreads();
+}
+
+// ---- sharded completion ----------------------------------------------------------------------
+// k_signal runs after k_serve and k_fetch of a batch: every row this rank owes its peers has been
+// stored, tell them.  k_wait holds the stream until every peer has said the same to us.
+__global__ void k_signal(const __grid_constant__ Params p) {
+    const ShardArgs sh = p.args->sh;
+    __threadfence_system();
+    if (static_cast<int>(threadIdx.x) < sh.world) *reinterpret_cast<volatile unsigned *>(sh.out_flag[threadIdx.x]) = sh.epoch;
+}
+__global__ void k_wait(const __grid_constant__ Params p) {
+    const ShardArgs sh = p.args->sh;
+    wait_flags(sh.my_out_flags, sh.world, sh.epoch, threadIdx.x & 31, p.g);
 }
 
 // ---- k_compact ---------------------------------------------------------------------------

@@ -123,13 +123,36 @@ struct C3Dev {
 
 struct GlobalCtl {
     unsigned long long lookups, samples, hits[2], c3_hits, approx_subst, misses, perfect_hits, batches;
-    unsigned int error;
+    unsigned int error;                    // 1 = index out of range, 7 = a peer did not answer in time
     unsigned int pad;
 };
+constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;   // spin-waits on peer flags give up after 4 s
 
 // Arguments that change from batch to batch.  k_serve receives them as a kernel parameter (the
 // only graph node whose parameters are updated per batch) and stores them in device memory for
 // the kernels that follow it.
+constexpr int kMaxPeers = 8;                 // GPUs of one NVSwitch box
+
+// Table-wise sharding over peer memory (evs_shard_*): every rank maps one exchange block of each
+// peer (CUDA IPC).  Pooled rows are stored straight into the batch-sharded buffer of the rank
+// that owns the sample, per-sample hit counts straight into every peer's count table; epochs in
+// flag words tell a peer when a batch's counts / rows are complete.  All pointers below are
+// addresses in THIS process (peer r's memory for index r, our own for index rank).
+struct ShardArgs {
+    int world;                             // 0 = not sharded
+    int rank;
+    int Bl;                                // samples per rank (B / world)
+    int T_total;                           // tables of the whole model
+    unsigned epoch;                        // batch number, >= 1
+    float *recv[kMaxPeers];                // peer r's receive buffer of this epoch's parity: [Bl][T_total][D]
+    uint8_t *parts[kMaxPeers];             // peer r's count table of this parity, OUR row: [B]
+    unsigned *probe_flag[kMaxPeers];       // peer r's "rank `rank` has written its counts of epoch e" word
+    unsigned *out_flag[kMaxPeers];         // peer r's "rank `rank` has written its rows of epoch e" word
+    const uint8_t *my_parts;               // our count table of this parity: [world][B]
+    const unsigned *my_probe_flags;        // [world]
+    const unsigned *my_out_flags;          // [world]
+};
+
 struct BatchArgs {
     const long long *idx;                  // [T][B]
     float *out;
@@ -139,6 +162,7 @@ struct BatchArgs {
     uint8_t *agg_out;                      // [B]
     int B;
     int probe_only;
+    ShardArgs sh;
 };
 
 // Everything a kernel of the batch pipeline needs; constant for the life of a handle.
@@ -162,6 +186,7 @@ struct Params {
     unsigned int *tot;                     // [kSeqs] batch totals of the same (k_serve adds, k_evict clears)
     unsigned int stage_stride;             // max row_stride of the tiers (shared-memory staging of unaligned rows)
     unsigned int *done;                    // k_evict: tiers finished (C3 needs both tiers' victims)
+    unsigned int *probe_done;              // sharded probe: CTAs finished (the last one raises the peers' flags)
     int store_aligned;                     // bit t: every backing row of tier t starts 16-byte aligned
     unsigned long long *dbg;               // [16] %globaltimer stamps of the last batch's phases (ns)
 };

@@ -33,10 +33,22 @@ class ShardedLookup:
     (``EvStore`` built with table_base / n_tables_total; any object with ``probe`` and ``lookup``
     of the same signatures works, which is how the CPU tests drive the host logic)."""
 
-    def __init__(self, store, n_tables_total: int, dim: int, rank: int, world: int, group=None, exact_agg: bool = True):
+    def __init__(self, store, n_tables_total: int, dim: int, rank: int, world: int, group=None, exact_agg: bool = True,
+                 transport: str = "nccl", batch_max: int = 0):
+        """transport "nccl": torch.distributed all-reduce + all_to_all_single (any backend; what the reference does).
+        transport "p2p": the exchange is fused into the kernels over NVLink peer memory (evs_shard_*); needs
+        ``batch_max`` (the global batch) and a store with shard_create / shard_connect / shard_lookup."""
         self.store, self.T, self.dim = store, n_tables_total, dim
         self.rank, self.world, self.group = rank, world, group
         self.exact_agg = exact_agg
+        self.transport = transport if world > 1 else "nccl"
+        if self.transport == "p2p":
+            import torch.distributed as dist
+            mine = store.shard_create(rank, world, batch_max)
+            handles = [None] * world
+            dist.all_gather_object(handles, mine, group=group)
+            store.shard_connect(handles)
+            dist.barrier(group=group)
         self.splits = get_split_lengths(n_tables_total, world)
         self.my = get_my_slice(n_tables_total, rank, world)
         self.T_local = self.splits[rank]
@@ -62,6 +74,8 @@ class ShardedLookup:
         import torch.distributed as dist
         T_local, B = lS_i_local.shape
         assert T_local == self.T_local and B % self.world == 0
+        if self.transport == "p2p":
+            return self.store.shard_lookup(lS_i_local)
         send, recv, out, hit, agg = self._buffers(B, lS_i_local.device)
         agg_in = None
         if self.exact_agg and self.world > 1:

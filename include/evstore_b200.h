@@ -40,10 +40,12 @@ typedef enum {
     EVS_ERR_CUDA = -2,         /* a CUDA runtime call failed (see evs_last_error) */
     EVS_ERR_INDEX = -3,        /* an index was outside [0, rows[table]) */
     EVS_ERR_CAPACITY = -4,     /* internal structure overflow (should not happen) */
-    EVS_ERR_NOT_CONFIGURED = -5
+    EVS_ERR_NOT_CONFIGURED = -5,
+    EVS_ERR_PEER = -6          /* table-wise sharding: a peer rank did not answer within 4 s */
 } evs_status;
 
 typedef struct evs_handle_s *evs_handle;
+typedef struct evs_shard_s *evs_shard;
 
 /* Replaces cache_manager.cpp:13-20 (N_CACHING_LAYER, MAIN_PRECISION,
  * SECONDARY_PRECISION, TOTAL_SIZE, SIZE_PROPORTION) plus the hard-coded
@@ -170,6 +172,27 @@ int evs_dump_c3(evs_handle h, int64_t *keys, uint32_t *alt, uint8_t *recency, in
  */
 int evs_interact(const float *x_dev, const float *ly_dev, float *r_dev, int32_t B, int32_t n_f, int32_t dim,
                  void *stream);
+
+/* ---- table-wise sharding over NVLink peer memory ------------------------------------------- *
+ * The embedding part of DLRM_Net.distributed_forward (dlrm_s_pytorch.py:544-570): rank r owns the tables
+ * get_my_slice(n_tables_total) (extend_distributed.py:47-62; build its handle with table_base / n_tables_total),
+ * looks the WHOLE global batch up in them, and the pooled rows [B, T_local*d] must end up batch-sharded,
+ * [B/world, n_tables_total*d] (ext_dist.alltoall, extend_distributed.py:541-576; all_to_all_single :414).
+ * Here the exchange is part of the kernels: every rank exports one block of device memory over CUDA IPC
+ * (evs_shard_export, 64 bytes, exchanged by the caller), maps its peers' blocks (evs_shard_connect), and
+ *   - the probe kernel stores each sample's local hit count into every peer's count table, so that agg_hit is the
+ *     exact sum over all tables (the reference never ran its cache sharded; agg_hit is its only cross-table coupling);
+ *   - the gather and miss-fetch kernels store every fp32 row straight into the receive buffer of the rank that owns the
+ *     sample, already in the [B/world][n_tables_total][dim] layout;
+ *   - epoch words in peer memory order the two phases (no host synchronisation, no NCCL call).
+ * evs_shard_lookup: idx_dev int64 [n_tables][B] for the whole global batch B (a multiple of world); *out_dev receives
+ * this rank's [B/world][n_tables_total][dim] fp32 buffer, valid until the call after next (two alternate).  hit_dev as in
+ * evs_lookup_batch.  Every rank must make the same sequence of calls. */
+int evs_shard_create(evs_handle h, int32_t rank, int32_t world, int32_t batch_max, evs_shard *out);
+int evs_shard_export(evs_shard s, void *handle64);
+int evs_shard_connect(evs_shard s, const void *handles /* world x 64 bytes, rank order */);
+int evs_shard_lookup(evs_shard s, const int64_t *idx_dev, int32_t B, uint8_t *hit_dev, float **out_dev, void *stream);
+int evs_shard_destroy(evs_shard s);
 
 /* ---- sum pooling: nn.EmbeddingBag(mode="sum") of apply_emb_ori_dlrm ------------------- *
  * (dlrm_s_pytorch_C1_C2_C3.py:191-223)   out[b] = sum_{j = off[b] .. off[b+1]-1} w[j] * W[idx[j]], j ascending.

@@ -50,55 +50,68 @@ def test_two_shards_on_one_device_exact_groupability():
         st.close()
 
 
-def _nccl_worker(rank, world, port, q):
+CASES = {"small": (SMALL_ROWS, 16, 64, 260, 8), "skew": (SKEW_ROWS, 64, 256, 2000, 10)}
+
+
+def _worker(rank, world, port, q, backend, transport, same_device, case):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    devno = 0 if same_device else rank
+    torch.cuda.set_device(devno)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", devno))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     p = pkg()
-    dim, B, cap = 64, 256, 2000
-    tables = p.workload.make_tables(SKEW_ROWS, dim)
-    batches = p.workload.ZipfTrace(SKEW_ROWS, seed=43).batches(10, B)
+    rows, dim, B, cap, n = CASES[case]
+    tables = p.workload.make_tables(rows, dim)
+    batches = p.workload.ZipfTrace(rows, seed=43).batches(n, B)
     sl = p.sharded.get_my_slice(26, rank, world)
-    cfg = p.CacheConfig(total_size=cap, max_batch=B, n_tables_total=26, table_base=sl.start, device=rank)
+    cfg = p.CacheConfig(total_size=cap, max_batch=B, n_tables_total=26, table_base=sl.start, device=devno)
     store = p.EvStore(tables[sl], cfg)
-    sh = p.sharded.ShardedLookup(store, 26, dim, rank, world)
+    sh = p.sharded.ShardedLookup(store, 26, dim, rank, world, transport=transport, batch_max=B)
     res = []
-    for idx in batches:
-        ly, hit = sh.lookup(torch.from_numpy(np.ascontiguousarray(idx[sl])).cuda())
-        torch.cuda.synchronize()
-        res.append((ly.cpu().numpy().copy(), hit.cpu().numpy().copy()))
-    q.put((rank, res))
+    err = None
+    try:
+        for idx in batches:
+            ly, hit = sh.lookup(torch.from_numpy(np.ascontiguousarray(idx[sl])).cuda())
+            torch.cuda.synchronize()
+            res.append((ly.cpu().numpy().copy(), hit.cpu().numpy().copy()))
+        store.sync()
+    except Exception as e:                               # report instead of hanging the peer
+        err = repr(e)
+    q.put((rank, res, err))
     dist.barrier()
     store.close()
     dist.destroy_process_group()
 
 
-def test_sharded_lookup_nccl_two_gpus():
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+def _run_sharded(world, backend, transport, same_device, case):
     import torch.multiprocessing as mp
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 2000
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29600 + (os.getpid() + hash((backend, transport, case))) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, backend, transport, same_device, case)) for r in range(world)]
     for pr in procs:
         pr.start()
-    got = dict(q.get(timeout=300) for _ in range(world))
+    got = {}
+    for _ in range(world):
+        r, res, err = q.get(timeout=300)
+        assert err is None, f"rank {r}: {err}"
+        got[r] = res
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
     p = pkg()
-    dim, B, cap = 64, 256, 2000
-    tables = p.workload.make_tables(SKEW_ROWS, dim)
-    batches = p.workload.ZipfTrace(SKEW_ROWS, seed=43).batches(10, B)
+    rows, dim, B, cap, n = CASES[case]
+    tables = p.workload.make_tables(rows, dim)
+    batches = p.workload.ZipfTrace(rows, seed=43).batches(n, B)
     oracles = [BatchEvLFU(cap, n_tables=26) for _ in range(world)]
     slices = [p.sharded.get_my_slice(26, r, world) for r in range(world)]
     Bl = B // world
+    n_ev = 0
     for k, idx in enumerate(batches):
         agg = sum(np.array([[((sl.start + t) << 40 | int(idx[sl][t, s])) in o.entries for t in range(sl.stop - sl.start)]
                             for s in range(B)]).sum(axis=1) for o, sl in zip(oracles, slices))
@@ -106,6 +119,29 @@ def test_sharded_lookup_nccl_two_gpus():
         for r, (o, sl) in enumerate(zip(oracles, slices)):
             o_hit, s_t, s_r, _ = o.lookup_batch(idx[sl], agg=agg, table_base=sl.start)
             full[:, sl] = gather_rows(tables[sl], s_t - sl.start, s_r)
+            n_ev += len(o.evicted)
             assert np.array_equal(got[r][k][1].astype(bool), o_hit), (k, r)
         for r in range(world):
             assert np.array_equal(got[r][k][0], full[r * Bl:(r + 1) * Bl]), (k, r)
+    return n_ev
+
+
+def test_sharded_lookup_p2p_two_processes_on_one_gpu():
+    """The fused exchange (peer-memory stores + epoch flags, evs_shard_*) with both ranks on cuda:0: CUDA IPC
+    maps the peer's block just the same; the two processes' kernels time-slice, so this is slow but exact."""
+    n_ev = _run_sharded(2, "gloo", "p2p", True, "small")
+    assert n_ev > 0
+
+
+def test_sharded_lookup_nccl_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run_sharded(2, "nccl", "nccl", False, "skew")
+
+
+def test_sharded_lookup_p2p_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run_sharded(2, "nccl", "p2p", False, "skew")
