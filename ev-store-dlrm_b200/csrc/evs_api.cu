@@ -348,7 +348,7 @@ static size_t fetch_smem(evs_handle h) {
 }
 
 static int side_grid(evs_handle h, int n_chunks) {
-    const long long n = static_cast<long long>(n_chunks) * kSamplesPerCta * h->cfg.n_tables;
+    const long long n = static_cast<long long>(n_chunks) * h->params.spc * h->cfg.n_tables;
     static const int cap = [] {
         const char *e = getenv("EVSTORE_B200_FETCH_CTAS");      // tuning aid: CTAs of the miss-fetch kernel
         return (e && atoi(e) > 0) ? atoi(e) : 148 * 4;
@@ -369,7 +369,7 @@ static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const Batc
     const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
     Profiler &pf = h->prof;
     { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch_serve(ks.serve, n_chunks, st, p, a)); }
-    if (p.n_chunks_max > kQuadMaxChunks) {
+    if (p.n_chunks_max > kQuadMaxChunks || p.L < 32) {
         LaunchScope ls(pf, K_SCAN, st);
         EVS_CUDA(launch(k_scan, (h->n_tiers == 1 ? 1 : kSeqGroups) * h->tier[0].dev.n_buckets, 256, 0, st, p));
     }
@@ -532,7 +532,10 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         return fail(EVS_ERR_INVALID);
     }
     const long long n_max = static_cast<long long>(cfg->max_batch) * cfg->n_tables;
-    const int n_chunks_max = (cfg->max_batch + kSamplesPerCta - 1) / kSamplesPerCta;
+    int L = 1, L_shift = 0;                 // lanes per sample = next_pow2(n_tables)
+    while (L < cfg->n_tables) L <<= 1, ++L_shift;
+    const int spc = kSamplesPerCta * (32 / L);
+    const int n_chunks_max = (cfg->max_batch + spc - 1) / spc;
     Params &P = h->params;
     if ((rc = dev_alloc(h->dev_allocs, &h->g, 1))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &h->d_args, 1))) return fail(rc);
@@ -563,6 +566,9 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     P.n_tiers = h->n_tiers;
     P.T = cfg->n_tables;
     P.D = cfg->dim;
+    P.L = L;
+    P.L_shift = L_shift;
+    P.spc = spc;
     P.table_base = cfg->table_base;
     P.n_perfect_agg = h->cfg.n_tables_total;
     P.approx_thres = (h->n_tiers == 1) ? cfg->approx_emb_thres : 0;
@@ -603,7 +609,7 @@ static int run_batch(evs_handle h, const BatchArgs &a, cudaStream_t st) {
     const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
     if (a.probe_only) {
         LaunchScope ls(h->prof, K_PROBE, st);
-        EVS_CUDA(launch_serve(ks.serve, (a.B + kSamplesPerCta - 1) / kSamplesPerCta, st, h->params, a));
+        EVS_CUDA(launch_serve(ks.serve, (a.B + h->params.spc - 1) / h->params.spc, st, h->params, a));
         return EVS_OK;
     }
     if (h->use_graph && !h->prof.on) {
@@ -619,9 +625,9 @@ static int run_batch(evs_handle h, const BatchArgs &a, cudaStream_t st) {
         h->prof.launches[K_SERVE]++, h->prof.launches[K_UPDATE]++, h->prof.launches[K_EVICT]++;
         h->prof.launches[K_FETCH]++;
         if (h->sharded) h->prof.launches[K_SIGNAL]++, h->prof.launches[K_WAIT]++;
-        if (h->params.n_chunks_max > kQuadMaxChunks) h->prof.launches[K_SCAN]++;
+        if (h->params.n_chunks_max > kQuadMaxChunks || h->params.L < 32) h->prof.launches[K_SCAN]++;
     } else {
-        int rc = enqueue_batch(h, st, (a.B + kSamplesPerCta - 1) / kSamplesPerCta, a);
+        int rc = enqueue_batch(h, st, (a.B + h->params.spc - 1) / h->params.spc, a);
         if (rc) return rc;
     }
     h->batches++;

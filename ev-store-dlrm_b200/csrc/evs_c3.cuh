@@ -195,8 +195,11 @@ __device__ void c3_update(const Params &p) {
         const int tbl = static_cast<int>(key >> kKeyShift) - p.table_base;
         const unsigned long long row = key & ((1ull << kKeyShift) - 1ull);
         const unsigned alt = __ldg(c.alt[tbl] + row);
-        bool claimed;
-        const unsigned slot = c3_claim(c, key, claimed);
+        // upsert: a key that is already mapped keeps its slot (claiming the first free slot of its probe
+        // path would map it twice when an erased slot lies before its own)
+        bool claimed = false;
+        unsigned slot, old_alt;
+        if (!c3_find(c, key, slot, old_alt)) slot = c3_claim(c, key, claimed);
         c.slots[slot].alt = alt;
         c.slots[slot].flag = 0u;
         my_new += claimed ? 1u : 0u;

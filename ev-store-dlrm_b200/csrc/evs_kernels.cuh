@@ -253,29 +253,53 @@ __global__ void __launch_bounds__(256) k_fetch(const __grid_constant__ Params p)
 }
 
 // ---- k_serve ---------------------------------------------------------------------------
-// Gather the rows tier `k` serves for this warp's sample: lanes walk the sample's T*CPR 16-byte
-// chunks so consecutive lanes read consecutive 16 B of a row and write consecutive floats of
-// the output; all loads of an unrolled group are issued before the first decode/store.
+// A sample is handled by a GROUP of L = next_pow2(T) consecutive lanes (lane gl of the group holds
+// the key of table gl); a warp carries 32 / L samples.  With the 26 tables of the whole model
+// L = 32 and a warp is one sample; a rank of a table-wise sharded run owns 3-13 tables and packs
+// 8-2 samples into each warp instead of idling most lanes.
+struct Grp {
+    int L, g, gl;            // lanes per sample, group of this lane, lane within the group
+    unsigned mask;           // the group's lanes
+    int base;                // first lane of the group
+};
+__device__ __forceinline__ Grp make_grp(const Params &p, int lane) {
+    Grp q;
+    q.L = p.L;
+    q.g = lane >> p.L_shift;
+    q.gl = lane & (q.L - 1);
+    q.base = q.g << p.L_shift;
+    q.mask = (q.L == 32) ? kFull : (((1u << q.L) - 1u) << q.base);
+    return q;
+}
+// sum over the lanes of a group (L a power of two, groups aligned)
+__device__ __forceinline__ int grp_sum(int v, int L) {
+    for (int d = L >> 1; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+    return v;
+}
+
+// Gather the rows tier `k` serves for this group's sample: the group's lanes walk the sample's
+// T*CPR 16-byte chunks so consecutive lanes read consecutive 16 B of a row and write consecutive
+// floats of the output; all loads of an unrolled round are issued before the first decode/store.
 template <int PREC>
-__device__ __forceinline__ void gather_tier(const TierDev &t, int k, int src_t, unsigned src_s, float *orow, int T, int D,
-                                            bool vec, int lane, const CodecLut *lut) {
+__device__ __forceinline__ void gather_tier(const TierDev &t, int k, int src_t, unsigned src_s, float *orow, bool sact, int T,
+                                            int D, bool vec, const Grp &q, const CodecLut *lut) {
     if (__ballot_sync(kFull, src_t == k) == 0u) return;
     constexpr int U = 4;
     const int cpr = static_cast<int>(t.row_stride >> 4);
     const int total = T * cpr;
-    for (int c0 = 0; c0 < total; c0 += 32 * U) {
+    for (int c0 = 0; c0 < total; c0 += q.L * U) {
         uint4 v[U];
         int tt[U], part[U];
         bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int c = c0 + u * 32 + lane;
+            const int c = c0 + u * q.L + q.gl;
             const bool inb = c < total;
             tt[u] = inb ? c / cpr : 0;
             part[u] = c - tt[u] * cpr;
-            const int st = __shfl_sync(kFull, src_t, tt[u]);
-            const unsigned sl = __shfl_sync(kFull, src_s, tt[u]);
-            ok[u] = inb && (st == k);
+            const int st = __shfl_sync(kFull, src_t, q.base + tt[u]);
+            const unsigned sl = __shfl_sync(kFull, src_s, q.base + tt[u]);
+            ok[u] = inb && sact && (st == k);
             if (ok[u]) v[u] = ldg16(t.slab + static_cast<size_t>(sl) * t.row_stride + (part[u] << 4));
         }
 #pragma unroll
@@ -284,12 +308,12 @@ __device__ __forceinline__ void gather_tier(const TierDev &t, int k, int src_t, 
     }
 }
 
-// One warp per sample, lane t < T holds the key of table t.  A CTA covers kSamplesPerCta
-// consecutive samples so the int64 index tile is read as T runs of 64 contiguous bytes.
-// P1 == 0: single tier.  The cache state is only read here (C3 recency flags excepted).
+// A CTA covers p.spc = 8 * (32 / L) consecutive samples, so the int64 index tile is read as T runs
+// of 8*spc contiguous bytes.  P1 == 0: single tier.  The cache state is only read here (C3 recency
+// flags excepted).
 template <int P0, int P1>
 __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant__ Params p, const __grid_constant__ BatchArgs a) {
-    __shared__ long long s_idx[kSamplesPerCta][kMaxTables];
+    __shared__ long long s_idx[kLookupThreads];          // [sample in CTA][L]
     __shared__ unsigned s_hist[kSeqs];
     __shared__ unsigned s_stat[8];           // hits C1, hits C2, C3, approx, misses, perfect
     __shared__ CodecLut s_lut;
@@ -302,13 +326,15 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int T = p.T, B = a.B, D = p.D;
-    const int s0 = blockIdx.x * kSamplesPerCta;
+    const Grp q = make_grp(p, lane);
+    const int spc = p.spc;
+    const int s0 = blockIdx.x * spc;
     if (s0 >= B) return;
 
-    for (int i = threadIdx.x; i < kSamplesPerCta * T; i += kLookupThreads) {
-        const int t = i / kSamplesPerCta, j = i - t * kSamplesPerCta;
+    for (int i = threadIdx.x; i < spc * T; i += kLookupThreads) {
+        const int t = i / spc, j = i - t * spc;
         const int s = s0 + j;
-        s_idx[j][t] = (s < B) ? __ldg(a.idx + static_cast<size_t>(t) * B + s) : 0;
+        s_idx[(j << p.L_shift) + t] = (s < B) ? __ldg(a.idx + static_cast<size_t>(t) * B + s) : 0;
     }
     if (threadIdx.x < kSeqs) s_hist[threadIdx.x] = 0;
     if (threadIdx.x < 8) s_stat[threadIdx.x] = 0;
@@ -318,19 +344,21 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
     const int full = (P1 != 0) ? static_cast<int>(t0.ctl->full_at_start) : 0;
     __syncthreads();
 
-    const int s = s0 + warp;
-    const bool wact = s < B;                   // a warp past the batch end only joins the barriers
-    const bool act = wact && lane < T;
+    const int j = warp * (32 >> p.L_shift) + q.g;     // sample within the CTA
+    const int s = s0 + j;
+    const bool sact = s < B;                   // a group past the batch end only joins the warp-wide operations
+    const bool act = sact && q.gl < T;
+    const int tbl = q.gl;
     unsigned long long key = 0, m0 = 0, m1 = 0;
     unsigned slot0 = 0, slot1 = 0;
     bool h0 = false, h1 = false;
     if (act) {
-        long long r = s_idx[warp][lane];
-        if (r < 0 || r >= __ldg(p.rows + lane)) {
+        long long r = s_idx[(j << p.L_shift) + tbl];
+        if (r < 0 || r >= __ldg(p.rows + tbl)) {
             p.g->error = 1u;                   // EVS_ERR_INDEX; answer from row 0
             r = 0;
         }
-        key = make_key(p.table_base + lane, r);
+        key = make_key(p.table_base + tbl, r);
         // both tiers' first rounds are in flight together
         const unsigned i0 = hash_key(key, t0.hash_mask);
         uint4 v0[4];
@@ -369,10 +397,9 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
         }
     }
 
-    const unsigned long long t_probe = gtime();
-    const unsigned m_h0 = __ballot_sync(kFull, h0);
-    const unsigned m_h1 = __ballot_sync(kFull, h1);
-    const unsigned m_c3 = __ballot_sync(kFull, c3hit);
+    const unsigned m_h0 = __ballot_sync(kFull, h0) & q.mask;
+    const unsigned m_h1 = __ballot_sync(kFull, h1) & q.mask;
+    const unsigned m_c3 = __ballot_sync(kFull, c3hit) & q.mask;
     int agg;
     if (P1 == 0) agg = __popc(m_h0);                                   // evlfu_32.cpp:477-492
     else if (full) agg = __popc(m_h0 | m_h1) + __popc(m_c3);           // evlfu_8.cpp:512-541
@@ -382,7 +409,8 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
         if (a.sh.world > 1) {
             // sharded probe: our count of every sample goes into every rank's count table; the last
             // CTA raises the ranks' "counts of epoch e complete" words
-            if (wact && lane < a.sh.world) a.sh.parts[lane][s] = static_cast<uint8_t>(local_agg);
+            if (sact)
+                for (int r = q.gl; r < a.sh.world; r += q.L) a.sh.parts[r][s] = static_cast<uint8_t>(local_agg);
             __threadfence_system();
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -393,27 +421,27 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
                     for (int r = 0; r < a.sh.world; ++r) *reinterpret_cast<volatile unsigned *>(a.sh.probe_flag[r]) = a.sh.epoch;
                 }
             }
-        } else if (lane == 0 && wact) {
+        } else if (q.gl == 0 && sact) {
             a.agg_out[s] = static_cast<uint8_t>(local_agg);
         }
         return;
     }
     if (a.agg_in != nullptr) {
-        if (wact) agg = a.agg_in[s];
-    } else if (a.sh.world > 1 && wact) {
+        if (sact) agg = a.agg_in[s];
+    } else if (a.sh.world > 1) {
         // exact groupability: agg_hit = sum over the ranks of their local hit counts
         wait_flags(a.sh.my_probe_flags, a.sh.world, a.sh.epoch, lane, p.g);
-        int v = (lane < a.sh.world) ? static_cast<int>(__ldcg(a.sh.my_parts + static_cast<size_t>(lane) * a.B + s)) : 0;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-        agg = v;
+        int v = 0;
+        if (sact)
+            for (int r = q.gl; r < a.sh.world; r += q.L) v += static_cast<int>(__ldcg(a.sh.my_parts + static_cast<size_t>(r) * a.B + s));
+        agg = grp_sum(v, q.L);
     }
     const bool approx = (P1 == 0) && (p.approx_thres > 0) && (agg >= p.approx_thres) && (m_h0 != 0u);
 
     uint8_t f = 0, hc = kHitMiss;
     int src_t = -1;
     unsigned src_s = 0;
-    const int pos = s * T + lane;
+    const int pos = s * T + tbl;
     if (act) {
         if (h0) {                                                      // C1 serves (and overrides C2)
             hc = kHitC1;
@@ -442,7 +470,7 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
             // fetch and insert.  C1 not full: everything goes to C1 (evlfu_8.cpp:590-602).  C1 full:
             // odd tables to C1, even to C2 while agg < high_agghit_threshold, else all to C2 (:573-588).
             int tier_ins = 0;
-            if (P1 != 0 && full) tier_ins = (agg < p.high_thres && ((p.table_base + lane) & 1)) ? 0 : 1;
+            if (P1 != 0 && full) tier_ins = (agg < p.high_thres && ((p.table_base + tbl) & 1)) ? 0 : 1;
             f = static_cast<uint8_t>(kFlagMiss | (tier_ins ? kFlagTier : 0) | (agg + 1));
         }
         p.flags[pos] = f;
@@ -450,19 +478,20 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
     }
     if (P1 == 0 && p.approx_thres > 0) {
         // value of the latest earlier hit in table order, else of the first hit
-        const unsigned lower = m_h0 & ((1u << lane) - 1u);
-        const int j = lower ? (31 - __clz(lower)) : (m_h0 ? __ffs(m_h0) - 1 : 0);
-        const unsigned subst = __shfl_sync(kFull, slot0, j);
+        const unsigned gm = m_h0 >> q.base;
+        const unsigned lower = gm & ((1u << q.gl) - 1u);
+        const int jj = lower ? (31 - __clz(lower)) : (gm ? __ffs(gm) - 1 : 0);
+        const unsigned subst = __shfl_sync(kFull, slot0, q.base + jj);
         if (hc == kHitApprox) src_s = subst;
     }
 
-    const unsigned m_f0 = __ballot_sync(kFull, f != 0 && !(f & kFlagTier));
-    const unsigned m_p1 = __ballot_sync(kFull, (f & kFlagTier) != 0 && !(f & kFlagMiss));
-    const unsigned m_i1 = __ballot_sync(kFull, (f & kFlagTier) != 0 && (f & kFlagMiss) != 0);
-    const unsigned m_miss = __ballot_sync(kFull, (f & kFlagMiss) != 0);
-    const unsigned m_c2 = __ballot_sync(kFull, hc == kHitC2);
-    const unsigned m_ap = __ballot_sync(kFull, hc == kHitApprox);
-    if (lane == 0 && wact) {
+    const unsigned m_f0 = __ballot_sync(kFull, f != 0 && !(f & kFlagTier)) & q.mask;
+    const unsigned m_p1 = __ballot_sync(kFull, (f & kFlagTier) != 0 && !(f & kFlagMiss)) & q.mask;
+    const unsigned m_i1 = __ballot_sync(kFull, (f & kFlagTier) != 0 && (f & kFlagMiss) != 0) & q.mask;
+    const unsigned m_miss = __ballot_sync(kFull, (f & kFlagMiss) != 0) & q.mask;
+    const unsigned m_c2 = __ballot_sync(kFull, hc == kHitC2) & q.mask;
+    const unsigned m_ap = __ballot_sync(kFull, hc == kHitApprox) & q.mask;
+    if (q.gl == 0 && sact) {
         a.agg_out[s] = static_cast<uint8_t>(agg);
         if (m_f0) atomicAdd(&s_hist[agg], static_cast<unsigned>(__popc(m_f0)));
         if (m_p1) atomicAdd(&s_hist[kMaxBuckets + agg], static_cast<unsigned>(__popc(m_p1)));
@@ -475,11 +504,11 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
         if (agg == p.n_perfect_agg) atomicAdd(&s_stat[5], 1u);
     }
 
-    if (wact) {
-        float *orow = out_row(a, p, s);
+    {
+        float *orow = sact ? out_row(a, p, s) : nullptr;
         const bool vec = out_vec_ok(a, D);
-        gather_tier<P0>(t0, 0, src_t, src_s, orow, T, D, vec, lane, &s_lut);
-        if (P1 != 0) gather_tier<(P1 != 0 ? P1 : 32)>(t1, 1, src_t, src_s, orow, T, D, vec, lane, &s_lut);
+        gather_tier<P0>(t0, 0, src_t, src_s, orow, sact, T, D, vec, q, &s_lut);
+        if (P1 != 0) gather_tier<(P1 != 0 ? P1 : 32)>(t1, 1, src_t, src_s, orow, sact, T, D, vec, q, &s_lut);
     }
 
     __syncthreads();
@@ -491,10 +520,9 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
     }
     if (threadIdx.x == 0) {
         const unsigned long long t_end = gtime();
-        (void)t_probe;
         atomicMax(&p.dbg[1], t_end);
         GlobalCtl *g = p.g;
-        const int ns = min(kSamplesPerCta, B - s0);
+        const int ns = min(spc, B - s0);
         atomicAdd(&g->lookups, static_cast<unsigned long long>(ns) * T);
         atomicAdd(&g->samples, static_cast<unsigned long long>(ns));
         if (s_stat[0]) atomicAdd(&g->hits[0], static_cast<unsigned long long>(s_stat[0]));
@@ -516,8 +544,8 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
 __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Params p) {
     __shared__ unsigned s_w[8];
     const int B = p.args->B;
-    const int n_chunks = (B + kSamplesPerCta - 1) / kSamplesPerCta;
-    if (n_chunks <= kQuadMaxChunks) return;          // k_update sums its predecessors directly
+    const int n_chunks = (B + p.spc - 1) / p.spc;
+    if (p.L == 32 && n_chunks <= kQuadMaxChunks) return;          // k_update sums its predecessors directly
     const int nb = p.tier[0].n_buckets;
     const int grp = blockIdx.x / nb, b = blockIdx.x - grp * nb;
     unsigned *h = p.hist + static_cast<size_t>(grp * kMaxBuckets + b) * p.n_chunks_max;

@@ -30,7 +30,7 @@ constexpr int kSeqGroups = 3;
 constexpr int kSeqs = kSeqGroups * kMaxBuckets;
 constexpr int kTierCtas = 192;               // CTAs of k_evict per tier
 constexpr int kEvictWindow = 256;            // ring records per eviction chunk (one per thread)
-constexpr int kSamplesPerCta = 8;            // one warp per sample
+constexpr int kSamplesPerCta = 8;            // warps per serve / update CTA (one sample per warp when T > 16)
 constexpr int kLookupThreads = kSamplesPerCta * 32;
 constexpr int kKeyShift = 40;
 constexpr unsigned long long kKeyMask = 0x0000FFFFFFFFFFFFull;
@@ -171,6 +171,8 @@ struct Params {
     C3Dev c3;
     int n_tiers;
     int T, D;
+    int L, L_shift;                        // lanes per sample: next_pow2(T) and its log2
+    int spc;                               // samples per serve / update CTA: 8 warps * 32 / L
     int table_base;
     int n_perfect_agg;                     // agg value that counts as a perfect hit (n_tables_total)
     int approx_thres;

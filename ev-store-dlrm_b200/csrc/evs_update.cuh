@@ -23,8 +23,8 @@
 namespace evs {
 
 __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant__ Params p) {
-    __shared__ unsigned s_cnt[kSamplesPerCta][kSeqGroups];
-    __shared__ int s_b[kSamplesPerCta];
+    __shared__ unsigned s_cnt[kLookupThreads][kSeqGroups];      // per sample of the CTA (at most 256 when L = 1)
+    __shared__ int s_b[kLookupThreads];
     __shared__ int s_delta[kMaxTiers * kMaxBuckets];
     __shared__ unsigned s_new[kMaxTiers], s_ins[kMaxTiers];
     __shared__ unsigned long long s_prot[kMaxTiers];
@@ -33,16 +33,20 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
     const BatchArgs a = *p.args;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int T = p.T, B = a.B;
-    const int n_chunks = (B + kSamplesPerCta - 1) / kSamplesPerCta;
+    const Grp q = make_grp(p, lane);
+    const int spc = p.spc;
+    const int n_chunks = (B + spc - 1) / spc;
     if (static_cast<int>(blockIdx.x) >= n_chunks) return;
-    const int s = blockIdx.x * kSamplesPerCta + warp;
-    const bool act = (s < B) && (lane < T);
-    const int pos = s * T + lane;
+    const int j = warp * (32 >> p.L_shift) + q.g;      // sample within the CTA
+    const int s = blockIdx.x * spc + j;
+    const int tbl = q.gl;
+    const bool act = (s < B) && (tbl < T);
+    const int pos = s * T + tbl;
     const unsigned f = act ? p.flags[pos] : 0u;
     long long r = 0;
     if (f & kFlagMiss) {
-        r = __ldg(a.idx + static_cast<size_t>(lane) * B + s);
-        if (r < 0 || r >= __ldg(p.rows + lane)) r = 0;
+        r = __ldg(a.idx + static_cast<size_t>(tbl) * B + s);
+        if (r < 0 || r >= __ldg(p.rows + tbl)) r = 0;
     }
     if (threadIdx.x < kMaxTiers * kMaxBuckets) s_delta[threadIdx.x] = 0;
     if (threadIdx.x < kMaxTiers) {
@@ -55,16 +59,16 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
     const int b = static_cast<int>(f & 0x3Fu) - 1;
     // sequence group of this position: 0 = C1, 1 = C2 promotion, 2 = C2 insert
     const int grp = (f == 0u) ? -1 : (tr == 0 ? 0 : ((f & kFlagMiss) ? 2 : 1));
-    const unsigned m0 = __ballot_sync(kFull, grp == 0);
-    const unsigned m1 = __ballot_sync(kFull, grp == 1);
-    const unsigned m2 = __ballot_sync(kFull, grp == 2);
+    const unsigned m0 = __ballot_sync(kFull, grp == 0) & q.mask;
+    const unsigned m1 = __ballot_sync(kFull, grp == 1) & q.mask;
+    const unsigned m2 = __ballot_sync(kFull, grp == 2) & q.mask;
     const unsigned any = m0 | m1 | m2;
-    const int wb = __shfl_sync(kFull, b, any ? (__ffs(any) - 1) : 0);    // all flagged lanes share it
-    if (lane == 0) {
-        s_cnt[warp][0] = __popc(m0);
-        s_cnt[warp][1] = __popc(m1);
-        s_cnt[warp][2] = __popc(m2);
-        s_b[warp] = any ? wb : -1;
+    const int wb = __shfl_sync(kFull, b, any ? (__ffs(any) - 1) : q.base);    // all flagged lanes of a sample share it
+    if (q.gl == 0) {
+        s_cnt[j][0] = __popc(m0);
+        s_cnt[j][1] = __popc(m1);
+        s_cnt[j][2] = __popc(m2);
+        s_b[j] = any ? wb : -1;
     }
     __syncthreads();
 
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
         unsigned slot = 0;
         bool claimed = false;
         if (f & kFlagMiss) {
-            slot = claim_slot(p.tier[tr], make_key(p.table_base + lane, r), claimed);
+            slot = claim_slot(p.tier[tr], make_key(p.table_base + tbl, r), claimed);
             p.pos_slot[pos] = slot | (claimed ? kClaimedBit : 0u);
             if (claimed) atomicAdd(&s_new[tr], 1u);
             atomicMax(&s_prot[tr], (static_cast<unsigned long long>(f & 0x3Fu) << 32) | static_cast<unsigned>(pos));
@@ -82,13 +86,13 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
         }
 
         // records of earlier chunks in my bucket's sequences (k_scan already made them prefixes for
-        // very large batches), then of earlier samples of this chunk
+        // very large batches and for packed warps), then of earlier samples of this chunk
         unsigned base[kSeqGroups] = {0, 0, 0};
         const unsigned msk[kSeqGroups] = {m0, m1, m2};
         const unsigned *h[kSeqGroups];
 #pragma unroll
         for (int g = 0; g < kSeqGroups; ++g) h[g] = p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max;
-        if (n_chunks > kQuadMaxChunks) {
+        if (q.L < 32 || n_chunks > kQuadMaxChunks) {
 #pragma unroll
             for (int g = 0; g < kSeqGroups; ++g)
                 if (msk[g]) base[g] = __ldcg(h[g] + blockIdx.x);
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
                 base[g] = acc[g];
             }
         }
-        for (int w = 0; w < warp; ++w)
+        for (int w = 0; w < j; ++w)
             if (s_b[w] == wb) {
 #pragma unroll
                 for (int g = 0; g < kSeqGroups; ++g) base[g] += s_cnt[w][g];
@@ -128,9 +132,9 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
             const unsigned mine_mask = grp == 0 ? m0 : (grp == 1 ? m1 : m2);
             const unsigned rank = __popc(mine_mask & ((1u << lane) - 1u));
             const volatile TierCtl *c = tier.ctl;
-            const unsigned long long q = c->tail[b] + (grp == 0 ? base[0] : (grp == 1 ? base[1] : base[2])) + rank;
-            tier.ring[static_cast<size_t>(b) * tier.ring_cap + (q & (tier.ring_cap - 1))] = slot;
-            const unsigned long long mine = pack_meta(b, q);
+            const unsigned long long qq = c->tail[b] + (grp == 0 ? base[0] : (grp == 1 ? base[1] : base[2])) + rank;
+            tier.ring[static_cast<size_t>(b) * tier.ring_cap + (qq & (tier.ring_cap - 1))] = slot;
+            const unsigned long long mine = pack_meta(b, qq);
             const unsigned long long old = atomicMax(&tier.slots[slot].meta, mine);
             if (mine > old) {
                 const int ob = meta_bucket(old);

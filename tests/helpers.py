@@ -116,7 +116,12 @@ def run_tier_parity(rows, dim, layers, main, sec, total, B_list, n_batches, prop
                 if layers == 3:
                     k, a, r = store.dump_c3()
                     ok, oa, orr = oracle.c3.dump() if oracle.c3 is not None else ([], [], [])
-                    assert k.tolist() == ok and a.tolist() == oa and r.tolist() == orr, f"C3 contents, batch {it}"
+                    if not (k.tolist() == ok and a.tolist() == oa and r.tolist() == orr):
+                        kk = k.tolist()
+                        d = next((i for i in range(min(len(kk), len(ok))) if kk[i] != ok[i] or r[i] != orr[i]), -1)
+                        raise AssertionError(f"C3 contents, batch {it}: len {len(kk)} vs {len(ok)}, first diff at {d}: "
+                                             f"{kk[max(0, d - 2):d + 3]} / {r.tolist()[max(0, d - 2):d + 3]} vs {ok[max(0, d - 2):d + 3]} / {orr[max(0, d - 2):d + 3]}; "
+                                             f"sets equal {sorted(kk) == sorted(ok)}; group sizes ev2 {len(oracle.c2.evicted)} ev1 {len(oracle.c1.evicted)} c3 size {len(oracle.c3.vals)}")
             tot["c1"] += int((code == 1).sum())
             tot["c2"] += int((code == 2).sum())
             tot["c3"] += int((code == 3).sum())

@@ -11,10 +11,11 @@ from oracle.evlfu import BatchEvLFU, gather_rows
 pytestmark = pytest.mark.gpu
 
 
-def test_two_shards_on_one_device_exact_groupability():
+@pytest.mark.parametrize("world", [2, 8])
+def test_shards_on_one_device_exact_groupability(world):
     import torch
     p = pkg()
-    dim, B, cap, world = 16, 64, 260, 2
+    dim, B, cap = 16, 64, (260 if world == 2 else 70)
     tables = p.workload.make_tables(SMALL_ROWS, dim)
     trace = p.workload.ZipfTrace(SMALL_ROWS, seed=41)
     stores, oracles, slices = [], [], []
@@ -28,7 +29,7 @@ def test_two_shards_on_one_device_exact_groupability():
     for it in range(30):
         idx = trace.batch(B)
         aggs = [st.probe(torch.from_numpy(np.ascontiguousarray(idx[sl])).cuda()) for st, sl in zip(stores, slices)]
-        agg = (aggs[0].to(torch.int32) + aggs[1].to(torch.int32)).to(torch.uint8)       # the all-reduce
+        agg = torch.stack([x.to(torch.int32) for x in aggs]).sum(dim=0).to(torch.uint8)      # the all-reduce
         # the probe equals the oracle's view of the state
         o_agg = sum(np.array([[((sl.start + t) << 40 | int(idx[sl][t, s])) in o.entries for t in range(sl.stop - sl.start)]
                               for s in range(B)]).sum(axis=1) for o, sl in zip(oracles, slices))

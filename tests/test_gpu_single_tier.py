@@ -150,3 +150,19 @@ def test_fp32_very_large_batch_scan_path():
     """More than 2048 serve-CTAs (B > 16384): ring positions come from the k_scan prefix pass."""
     t = run_single_tier_parity(SKEW_ROWS, 16, 32, 5000, [17000, 16500, 3], 5)
     assert t["evicted"] > 0
+
+
+@pytest.mark.parametrize("n_tables", [1, 2, 3, 5, 13, 16, 17])
+def test_fewer_tables_pack_several_samples_per_warp(n_tables):
+    """A handle with T <= 16 tables packs 32 / next_pow2(T) samples into each warp (what a rank of a
+    table-wise sharded run does); every stream must still equal the oracle's."""
+    rows = SKEW_ROWS[2:2 + n_tables]
+    cap = max(40, int(sum(rows) * 0.2))
+    t = run_single_tier_parity(rows, 16, 32, cap, [257, 64, 1, 33, 700], 25, check_state_every=2)
+    assert t["evicted"] > 0
+
+
+def test_fewer_tables_approx_threshold_and_quantised():
+    rows = SMALL_ROWS[:6]
+    run_single_tier_parity(rows, 16, 32, 300, [96, 7], 30, approx=4, check_state_every=3)
+    run_single_tier_parity(SMALL_ROWS[3:7], 36, 8, 60, [130], 12, check_state_every=3)

@@ -56,3 +56,11 @@ def test_two_tier_very_large_batch_scan_path():
     """More than 2048 serve-CTAs (B > 16384): ring positions come from the k_scan prefix pass."""
     t = run_tier_parity(SKEW_ROWS, 16, 2, 8, 4, 2000, [17000, 16400], 4, check_state_every=1)
     assert t["ev1"] > 0 and t["c2"] > 0, t
+
+
+@pytest.mark.parametrize("n_tables", [3, 4, 7])
+def test_two_and_three_tier_with_packed_warps(n_tables):
+    rows = SMALL_ROWS[2:2 + n_tables]
+    t = run_tier_parity(rows, 16, 2, 8, 4, 60, [200, 33], 30, check_state_every=3)
+    assert t["ev1"] > 0, t
+    run_tier_parity(rows, 16, 3, 8, 4, 90, [150], 30, prop="40-40-20", check_state_every=3)
