@@ -59,13 +59,24 @@ def needed_precisions(variant: str):
 
 
 class RefCache:
-    def __init__(self, variant: str):
+    def __init__(self, variant: str, fresh_copy: bool = False):
+        """fresh_copy: dlopen a private copy of the library, i.e. a second, empty cache instance in
+        this process (the library's state is process-global per loaded file)."""
         v = VARIANTS[variant]
         self.variant, self.dim, self.n_tables = variant, v["dim"], 26
         path = os.path.join(REF_DIR, lib_name(variant))
         if not os.path.exists(path):
             raise RuntimeError(f"{path} missing: run oracle/build_ref.py where /root/reference exists")
+        if fresh_copy:
+            import shutil
+            import tempfile
+            fd, tmp = tempfile.mkstemp(prefix="evs_ref_", suffix=".so")
+            os.close(fd)
+            shutil.copyfile(path, tmp)
+            path = tmp
         self.lib = C.CDLL(path)                       # static ctors run here
+        if fresh_copy:
+            os.unlink(path)                           # the mapping stays valid
         self.lib.ev_lookup.argtypes = [C.POINTER(C.c_int)]
         self.lib.ev_lookup.restype = C.POINTER(C.c_float)
         self.lib.print_perfect_hit.restype = None
@@ -85,6 +96,18 @@ class RefCache:
         if sec < 0:
             raise RuntimeError("reference ev_lookup returned NULL")
         return sec, out
+
+    def drive_slow(self, trace: np.ndarray, gap_s: float):
+        """One ev_lookup per sample with a pause after each, so that the library's C3 worker threads
+        (aprx_embedding.cpp:36-101) finish their queued group before the next request probes C3."""
+        import time
+        trace = np.ascontiguousarray(trace, dtype=np.int32)
+        out = np.empty((trace.shape[0], self.n_tables, self.dim), dtype=np.float32)
+        for i in range(trace.shape[0]):
+            p = self.lib.ev_lookup(trace[i].ctypes.data_as(C.POINTER(C.c_int)))
+            out[i] = np.ctypeslib.as_array(p, shape=(self.n_tables, self.dim))
+            time.sleep(gap_s)
+        return out
 
     def lookup(self, row_ids):
         arr = (C.c_int * self.n_tables)(*[int(x) for x in row_ids])

@@ -26,6 +26,9 @@ VARIANTS = {
     "test_c2_16_4_small_d36": dict(layers=2, main=16, sec=4, total=200, prop="", dim=36, fixture="test_d36"),
     "test_c2_8_4_d36": dict(layers=2, main=8, sec=4, total=100000, prop="", dim=36, fixture="test_d36"),
     "test_c2_8_4_small_d36": dict(layers=2, main=8, sec=4, total=200, prop="", dim=36, fixture="test_d36"),
+    # three layers (C1 8-bit 192 entries, C2 4-bit 384, C3 144 alt keys); needs alt-keys/binary/ in the fixture.
+    # Only usable when driven slowly: C3 is populated by the library's worker threads (tests/test_oracle_c3_pin.py)
+    "test_c3_8_4_d36": dict(layers=3, main=8, sec=4, total=100, prop="48-48-4", dim=36, fixture="test_d36"),
 }
 
 PRECISION_DIRS = {32: "ev-table", 16: "ev-table-16", 8: "ev-table-8", 4: "ev-table-4"}

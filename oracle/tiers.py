@@ -26,10 +26,14 @@ Two restatements live here:
   position order, then flushes / evicts down to capacity, then the victims (C2's, then C1's)
   enter C3 as one group.
 
-C3 is synchronous here: the reference feeds it from worker threads in groups of IO_JOB_Q_SIZE=50
-evicted keys, is timing dependent, and aborts on fast traces ("Too many items in the queue",
-aprx_embedding.cpp:146-148), so **C3 parity is pinned only by this restatement** (parity unpinned
-against a reference run).
+C3: the reference feeds it from worker threads in groups of IO_JOB_Q_SIZE=50 queued victims and
+aborts on fast traces ("Too many items in the queue", aprx_embedding.cpp:146-148).  Driven with a
+pause after every request it is deterministic, and ``SeqTiers(order="stdset", flush="cpp",
+c3_group=50)`` reproduces it request by request (tests/test_oracle_c3_pin.py: returned rows incl.
+the alternative keys' rows, perfect-hit counter).  The policy the CUDA path implements differs in
+ONE documented way: the victims of a request / batch enter C3 as one group when it ends
+(``c3_group=None``) instead of waiting in a 50-key job queue; lookup, routing, second-chance
+eviction and the recency flag are the same code in both modes.
 """
 from __future__ import annotations
 
@@ -287,11 +291,29 @@ class SeqTiers:
     """request_to_c1_c2 / request_to_c1_c2_c3, one request of T row ids at a time."""
 
     def __init__(self, caps, n_layers: int = 2, T: int = 26, order: str = "fifo", flush: str = "py",
-                 high_thres: int = 23, alt_keys=None):
+                 high_thres: int = 23, alt_keys=None, c3_group: int | None = None):
+        """c3_group=None: the victims of a request enter C3 as one group when the request ends (the
+        synchronous policy the CUDA path follows).  c3_group=n: the reference's own queueing -- victims
+        are appended to a job queue key by key and every n-th key (IO_JOB_Q_SIZE = 50,
+        aprx_embedding.hpp:29) releases the oldest n of them into C3 as one group
+        (check_curr_batch_size / insert_altkey_batched_obj, aprx_embedding.cpp:125-150,304-329); this
+        is what the compiled reference does when its worker threads finish before the next request."""
         self.T, self.n_layers, self.high_thres = T, n_layers, high_thres
         self.c1 = SeqTier(caps[0], T, order, flush)
         self.c2 = SeqTier(caps[1], T, order, flush)
         self.c3 = C3State(caps[2], alt_keys) if n_layers == 3 and caps[2] > 0 else None
+        self.c3_group = c3_group
+        self.c3_pending: list[int] = []
+
+    def _feed_c3(self, victims):
+        if self.c3_group is None:
+            self.c3.insert_group(victims)
+            return
+        for k in victims:
+            self.c3_pending.append(k)
+            if len(self.c3_pending) == self.c3_group:
+                self.c3.insert_group(self.c3_pending)
+                self.c3_pending = []
 
     def request(self, row_ids):
         """Returns (code[T], val_tier[T], src_key[T], stale[T], perfect):
@@ -385,7 +407,7 @@ class SeqTiers:
                 c1.set_key(k, agg)
                 code[i], val_tier[i] = HIT_MISS, 0
         if c3 is not None:
-            c3.insert_group(c2.evicted + c1.evicted)               # evlfu_8.cpp:617-620, 654-658 (one group per request)
+            self._feed_c3(c2.evicted + c1.evicted)                 # evlfu_8.cpp:617-620, 654-658
         perfect = 0
         if agg == T:
             c1.n_perfect = len(c1.lists[T])
