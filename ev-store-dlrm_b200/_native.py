@@ -26,7 +26,7 @@ class EvsConfig(C.Structure):
         ("rows", C.POINTER(C.c_int64)),
         ("store_main", C.POINTER(C.c_void_p)), ("store_secondary", C.POINTER(C.c_void_p)),
         ("alt_keys", C.POINTER(C.c_void_p)),
-        ("store_in_hbm", C.c_int32), ("record_events", C.c_int32),
+        ("store_in_hbm", C.c_int32), ("record_events", C.c_int32), ("policy", C.c_int32),
     ]
 
 

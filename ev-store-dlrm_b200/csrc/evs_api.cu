@@ -307,12 +307,14 @@ using ServeFn = void (*)(const Params, const BatchArgs);
 struct KernelSet {
     ServeFn serve = nullptr;
     KernelFn fetch = nullptr;
+    KernelFn fetch_list = nullptr;
 };
 template <int P0, int P1>
 static KernelSet kernels_of() {
     KernelSet k;
     k.serve = k_serve<P0, P1>;
     k.fetch = k_fetch<P0, P1>;
+    k.fetch_list = k_fetch_list<P0, P1>;
     return k;
 }
 static KernelSet pick_kernels(int p0, int p1) {
@@ -376,8 +378,12 @@ static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const Batc
     { LaunchScope ls(pf, K_UPDATE, st); EVS_CUDA(launch(k_update, n_chunks, kLookupThreads, 0, st, p)); }
     EVS_CUDA(cudaEventRecord(h->ev_updated, st));
     EVS_CUDA(cudaStreamWaitEvent(h->side, h->ev_updated, 0));
-    { LaunchScope ls(pf, K_EVICT, st); EVS_CUDA(launch(k_evict, dim3(kTierCtas, h->n_tiers), kEvictThreads, 0, st, p)); }
-    { LaunchScope ls(pf, K_FETCH, h->side); EVS_CUDA(launch(ks.fetch, side_grid(h, n_chunks), 256, fetch_smem(h), h->side, p)); }
+    { LaunchScope ls(pf, K_EVICT, st); EVS_CUDA(launch(k_evict, dim3(h->evict_ctas, h->n_tiers), kEvictThreads, 0, st, p)); }
+    {
+        LaunchScope ls(pf, K_FETCH, h->side);
+        if (p.fetch_mode != 0) EVS_CUDA(launch(ks.fetch_list, h->fetch_list_ctas, 256, fetch_smem(h), h->side, p));
+        else EVS_CUDA(launch(ks.fetch, side_grid(h, n_chunks), 256, fetch_smem(h), h->side, p));
+    }
     EVS_CUDA(cudaEventRecord(h->ev_filled, h->side));
     EVS_CUDA(cudaStreamWaitEvent(st, h->ev_filled, 0));
     if (h->sharded) {
@@ -484,6 +490,16 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         return EVS_ERR_INVALID;
     }
     if (h->cfg.high_agghit_threshold <= 0) h->cfg.high_agghit_threshold = 23;
+    if (cfg->policy != EVS_POLICY_EVLFU && cfg->policy != EVS_POLICY_LRU) {
+        set_error("evs_create: unknown policy");
+        delete h;
+        return EVS_ERR_INVALID;
+    }
+    if (cfg->policy == EVS_POLICY_LRU && (cfg->n_layers != 1 || cfg->approx_emb_thres > 0)) {
+        set_error("evs_create: the LRU policy (cache_algo/LRU.py) is single-layer and has no approximate substitution");
+        delete h;
+        return EVS_ERR_INVALID;
+    }
     if ((static_cast<long long>(cfg->dim) * cfg->main_precision) % 8 != 0) {
         set_error("evs_create: dim*precision must be a whole number of bytes");
         delete h;
@@ -548,6 +564,8 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     if ((rc = dev_alloc(h->dev_allocs, &h->d_hit[0], n_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.flags, n_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.pos_slot, n_max))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &P.miss_list, n_max))) return fail(rc);
+    if ((rc = dev_alloc(h->dev_allocs, &P.miss_ctl, 2))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.hist, static_cast<size_t>(kSeqs) * n_chunks_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.tot, kSeqs))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.done, 1))) return fail(rc);
@@ -572,8 +590,19 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     P.table_base = cfg->table_base;
     P.n_perfect_agg = h->cfg.n_tables_total;
     P.approx_thres = (h->n_tiers == 1) ? cfg->approx_emb_thres : 0;
+    P.policy = cfg->policy;
     P.high_thres = h->cfg.high_agghit_threshold;
     P.n_chunks_max = n_chunks_max;
+    {
+        const char *em = getenv("EVSTORE_B200_EVICT_MODE");        // tuning aid: 0 = ticket-until-stopped chunk loop of k_evict
+        P.evict_mode = (em && em[0] == '0') ? 0 : 1;
+        const char *fm = getenv("EVSTORE_B200_FETCH_MODE");        // tuning aid: 0 = k_fetch scans the flags (all misses issue at once)
+        P.fetch_mode = (fm && fm[0] == '0') ? 0 : 1;
+        const char *fc = getenv("EVSTORE_B200_FETCH_LIST_CTAS");   // tuning aid: CTAs of k_fetch_list = PCIe reads kept in flight
+        if (fc && atoi(fc) > 0) h->fetch_list_ctas = atoi(fc);
+        const char *ec = getenv("EVSTORE_B200_EVICT_CTAS");        // tuning aid: CTAs of k_evict per tier (<= 256)
+        if (ec && atoi(ec) > 0) h->evict_ctas = std::min(atoi(ec), kEvictThreads);
+    }
     P.rows = h->d_rows;
     P.args = h->d_args;
     P.g = h->g;
@@ -587,6 +616,8 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     if (us > 40 * 1024) {
         const KernelSet ks = pick_kernels(cfg->main_precision, h->n_tiers == 2 ? cfg->secondary_precision : 0);
         if (cudaFuncSetAttribute(reinterpret_cast<const void *>(ks.fetch), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(us)) != cudaSuccess ||
+            cudaFuncSetAttribute(reinterpret_cast<const void *>(ks.fetch_list), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(us)) != cudaSuccess) {
             set_error("row too large for the fetch kernel's staging buffer");
             return fail(EVS_ERR_INVALID);
@@ -834,7 +865,7 @@ int evs_phase_times(evs_handle h, uint64_t *ns8) {
     ns8[15] = sc;
     ns8[1] = ap;
     EVS_CUDA(cudaMemset(h->params.dbg + 8, 0, 7 * sizeof(uint64_t)));
-    EVS_CUDA(cudaMemset(h->params.dbg + 20, 0, 6 * sizeof(uint64_t)));
+    EVS_CUDA(cudaMemset(h->params.dbg + 20, 0, 12 * sizeof(uint64_t)));
     return EVS_OK;
 }
 

@@ -252,6 +252,69 @@ __global__ void __launch_bounds__(256) k_fetch(const __grid_constant__ Params p)
     }
 }
 
+// ---- k_fetch_list ------------------------------------------------------------------------
+// The same fetch driven by the compact miss list k_serve wrote (entry = position | tier << 31): every group
+// of lanes takes one missing row per round, so a SMALL grid keeps a bounded number of PCIe reads in flight
+// all the time.  Why: the link serves ~110 row reads / us whatever is asked of it; k_fetch above lets every
+// miss of the batch issue at once (thousands of warps each finding < 1 miss), and the reads queued beyond what
+// the link takes delay the HBM accesses of k_evict running next to it (12 -> 20 us); with few warps scanning
+// the flags the fetch itself becomes a chain of dependent round trips (profiles/r1_fetch_ctas_*.json).
+template <int P0, int P1>
+__global__ void __launch_bounds__(256) k_fetch_list(const __grid_constant__ Params p) {
+    extern __shared__ __align__(16) unsigned char s_stage[];    // warps * max(row_stride); unaligned rows only
+    __shared__ CodecLut s_lut;
+    codec_lut_init<P0, P1>(&s_lut);
+    __syncthreads();
+    const BatchArgs a = *p.args;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpc = blockDim.x >> 5;
+    const int T = p.T, D = p.D;
+    const unsigned n = __ldcg(p.miss_ctl);
+    const TierDev &t0 = p.tier[0];
+    const TierDev &t1 = p.tier[1];
+    const bool vec = out_vec_ok(a, D);
+    const bool al0 = (p.store_aligned & 1) != 0, al1 = (P1 == 0) || (p.store_aligned & 2) != 0;
+    // all rows 16-byte aligned: groups of lanes share a row straight through registers; else a warp per row
+    int gsize = 32;
+    if (al0 && al1) {
+        unsigned cpr = t0.row_stride >> 4;
+        if (P1 != 0 && (t1.row_stride >> 4) > cpr) cpr = t1.row_stride >> 4;
+        gsize = 1;
+        while (gsize < static_cast<int>(cpr) && gsize < 32) gsize <<= 1;
+    }
+    const int rpw = 32 / gsize, grp = lane / gsize, gl = lane - grp * gsize;
+    unsigned char *stage = s_stage + static_cast<size_t>(warp) * p.stage_stride;
+    const unsigned gw = blockIdx.x * wpc + warp, nw = gridDim.x * wpc;
+    for (unsigned i0 = gw * rpw; i0 < n; i0 += nw * rpw) {
+        const unsigned i = i0 + grp;
+        if (i < n) {
+            const unsigned e = __ldcg(p.miss_list + i);
+            const int pos = static_cast<int>(e & 0x7FFFFFFFu);
+            const int s = pos / T, t = pos - s * T;
+            long long r = __ldg(a.idx + static_cast<size_t>(t) * a.B + s);
+            if (r < 0 || r >= __ldg(p.rows + t)) r = 0;
+            const unsigned sw = __ldcg(p.pos_slot + pos);       // the slot this position claimed in k_update, if it is the claimer
+            float *orow = out_row(a, p, s) + t * D;
+            if (P1 == 0 || !(e >> 31)) {
+                unsigned char *dst = (sw & kClaimedBit) ? t0.slab + static_cast<size_t>(sw & ~kClaimedBit) * t0.row_stride : nullptr;
+                fetch_one<P0>(t0, orow, D, t, r, dst, lane, gl, gsize, al0 ? nullptr : stage, vec, &s_lut);
+            } else {
+                unsigned char *dst = (sw & kClaimedBit) ? t1.slab + static_cast<size_t>(sw & ~kClaimedBit) * t1.row_stride : nullptr;
+                fetch_one<(P1 != 0 ? P1 : 32)>(t1, orow, D, t, r, dst, lane, gl, gsize, al1 ? nullptr : stage, vec, &s_lut);
+            }
+        }
+    }
+    // the last CTA empties the list for the next batch (every CTA has read the count by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(p.miss_ctl + 1, 1u) == gridDim.x - 1) {
+            p.miss_ctl[0] = 0u;
+            p.miss_ctl[1] = 0u;
+        }
+    }
+}
+
 // ---- k_serve ---------------------------------------------------------------------------
 // A sample is handled by a GROUP of L = next_pow2(T) consecutive lanes (lane gl of the group holds
 // the key of table gl); a warp carries 32 / L samples.  With the 26 tables of the whole model
@@ -437,6 +500,9 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
         agg = grp_sum(v, q.L);
     }
     const bool approx = (P1 == 0) && (p.approx_thres > 0) && (agg >= p.approx_thres) && (m_h0 != 0u);
+    // LRU (cache_algo/LRU.py): one recency ring (bucket 0); every hit moves its key to the MRU end (:30)
+    const bool lru = (P1 == 0) && (p.policy == 1);
+    const int bkt = lru ? 0 : agg;
 
     uint8_t f = 0, hc = kHitMiss;
     int src_t = -1;
@@ -447,8 +513,8 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
             hc = kHitC1;
             src_t = 0;
             src_s = slot0;
-            if (meta_bucket(m0) < agg) {
-                f = static_cast<uint8_t>(agg + 1);
+            if (lru || meta_bucket(m0) < agg) {
+                f = static_cast<uint8_t>(bkt + 1);
                 p.pos_slot[pos] = slot0;
             }
         } else if (c3hit) {
@@ -471,7 +537,7 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
             // odd tables to C1, even to C2 while agg < high_agghit_threshold, else all to C2 (:573-588).
             int tier_ins = 0;
             if (P1 != 0 && full) tier_ins = (agg < p.high_thres && ((p.table_base + tbl) & 1)) ? 0 : 1;
-            f = static_cast<uint8_t>(kFlagMiss | (tier_ins ? kFlagTier : 0) | (agg + 1));
+            f = static_cast<uint8_t>(kFlagMiss | (tier_ins ? kFlagTier : 0) | (bkt + 1));
         }
         p.flags[pos] = f;
         if (a.hit != nullptr) a.hit[pos] = hc;
@@ -491,9 +557,13 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
     const unsigned m_miss = __ballot_sync(kFull, (f & kFlagMiss) != 0) & q.mask;
     const unsigned m_c2 = __ballot_sync(kFull, hc == kHitC2) & q.mask;
     const unsigned m_ap = __ballot_sync(kFull, hc == kHitApprox) & q.mask;
+    // compact miss list for k_fetch_list: one atomic per sample that missed anything, issued here so that
+    // its round trip hides behind the gather below
+    unsigned mbase = 0;
+    if (p.fetch_mode != 0 && q.gl == 0 && sact && m_miss) mbase = atomicAdd(p.miss_ctl, static_cast<unsigned>(__popc(m_miss)));
     if (q.gl == 0 && sact) {
         a.agg_out[s] = static_cast<uint8_t>(agg);
-        if (m_f0) atomicAdd(&s_hist[agg], static_cast<unsigned>(__popc(m_f0)));
+        if (m_f0) atomicAdd(&s_hist[bkt], static_cast<unsigned>(__popc(m_f0)));
         if (m_p1) atomicAdd(&s_hist[kMaxBuckets + agg], static_cast<unsigned>(__popc(m_p1)));
         if (m_i1) atomicAdd(&s_hist[2 * kMaxBuckets + agg], static_cast<unsigned>(__popc(m_i1)));
         if (m_h0) atomicAdd(&s_stat[0], static_cast<unsigned>(__popc(m_h0)));
@@ -509,6 +579,12 @@ __global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant_
         const bool vec = out_vec_ok(a, D);
         gather_tier<P0>(t0, 0, src_t, src_s, orow, sact, T, D, vec, q, &s_lut);
         if (P1 != 0) gather_tier<(P1 != 0 ? P1 : 32)>(t1, 1, src_t, src_s, orow, sact, T, D, vec, q, &s_lut);
+    }
+
+    if (p.fetch_mode != 0) {
+        mbase = __shfl_sync(kFull, mbase, q.base);
+        if (f & kFlagMiss)
+            p.miss_list[mbase + __popc(m_miss & ((1u << lane) - 1u))] = static_cast<unsigned>(pos) | ((f & kFlagTier) ? 0x80000000u : 0u);
     }
 
     __syncthreads();

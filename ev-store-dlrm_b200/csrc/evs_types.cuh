@@ -178,6 +178,8 @@ struct Params {
     int approx_thres;
     int high_thres;                        // high_agghit_threshold (evlfu_32.hpp:74)
     int n_chunks_max;
+    int policy;                            // 0 = EvLFU, 1 = LRU (single tier: one recency ring, every hit re-appends)
+    int evict_mode;                        // 1: k_evict CTAs take further chunks only when the victims cannot be complete (default); 0: ticket until stopped
     const long long *rows;                 // [T] cardinalities
     BatchArgs *args;
     GlobalCtl *g;
@@ -189,6 +191,9 @@ struct Params {
     unsigned int stage_stride;             // max row_stride of the tiers (shared-memory staging of unaligned rows)
     unsigned int *done;                    // k_evict: tiers finished (C3 needs both tiers' victims)
     unsigned int *probe_done;              // sharded probe: CTAs finished (the last one raises the peers' flags)
+    int fetch_mode;                        // 1: k_serve lists the misses, k_fetch_list fetches them (default); 0: k_fetch scans the flags
+    unsigned int *miss_list;               // [N] position | tier << 31 of every miss of the batch in flight
+    unsigned int *miss_ctl;                // [0] entries in miss_list, [1] k_fetch_list CTAs finished
     int store_aligned;                     // bit t: every backing row of tier t starts 16-byte aligned
     unsigned long long *dbg;               // [16] %globaltimer stamps of the last batch's phases (ns)
 };

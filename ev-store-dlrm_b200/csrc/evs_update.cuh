@@ -185,27 +185,36 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return *reinterpret_cast<const volatile unsigned long long *>(p);
 }
 
+// Look-back entries of the eviction chunks: status << 62 | own count << 31 | inclusive prefix.
+// status 1: the chunk knows its own count; status 2: it also knows how many candidates precede it.
+__device__ __forceinline__ unsigned long long lb_pack(unsigned status, unsigned own, unsigned incl) {
+    return (static_cast<unsigned long long>(status) << 62) | (static_cast<unsigned long long>(own) << 31) | incl;
+}
+__device__ __forceinline__ unsigned lb_status(unsigned long long e) { return static_cast<unsigned>(e >> 62); }
+__device__ __forceinline__ unsigned lb_own(unsigned long long e) { return static_cast<unsigned>(e >> 31) & 0x7FFFFFFFu; }
+__device__ __forceinline__ unsigned lb_incl(unsigned long long e) { return static_cast<unsigned>(e) & 0x7FFFFFFFu; }
+
 // Warp 0 of a chunk: publish this chunk's victim-candidate count, sum the counts of all earlier
-// chunks (decoupled look-back: an entry is  1 << 32 | count  once the chunk knows its own count
-// and  2 << 32 | inclusive prefix  once it knows its predecessors'), publish the inclusive prefix.
+// chunks (decoupled look-back: walk back 32 entries at a time until one carries a full prefix),
+// publish the inclusive prefix.
 __device__ __forceinline__ unsigned lookback_excl(unsigned long long *lb, unsigned ch, unsigned total, int lane) {
     if (ch == 0) {
-        if (lane == 0) atomicExch(&lb[0], (2ull << 32) | total);
+        if (lane == 0) atomicExch(&lb[0], lb_pack(2u, total, total));
         return 0u;
     }
-    if (lane == 0) atomicExch(&lb[ch], (1ull << 32) | total);
+    if (lane == 0) atomicExch(&lb[ch], lb_pack(1u, total, 0u));
     unsigned excl = 0;
     long long j = static_cast<long long>(ch) - 1;
     while (true) {
         const long long k = j - lane;
-        unsigned long long e = 2ull << 32;                   // before chunk 0: inclusive prefix 0
+        unsigned long long e = lb_pack(2u, 0u, 0u);          // before chunk 0: inclusive prefix 0
         if (k >= 0) {
             do {
                 e = ld_volatile_u64(lb + k);
-            } while ((e >> 32) == 0ull);
+            } while (lb_status(e) == 0u);
         }
-        const unsigned incl = __ballot_sync(kFull, (e >> 32) == 2ull);
-        unsigned v = static_cast<unsigned>(e & 0xFFFFFFFFull);
+        const unsigned incl = __ballot_sync(kFull, lb_status(e) == 2u);
+        unsigned v = lb_status(e) == 2u ? lb_incl(e) : lb_own(e);
         if (incl) {
             const int first = __ffs(incl) - 1;               // nearest predecessor with a full prefix
             if (lane > first) v = 0;
@@ -216,14 +225,38 @@ __device__ __forceinline__ unsigned lookback_excl(unsigned long long *lb, unsign
         if (incl) break;
         j -= 32;
     }
-    if (lane == 0) atomicExch(&lb[ch], (2ull << 32) | (excl + total));
+    if (lane == 0) atomicExch(&lb[ch], lb_pack(2u, total, excl + total));
+    return excl;
+}
+
+// The same for one of the first blockDim.x chunks, by the whole CTA in one round trip: thread i reads
+// the own count of chunk i < ch (every chunk publishes it before it waits for anything), the CTA sums.
+__device__ __forceinline__ unsigned lookback_excl_wide(unsigned long long *lb, unsigned ch, unsigned total, unsigned *s_w) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    if (threadIdx.x == 0) atomicExch(&lb[ch], lb_pack(1u, total, 0u));
+    unsigned v = 0;
+    if (threadIdx.x < ch) {
+        unsigned long long e;
+        do {
+            e = ld_volatile_u64(lb + threadIdx.x);
+        } while (lb_status(e) == 0u);
+        v = lb_own(e);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+    __syncthreads();                            // s_w may still be read from the block scan
+    if (lane == 0) s_w[warp] = v;
+    __syncthreads();
+    unsigned excl = 0;
+    for (int w = 0; w < nwarp; ++w) excl += s_w[w];
+    if (threadIdx.x == 0) atomicExch(&lb[ch], lb_pack(2u, total, excl + total));
     return excl;
 }
 
 __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__ Params p) {
     __shared__ EvictPlan P;
     __shared__ unsigned s_w[33];
-    __shared__ unsigned s_chunk, s_excl, s_last, s_taken;
+    __shared__ unsigned s_chunk, s_excl, s_last, s_taken, s_more;
     const int t = blockIdx.y;
     const TierDev &tier = p.tier[t];
     TierCtl *ctl = tier.ctl;
@@ -322,6 +355,7 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
         const unsigned need = P.need;
         const int n_seg = P.n_seg;
         const unsigned long long total_v = P.seg_off[n_seg];
+        const bool lean = p.evict_mode != 0;
         bool first = true;
         while (true) {
             // the first chunk of a CTA is its block index (no round trip); further ones are handed out
@@ -355,12 +389,39 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
             const bool cand = live && slot != P.prot_slot;
             unsigned total;
             const unsigned idx = block_excl_scan(cand ? 1u : 0u, s_w, &total);
-            if (warp == 0) {
-                const unsigned e = lookback_excl(tier.lookback, ch, total, lane);
-                if (lane == 0) s_excl = e;
+            unsigned before;
+            if (lean && ch < blockDim.x) {
+                before = lookback_excl_wide(tier.lookback, ch, total, s_w);
+            } else {
+                if (warp == 0) {
+                    const unsigned e = lookback_excl(tier.lookback, ch, total, lane);
+                    if (lane == 0) s_excl = e;
+                }
+                __syncthreads();
+                before = s_excl;
             }
-            __syncthreads();
-            const unsigned before = s_excl;
+            if (lean && threadIdx.x == 0) {
+                // Does this CTA go on to another chunk?  Not when the victims are complete at or before
+                // this chunk, nor when -- at the density seen so far -- the chunks already handed out
+                // reach the last victim with a margin.  The CTA holding the LAST chunk handed out is the
+                // one that must not leave while victims are missing (it then takes a ticket; so does
+                // every CTA whose estimate says the static chunks fall short, and they work in parallel).
+                const unsigned incl = before + total;
+                unsigned more = 0u;
+                if (incl >= need) {
+                    if (before < need) {
+                        c->stop = 1u;
+                        atomicAdd(&p.dbg[26], static_cast<unsigned long long>(ch));
+                        atomicMax(&p.dbg[27], static_cast<unsigned long long>(ch));
+                    }
+                } else {
+                    const unsigned long long pred = (static_cast<unsigned long long>(ch) + 1ull) * need / max(incl, 1u) + 1ull;
+                    const bool covered = pred + (pred >> 2) + 2ull <= gridDim.x;
+                    if (!covered) more = 1u;
+                    else if (ch + 1u >= gridDim.x) more = (ch + 1u == gridDim.x + c->ticket) ? 1u : 0u;
+                }
+                s_more = more;
+            }
             const bool takeit = cand && (before + idx < need);
             if (takeit) {
                 const unsigned long long key = u64_of(sv.x, sv.y) & kKeyMask;
@@ -383,7 +444,15 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
                 if (seg_end) atomicMax(&ctl->scan_end[b], q + 1);
                 const unsigned nt = __popc(__ballot_sync(kFull, takeit));
                 if (lane == 0 && nt) atomicAdd(&s_taken, nt);
-                if (threadIdx.x == 0 && before + total >= need) c->stop = 1u;
+                if (!lean && threadIdx.x == 0 && before + total >= need) {
+                    c->stop = 1u;
+                    atomicAdd(&p.dbg[26], static_cast<unsigned long long>(ch));
+                    atomicMax(&p.dbg[27], static_cast<unsigned long long>(ch));
+                }
+            }
+            if (lean) {
+                __syncthreads();
+                if (!s_more) break;
             }
         }
     }
@@ -457,34 +526,37 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
     // ---- the last tier to finish feeds C3 and closes the batch ---------------------------------
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned prev = atomicAdd(p.done, 1u);
-        s_last = (prev == static_cast<unsigned>(p.n_tiers) - 1u) ? 1u : 0u;
-        if (s_last) *p.done = 0u;
+        if (p.n_tiers == 1) {
+            s_last = 1u;                                  // nobody else to wait for: no round trip
+        } else {
+            __threadfence();
+            const unsigned prev = atomicAdd(p.done, 1u);
+            s_last = (prev == static_cast<unsigned>(p.n_tiers) - 1u) ? 1u : 0u;
+            if (s_last) *p.done = 0u;
+        }
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     if (threadIdx.x == 0) p.dbg[5] = gtime();
     if (p.c3.active) c3_update(p);
-    if (threadIdx.x == 0) {
-        p.dbg[6] = gtime();
-        p.dbg[7] = p.dbg[1];
-        p.dbg[1] = 0ull;
-        // running sums over batches (ns): serve, gap, update, gap, evict(+c3), count
-        p.dbg[8] += p.dbg[7] - p.dbg[0];
-        p.dbg[9] += p.dbg[2] - p.dbg[7];
-        p.dbg[10] += p.dbg[3] - p.dbg[2];
-        p.dbg[11] += p.dbg[4] - p.dbg[3];
-        p.dbg[12] += p.dbg[6] - p.dbg[4];
-        p.dbg[13] += 1ull;
-        // k_evict in detail: plan, chunk loops (slowest CTA), wait for the last CTA, write-back + C3
-        p.dbg[22] += p.dbg[16] - p.dbg[4];
-        p.dbg[23] += p.dbg[17] - p.dbg[16];
-        p.dbg[24] += p.dbg[18] - p.dbg[17];
-        p.dbg[25] += p.dbg[6] - p.dbg[18];
-        p.dbg[17] = 0ull;
-        atomicAdd(&p.g->batches, 1ull);
+    if (warp == 0) {
+        // phase accounting, one accumulator per lane (a single round trip at the very end of the batch):
+        // running sums over batches (ns): [8] serve, [9] gap, [10] update, [11] gap, [12] evict(+c3), [13] count;
+        // k_evict in detail: [22] plan, [23] chunk loops (slowest CTA), [24] wait for the last CTA, [25] write-back + C3
+        unsigned long long t6 = (lane == 0) ? gtime() : 0ull;
+        t6 = __shfl_sync(kFull, t6, 0);
+        const unsigned long long d = __ldcg(&p.dbg[lane]);
+        const unsigned long long v0 = __shfl_sync(kFull, d, 0), v1 = __shfl_sync(kFull, d, 1), v2 = __shfl_sync(kFull, d, 2),
+                                 v3 = __shfl_sync(kFull, d, 3), v4 = __shfl_sync(kFull, d, 4), v16 = __shfl_sync(kFull, d, 16),
+                                 v17 = __shfl_sync(kFull, d, 17), v18 = __shfl_sync(kFull, d, 18);
+        const unsigned long long nv = lane == 6 ? t6 : lane == 7 ? v1 : lane == 8 ? d + (v1 - v0) : lane == 9 ? d + (v2 - v1)
+                                    : lane == 10 ? d + (v3 - v2) : lane == 11 ? d + (v4 - v3) : lane == 12 ? d + (t6 - v4)
+                                    : lane == 13 ? d + 1ull : lane == 22 ? d + (v16 - v4) : lane == 23 ? d + (v17 - v16)
+                                    : lane == 24 ? d + (v18 - v17) : d + (t6 - v18);
+        const bool wr = (lane >= 6 && lane <= 13) || (lane >= 22 && lane <= 25);
+        if (wr) p.dbg[lane] = nv;
+        if (lane == 0) atomicAdd(&p.g->batches, 1ull);
     }
 }
 

@@ -7,6 +7,8 @@ layout lS_i[n_tables, B] int64 (collate_wrapper_criteo_offset, dlrm_data_pytorch
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 # logs/sample-inference-criteo_kaggle_all.txt:31
@@ -53,9 +55,21 @@ class ZipfTrace:
     def batches(self, n: int, B: int) -> np.ndarray:
         """n consecutive batches at once: int64 [n, n_tables, B]."""
         out = np.empty((n, len(self.rows), B), dtype=np.int64)
-        for t, rows in enumerate(self.rows):
-            r = np.searchsorted(self.cdfs[t], self.rng.random(n * B), side="left")
-            out[:, t, :] = self.perms[t][np.minimum(r, rows - 1)].reshape(n, B)
+        # the uniform draws are taken table by table from the one generator (the sequence is part of the
+        # golden fixtures); the inverse-CDF searches are independent and run on a thread pool
+        u = [self.rng.random(n * B) for _ in self.rows]
+
+        def one(t):
+            r = np.searchsorted(self.cdfs[t], u[t], side="left")
+            out[:, t, :] = self.perms[t][np.minimum(r, self.rows[t] - 1)].reshape(n, B)
+
+        if n * B >= (1 << 16):
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(len(self.rows), os.cpu_count() or 1)) as ex:
+                list(ex.map(one, range(len(self.rows))))
+        else:
+            for t in range(len(self.rows)):
+                one(t)
         return out
 
     def batch(self, B: int) -> np.ndarray:

@@ -80,7 +80,15 @@ typedef struct {
     const uint32_t *const *alt_keys;
     int32_t store_in_hbm;        /* testing aid: copy the backing store into HBM instead of mapping it */
     int32_t record_events;       /* keep per-batch eviction / flush key streams for evs_last_events */
+    /* Replacement policy of the (single) tier: EVS_POLICY_EVLFU = the EvLFU of cache_algo/EvLFU_C1.py and
+     * mixed_precs_caching/ (default, every layer count); EVS_POLICY_LRU = the comparison policy of
+     * cache_algo/LRU.py:15-37 (n_layers == 1 only), selected in the reference by --cache-algo
+     * (dlrm_s_pytorch_C1_C2_C3.py:249-254). */
+    int32_t policy;
 } evs_config;
+
+#define EVS_POLICY_EVLFU 0
+#define EVS_POLICY_LRU 1
 
 typedef struct {
     uint64_t lookups;            /* keys looked up */

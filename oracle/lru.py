@@ -1,0 +1,109 @@
+"""LRU oracles (TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py).
+
+The reference's comparison policy ``/root/reference/cache_algo/LRU.py``:
+an ``OrderedDict`` in recency order, a hit moves the key to the MRU end (:30), a miss evicts the LRU
+key when ``len >= cap`` (:17-19) and inserts.
+
+* ``SeqLRU``   -- statement-for-statement restatement, one request of n_tables keys at a time, each key
+                  probed when its turn comes (LRU.py:40-65).  Pinned by tests/golden/lru_*.npz, generated
+                  from the reference module itself (tests/golden/make_golden.py).
+* ``BatchLRU`` -- the batch-granular generalisation the CUDA path implements (``policy="lru"``): all keys
+                  of a batch are probed against the state at batch start; per key the LAST occurrence
+                  (highest position, sample-major / table-minor) decides its place in the recency order;
+                  occurrences are applied in position order; then the cache is evicted back down to
+                  capacity from the LRU end, never the last inserted key (the reference evicts before it
+                  inserts).  With one sample per batch it equals ``SeqLRU`` on every request that does not
+                  take the same-request corner (a key resident at request start that an earlier insert of
+                  the same request evicted: the reference then misses and re-inserts it).
+Keys are ``(table0 << 40) | row`` as in oracle/evlfu.py.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+
+from .evlfu import make_key
+
+
+class SeqLRU:
+    def __init__(self, capacity: int, n_tables: int = 26):
+        self.cap, self.T = int(capacity), int(n_tables)
+        self.od: OrderedDict[int, None] = OrderedDict()        # LRU.py:8
+        self.evicted: list[int] = []
+        self.corner = False
+
+    def request(self, row_ids):
+        """Returns hit[T].  self.evicted: keys evicted by this request, in order."""
+        self.evicted = []
+        self.corner = False
+        start = set(self.od) if self.cap <= 4096 else None
+        hit = []
+        for i, r in enumerate(row_ids):
+            k = make_key(i, r)
+            if k in self.od:                                   # :27-31
+                self.od.move_to_end(k, last=True)
+                hit.append(True)
+            else:                                              # :32-36 -> set() :15-22
+                if start is not None and k in start:
+                    self.corner = True
+                if len(self.od) >= self.cap:
+                    ek, _ = self.od.popitem(last=False)
+                    self.evicted.append(ek)
+                self.od[k] = None
+                hit.append(False)
+        return hit
+
+    def state(self):
+        return list(self.od.keys())
+
+
+class BatchLRU:
+    """Same interface as oracle.evlfu.BatchEvLFU (the GPU parity helpers drive either)."""
+
+    def __init__(self, capacity: int, n_tables: int = 26):
+        self.cap, self.T = int(capacity), int(n_tables)
+        self.entries: OrderedDict[int, None] = OrderedDict()
+        self.n_perfect = 0
+        self.evicted: list[int] = []
+        self.flushed: list[int] = []
+        self.inserted: list[int] = []
+
+    def lookup_batch(self, idx, approx_emb_thres: int = -1, agg=None, table_base: int = 0):
+        idx = np.asarray(idx)
+        Tl, B = idx.shape
+        ent = self.entries
+        hit = np.zeros((B, Tl), dtype=bool)
+        last: dict[int, int] = {}
+        for s in range(B):
+            for t in range(Tl):
+                k = make_key(table_base + t, idx[t, s])
+                hit[s, t] = k in ent
+                last[k] = s * Tl + t
+        self.inserted = []
+        prot = None
+        for k, _p in sorted(last.items(), key=lambda kv: kv[1]):
+            if k in ent:
+                ent.move_to_end(k, last=True)
+            else:
+                ent[k] = None
+                self.inserted.append(k)
+                prot = k
+        self.evicted = []
+        need = len(ent) - self.cap
+        if need > 0:
+            for k in ent:
+                if k == prot:
+                    continue
+                self.evicted.append(k)
+                if len(self.evicted) == need:
+                    break
+            for k in self.evicted:
+                del ent[k]
+        src_t = np.tile(np.arange(Tl, dtype=np.int32) + table_base, (B, 1))
+        src_r = np.ascontiguousarray(idx.T).astype(np.int64)
+        return hit, src_t, src_r, hit.sum(axis=1).astype(np.int64)
+
+    def state(self):
+        """Per-bucket FIFO lists in the layout of the CUDA path's dump: everything lives in bucket 0."""
+        return [list(self.entries.keys())] + [[] for _ in range(self.T)]

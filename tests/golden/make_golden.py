@@ -13,6 +13,8 @@ Run in the build container only (needs /root/reference); the outputs
    plus the final per-bucket FIFO lists.
 2. ``codecs.npz``       -- the reference's offline quantisers / dequantisers
    (script/reduce_precision.py) evaluated on a fixed vector of floats.
+3. ``lru_*.npz``        -- /root/reference/cache_algo/LRU.py (the comparison policy) the same way:
+   per request hit vector and evicted keys, plus the final recency order.
 """
 import os
 import sys
@@ -171,6 +173,65 @@ def golden_codecs():
     print("codecs", len(x), "values; q16 max", q16.max(), "q4 range", q4.min(), q4.max())
 
 
+def run_reference_lru(trace, cap):
+    """/root/reference/cache_algo/LRU.py driven one request at a time; the module's OrderedDict is
+    replaced by a subclass that logs popitem (the only way LRU.py evicts, :19)."""
+    import collections
+    sm = types.ModuleType("storage_manager")
+    sm.get_val_from_storage = lambda table_id, row_id: [float(table_id - 1), float(row_id)] + [0.5] * (DIM - 2)
+    sys.modules["storage_manager"] = sm
+    sys.path.insert(0, os.path.join(REF, "cache_algo"))
+    sys.modules.pop("LRU", None)
+    import LRU as ref  # noqa: the reference module itself
+
+    events = []
+
+    class LogOD(collections.OrderedDict):
+        def popitem(self, last=True):
+            k, v = super().popitem(last)
+            events.append(k)
+            return k, v
+
+    ref.LRUCache = LogOD()
+    ref.init(cap)
+    n = len(trace)
+    hits = np.zeros((n, T), dtype=bool)
+    ev_keys, ev_off = [], [0]
+    for i in range(n):
+        events.clear()
+        hit, embs = ref.request_to_lru([int(x) for x in trace[i]], False)
+        hits[i] = hit
+        for t in range(T):                       # the value returned is the row of the requested key
+            v = embs[t][0]
+            assert int(v[0]) == t and int(v[1]) == int(trace[i, t])
+        ev_keys.extend(str_key_to_int(k) for k in events)
+        ev_off.append(len(ev_keys))
+    state = [str_key_to_int(k) for k in ref.LRUCache.keys()]
+    return dict(hits=np.packbits(hits, axis=1), ev_keys=np.array(ev_keys, dtype=np.int64),
+                ev_off=np.array(ev_off, dtype=np.int32), state_keys=np.array(state, dtype=np.int64))
+
+
+def golden_lru():
+    cases = [
+        ("lru_small", [40 + 13 * t for t in range(T)], 2500, 300, 52),
+        ("lru_skew", [3, 5, 4000, 2500, 7, 4, 60, 9, 3, 300, 50, 3500, 40, 4, 80, 3000,
+                      5, 45, 30, 4, 3800, 6, 5, 600, 11, 400], 4000, 1500, 53),
+    ]
+    for name, rows, n_req, cap, seed in cases:
+        rng = np.random.default_rng(seed)
+        trace = zipf_trace(rng, rows, n_req)
+        g = run_reference_lru(trace, cap)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), trace=trace.astype(np.int32),
+                            rows=np.array(rows, dtype=np.int64), cap=np.int64(cap), **g)
+        print(name, "requests", n_req, "evictions", len(g["ev_keys"]),
+              "hit rate %.3f" % np.unpackbits(g["hits"], axis=1)[:, :T].mean())
+
+
 if __name__ == "__main__":
-    golden_evlfu()
-    golden_codecs()
+    which = sys.argv[1:] or ["evlfu", "codecs", "lru"]
+    if "evlfu" in which:
+        golden_evlfu()
+    if "codecs" in which:
+        golden_codecs()
+    if "lru" in which:
+        golden_lru()

@@ -5,6 +5,7 @@ import numpy as np
 
 from oracle import codecs as ocodecs
 from oracle.evlfu import BatchEvLFU, gather_rows
+from oracle.lru import BatchLRU
 
 SMALL_ROWS = [50, 7, 400, 300, 9, 4, 60, 12, 3, 120, 30, 350, 40, 5, 45, 280, 4, 33, 21, 4, 390, 6, 5, 90, 11, 70]
 SKEW_ROWS = [3, 5, 4000, 2500, 7, 4, 60, 9, 3, 300, 50, 3500, 40, 4, 80, 3000, 5, 45, 30, 4, 3800, 6, 5, 600, 11, 400]
@@ -23,8 +24,8 @@ def decoded_tables(tables, prec):
 
 
 def run_single_tier_parity(rows, dim, prec, total_size, B_list, n_batches, seed=42, approx=-1,
-                           store_in_hbm=False, host_path=False, check_state_every=1, alpha=1.05):
-    """Drive the CUDA path and BatchEvLFU with the same batches; compare everything, every batch."""
+                           store_in_hbm=False, host_path=False, check_state_every=1, alpha=1.05, policy="evlfu"):
+    """Drive the CUDA path and BatchEvLFU (or BatchLRU) with the same batches; compare everything, every batch."""
     import torch
     p = pkg()
     tables = p.workload.make_tables(rows, dim)
@@ -32,9 +33,9 @@ def run_single_tier_parity(rows, dim, prec, total_size, B_list, n_batches, seed=
     trace = p.workload.ZipfTrace(rows, alpha=alpha, seed=seed)
     cap = total_size * (32 // prec)
     cfg = p.CacheConfig(n_layers=1, main_precision=prec, total_size=total_size, max_batch=max(B_list),
-                        approx_emb_thres=approx, record_events=True, store_in_hbm=store_in_hbm)
+                        approx_emb_thres=approx, record_events=True, store_in_hbm=store_in_hbm, policy=policy)
     store = p.EvStore(tables, cfg)
-    oracle = BatchEvLFU(cap, n_tables=len(rows))
+    oracle = BatchLRU(cap, n_tables=len(rows)) if policy == "lru" else BatchEvLFU(cap, n_tables=len(rows))
     T = len(rows)
     totals = dict(hits=0, lookups=0, evicted=0, flushed=0)
     try:

@@ -1,0 +1,67 @@
+"""The LRU oracles (oracle/lru.py) against the reference's own outputs (tests/golden/lru_*.npz, made by
+tests/golden/make_golden.py from /root/reference/cache_algo/LRU.py)."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+from oracle.lru import BatchLRU, SeqLRU
+
+T = 26
+CASES = ["lru_small", "lru_skew"]
+
+
+def _load(golden_dir, name):
+    with np.load(os.path.join(golden_dir, name + ".npz")) as z:
+        g = {k: z[k] for k in z.files}
+    return g, np.unpackbits(g["hits"], axis=1)[:, :T].astype(bool)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_seq_lru_equals_reference(golden_dir, name):
+    """Hit vector and eviction order of every request, final recency order: bit-exact."""
+    g, hits = _load(golden_dir, name)
+    o = SeqLRU(int(g["cap"]))
+    for i, req in enumerate(g["trace"]):
+        assert o.request(req) == list(hits[i]), f"hit vector, request {i}"
+        assert o.evicted == list(g["ev_keys"][g["ev_off"][i]:g["ev_off"][i + 1]]), f"evictions, request {i}"
+    assert o.state() == list(g["state_keys"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_batch_lru_at_b1_equals_sequential(golden_dir, name):
+    """From the same pre-state one sample through the batch policy gives the sequential policy's hits,
+    victims and recency order, on every request that does not take the same-request corner."""
+    g, _ = _load(golden_dir, name)
+    o = SeqLRU(int(g["cap"]))
+    corners = 0
+    for i, req in enumerate(g["trace"]):
+        p = BatchLRU(o.cap)
+        p.entries = OrderedDict((k, None) for k in o.od)
+        h = o.request(req)
+        ph, _st, _sr, _agg = p.lookup_batch(np.asarray(req).reshape(T, 1))
+        if o.corner:
+            corners += 1
+            continue
+        assert list(ph[0]) == h, i
+        assert p.evicted == o.evicted, i
+        assert p.state()[0] == o.state(), i
+    assert corners < len(g["trace"]) // 3
+
+
+def test_batch_lru_duplicates_capacity_and_protection():
+    rng = np.random.default_rng(1)
+    p = BatchLRU(48, n_tables=4)
+    for _ in range(60):
+        idx = rng.integers(0, 60, size=(4, 40))
+        idx[:, 1] = idx[:, 0]
+        hit, _st, _sr, _agg = p.lookup_batch(idx)
+        assert len(p.entries) <= 48 and len(set(p.inserted)) == len(p.inserted)
+        assert (hit[0] == hit[1]).all()
+        if p.inserted:
+            assert p.inserted[-1] in p.entries          # the last insert survives (LRU.py evicts before it inserts)
+    # a batch with more new keys than the cache holds keeps the most recent ones
+    p = BatchLRU(8, n_tables=1)
+    p.lookup_batch(np.arange(100, 130).reshape(1, 30))
+    assert p.state()[0] == list(range(100 + 22, 130))
