@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--prop", default="", help='SIZE_PROPORTION "c1-c2-c3" (3 layers)')
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1 only: exchange fused into the kernels over NVLink peer memory, or NCCL all-reduce + all-to-all")
+    ap.add_argument("--policy", default="evlfu", choices=["evlfu", "lru"],
+                    help="replacement policy: evlfu = the reference's EvLFU (BASELINE configs), lru = its comparison policy cache_algo/LRU.py (1 layer)")
     ap.add_argument("--shape", default="kaggle", choices=["kaggle", "terabyte"], help="N > 1 only: table shape of the sharded run")
     return ap.parse_args()
 
@@ -255,7 +257,7 @@ def main_ours(args):
     # takes cache_rows * prec / 32 of them; the multi-layer configs get the same memory budget as configs[1]
     total_size = cache_rows * prec // 32 if layers == 1 else cache_rows
     cfg = pkg.CacheConfig(n_layers=layers, main_precision=prec, secondary_precision=sec, size_proportion=args.prop,
-                          total_size=total_size, max_batch=B, device=local_rank, store_in_hbm=args.store_in_hbm)
+                          total_size=total_size, max_batch=B, device=local_rank, store_in_hbm=args.store_in_hbm, policy=args.policy)
     alt = pkg.workload.make_alt_keys(rows) if layers == 3 else None
     t0 = time.time()
     stores = None
@@ -397,7 +399,7 @@ def main_ours(args):
 
     # ---- CPU baseline: the reference's own library on this host -------------------------------
     cpu = None
-    if not args.no_cpu_baseline and args.scale == 1.0 and dim == 16 and prec == 32 and layers == 1:
+    if not args.no_cpu_baseline and args.scale == 1.0 and dim == 16 and prec == 32 and layers == 1 and args.policy == "evlfu":
         try:
             from oracle import ref_driver
             variant = "bench_c1_fp32_d16"
@@ -422,12 +424,12 @@ def main_ours(args):
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if prec == 32 else f"u{prec}->f32", "data": "synthetic",
         "samples_per_s": value / T, "hit_rate": hit_rate, "hit_rate_by_tier": tier_rates, "perfect_hit_rate": perfect_rate,
-        "config": {"workload": ("configs[1]: C1 EvLFU fp%d tier" % prec if layers == 1 else
+        "config": {"workload": ("configs[1]: C1 %s fp%d tier" % ("EvLFU" if args.policy == "evlfu" else "LRU (cache_algo/LRU.py, comparison policy)", prec) if layers == 1 else
                                 "configs[%d]: C1 %d-bit + C2 %d-bit%s, TOTAL_SIZE %d fp32-row units%s" % (
                                     layers, prec, sec, " + C3" if layers == 3 else "", total_size, (" split " + args.prop) if args.prop else ""))
                                + ", Kaggle-shape 26 tables (%.2fM rows), dim %d, Zipf(1.05), batch %d, cache %d rows, "
                                  "host-pinned backing store" % (sum(rows) / 1e6, dim, B, cache_rows),
-                   "layers": layers, "secondary_precision": sec,
+                   "layers": layers, "secondary_precision": sec, "policy": args.policy,
                    "batch": B, "dim": dim, "precision": prec, "cache_rows": cache_rows, "cache_fill": fill,
                    "cache_warm_batches": warm,
                    "l2": "no flush: index+slab working set (%.2f GB) exceeds the 126 MB L2 and every step reads a distinct index batch"

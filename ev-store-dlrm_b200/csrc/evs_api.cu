@@ -381,7 +381,7 @@ static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const Batc
     { LaunchScope ls(pf, K_EVICT, st); EVS_CUDA(launch(k_evict, dim3(h->evict_ctas, h->n_tiers), kEvictThreads, 0, st, p)); }
     {
         LaunchScope ls(pf, K_FETCH, h->side);
-        if (p.fetch_mode != 0) EVS_CUDA(launch(ks.fetch_list, h->fetch_list_ctas, 256, fetch_smem(h), h->side, p));
+        if (p.fetch_mode != 0) EVS_CUDA(launch(ks.fetch_list, h->fetch_list_ctas, h->fetch_list_threads, fetch_smem(h), h->side, p));
         else EVS_CUDA(launch(ks.fetch, side_grid(h, n_chunks), 256, fetch_smem(h), h->side, p));
     }
     EVS_CUDA(cudaEventRecord(h->ev_filled, h->side));
@@ -598,6 +598,8 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         P.evict_mode = (em && em[0] == '0') ? 0 : 1;
         const char *fm = getenv("EVSTORE_B200_FETCH_MODE");        // tuning aid: 0 = k_fetch scans the flags (all misses issue at once)
         P.fetch_mode = (fm && fm[0] == '0') ? 0 : 1;
+        const char *ft = getenv("EVSTORE_B200_FETCH_LIST_THREADS"); // tuning aid: threads per CTA of k_fetch_list (32..256)
+        if (ft && atoi(ft) >= 32 && atoi(ft) <= 256) h->fetch_list_threads = atoi(ft) & ~31;
         const char *fc = getenv("EVSTORE_B200_FETCH_LIST_CTAS");   // tuning aid: CTAs of k_fetch_list = PCIe reads kept in flight
         if (fc && atoi(fc) > 0) h->fetch_list_ctas = atoi(fc);
         const char *ec = getenv("EVSTORE_B200_EVICT_CTAS");        // tuning aid: CTAs of k_evict per tier (<= 256)

@@ -107,6 +107,7 @@ struct evs_handle_s {
     cudaGraph_t graph_src = nullptr;
     cudaGraphExec_t graph = nullptr;         // k_serve -> [k_scan ->] k_update -> {k_evict || k_fetch}
     bool use_graph = true;
+    int fetch_list_threads = 256;            // threads per CTA of k_fetch_list
     int fetch_list_ctas = 8;                 // CTAs of k_fetch_list (EVSTORE_B200_FETCH_LIST_CTAS overrides)
     int evict_ctas = evs::kTierCtas;         // CTAs of k_evict per tier (EVSTORE_B200_EVICT_CTAS overrides)
     evs::GlobalCtl *g = nullptr;             // device

@@ -259,20 +259,32 @@ __global__ void __launch_bounds__(256) k_fetch(const __grid_constant__ Params p)
 // miss of the batch issue at once (thousands of warps each finding < 1 miss), and the reads queued beyond what
 // the link takes delay the HBM accesses of k_evict running next to it (12 -> 20 us); with few warps scanning
 // the flags the fetch itself becomes a chain of dependent round trips (profiles/r1_fetch_ctas_*.json).
+// Measured (profiles/r1_fetch_list_ab.md): ~512 rows in flight is the optimum however they are spread over
+// SMs (8 x 256, 16 x 128, 32 x 64, 64 x 32 threads all within 0.5 us); several rows per lane group and round
+// (fewer warps, same reads in flight) is much slower -- one SM does not keep more than a few dozen sysmem
+// reads going.
 template <int P0, int P1>
 __global__ void __launch_bounds__(256) k_fetch_list(const __grid_constant__ Params p) {
     extern __shared__ __align__(16) unsigned char s_stage[];    // warps * max(row_stride); unaligned rows only
     __shared__ CodecLut s_lut;
     codec_lut_init<P0, P1>(&s_lut);
     __syncthreads();
-    const BatchArgs a = *p.args;
+    // the few per-batch arguments this kernel needs, in registers (a by-value copy of BatchArgs would live in
+    // local memory: ShardArgs' pointer arrays are indexed dynamically); peers' buffers are looked up on demand
+    const BatchArgs *ga = p.args;
+    const long long *idx = ga->idx;
+    const int B = ga->B;
+    float *out = ga->out;
+    const long long out_stride = ga->out_stride;
+    const int world = ga->sh.world, Bl = ga->sh.Bl, T_total = ga->sh.T_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
     const int T = p.T, D = p.D;
     const unsigned n = __ldcg(p.miss_ctl);
     const TierDev &t0 = p.tier[0];
     const TierDev &t1 = p.tier[1];
-    const bool vec = out_vec_ok(a, D);
+    const bool vec = (world > 1) ? ((D & 3) == 0)
+                                 : (((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && ((out_stride & 3) == 0) && ((D & 3) == 0));
     const bool al0 = (p.store_aligned & 1) != 0, al1 = (P1 == 0) || (p.store_aligned & 2) != 0;
     // all rows 16-byte aligned: groups of lanes share a row straight through registers; else a warp per row
     int gsize = 32;
@@ -291,10 +303,16 @@ __global__ void __launch_bounds__(256) k_fetch_list(const __grid_constant__ Para
             const unsigned e = __ldcg(p.miss_list + i);
             const int pos = static_cast<int>(e & 0x7FFFFFFFu);
             const int s = pos / T, t = pos - s * T;
-            long long r = __ldg(a.idx + static_cast<size_t>(t) * a.B + s);
+            long long r = __ldg(idx + static_cast<size_t>(t) * B + s);
             if (r < 0 || r >= __ldg(p.rows + t)) r = 0;
             const unsigned sw = __ldcg(p.pos_slot + pos);       // the slot this position claimed in k_update, if it is the claimer
-            float *orow = out_row(a, p, s) + t * D;
+            float *orow;
+            if (world <= 1) {
+                orow = out + static_cast<size_t>(s) * out_stride + t * D;
+            } else {                                            // as out_row(): the owner rank's receive buffer
+                const int dst = s / Bl, ls = s - dst * Bl;
+                orow = ga->sh.recv[dst] + (static_cast<size_t>(ls) * T_total + p.table_base + t) * D;
+            }
             if (P1 == 0 || !(e >> 31)) {
                 unsigned char *dst = (sw & kClaimedBit) ? t0.slab + static_cast<size_t>(sw & ~kClaimedBit) * t0.row_stride : nullptr;
                 fetch_one<P0>(t0, orow, D, t, r, dst, lane, gl, gsize, al0 ? nullptr : stage, vec, &s_lut);
@@ -311,6 +329,7 @@ __global__ void __launch_bounds__(256) k_fetch_list(const __grid_constant__ Para
         if (atomicAdd(p.miss_ctl + 1, 1u) == gridDim.x - 1) {
             p.miss_ctl[0] = 0u;
             p.miss_ctl[1] = 0u;
+            p.dbg[28] += gtime() - p.dbg[4];      // fetch span, counted from the start of the k_evict it runs beside
         }
     }
 }

@@ -73,7 +73,38 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
     __syncthreads();
 
     if (any) {
-        // the claim (a chain of dependent accesses) goes first so that it overlaps the prefix sums
+        // Everything that does not depend on the claim is LOADED first and consumed after it, so that these
+        // round trips run under the claim's chain of dependent accesses (a warp issues in order: loads placed
+        // after the CAS loop would only start when it ends): the per-CTA append counts of the earlier chunks
+        // in my bucket's sequences (k_scan already made them prefixes for very large batches and for packed
+        // warps), the batch's C2 promotion total, the ring tail.
+        const unsigned msk[kSeqGroups] = {m0, m1, m2};
+        const unsigned *h[kSeqGroups];
+#pragma unroll
+        for (int g = 0; g < kSeqGroups; ++g) h[g] = p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max;
+        const bool direct = !(q.L < 32 || n_chunks > kQuadMaxChunks);
+        const int nc = static_cast<int>(blockIdx.x);
+        unsigned base[kSeqGroups] = {0, 0, 0};
+        unsigned x[kSeqGroups][8];
+#pragma unroll
+        for (int g = 0; g < kSeqGroups; ++g) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[g][u] = 0u;
+            if (!msk[g]) continue;
+            if (!direct) {
+                base[g] = __ldcg(h[g] + blockIdx.x);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = u * 32 + lane;
+                    if (c < nc) x[g][u] = __ldcg(h[g] + c);
+                }
+            }
+        }
+        const unsigned tot_p1 = m2 ? __ldcg(p.tot + kMaxBuckets + wb) : 0u;
+        unsigned long long tail_b = 0ull;
+        if (f) tail_b = static_cast<const volatile TierCtl *>(p.tier[tr].ctl)->tail[b];
+
         unsigned slot = 0;
         bool claimed = false;
         if (f & kFlagMiss) {
@@ -85,31 +116,25 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
             slot = p.pos_slot[pos];
         }
 
-        // records of earlier chunks in my bucket's sequences (k_scan already made them prefixes for
-        // very large batches and for packed warps), then of earlier samples of this chunk
-        unsigned base[kSeqGroups] = {0, 0, 0};
-        const unsigned msk[kSeqGroups] = {m0, m1, m2};
-        const unsigned *h[kSeqGroups];
+        if (direct) {
+            unsigned acc[kSeqGroups];
 #pragma unroll
-        for (int g = 0; g < kSeqGroups; ++g) h[g] = p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max;
-        if (q.L < 32 || n_chunks > kQuadMaxChunks) {
+            for (int g = 0; g < kSeqGroups; ++g) {
+                acc[g] = 0u;
 #pragma unroll
-            for (int g = 0; g < kSeqGroups; ++g)
-                if (msk[g]) base[g] = __ldcg(h[g] + blockIdx.x);
-        } else {
-            unsigned acc[kSeqGroups] = {0, 0, 0};
-            const int nc = static_cast<int>(blockIdx.x);
-            for (int c0 = 0; c0 < nc; c0 += 128) {             // 4 independent loads per lane, group and round
+                for (int u = 0; u < 8; ++u) acc[g] += x[g][u];
+            }
+            for (int c0 = 256; c0 < nc; c0 += 128) {           // batches of more than 2048 samples: 4 loads per lane, group and round
 #pragma unroll
                 for (int g = 0; g < kSeqGroups; ++g) {
                     if (!msk[g]) continue;
-                    unsigned x[4] = {0, 0, 0, 0};
+                    unsigned y[4] = {0, 0, 0, 0};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const int c = c0 + u * 32 + lane;
-                        if (c < nc) x[u] = __ldcg(h[g] + c);
+                        if (c < nc) y[u] = __ldcg(h[g] + c);
                     }
-                    acc[g] += x[0] + x[1] + x[2] + x[3];
+                    acc[g] += y[0] + y[1] + y[2] + y[3];
                 }
             }
 #pragma unroll
@@ -119,20 +144,20 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
                 base[g] = acc[g];
             }
         }
+        // records of earlier samples of this chunk
         for (int w = 0; w < j; ++w)
             if (s_b[w] == wb) {
 #pragma unroll
                 for (int g = 0; g < kSeqGroups; ++g) base[g] += s_cnt[w][g];
             }
         // C2 inserts start after ALL of the batch's C2 promotions in this bucket
-        if (m2) base[2] += __ldcg(p.tot + kMaxBuckets + wb);
+        if (m2) base[2] += tot_p1;
 
         if (f) {
             const TierDev &tier = p.tier[tr];
             const unsigned mine_mask = grp == 0 ? m0 : (grp == 1 ? m1 : m2);
             const unsigned rank = __popc(mine_mask & ((1u << lane) - 1u));
-            const volatile TierCtl *c = tier.ctl;
-            const unsigned long long qq = c->tail[b] + (grp == 0 ? base[0] : (grp == 1 ? base[1] : base[2])) + rank;
+            const unsigned long long qq = tail_b + (grp == 0 ? base[0] : (grp == 1 ? base[1] : base[2])) + rank;
             tier.ring[static_cast<size_t>(b) * tier.ring_cap + (qq & (tier.ring_cap - 1))] = slot;
             const unsigned long long mine = pack_meta(b, qq);
             const unsigned long long old = atomicMax(&tier.slots[slot].meta, mine);

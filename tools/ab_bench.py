@@ -85,7 +85,7 @@ def main():
         kt = {nm: round(1e3 * ms / max(1, timed), 2) for nm, (ms, timed, _l) in store.kernel_times(reset=True).items() if timed}
         store.set_profiling(False)
         keys = ("avg_serve", "avg_gap1", "avg_update", "avg_gap2", "avg_evict", "evict_plan", "evict_chunks", "evict_wait_last",
-                "evict_writeback", "evict_chunks_per_batch", "evict_last_chunk_avg", "evict_last_chunk_max")
+                "evict_writeback", "avg_fetch_since_evict_start", "evict_chunks_per_batch", "evict_last_chunk_avg", "evict_last_chunk_max")
         print(json.dumps({"variant": var, "us_per_step": 1e3 * best, "lookups_per_s": B * T / (best * 1e-3),
                           "evictions_per_step": st["evictions"][0] / (a.steps * a.repeat),
                           "phases_us": {k: round(ph[k], 3) for k in keys if k in ph}, "kernel_event_us": kt}), flush=True)
