@@ -382,7 +382,7 @@ def main_ours(args):
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
         if tj.get("batch") == B and tj.get("dim") == dim and tj.get("precision") == prec:
-            traffic = tj["dram_bytes_per_launch"].get(dom)
+            traffic = tj["dram_bytes_per_launch"].get(dom, tj["dram_bytes_per_launch"].get(dom + "_list"))
     except Exception:
         pass
     # the gather kernel the north-star's 50 % target is about: in-kernel %globaltimer span (first CTA start to

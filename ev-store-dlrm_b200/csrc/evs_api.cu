@@ -371,11 +371,11 @@ static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const Batc
     const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
     Profiler &pf = h->prof;
     { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch_serve(ks.serve, n_chunks, st, p, a)); }
-    if (p.n_chunks_max > kQuadMaxChunks || p.L < 32) {
+    if (p.n_chunks_max > p.quad_max || p.L < 32) {
         LaunchScope ls(pf, K_SCAN, st);
         EVS_CUDA(launch(k_scan, (h->n_tiers == 1 ? 1 : kSeqGroups) * h->tier[0].dev.n_buckets, 256, 0, st, p));
     }
-    { LaunchScope ls(pf, K_UPDATE, st); EVS_CUDA(launch(k_update, n_chunks, kLookupThreads, 0, st, p)); }
+    { LaunchScope ls(pf, K_UPDATE, st); EVS_CUDA(launch(h->n_tiers == 1 ? k_update<1, 8> : k_update<kSeqGroups, 4>, n_chunks, kLookupThreads, 0, st, p)); }
     EVS_CUDA(cudaEventRecord(h->ev_updated, st));
     EVS_CUDA(cudaStreamWaitEvent(h->side, h->ev_updated, 0));
     { LaunchScope ls(pf, K_EVICT, st); EVS_CUDA(launch(k_evict, dim3(h->evict_ctas, h->n_tiers), kEvictThreads, 0, st, p)); }
@@ -594,15 +594,44 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     P.high_thres = h->cfg.high_agghit_threshold;
     P.n_chunks_max = n_chunks_max;
     {
-        const char *em = getenv("EVSTORE_B200_EVICT_MODE");        // tuning aid: 0 = ticket-until-stopped chunk loop of k_evict
-        P.evict_mode = (em && em[0] == '0') ? 0 : 1;
         const char *fm = getenv("EVSTORE_B200_FETCH_MODE");        // tuning aid: 0 = k_fetch scans the flags (all misses issue at once)
         P.fetch_mode = (fm && fm[0] == '0') ? 0 : 1;
+        const char *qm = getenv("EVSTORE_B200_QUAD_MAX");          // tuning aid: largest serve grid whose k_update sums its predecessors directly
+        P.quad_max = (qm && atoi(qm) > 0) ? atoi(qm) : kQuadMaxChunks;
+        // Grid of k_fetch_list: ~512 64-byte row reads in flight (32 KB; fewer rows when they are larger), at most 64 rows
+        // per CTA -- measured optimum of profiles/r1_fetch_list_ab.md.  Rows that are 16-byte aligned are shared by
+        // groups of gsize lanes (32 / gsize rows per warp and round), others take a whole warp each.
+        {
+            unsigned stride = h->tier[0].dev.row_stride;
+            bool aligned = true;
+            for (int i = 0; i < h->n_tiers; ++i) {
+                stride = std::max(stride, h->tier[i].dev.row_stride);
+                bool al = (h->tier[i].dev.row_bytes & 15u) == 0;
+                for (const unsigned char *q : h->tier[i].store_dev) al = al && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0);
+                aligned = aligned && al;
+            }
+            int gsize = 32;
+            if (aligned) {
+                gsize = 1;
+                while (gsize < static_cast<int>(stride >> 4) && gsize < 32) gsize <<= 1;
+            }
+            const int rpw = 32 / gsize;
+            const int threads = std::max(32, std::min(256, 64 * gsize));
+            const int rows_per_cta = (threads / 32) * rpw;
+            const int target = static_cast<int>(std::min(512u, std::max(128u, 32768u / stride)));
+            h->fetch_list_threads = threads;
+            h->fetch_list_ctas = std::max(1, (target + rows_per_cta - 1) / rows_per_cta);
+        }
         const char *ft = getenv("EVSTORE_B200_FETCH_LIST_THREADS"); // tuning aid: threads per CTA of k_fetch_list (32..256)
         if (ft && atoi(ft) >= 32 && atoi(ft) <= 256) h->fetch_list_threads = atoi(ft) & ~31;
         const char *fc = getenv("EVSTORE_B200_FETCH_LIST_CTAS");   // tuning aid: CTAs of k_fetch_list = PCIe reads kept in flight
         if (fc && atoi(fc) > 0) h->fetch_list_ctas = atoi(fc);
-        const char *ec = getenv("EVSTORE_B200_EVICT_CTAS");        // tuning aid: CTAs of k_evict per tier (<= 256)
+        // CTAs of k_evict per tier = 256-record chunks of the rings examined at once.  A batch evicts about as many keys
+        // as it misses (a few per cent of its positions) and most records at the ring heads are live, so one chunk per
+        // 2048 positions covers the usual batch several times over (configs[1]: victims complete after 5-7 chunks of 26);
+        // batches that need more take further chunks by ticket.  More CTAs only add DRAM reads (ncu: 8.3 MB -> 1.2 MB).
+        h->evict_ctas = static_cast<int>(std::min<long long>(kTierCtas, std::max<long long>(16, n_max / 2048)));
+        const char *ec = getenv("EVSTORE_B200_EVICT_CTAS");        // tuning aid (<= 256)
         if (ec && atoi(ec) > 0) h->evict_ctas = std::min(atoi(ec), kEvictThreads);
     }
     P.rows = h->d_rows;
@@ -658,7 +687,7 @@ static int run_batch(evs_handle h, const BatchArgs &a, cudaStream_t st) {
         h->prof.launches[K_SERVE]++, h->prof.launches[K_UPDATE]++, h->prof.launches[K_EVICT]++;
         h->prof.launches[K_FETCH]++;
         if (h->sharded) h->prof.launches[K_SIGNAL]++, h->prof.launches[K_WAIT]++;
-        if (h->params.n_chunks_max > kQuadMaxChunks || h->params.L < 32) h->prof.launches[K_SCAN]++;
+        if (h->params.n_chunks_max > h->params.quad_max || h->params.L < 32) h->prof.launches[K_SCAN]++;
     } else {
         int rc = enqueue_batch(h, st, (a.B + h->params.spc - 1) / h->params.spc, a);
         if (rc) return rc;

@@ -21,7 +21,7 @@ namespace evs {
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kEvictThreads = 256;         // small CTAs: they must fit on SMs that k_fetch occupies
 constexpr int kEvictPerThread = 4;           // ring records one thread examines per window
-constexpr int kQuadMaxChunks = 2048;         // above this a k_scan launch replaces the direct prefix sums
+constexpr int kQuadMaxChunks = 512;          // above this a k_scan launch replaces the direct prefix sums (B = 16384: 150 -> 141 us)
 
 __device__ __forceinline__ uint4 ldg16(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 __device__ __forceinline__ unsigned long long gtime() {
@@ -394,7 +394,7 @@ __device__ __forceinline__ void gather_tier(const TierDev &t, int k, int src_t, 
 // of 8*spc contiguous bytes.  P1 == 0: single tier.  The cache state is only read here (C3 recency
 // flags excepted).
 template <int P0, int P1>
-__global__ void __launch_bounds__(kLookupThreads) k_serve(const __grid_constant__ Params p, const __grid_constant__ BatchArgs a) {
+__global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(const __grid_constant__ Params p, const __grid_constant__ BatchArgs a) {
     __shared__ long long s_idx[kLookupThreads];          // [sample in CTA][L]
     __shared__ unsigned s_hist[kSeqs];
     __shared__ unsigned s_stat[8];           // hits C1, hits C2, C3, approx, misses, perfect
@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Params p) 
     __shared__ unsigned s_w[8];
     const int B = p.args->B;
     const int n_chunks = (B + p.spc - 1) / p.spc;
-    if (p.L == 32 && n_chunks <= kQuadMaxChunks) return;          // k_update sums its predecessors directly
+    if (p.L == 32 && n_chunks <= p.quad_max) return;          // k_update sums its predecessors directly
     const int nb = p.tier[0].n_buckets;
     const int grp = blockIdx.x / nb, b = blockIdx.x - grp * nb;
     unsigned *h = p.hist + static_cast<size_t>(grp * kMaxBuckets + b) * p.n_chunks_max;

@@ -178,8 +178,8 @@ struct Params {
     int approx_thres;
     int high_thres;                        // high_agghit_threshold (evlfu_32.hpp:74)
     int n_chunks_max;
+    int quad_max;                          // batches of more serve CTAs than this get their append offsets from k_scan
     int policy;                            // 0 = EvLFU, 1 = LRU (single tier: one recency ring, every hit re-appends)
-    int evict_mode;                        // 1: k_evict CTAs take further chunks only when the victims cannot be complete (default); 0: ticket until stopped
     const long long *rows;                 // [T] cardinalities
     BatchArgs *args;
     GlobalCtl *g;

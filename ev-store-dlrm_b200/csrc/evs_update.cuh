@@ -22,7 +22,10 @@
 
 namespace evs {
 
-__global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant__ Params p) {
+// NG = sequence groups in use: 1 for a single tier (only C1's interleaved sequence exists), kSeqGroups with a C2.
+// XU = rounds of 32 per-CTA counts a lane holds in registers across the claim.
+template <int NG, int XU>
+__global__ void __launch_bounds__(kLookupThreads, NG == 1 ? 5 : 4) k_update(const __grid_constant__ Params p) {
     __shared__ unsigned s_cnt[kLookupThreads][kSeqGroups];      // per sample of the CTA (at most 256 when L = 1)
     __shared__ int s_b[kLookupThreads];
     __shared__ int s_delta[kMaxTiers * kMaxBuckets];
@@ -78,24 +81,27 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
         // after the CAS loop would only start when it ends): the per-CTA append counts of the earlier chunks
         // in my bucket's sequences (k_scan already made them prefixes for very large batches and for packed
         // warps), the batch's C2 promotion total, the ring tail.
-        const unsigned msk[kSeqGroups] = {m0, m1, m2};
-        const unsigned *h[kSeqGroups];
+        const unsigned msk3[kSeqGroups] = {m0, m1, m2};
+        unsigned msk[NG];
 #pragma unroll
-        for (int g = 0; g < kSeqGroups; ++g) h[g] = p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max;
-        const bool direct = !(q.L < 32 || n_chunks > kQuadMaxChunks);
+        for (int g = 0; g < NG; ++g) msk[g] = msk3[g];
+        const unsigned *h[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) h[g] = p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max;
+        const bool direct = !(q.L < 32 || n_chunks > p.quad_max);
         const int nc = static_cast<int>(blockIdx.x);
         unsigned base[kSeqGroups] = {0, 0, 0};
-        unsigned x[kSeqGroups][8];
+        unsigned x[NG][XU];
 #pragma unroll
-        for (int g = 0; g < kSeqGroups; ++g) {
+        for (int g = 0; g < NG; ++g) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) x[g][u] = 0u;
+            for (int u = 0; u < XU; ++u) x[g][u] = 0u;
             if (!msk[g]) continue;
             if (!direct) {
                 base[g] = __ldcg(h[g] + blockIdx.x);
             } else {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < XU; ++u) {
                     const int c = u * 32 + lane;
                     if (c < nc) x[g][u] = __ldcg(h[g] + c);
                 }
@@ -117,16 +123,16 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
         }
 
         if (direct) {
-            unsigned acc[kSeqGroups];
+            unsigned acc[NG];
 #pragma unroll
-            for (int g = 0; g < kSeqGroups; ++g) {
+            for (int g = 0; g < NG; ++g) {
                 acc[g] = 0u;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc[g] += x[g][u];
+                for (int u = 0; u < XU; ++u) acc[g] += x[g][u];
             }
-            for (int c0 = 256; c0 < nc; c0 += 128) {           // batches of more than 2048 samples: 4 loads per lane, group and round
+            for (int c0 = XU * 32; c0 < nc; c0 += 128) {       // the rest: 4 loads per lane, group and round
 #pragma unroll
-                for (int g = 0; g < kSeqGroups; ++g) {
+                for (int g = 0; g < NG; ++g) {
                     if (!msk[g]) continue;
                     unsigned y[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
                 }
             }
 #pragma unroll
-            for (int g = 0; g < kSeqGroups; ++g) {
+            for (int g = 0; g < NG; ++g) {
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) acc[g] += __shfl_xor_sync(kFull, acc[g], d);
                 base[g] = acc[g];
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(kLookupThreads) k_update(const __grid_constant
         for (int w = 0; w < j; ++w)
             if (s_b[w] == wb) {
 #pragma unroll
-                for (int g = 0; g < kSeqGroups; ++g) base[g] += s_cnt[w][g];
+                for (int g = 0; g < NG; ++g) base[g] += s_cnt[w][g];
             }
         // C2 inserts start after ALL of the batch's C2 promotions in this bucket
         if (m2) base[2] += tot_p1;
@@ -380,7 +386,6 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
         const unsigned need = P.need;
         const int n_seg = P.n_seg;
         const unsigned long long total_v = P.seg_off[n_seg];
-        const bool lean = p.evict_mode != 0;
         bool first = true;
         while (true) {
             // the first chunk of a CTA is its block index (no round trip); further ones are handed out
@@ -415,7 +420,7 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
             unsigned total;
             const unsigned idx = block_excl_scan(cand ? 1u : 0u, s_w, &total);
             unsigned before;
-            if (lean && ch < blockDim.x) {
+            if (ch < blockDim.x) {
                 before = lookback_excl_wide(tier.lookback, ch, total, s_w);
             } else {
                 if (warp == 0) {
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
                 __syncthreads();
                 before = s_excl;
             }
-            if (lean && threadIdx.x == 0) {
+            if (threadIdx.x == 0) {
                 // Does this CTA go on to another chunk?  Not when the victims are complete at or before
                 // this chunk, nor when -- at the density seen so far -- the chunks already handed out
                 // reach the last victim with a margin.  The CTA holding the LAST chunk handed out is the
@@ -469,16 +474,9 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
                 if (seg_end) atomicMax(&ctl->scan_end[b], q + 1);
                 const unsigned nt = __popc(__ballot_sync(kFull, takeit));
                 if (lane == 0 && nt) atomicAdd(&s_taken, nt);
-                if (!lean && threadIdx.x == 0 && before + total >= need) {
-                    c->stop = 1u;
-                    atomicAdd(&p.dbg[26], static_cast<unsigned long long>(ch));
-                    atomicMax(&p.dbg[27], static_cast<unsigned long long>(ch));
-                }
             }
-            if (lean) {
-                __syncthreads();
-                if (!s_more) break;
-            }
+            __syncthreads();
+            if (!s_more) break;
         }
     }
 

@@ -147,9 +147,26 @@ def test_pipelined_host_buffer_path():
 
 
 def test_fp32_very_large_batch_scan_path():
-    """More than 2048 serve-CTAs (B > 16384): ring positions come from the k_scan prefix pass."""
+    """More than 512 serve-CTAs (B > 4096): ring positions come from the k_scan prefix pass."""
     t = run_single_tier_parity(SKEW_ROWS, 16, 32, 5000, [17000, 16500, 3], 5)
     assert t["evicted"] > 0
+
+
+def test_fp32_direct_prefix_beyond_the_preloaded_rounds_and_medium_scan_path():
+    """257..512 serve-CTAs: k_update sums its predecessors' counts itself, the first 256 from registers
+    loaded before the claim and the rest in a loop after it; 513+ CTAs: k_scan."""
+    t = run_single_tier_parity(SKEW_ROWS, 16, 32, 5000, [4096, 2049, 3000, 1], 6)
+    assert t["evicted"] > 0
+    t = run_single_tier_parity(SKEW_ROWS, 16, 32, 5000, [4097, 6000, 2], 5)
+    assert t["evicted"] > 0
+
+
+def test_flag_scan_fetch_kernel_still_matches(monkeypatch):
+    """EVSTORE_B200_FETCH_MODE=0 selects the earlier miss fetch (k_fetch scans the flags instead of reading
+    the compact miss list); kept as the A/B baseline of profiles/r1_fetch_list_ab.md."""
+    monkeypatch.setenv("EVSTORE_B200_FETCH_MODE", "0")
+    run_single_tier_parity(SMALL_ROWS, 16, 32, 600, [64, 5], 12)
+    run_single_tier_parity(SMALL_ROWS, 36, 8, 150, [33], 8)
 
 
 @pytest.mark.parametrize("n_tables", [1, 2, 3, 5, 13, 16, 17])
