@@ -15,6 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle.evlfu import BatchEvLFU, SeqEvLFU  # noqa: E402
+from oracle.lru import BatchLRU, SeqLRU  # noqa: E402
 
 
 def main():
@@ -58,6 +59,30 @@ def main():
                 perfect += int((agg == 26).sum())
                 ev += len(o.evicted)
         out.append(f"| batch-granular, B = {B} | {hits / (26 * (n - half)):.4f} | {perfect} | {ev} |")
+        print(out[-1], f"({time.time() - t0:.0f}s)")
+    # the reference's comparison policy (cache_algo/LRU.py) on the same trace
+    t0 = time.time()
+    lru = SeqLRU(cap)
+    hits = perfect = ev = 0
+    for s in range(n):
+        h = lru.request(trace[:, s])
+        if s >= half:
+            hits += sum(h)
+            perfect += int(all(h))
+            ev += len(lru.evicted)
+    out.append(f"| sequential LRU (LRU.py, 1 sample per request) | {hits / (26 * (n - half)):.4f} | {perfect} | {ev} |")
+    print(out[-1], f"({time.time() - t0:.0f}s)")
+    for B in (1, 2048):
+        t0 = time.time()
+        o = BatchLRU(cap)
+        hits = perfect = ev = 0
+        for k in range(0, n, B):
+            h, _st, _sr, agg = o.lookup_batch(trace[:, k:k + B])
+            if k >= half:
+                hits += int(h.sum())
+                perfect += int((agg == 26).sum())
+                ev += len(o.evicted)
+        out.append(f"| batch-granular LRU, B = {B} | {hits / (26 * (n - half)):.4f} | {perfect} | {ev} |")
         print(out[-1], f"({time.time() - t0:.0f}s)")
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     open(os.path.join(ROOT, "profiles", f"{rnd}_hit_rate.md"), "w").write("\n".join(out) + "\n")
