@@ -74,6 +74,13 @@ def _tensor_from_ptr(ptr, shape, device):
     return torch.as_tensor(_DevArray(ptr, shape), device=device)
 
 
+class _ShapeOnly:
+    """Stands in for an fp32 table whose rows are only available quantised / on disk."""
+
+    def __init__(self, rows: int, dim: int):
+        self.shape = (rows, dim)
+
+
 class EvStore:
     def __init__(self, tables_fp32, cfg: CacheConfig, stores: dict | None = None, alt_keys=None):
         """tables_fp32: list of [rows, dim] float32 arrays (the trained embedding tables).
@@ -83,6 +90,17 @@ class EvStore:
         self.handle = C.c_void_p()
         self._owns_handle = True
         _native.check(self.lib.evs_create(C.byref(self._c), C.byref(self.handle)), "evs_create")
+
+    @classmethod
+    def from_raw_stores(cls, rows, dim: int, cfg: CacheConfig, stores: dict, alt_keys=None):
+        """Build the cache over backing rows that already exist in the reference's on-disk layout
+        (``storage_manager.open_model_dir`` / ``load_ev_table_into_emb_stor``): ``stores`` maps every precision
+        the configuration uses to its per-table raw arrays; no fp32 copy of the tables is needed."""
+        need = [cfg.main_precision] + ([cfg.secondary_precision] if cfg.n_layers >= 2 else [])
+        missing = [p for p in need if p not in stores]
+        if missing:
+            raise ValueError(f"stores lacks the rows at {missing} bits")
+        return cls([_ShapeOnly(int(r), int(dim)) for r in rows], cfg, stores=stores, alt_keys=alt_keys)
 
     def _init_config(self, tables_fp32, cfg: CacheConfig, stores=None, alt_keys=None):
         """Marshal the tables and the configuration into an evs_config (kept alive in self._c)."""

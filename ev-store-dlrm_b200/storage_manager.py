@@ -93,6 +93,102 @@ def save_ev_tables(ev_path, precision=None):
         np.ascontiguousarray(a).tofile(os.path.join(d, f"ev-table-{t + 1}.bin"))
 
 
+# ---- alternative keys (C3) ---------------------------------------------------------------------
+def load_alt_keys(alt_path, rows=None):
+    """Read <alt_path>/binary/ev-table-{1..n}.bin: one big-endian uint32 per row,
+    alt_key = alt_row * 100 + alt_table (1-based) -- written by script/convert_altkeys_to_binary.py:27-57
+    (struct.pack('>I')), read by APRX_EV::get_from_file_as_uint (aprx_embedding.cpp:222-250).  Returns per
+    table a host-order uint32 array, the form evs_config.alt_keys takes."""
+    out = []
+    for t in range(n_tables):
+        path = os.path.join(alt_path, BINARY_DIR_NAME, f"ev-table-{t + 1}.bin")
+        if not os.path.exists(path):
+            raise StorageError(f"ERROR: cannot open {path}")
+        if os.path.getsize(path) % 4:
+            raise StorageError(f"{path}: size is not a multiple of 4 bytes")
+        a = np.fromfile(path, dtype=">u4").astype(np.uint32)
+        if rows is not None and len(a) != int(rows[t]):
+            raise StorageError(f"{path}: {len(a)} alternative keys for a table of {int(rows[t])} rows")
+        tab = a % 100
+        if len(a) and (tab.min() < 1 or tab.max() > n_tables):
+            raise StorageError(f"{path}: alternative key with table id outside 1..{n_tables}")
+        out.append(a)
+    return out
+
+
+def save_alt_keys(alt_path, alt_keys):
+    """The inverse: per table uint32 alt keys -> big-endian binary/ev-table-N.bin."""
+    d = os.path.join(alt_path, BINARY_DIR_NAME)
+    os.makedirs(d, exist_ok=True)
+    for t, a in enumerate(alt_keys):
+        np.asarray(a, dtype=">u4").tofile(os.path.join(d, f"ev-table-{t + 1}.bin"))
+
+
+def alt_keys_from_text(lines):
+    """One "<tableId>-<rowId>" per row (the CSV the kNN notebooks emit) -> uint32 alt keys, as
+    convert_altkeys_to_binary (script/convert_altkeys_to_binary.py:41-52) computes them."""
+    out = np.empty(len(lines), dtype=np.uint32)
+    for i, ln in enumerate(lines):
+        t, r = ln.strip().split("-")
+        out[i] = int(t) + 100 * int(r)
+    return out
+
+
+# ---- training_config.txt -------------------------------------------------------------------------
+def read_training_config(file_path):
+    """evstore_utils.read_training_config (evstore_utils.py:43-53): line 0 is a caption, then
+    table_feature_map, nbatches, nbatches_test, ln_emb (table cardinalities), m_den."""
+    import ast
+    with open(file_path) as f:
+        lines = [line.rstrip() for line in f]
+    if len(lines) < 6:
+        raise StorageError(f"{file_path}: expected 6 lines, found {len(lines)}")
+    table_feature_map = ast.literal_eval(lines[1])
+    nbatches = int(lines[2])
+    nbatches_test = int(lines[3])
+    ln_emb = np.array(ast.literal_eval(lines[4]))
+    m_den = int(lines[5])
+    return table_feature_map, nbatches, nbatches_test, ln_emb, m_den
+
+
+def store_training_config(file_path, table_feature_map, nbatches, nbatches_test, ln_emb, m_den):
+    """evstore_utils.store_training_config (evstore_utils.py:31-41), same text."""
+    with open(file_path, "w") as f:
+        f.write("The order of the arguments: table_feature_map, nbatches, nbatches_test, ln_emb, m_den\n")
+        f.write(str(table_feature_map) + "\n")
+        f.write(str(nbatches) + "\n")
+        f.write(str(nbatches_test) + "\n")
+        f.write(str(np.asarray(ln_emb).tolist()) + "\n")
+        f.write(str(m_den) + "\n")
+
+
+def open_model_dir(model_dir, precisions, dim=None, alt_path=None):
+    """Everything the GPU cache needs from the reference's stored model, unchanged on disk:
+    <model_dir>/training_config.txt (cardinalities), <model_dir>/<ev-table[-16|-8|-4]>/binary/ev-table-N.bin per
+    precision (evlfu_32.hpp:61, evlfu_16.hpp, evlfu_8.hpp:58, evlfu_4.hpp:61) and, for three layers, the alt-key
+    directory.  Returns (rows, {precision: [raw tables]}, alt_keys | None) -- pass them to
+    ``EvStore.from_raw_stores``."""
+    global ev_precs, ev_dimension, n_tables
+    cfg = os.path.join(model_dir, "training_config.txt")
+    rows = None
+    if os.path.exists(cfg):
+        rows = [int(x) for x in read_training_config(cfg)[3]]
+        n_tables = len(rows)
+    if dim is not None:
+        ev_dimension = int(dim)
+    stores = {}
+    keep = ev_precs
+    try:
+        for p in precisions:
+            ev_precs = int(p)
+            stores[int(p)] = load_ev_table_into_emb_stor(os.path.join(model_dir, PRECISION_DIRS[int(p)]), rows=rows)
+    finally:
+        ev_precs = keep
+    rows = rows or list(_rows)
+    alt = load_alt_keys(alt_path, rows) if alt_path else None
+    return rows, stores, alt
+
+
 def raw_tables(precision=None):
     p = precision or ev_precs
     if p not in _raw:

@@ -15,6 +15,8 @@ Run in the build container only (needs /root/reference); the outputs
    (script/reduce_precision.py) evaluated on a fixed vector of floats.
 3. ``lru_*.npz``        -- /root/reference/cache_algo/LRU.py (the comparison policy) the same way:
    per request hit vector and evicted keys, plus the final recency order.
+4. ``formats/``         -- files written by the reference's own writers: the big-endian alt-key binary
+   (script/convert_altkeys_to_binary.py) from ``altkeys.txt``, and ``training_config.txt`` (evstore_utils.py).
 """
 import os
 import sys
@@ -227,8 +229,33 @@ def golden_lru():
               "hit rate %.3f" % np.unpackbits(g["hits"], axis=1)[:, :T].mean())
 
 
+def golden_formats():
+    """On-disk formats written by the reference's own code: the alt-key binary
+    (script/convert_altkeys_to_binary.py:27-57) and training_config.txt (evstore_utils.py:31-41)."""
+    out = os.path.join(HERE, "formats")
+    os.makedirs(out, exist_ok=True)
+    rng = np.random.default_rng(123)
+    lines = [f"{int(rng.integers(1, 27))}-{int(rng.integers(0, 10131227))}" for _ in range(200)]
+    lines += ["1-0", "26-10131226", "3-42949671"]            # smallest key, a big row, near the uint32 limit
+    txt = os.path.join(out, "altkeys.txt")
+    with open(txt, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    sys.path.insert(0, os.path.join(REF, "script"))
+    sys.modules.pop("convert_altkeys_to_binary", None)
+    import convert_altkeys_to_binary as cab  # the reference's converter
+    cab.convert_altkeys_to_binary(txt, os.path.join(out, "altkeys.bin"))
+    sys.path.insert(0, REF)
+    import evstore_utils as eu  # the reference's training-config writer
+    ln_emb = np.array([1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27, 14992,
+                       5461306, 10, 5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572])
+    eu.store_training_config(os.path.join(out, "training_config.txt"), {i: i for i in range(26)}, 306969, 3274, ln_emb, 13)
+    print("formats:", os.listdir(out))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["evlfu", "codecs", "lru"]
+    which = sys.argv[1:] or ["evlfu", "codecs", "lru", "formats"]
+    if "formats" in which:
+        golden_formats()
     if "evlfu" in which:
         golden_evlfu()
     if "codecs" in which:

@@ -64,3 +64,53 @@ def test_two_and_three_tier_with_packed_warps(n_tables):
     t = run_tier_parity(rows, 16, 2, 8, 4, 60, [200, 33], 30, check_state_every=3)
     assert t["ev1"] > 0, t
     run_tier_parity(rows, 16, 3, 8, 4, 90, [150], 30, prop="40-40-20", check_state_every=3)
+
+
+def test_three_tier_cache_over_a_stored_model_directory(tmp_path):
+    """The reference's stored model, unchanged on disk (ev-table-8/binary, ev-table-4/binary, training_config.txt,
+    alt-key binaries) -> storage_manager.open_model_dir -> EvStore.from_raw_stores:
+    same streams and rows as the oracle, without an fp32 copy of the tables."""
+    import numpy as np
+    import torch
+    from helpers import decoded_tables, pkg
+    from oracle import tiers as otiers
+    p = pkg()
+    sm = p.storage_manager
+    rows, dim = SMALL_ROWS, 36
+    tables = p.workload.make_tables(rows, dim)
+    alt = p.workload.make_alt_keys(rows)
+    sm.ev_dimension, sm.n_tables = dim, 26
+    try:
+        for prec in (8, 4):
+            sm.load_tables(tables, precisions=(prec,))
+            sm.save_ev_tables(str(tmp_path / sm.PRECISION_DIRS[prec]), prec)
+        sm.store_training_config(str(tmp_path / "training_config.txt"), {i: i for i in range(26)}, 1, 1, np.array(rows), 13)
+        sm.save_alt_keys(str(tmp_path / "alt"), alt)
+        sm.close_any_db_conn()
+        rows_back, stores, alt_back = sm.open_model_dir(str(tmp_path), (8, 4), dim=dim, alt_path=str(tmp_path / "alt"))
+    finally:
+        sm.ev_precs, sm.ev_dimension, sm.n_tables = 32, 36, 26
+    total, prop, B = 150, "45-45-10", 48
+    cfg = p.CacheConfig(n_layers=3, main_precision=8, secondary_precision=4, total_size=total, size_proportion=prop,
+                        max_batch=B, record_events=True)
+    store = p.EvStore.from_raw_stores(rows_back, dim, cfg, stores, alt_keys=alt_back)
+    caps = otiers.capacities(3, 8, 4, total, prop, dim)
+    oracle = otiers.BatchTiers(caps, n_layers=3, T=26, alt_keys=alt)
+    dec = [decoded_tables(tables, 8), decoded_tables(tables, 4)]
+    trace = p.workload.ZipfTrace(rows, seed=21)
+    c3 = 0
+    try:
+        for it in range(40):
+            idx = trace.batch(B)
+            o, h = store.lookup(torch.from_numpy(idx).cuda())
+            torch.cuda.synchronize()
+            code, val_tier, st, sr, _agg = oracle.lookup_batch(idx)
+            assert (h.cpu().numpy() == code).all(), it
+            assert (o.cpu().numpy() == otiers.gather_tier_rows(dec, val_tier, st, sr)).all(), it
+            for ti, ot in ((0, oracle.c1), (1, oracle.c2)):
+                ev, _fl = store.last_events(ti)
+                assert ev.tolist() == ot.evicted, (it, ti)
+            c3 += int((code == 3).sum())
+        assert c3 > 0
+    finally:
+        store.close()

@@ -79,3 +79,70 @@ def test_table_split_matches_extend_distributed():
             got += list(range(26))[sl]
             assert sl.stop - sl.start == s.get_split_lengths(26, size)[r]
         assert got == list(range(26))
+
+
+# ---- on-disk formats of the reference --------------------------------
+def test_alt_key_file_format_equals_reference_writer(tmp_path, golden_dir):
+    """tests/golden/formats/altkeys.bin was written by the reference's convert_altkeys_to_binary from altkeys.txt
+    (tests/golden/make_golden.py formats): our text -> key conversion, writer and reader agree with it byte for byte."""
+    sm = pkg().storage_manager
+    fdir = os.path.join(golden_dir, "formats")
+    lines = open(os.path.join(fdir, "altkeys.txt")).read().split()
+    keys = sm.alt_keys_from_text(lines)
+    want = open(os.path.join(fdir, "altkeys.bin"), "rb").read()
+    assert np.asarray(keys, dtype=">u4").tobytes() == want
+    sm.n_tables = 1
+    try:
+        sm.save_alt_keys(str(tmp_path), [keys])
+        assert open(tmp_path / "binary" / "ev-table-1.bin", "rb").read() == want
+        sm.n_tables = 26                                        # the file only holds table 1 of 26
+        with pytest.raises(sm.StorageError):
+            sm.load_alt_keys(str(tmp_path))
+        sm.n_tables = 1
+        with pytest.raises(sm.StorageError):                    # table ids reach 26 > n_tables = 1
+            sm.load_alt_keys(str(tmp_path))
+        (back,) = [np.fromfile(tmp_path / "binary" / "ev-table-1.bin", dtype=">u4").astype(np.uint32)]
+        assert np.array_equal(back, keys) and back.dtype == np.uint32
+        assert int(back[-1]) // 100 == 42949671 and int(back[-1]) % 100 == 3       # alt_row*100 + alt_table
+    finally:
+        sm.n_tables = 26
+
+
+def test_training_config_reader_reads_the_reference_file(tmp_path, golden_dir):
+    sm = pkg().storage_manager
+    path = os.path.join(golden_dir, "formats", "training_config.txt")
+    tfm, nb, nbt, ln_emb, m_den = sm.read_training_config(path)
+    assert (nb, nbt, m_den) == (306969, 3274, 13) and tfm[25] == 25
+    assert ln_emb.tolist() == pkg().workload.KAGGLE_ROWS
+    sm.store_training_config(str(tmp_path / "training_config.txt"), tfm, nb, nbt, ln_emb, m_den)
+    assert open(tmp_path / "training_config.txt").read() == open(path).read()
+
+
+def test_open_model_dir_reads_every_precision_and_the_alt_keys(tmp_path):
+    """A stored model laid out like the reference's (ev-table-8/binary, ev-table-4/binary, training_config.txt,
+    alt-key binaries) comes back as the raw stores evs_config takes."""
+    p = pkg()
+    sm = p.storage_manager
+    tables = p.workload.make_tables(SMALL_ROWS, 36)
+    alt = p.workload.make_alt_keys(SMALL_ROWS)
+    sm.ev_dimension, sm.n_tables = 36, 26
+    try:
+        for prec in (8, 4):
+            sm.load_tables(tables, precisions=(prec,))
+            sm.save_ev_tables(str(tmp_path / sm.PRECISION_DIRS[prec]), prec)
+        sm.store_training_config(str(tmp_path / "training_config.txt"), {i: i for i in range(26)}, 10, 2, np.array(SMALL_ROWS), 13)
+        sm.save_alt_keys(str(tmp_path / "alt"), alt)
+        rows, stores, alt_back = sm.open_model_dir(str(tmp_path), (8, 4), dim=36, alt_path=str(tmp_path / "alt"))
+        assert rows == SMALL_ROWS and sorted(stores) == [4, 8]
+        assert np.array_equal(stores[8][3], ocodecs.quantize_table(tables[3], 8))
+        assert np.array_equal(stores[4][11], ocodecs.quantize_table(tables[11], 4))
+        assert all(np.array_equal(a, b) for a, b in zip(alt, alt_back))
+        # a cardinality that disagrees with the file sizes is an error, not a silent truncation
+        bad = list(SMALL_ROWS)
+        bad[0] += 1
+        sm.store_training_config(str(tmp_path / "training_config.txt"), {}, 10, 2, np.array(bad), 13)
+        with pytest.raises(sm.StorageError):
+            sm.open_model_dir(str(tmp_path), (8,), dim=36)
+    finally:
+        sm.ev_precs, sm.ev_dimension, sm.n_tables = 32, 36, 26
+        sm.close_any_db_conn()
