@@ -63,7 +63,10 @@ def parse_args():
                     help="N > 1 only: exchange fused into the kernels over NVLink peer memory, or NCCL all-reduce + all-to-all")
     ap.add_argument("--policy", default="evlfu", choices=["evlfu", "lru"],
                     help="replacement policy: evlfu = the reference's EvLFU (BASELINE configs), lru = its comparison policy cache_algo/LRU.py (1 layer)")
-    ap.add_argument("--shape", default="kaggle", choices=["kaggle", "terabyte"], help="N > 1 only: table shape of the sharded run")
+    ap.add_argument("--shape", default="kaggle", choices=["kaggle", "terabyte"],
+                    help="table shape: kaggle (configs[1-3]) or terabyte (configs[4]: dim 64, cardinalities capped at 40 M); N = 1 with "
+                         "terabyte needs --table-slice (one rank's tables fit one host, all 48 GB of them do not)")
+    ap.add_argument("--table-slice", default="", help="N = 1 only: serve tables a:b of the shape, e.g. 0:4 = what rank 0 of an 8-GPU run owns")
     return ap.parse_args()
 
 
@@ -244,9 +247,17 @@ def main_ours(args):
     prec = args.precision
     K, W = args.steps, max(args.warmup, 3)
     pkg = importlib.import_module("ev-store-dlrm_b200")
-    rows = pkg.workload.KAGGLE_ROWS if args.scale == 1.0 else pkg.workload.scaled_rows(pkg.workload.KAGGLE_ROWS, args.scale)
+    shape_rows = pkg.workload.TERABYTE_ROWS if args.shape == "terabyte" else pkg.workload.KAGGLE_ROWS
+    rows = shape_rows if args.scale == 1.0 else pkg.workload.scaled_rows(shape_rows, args.scale)
+    sliced = bool(args.table_slice)
+    if sliced:
+        a_, b_ = (int(x) for x in args.table_slice.split(":"))
+        rows = rows[a_:b_]
+    if args.shape == "terabyte":
+        dim = args.dim or 64
+        assert sliced or args.scale < 1.0, "the whole Terabyte shape is 48 GB of host memory: pass --table-slice a:b (one rank's tables)"
     T = len(rows)
-    cache_rows = pkg.workload.KAGGLE_CACHE_ROWS if args.scale == 1.0 else int(sum(rows) * 0.13)
+    cache_rows = pkg.workload.KAGGLE_CACHE_ROWS if (args.scale == 1.0 and args.shape == "kaggle" and not sliced) else int(sum(rows) * 0.13)
     warm = args.cache_warm if args.cache_warm >= 0 else 4800
     n_batches = warm + 4 * (W + K)
     _, tables, idx = build_workload(args, n_batches, rows, dim, B)
@@ -411,7 +422,8 @@ def main_ours(args):
 
     # ---- CPU baseline: the reference's own library on this host -------------------------------
     cpu = None
-    if not args.no_cpu_baseline and args.scale == 1.0 and dim == 16 and prec == 32 and layers == 1 and args.policy == "evlfu":
+    if (not args.no_cpu_baseline and args.scale == 1.0 and dim == 16 and prec == 32 and layers == 1 and args.policy == "evlfu"
+            and args.shape == "kaggle" and not sliced):
         try:
             from oracle import ref_driver
             variant = "bench_c1_fp32_d16"
@@ -439,8 +451,11 @@ def main_ours(args):
         "config": {"workload": ("configs[1]: C1 %s fp%d tier" % ("EvLFU" if args.policy == "evlfu" else "LRU (cache_algo/LRU.py, comparison policy)", prec) if layers == 1 else
                                 "configs[%d]: C1 %d-bit + C2 %d-bit%s, TOTAL_SIZE %d fp32-row units%s" % (
                                     layers, prec, sec, " + C3" if layers == 3 else "", total_size, (" split " + args.prop) if args.prop else ""))
-                               + ", Kaggle-shape 26 tables (%.2fM rows), dim %d, Zipf(1.05), batch %d, cache %d rows, "
-                                 "host-pinned backing store" % (sum(rows) / 1e6, dim, B, cache_rows),
+                               + ", %s %d tables (%.2fM rows), dim %d, Zipf(1.05), batch %d, cache %d rows, "
+                                 "host-pinned backing store" % (
+                                     ("Kaggle-shape" if args.shape == "kaggle" else "Terabyte-shape (configs[4])")
+                                     + ((" tables %s only (one rank's shard, local agg_hit)," % args.table_slice) if sliced else ""),
+                                     T, sum(rows) / 1e6, dim, B, cache_rows),
                    "layers": layers, "secondary_precision": sec, "policy": args.policy,
                    "batch": B, "dim": dim, "precision": prec, "cache_rows": cache_rows, "cache_fill": fill,
                    "cache_warm_batches": warm,
