@@ -8,8 +8,11 @@ Differences from the reference, on purpose:
   its drivers force --test-mini-batch-size=1); here the whole ``lS_i [n_tables, B]`` batch is
   served in one call and every returned tensor is ``[B, dim]`` (a view of one ``[B, n_tables, dim]``
   buffer) instead of ``[1, dim]``;
-* ``cache_algo`` selects between the GPU cache ("cpp_algo", "evlfu", "lfu" -- the reference's
-  EvLFU branch is keyed "lfu", :249) and nothing else; LRU / LFU are out of scope.
+* ``cache_algo`` names the policy of the GPU cache: "cpp_algo", "evlfu" and "lfu" (the reference's
+  EvLFU_C1 branch is keyed "lfu", :249) need an EvStore built with ``policy="evlfu"``, "lru" (:251,
+  cache_algo/LRU.py) one built with ``policy="lru"``; the policy is a property of the cache, so a mismatch
+  raises instead of silently serving another policy.  The plain LFU of cache_algo/LFU.py (unreachable in
+  the reference too: its ``elif cache_algo == "lfu"`` at :253 is shadowed by :249) is not available.
 """
 from __future__ import annotations
 
@@ -44,8 +47,11 @@ def apply_emb_evstore(lS_o, lS_i, emb_l=None, v_W_l=None, use_gpu=True, use_emb_
         raise RuntimeError("apply_emb_evstore runs on the GPU cache: pass CUDA indices (there is no CPU fallback)")
     lS_i = lS_i.contiguous()
     if use_emb_cache:
-        if cache_algo not in ("cpp_algo", "evlfu", "lfu"):
+        if cache_algo not in ("cpp_algo", "evlfu", "lfu", "lru"):
             raise ValueError("ERROR: This algorithm is not yet supported! " + str(cache_algo))
+        want = "lru" if cache_algo == "lru" else "evlfu"
+        if st.cfg.policy != want:
+            raise ValueError(f"cache_algo {cache_algo!r} needs an EvStore with policy={want!r}; this one has policy={st.cfg.policy!r}")
         if approx_emb_threshold > 0 and st.cfg.approx_emb_thres != approx_emb_threshold:
             raise ValueError("approx_emb_threshold is a property of the cache: set CacheConfig.approx_emb_thres")
         buf, last_hit = st.lookup(lS_i, out=out)
@@ -103,3 +109,67 @@ def interact_features(x, ly, out=None, stream=None):
     st = _stream_handle(stream, x.device)
     _native.check(lib.evs_interact(x.contiguous().data_ptr(), lyt.data_ptr(), out.data_ptr(), B, n_f, d, st), "evs_interact")
     return out
+
+
+class DLRMInference:
+    """The inference half of ``DLRM_Net`` around the cache: ``sequential_forward``
+    (dlrm_s_pytorch_C1_C2_C3.py:742-768) = bottom MLP -> apply_emb -> interact_features -> top MLP ->
+    optional clamp, with ``apply_mlp`` / ``create_mlp`` semantics (:117-119, 207-245: Linear + ReLU, a
+    Sigmoid after layer ``sigmoid_layer``).  The MLPs are plain library GEMMs (``F.linear`` -> cuBLAS, fp32,
+    TF32 off); the lookup and the interaction are this package's kernels.  The bottom MLP does not depend
+    on the lookup, so it runs on a side stream next to it.
+
+    bot / top: lists of (weight [out, in], bias [out]) -- ``nn.Linear`` parameters as numpy arrays or tensors.
+    """
+
+    def __init__(self, bot, top, store: EvStore, sigmoid_bot: int = -1, sigmoid_top: int | None = None,
+                 loss_threshold: float = 0.0, use_emb_cache: bool = True):
+        import torch
+        self.store = store
+        self.device = torch.device("cuda", store.cfg.device)
+        as_t = lambda a: torch.as_tensor(a, dtype=torch.float32).to(self.device).contiguous()
+        self.bot = [(as_t(w), as_t(b)) for w, b in bot]
+        self.top = [(as_t(w), as_t(b)) for w, b in top]
+        self.sigmoid_bot = sigmoid_bot
+        self.sigmoid_top = len(self.top) - 1 if sigmoid_top is None else sigmoid_top
+        self.loss_threshold = loss_threshold
+        self.use_emb_cache = use_emb_cache
+        self._side = torch.cuda.Stream(device=self.device)
+        d = self.bot[-1][0].shape[0]
+        if d != store.dim:
+            raise ValueError(f"bottom MLP ends in {d} features, the embedding dimension is {store.dim}")
+        n_f = store.n_tables
+        want = d + (n_f + 1) * n_f // 2
+        if self.top[0][0].shape[1] != want:
+            raise ValueError(f"top MLP takes {self.top[0][0].shape[1]} features, the dot interaction produces {want}")
+
+    @staticmethod
+    def apply_mlp(x, layers, sigmoid_layer: int):
+        import torch
+        import torch.nn.functional as F
+        for i, (w, b) in enumerate(layers):
+            x = F.linear(x, w, b)
+            x = torch.sigmoid(x) if i == sigmoid_layer else torch.relu(x)
+        return x
+
+    def sequential_forward(self, dense_x, lS_o, lS_i):
+        """dense_x [B, 13] fp32, lS_i int64 [n_tables, B] (CUDA); lS_o is ignored like in apply_emb_evstore.
+        Returns the click probabilities [B, 1]."""
+        import torch
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            cur = torch.cuda.current_stream(self.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                x = self.apply_mlp(dense_x, self.bot, self.sigmoid_bot)
+            ly = apply_emb_evstore(lS_o, lS_i, use_emb_cache=self.use_emb_cache, store=self.store)
+            cur.wait_stream(self._side)
+            x.record_stream(cur)
+            z = interact_features(x, ly)
+            p = self.apply_mlp(z, self.top, self.sigmoid_top)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        if 0.0 < self.loss_threshold < 1.0:
+            p = torch.clamp(p, min=self.loss_threshold, max=1.0 - self.loss_threshold)
+        return p

@@ -15,6 +15,8 @@ Run in the build container only (needs /root/reference); the outputs
    (script/reduce_precision.py) evaluated on a fixed vector of floats.
 3. ``lru_*.npz``        -- /root/reference/cache_algo/LRU.py (the comparison policy) the same way:
    per request hit vector and evicted keys, plus the final recency order.
+5. ``dlrm_forward.npz`` -- the reference's DLRM_Net (BASELINE configs[0] architecture, small tables) run on the CPU:
+   weights, one input batch, interaction output and click probabilities.
 4. ``formats/``         -- files written by the reference's own writers: the big-endian alt-key binary
    (script/convert_altkeys_to_binary.py) from ``altkeys.txt``, and ``training_config.txt`` (evstore_utils.py).
 """
@@ -252,8 +254,49 @@ def golden_formats():
     print("formats:", os.listdir(out))
 
 
+def golden_dlrm():
+    """BASELINE configs[0]: the reference's DLRM_Net (dlrm_s_pytorch.py:206-613) itself, Kaggle architecture
+    (13 dense, 26 tables, dim 16, bot 13-512-256-64-16, top 367-512-256-1, dot interaction), small random
+    tables, one batch of 128 through sequential_forward on the CPU.  Saved: every weight, the inputs, the
+    click probabilities -- the end-to-end known answer for bottom MLP -> lookup -> interaction -> top MLP."""
+    import torch
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(REF, "script"))
+    import dlrm_s_pytorch as ref  # the reference model
+    np.random.seed(777)
+    torch.manual_seed(777)
+    rows = [50, 7, 400, 300, 9, 4, 60, 12, 3, 120, 30, 350, 40, 5, 45, 280, 4, 33, 21, 4, 390, 6, 5, 90, 11, 70]
+    m_spa, B = 16, 128
+    ln_bot = np.array([13, 512, 256, 64, m_spa])
+    ln_top = np.array([m_spa + 27 * 26 // 2, 512, 256, 1])
+    net = ref.DLRM_Net(m_spa, np.array(rows), ln_bot, ln_top, arch_interaction_op="dot", arch_interaction_itself=False,
+                       sigmoid_bot=-1, sigmoid_top=ln_top.size - 2, sync_dense_params=True, loss_threshold=0.0, ndevices=-1)
+    net.eval()
+    rng = np.random.default_rng(778)
+    X = torch.from_numpy(rng.random((B, 13), dtype=np.float32))
+    lS_i = torch.from_numpy(np.stack([rng.integers(0, r, size=B) for r in rows]).astype(np.int64))
+    lS_o = torch.arange(B, dtype=torch.int64).repeat(len(rows), 1)
+    with torch.no_grad():
+        Z = net.sequential_forward(X, lS_o, lS_i)
+        x = net.apply_mlp(X, net.bot_l)
+        ly = net.apply_emb(lS_o, lS_i, net.emb_l, net.v_W_l)
+        R = net.interact_features(x, ly)
+    out = dict(rows=np.array(rows), X=X.numpy(), lS_i=lS_i.numpy(), Z=Z.numpy(), R=R.numpy())
+    for k, e in enumerate(net.emb_l):
+        out[f"emb_{k}"] = e.weight.detach().numpy()
+    for name, mlp in (("bot", net.bot_l), ("top", net.top_l)):
+        lin = [l for l in mlp if isinstance(l, torch.nn.Linear)]
+        for i, l in enumerate(lin):
+            out[f"{name}_w{i}"] = l.weight.detach().numpy()
+            out[f"{name}_b{i}"] = l.bias.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "dlrm_forward.npz"), **out)
+    print("dlrm_forward: Z", Z.shape, float(Z.min()), float(Z.max()), "R", R.shape)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["evlfu", "codecs", "lru", "formats"]
+    which = sys.argv[1:] or ["evlfu", "codecs", "lru", "formats", "dlrm"]
+    if "dlrm" in which:
+        golden_dlrm()
     if "formats" in which:
         golden_formats()
     if "evlfu" in which:

@@ -1,0 +1,57 @@
+"""BASELINE configs[0] end to end: the reference's own DLRM_Net (Kaggle architecture, small random tables) was
+run on the CPU by tests/golden/make_golden.py; its weights, one input batch, the interaction output and the
+click probabilities are in tests/golden/dlrm_forward.npz.  ``dlrm_ops.DLRMInference.sequential_forward``
+(bottom MLP on cuBLAS next to the cached lookup, our interaction kernel, top MLP) must reproduce them:
+fp32 rows from the cache are exact copies, so only GEMM summation order differs -- tolerance 2e-6 absolute on
+the probabilities (they lie in 0.29..0.37), 1e-4 / 1e-5 (atol / rtol) on the 367 interaction features."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import pkg
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden(golden_dir):
+    with np.load(os.path.join(golden_dir, "dlrm_forward.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("use_cache,policy", [(True, "evlfu"), (True, "lru"), (False, "evlfu")])
+def test_sequential_forward_equals_reference_model(golden_dir, use_cache, policy):
+    import torch
+    p = pkg()
+    g = _golden(golden_dir)
+    tables = [np.ascontiguousarray(g[f"emb_{k}"]) for k in range(26)]
+    bot = [(g[f"bot_w{i}"], g[f"bot_b{i}"]) for i in range(4)]
+    top = [(g[f"top_w{i}"], g[f"top_b{i}"]) for i in range(3)]
+    store = p.EvStore(tables, p.CacheConfig(total_size=700, max_batch=128, policy=policy))
+    saved = p.dlrm_ops.cache_algo
+    p.dlrm_ops.cache_algo = "lru" if policy == "lru" else "cpp_algo"
+    try:
+        net = p.dlrm_ops.DLRMInference(bot, top, store, use_emb_cache=use_cache)
+        X = torch.from_numpy(g["X"]).cuda()
+        lS_i = torch.from_numpy(g["lS_i"]).cuda()
+        lS_o = torch.arange(128, device="cuda").repeat(26, 1)
+        for attempt in range(3):                       # cold cache, then warm: same answer
+            Z = net.sequential_forward(X, lS_o, lS_i)
+            torch.cuda.synchronize()
+            assert tuple(Z.shape) == (128, 1)
+            assert np.allclose(Z.cpu().numpy(), g["Z"], rtol=0, atol=2e-6), float(np.abs(Z.cpu().numpy() - g["Z"]).max())
+        # the interaction features on their own
+        x = net.apply_mlp(X, net.bot, -1)
+        ly = p.dlrm_ops.apply_emb_evstore(lS_o, lS_i, use_emb_cache=use_cache, store=store)
+        R = p.dlrm_ops.interact_features(x, ly)
+        assert np.allclose(R.cpu().numpy(), g["R"], rtol=1e-5, atol=1e-4)
+        if use_cache:
+            store.sync()
+            s = store.stats()
+            assert s["hits"][0] > 0 and s["misses"] > 0
+        with pytest.raises(ValueError):                  # a cache of the other policy is refused, not silently used
+            p.dlrm_ops.cache_algo = "cpp_algo" if policy == "lru" else "lru"
+            p.dlrm_ops.apply_emb_evstore(lS_o, lS_i, use_emb_cache=True, store=store)
+    finally:
+        p.dlrm_ops.cache_algo = saved
+        store.close()

@@ -146,3 +146,24 @@ def test_open_model_dir_reads_every_precision_and_the_alt_keys(tmp_path):
     finally:
         sm.ev_precs, sm.ev_dimension, sm.n_tables = 32, 36, 26
         sm.close_any_db_conn()
+
+
+def test_dlrm_forward_golden_describes_the_reference_model(golden_dir):
+    """The fixture is self-consistent: recomputing sequential_forward (dlrm_s_pytorch.py:588-613) from the saved
+    weights with plain torch on the CPU gives the saved interaction features and probabilities."""
+    import torch
+    with np.load(os.path.join(golden_dir, "dlrm_forward.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    X = torch.from_numpy(g["X"])
+    mlp = lambda x, name, n, sig: [x := (torch.sigmoid if i == sig else torch.relu)(
+        torch.nn.functional.linear(x, torch.from_numpy(g[f"{name}_w{i}"]), torch.from_numpy(g[f"{name}_b{i}"]))) for i in range(n)][-1]
+    x = mlp(X, "bot", 4, -1)
+    ly = [torch.from_numpy(g[f"emb_{k}"][g["lS_i"][k]]) for k in range(26)]
+    T = torch.cat([x.unsqueeze(1), torch.stack(ly, dim=1)], dim=1)
+    Zm = torch.bmm(T, T.transpose(1, 2))
+    li = torch.tensor([i for i in range(27) for j in range(i)])
+    lj = torch.tensor([j for i in range(27) for j in range(i)])
+    R = torch.cat([x, Zm[:, li, lj]], dim=1)
+    assert torch.allclose(R, torch.from_numpy(g["R"]), rtol=1e-5, atol=1e-6)
+    Z = mlp(R, "top", 3, 2)
+    assert torch.allclose(Z, torch.from_numpy(g["Z"]), rtol=0, atol=1e-6)
