@@ -139,3 +139,24 @@ def run_tier_parity(rows, dim, layers, main, sec, total, B_list, n_batches, prop
     finally:
         store.close()
     return tot
+
+
+def dlrm_forward_cpu(g, tables):
+    """sequential_forward of the reference's DLRM_Net (dlrm_s_pytorch.py:588-613) restated with plain torch on the
+    CPU over the weights of tests/golden/dlrm_forward.npz and the given embedding tables.  Returns (Z [B,1], R [B,367])."""
+    import torch
+
+    def mlp(x, name, n, sig):
+        for i in range(n):
+            x = torch.nn.functional.linear(x, torch.from_numpy(g[f"{name}_w{i}"]), torch.from_numpy(g[f"{name}_b{i}"]))
+            x = torch.sigmoid(x) if i == sig else torch.relu(x)
+        return x
+
+    x = mlp(torch.from_numpy(g["X"]), "bot", 4, -1)
+    ly = [torch.from_numpy(np.ascontiguousarray(tables[k][g["lS_i"][k]])) for k in range(26)]
+    T = torch.cat([x.unsqueeze(1), torch.stack(ly, dim=1)], dim=1)
+    Zm = torch.bmm(T, T.transpose(1, 2))
+    li = torch.tensor([i for i in range(27) for j in range(i)])
+    lj = torch.tensor([j for i in range(27) for j in range(i)])
+    R = torch.cat([x, Zm[:, li, lj]], dim=1)
+    return mlp(R, "top", 3, 2).numpy(), R.numpy()

@@ -55,3 +55,40 @@ def test_sequential_forward_equals_reference_model(golden_dir, use_cache, policy
     finally:
         p.dlrm_ops.cache_algo = saved
         store.close()
+
+
+@pytest.mark.parametrize("prec,tol_row,tol_z", [(16, 1e-3, 2e-5), (8, 4e-3, 2e-3), (4, 0.25, 6e-2)])
+def test_quantised_tier_predictions_within_the_stated_tolerance(golden_dir, prec, tol_row, tol_z):
+    """North-star part two: rows served from a quantised tier and the final CTR predictions stay within a stated
+    tolerance of the fp32 reference model.  The tolerances are the reference codecs' own resolution -- 16-bit:
+    step 2e-5, rows within 1e-3 (the north-star's figure) and probabilities within 2e-5; 8-bit: half a step of
+    2/254 = 3.94e-3 on rows, 2e-3 on probabilities; 4-bit (a 15-entry table, evlfu_4.hpp:46): 0.25 / 6e-2 --
+    and the CUDA path adds nothing to them: it equals the reference's dequantisers bit for bit, so its
+    probabilities equal a CPU forward over the dequantised tables within the GEMM tolerance (2e-6)."""
+    import torch
+    from helpers import dlrm_forward_cpu
+    from oracle import codecs as ocodecs
+    p = pkg()
+    g = _golden(golden_dir)
+    tables = [np.ascontiguousarray(g[f"emb_{k}"]) for k in range(26)]
+    dec = [ocodecs.dequantize_rows(ocodecs.quantize_table(t, prec), prec) for t in tables]
+    Zq, _ = dlrm_forward_cpu(g, dec)
+    bot = [(g[f"bot_w{i}"], g[f"bot_b{i}"]) for i in range(4)]
+    top = [(g[f"top_w{i}"], g[f"top_b{i}"]) for i in range(3)]
+    store = p.EvStore(tables, p.CacheConfig(main_precision=prec, total_size=700 * prec // 32 + 40, max_batch=128))
+    try:
+        net = p.dlrm_ops.DLRMInference(bot, top, store)
+        X = torch.from_numpy(g["X"]).cuda()
+        lS_i = torch.from_numpy(g["lS_i"]).cuda()
+        lS_o = torch.arange(128, device="cuda").repeat(26, 1)
+        for attempt in range(2):
+            Z = net.sequential_forward(X, lS_o, lS_i).cpu().numpy()
+            assert float(np.abs(Z - Zq).max()) <= 2e-6
+            assert float(np.abs(Z - g["Z"]).max()) <= tol_z
+        ly = p.dlrm_ops.apply_emb_evstore(lS_o, lS_i, store=store)
+        for k in range(26):
+            rows = ly[k].cpu().numpy()
+            assert np.array_equal(rows, dec[k][g["lS_i"][k]])                      # the reference's dequantiser, bit for bit
+            assert float(np.abs(rows - tables[k][g["lS_i"][k]]).max()) <= tol_row
+    finally:
+        store.close()

@@ -150,20 +150,17 @@ def test_open_model_dir_reads_every_precision_and_the_alt_keys(tmp_path):
 
 def test_dlrm_forward_golden_describes_the_reference_model(golden_dir):
     """The fixture is self-consistent: recomputing sequential_forward (dlrm_s_pytorch.py:588-613) from the saved
-    weights with plain torch on the CPU gives the saved interaction features and probabilities."""
-    import torch
+    weights with plain torch on the CPU gives the saved interaction features and probabilities; and the stated
+    tolerances of the quantised tiers (tests/test_gpu_dlrm_forward.py) hold for the reference's own codecs."""
+    from helpers import dlrm_forward_cpu
     with np.load(os.path.join(golden_dir, "dlrm_forward.npz")) as z:
         g = {k: z[k] for k in z.files}
-    X = torch.from_numpy(g["X"])
-    mlp = lambda x, name, n, sig: [x := (torch.sigmoid if i == sig else torch.relu)(
-        torch.nn.functional.linear(x, torch.from_numpy(g[f"{name}_w{i}"]), torch.from_numpy(g[f"{name}_b{i}"]))) for i in range(n)][-1]
-    x = mlp(X, "bot", 4, -1)
-    ly = [torch.from_numpy(g[f"emb_{k}"][g["lS_i"][k]]) for k in range(26)]
-    T = torch.cat([x.unsqueeze(1), torch.stack(ly, dim=1)], dim=1)
-    Zm = torch.bmm(T, T.transpose(1, 2))
-    li = torch.tensor([i for i in range(27) for j in range(i)])
-    lj = torch.tensor([j for i in range(27) for j in range(i)])
-    R = torch.cat([x, Zm[:, li, lj]], dim=1)
-    assert torch.allclose(R, torch.from_numpy(g["R"]), rtol=1e-5, atol=1e-6)
-    Z = mlp(R, "top", 3, 2)
-    assert torch.allclose(Z, torch.from_numpy(g["Z"]), rtol=0, atol=1e-6)
+    tables = [g[f"emb_{k}"] for k in range(26)]
+    Z, R = dlrm_forward_cpu(g, tables)
+    assert np.allclose(R, g["R"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(Z, g["Z"], rtol=0, atol=1e-6)
+    for prec, tol_row, tol_z in ((16, 1e-3, 2e-5), (8, 4e-3, 2e-3), (4, 0.25, 6e-2)):
+        dec = [ocodecs.dequantize_rows(ocodecs.quantize_table(t, prec), prec) for t in tables]
+        assert max(float(np.abs(d - t).max()) for d, t in zip(dec, tables)) <= tol_row, prec
+        Zq, _ = dlrm_forward_cpu(g, dec)
+        assert float(np.abs(Zq - g["Z"]).max()) <= tol_z, prec
