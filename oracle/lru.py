@@ -107,3 +107,50 @@ class BatchLRU:
     def state(self):
         """Per-bucket FIFO lists in the layout of the CUDA path's dump: everything lives in bucket 0."""
         return [list(self.entries.keys())] + [[] for _ in range(self.T)]
+
+
+class SeqLFU:
+    """``/root/reference/cache_algo/LFU.py`` restated (the third policy the reference's driver initialises,
+    dlrm_s_pytorch_C1_C2_C3.py:1294): per-frequency FIFO lists ``node_for_freq[f]`` (:9,33-34), ``node_for_key``
+    key -> frequency (:11,31), a lazily maintained ``least_freq`` pointer (:25-28 advances it by ONE when its list
+    empties, :50 resets it to 1 on every insert), eviction = the oldest key of ``node_for_freq[least_freq]``
+    (:40-44).  Sequential only: the frequency lists are unbounded, so this policy has no CUDA counterpart
+    (DESIGN.md section 5); it is here so that hit rates can be reported next to all three of the reference's
+    simulators (tools/hit_rate_compare.py).  Pinned by tests/golden/lfu_*.npz."""
+
+    def __init__(self, capacity: int, n_tables: int = 26):
+        self.cap, self.T = int(capacity), int(n_tables)
+        self.least = 1                                         # :7
+        self.freq: list = [0, OrderedDict()]                   # :16-17 (index 0 unused)
+        self.key: dict[int, int] = {}
+        self.evicted: list[int] = []
+
+    def request(self, row_ids):
+        self.evicted = []
+        hit = []
+        for i, r in enumerate(row_ids):
+            k = make_key(i, r)
+            f = self.key.get(k)
+            if f is not None:                                  # :56-61 -> _update :19-34
+                del self.freq[f][k]
+                if len(self.freq[self.least]) == 0:
+                    self.least += 1
+                self.key[k] = f + 1
+                if f + 1 == len(self.freq):
+                    self.freq.append(OrderedDict())
+                self.freq[f + 1][k] = None
+                hit.append(True)
+            else:                                              # :62-66 -> set :36-50
+                if len(self.key) >= self.cap:
+                    ek, _ = self.freq[self.least].popitem(last=False)
+                    del self.key[ek]
+                    self.evicted.append(ek)
+                self.key[k] = 1
+                self.freq[1][k] = None
+                self.least = 1
+                hit.append(False)
+        return hit
+
+    def state(self):
+        """(least_freq, per-frequency key lists from frequency 1 up)."""
+        return self.least, [list(d.keys()) for d in self.freq[1:]]

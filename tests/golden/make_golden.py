@@ -15,6 +15,8 @@ Run in the build container only (needs /root/reference); the outputs
    (script/reduce_precision.py) evaluated on a fixed vector of floats.
 3. ``lru_*.npz``        -- /root/reference/cache_algo/LRU.py (the comparison policy) the same way:
    per request hit vector and evicted keys, plus the final recency order.
+6. ``lfu_*.npz``        -- /root/reference/cache_algo/LFU.py: per request hit vector and the set of evicted keys,
+   plus the final frequency lists and least_freq.
 5. ``dlrm_forward.npz`` -- the reference's DLRM_Net (BASELINE configs[0] architecture, small tables) run on the CPU:
    weights, one input batch, interaction output and click probabilities.
 4. ``formats/``         -- files written by the reference's own writers: the big-endian alt-key binary
@@ -231,6 +233,53 @@ def golden_lru():
               "hit rate %.3f" % np.unpackbits(g["hits"], axis=1)[:, :T].mean())
 
 
+def run_reference_lfu(trace, cap):
+    """/root/reference/cache_algo/LFU.py driven one request at a time; evictions are read off node_for_key
+    (the keys that disappeared during the request, in the order of the frequency lists they left)."""
+    sm = types.ModuleType("storage_manager")
+    sm.get_val_from_storage = lambda table_id, row_id: [float(table_id - 1), float(row_id)] + [0.5] * (DIM - 2)
+    sys.modules["storage_manager"] = sm
+    sys.path.insert(0, os.path.join(REF, "cache_algo"))
+    sys.modules.pop("LFU", None)
+    import LFU as ref  # noqa: the reference module itself
+
+    ref.init(cap)
+    n = len(trace)
+    hits = np.zeros((n, T), dtype=bool)
+    ev_keys, ev_off = [], [0]
+    for i in range(n):
+        before = list(ref.node_for_key.keys())
+        hit, _embs = ref.request_to_lfu([int(x) for x in trace[i]], False)
+        hits[i] = hit
+        after = ref.node_for_key
+        gone = [k for k in before if k not in after]        # (a key evicted and re-inserted by the same request stays)
+        ev_keys.extend(sorted(str_key_to_int(k) for k in gone))
+        ev_off.append(len(ev_keys))
+    state_keys, state_off = [], [0]
+    for f in range(1, len(ref.node_for_freq)):
+        state_keys.extend(str_key_to_int(k) for k in ref.node_for_freq[f])
+        state_off.append(len(state_keys))
+    return dict(hits=np.packbits(hits, axis=1), ev_keys=np.array(ev_keys, dtype=np.int64), ev_off=np.array(ev_off, dtype=np.int32),
+                state_keys=np.array(state_keys, dtype=np.int64), state_off=np.array(state_off, dtype=np.int32),
+                least_freq=np.int64(ref.least_freq))
+
+
+def golden_lfu():
+    cases = [
+        ("lfu_small", [40 + 13 * t for t in range(T)], 2500, 300, 62),
+        ("lfu_skew", [3, 5, 4000, 2500, 7, 4, 60, 9, 3, 300, 50, 3500, 40, 4, 80, 3000,
+                      5, 45, 30, 4, 3800, 6, 5, 600, 11, 400], 3000, 1500, 63),
+    ]
+    for name, rows, n_req, cap, seed in cases:
+        rng = np.random.default_rng(seed)
+        trace = zipf_trace(rng, rows, n_req)
+        g = run_reference_lfu(trace, cap)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), trace=trace.astype(np.int32),
+                            rows=np.array(rows, dtype=np.int64), cap=np.int64(cap), **g)
+        print(name, "requests", n_req, "evictions", len(g["ev_keys"]),
+              "hit rate %.3f" % np.unpackbits(g["hits"], axis=1)[:, :T].mean(), "max freq", len(g["state_off"]) - 1)
+
+
 def golden_formats():
     """On-disk formats written by the reference's own code: the alt-key binary
     (script/convert_altkeys_to_binary.py:27-57) and training_config.txt (evstore_utils.py:31-41)."""
@@ -294,9 +343,11 @@ def golden_dlrm():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["evlfu", "codecs", "lru", "formats", "dlrm"]
+    which = sys.argv[1:] or ["evlfu", "codecs", "lru", "formats", "dlrm", "lfu"]
     if "dlrm" in which:
         golden_dlrm()
+    if "lfu" in which:
+        golden_lfu()
     if "formats" in which:
         golden_formats()
     if "evlfu" in which:

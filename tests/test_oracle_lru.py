@@ -65,3 +65,21 @@ def test_batch_lru_duplicates_capacity_and_protection():
     p = BatchLRU(8, n_tables=1)
     p.lookup_batch(np.arange(100, 130).reshape(1, 30))
     assert p.state()[0] == list(range(100 + 22, 130))
+
+
+@pytest.mark.parametrize("name", ["lfu_small", "lfu_skew"])
+def test_seq_lfu_equals_reference(golden_dir, name):
+    """cache_algo/LFU.py: hit vector and evicted keys of every request, final frequency lists and least_freq."""
+    from oracle.lru import SeqLFU
+    g, hits = _load(golden_dir, name)
+    o = SeqLFU(int(g["cap"]))
+    for i, req in enumerate(g["trace"]):
+        before = set(o.key)
+        assert o.request(req) == list(hits[i]), f"hit vector, request {i}"
+        # the fixture lists the keys resident before the request that are gone after it (a key inserted and evicted
+        # again by the same request -- LFU evicts among the newest keys -- never shows, nor does one that came back)
+        gone = sorted((set(o.evicted) & before) - set(o.key))
+        assert gone == list(g["ev_keys"][g["ev_off"][i]:g["ev_off"][i + 1]]), f"evictions, request {i}"
+    least, lists = o.state()
+    want = [list(g["state_keys"][g["state_off"][f]:g["state_off"][f + 1]]) for f in range(len(g["state_off"]) - 1)]
+    assert least == int(g["least_freq"]) and lists == want

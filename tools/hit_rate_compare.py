@@ -15,7 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle.evlfu import BatchEvLFU, SeqEvLFU  # noqa: E402
-from oracle.lru import BatchLRU, SeqLRU  # noqa: E402
+from oracle.lru import BatchLRU, SeqLFU, SeqLRU  # noqa: E402
 
 
 def main():
@@ -30,7 +30,7 @@ def main():
     rows = pkg.workload.scaled_rows(pkg.workload.KAGGLE_ROWS, scale)
     cap = int(sum(rows) * 0.13)
     trace = pkg.workload.ZipfTrace(rows, seed=42).batches(1, n)[0]            # [26, n]
-    out = [f"# {rnd}: hit rate, batch-granular EvLFU vs the reference's sequential EvLFU\n",
+    out = [f"# {rnd}: hit rate, batch-granular EvLFU (and LRU) vs the reference's sequential EvLFU_C1.py, LRU.py and LFU.py\n",
            f"Kaggle-shape tables scaled by {scale} ({sum(rows)} rows), cache {cap} rows (13 %), Zipf(1.05), {n} samples; "
            f"the second half of the trace is measured (the first half warms the cache).\n",
            "| policy | per-lookup hit rate | perfect-hit samples | evictions |", "|---|---|---|---|"]
@@ -84,6 +84,18 @@ def main():
                 ev += len(o.evicted)
         out.append(f"| batch-granular LRU, B = {B} | {hits / (26 * (n - half)):.4f} | {perfect} | {ev} |")
         print(out[-1], f"({time.time() - t0:.0f}s)")
+    # and its plain LFU (cache_algo/LFU.py; sequential only, no CUDA counterpart)
+    t0 = time.time()
+    lfu = SeqLFU(cap)
+    hits = perfect = ev = 0
+    for s in range(n):
+        h = lfu.request(trace[:, s])
+        if s >= half:
+            hits += sum(h)
+            perfect += int(all(h))
+            ev += len(lfu.evicted)
+    out.append(f"| sequential LFU (LFU.py, 1 sample per request) | {hits / (26 * (n - half)):.4f} | {perfect} | {ev} |")
+    print(out[-1], f"({time.time() - t0:.0f}s)")
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     open(os.path.join(ROOT, "profiles", f"{rnd}_hit_rate.md"), "w").write("\n".join(out) + "\n")
 
