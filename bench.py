@@ -448,7 +448,8 @@ def main_ours(args):
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if prec == 32 else f"u{prec}->f32", "data": "synthetic",
         "samples_per_s": value / T, "hit_rate": hit_rate, "hit_rate_by_tier": tier_rates, "perfect_hit_rate": perfect_rate,
-        "config": {"workload": ("configs[1]: C1 %s fp%d tier" % ("EvLFU" if args.policy == "evlfu" else "LRU (cache_algo/LRU.py, comparison policy)", prec) if layers == 1 else
+        "config": {"workload": ("%s: C1 %s fp%d tier" % ("configs[1]" if args.shape == "kaggle" else "configs[4], one GPU",
+                                                          "EvLFU" if args.policy == "evlfu" else "LRU (cache_algo/LRU.py, comparison policy)", prec) if layers == 1 else
                                 "configs[%d]: C1 %d-bit + C2 %d-bit%s, TOTAL_SIZE %d fp32-row units%s" % (
                                     layers, prec, sec, " + C3" if layers == 3 else "", total_size, (" split " + args.prop) if args.prop else ""))
                                + ", %s %d tables (%.2fM rows), dim %d, Zipf(1.05), batch %d, cache %d rows, "
