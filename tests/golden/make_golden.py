@@ -280,6 +280,31 @@ def golden_lfu():
               "hit rate %.3f" % np.unpackbits(g["hits"], axis=1)[:, :T].mean(), "max freq", len(g["state_off"]) - 1)
 
 
+def golden_cdf():
+    """calculate_and_write_cdf (dlrm_s_pytorch_C1_C2_C3.py:291-319) executed from the reference file itself (the
+    module cannot be imported: it needs the Cython EvLFU build) on seeded request start times."""
+    import ast
+    import subprocess
+    from pathlib import Path
+    import pandas as pd
+    path = os.path.join(REF, "dlrm_s_pytorch_C1_C2_C3.py")
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "calculate_and_write_cdf")
+    ns = dict(Path=Path, pd=pd, os=os, subprocess=subprocess)
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    rng = np.random.default_rng(321)
+    t = np.concatenate([[100.0], 100.0 + np.cumsum(rng.gamma(2.0, 0.0004, size=5003))])
+    out = os.path.join(HERE, "formats")
+    cwd = os.getcwd()
+    os.chdir("/tmp")                       # the function shells out to ./script/plot_cdf.py; let that fail quietly
+    try:
+        ns["calculate_and_write_cdf"](out, "evlfu_golden", [float(x) for x in t])
+    finally:
+        os.chdir(cwd)
+    np.save(os.path.join(out, "cdf_time_start.npy"), t)
+    print("cdf:", sum(1 for _ in open(os.path.join(out, "evlfu_golden-cdf.csv"))), "lines")
+
+
 def golden_formats():
     """On-disk formats written by the reference's own code: the alt-key binary
     (script/convert_altkeys_to_binary.py:27-57) and training_config.txt (evstore_utils.py:31-41)."""
@@ -343,11 +368,13 @@ def golden_dlrm():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["evlfu", "codecs", "lru", "formats", "dlrm", "lfu"]
+    which = sys.argv[1:] or ["evlfu", "codecs", "lru", "formats", "dlrm", "lfu", "cdf"]
     if "dlrm" in which:
         golden_dlrm()
     if "lfu" in which:
         golden_lfu()
+    if "cdf" in which:
+        golden_cdf()
     if "formats" in which:
         golden_formats()
     if "evlfu" in which:

@@ -164,3 +164,17 @@ def test_dlrm_forward_golden_describes_the_reference_model(golden_dir):
         assert max(float(np.abs(d - t).max()) for d, t in zip(dec, tables)) <= tol_row, prec
         Zq, _ = dlrm_forward_cpu(g, dec)
         assert float(np.abs(Zq - g["Z"]).max()) <= tol_z, prec
+
+
+def test_latency_cdf_file_equals_the_reference_function(tmp_path, golden_dir):
+    """tests/golden/formats/evlfu_golden-cdf.csv was written by the reference's calculate_and_write_cdf
+    (dlrm_s_pytorch_C1_C2_C3.py:291-319, executed from the reference file by make_golden.py cdf) from
+    cdf_time_start.npy; ours writes the same bytes."""
+    p = pkg()
+    t = np.load(os.path.join(golden_dir, "formats", "cdf_time_start.npy"))
+    out = p.evstore_utils.calculate_and_write_cdf(str(tmp_path), "evlfu_golden", [float(x) for x in t])
+    want = open(os.path.join(golden_dir, "formats", "evlfu_golden-cdf.csv")).read()
+    assert open(out).read() == want
+    # fewer requests than CDF points: every latency is kept
+    out = p.evstore_utils.calculate_and_write_cdf(str(tmp_path), "few", [0.0, 0.5, 0.75, 2.0, 9.0])
+    assert open(out).read().splitlines() == ["y,latency_ms", "0.3333333333333333,250.0", "0.6666666666666666,500.0", "1.0,1250.0"]
