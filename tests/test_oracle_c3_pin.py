@@ -64,7 +64,8 @@ def _compare(out, trace, dec, alt, v):
     return st
 
 
-def test_three_layer_sequential_equals_compiled_reference_driven_slowly():
+@pytest.mark.parametrize("seed,alpha,min_c3", [(5, 1.05, 300), (6, 0.8, 100), (7, 1.3, 100)])
+def test_three_layer_sequential_equals_compiled_reference_driven_slowly(seed, alpha, min_c3):
     if not (ref_driver.available(VARIANT) and tiers.shim_available()):
         pytest.skip("oracle/_ref not built (run oracle/build_ref.py where /root/reference exists)")
     p = pkg()
@@ -74,7 +75,7 @@ def test_three_layer_sequential_equals_compiled_reference_driven_slowly():
     dec = {prec: [ocodecs.dequantize_rows(r, prec) for r in raw[prec]] for prec in (8, 4)}
     alt = p.workload.make_alt_keys(SMALL_ROWS)
     ref_driver.write_fixture(VARIANT, raw, alt_keys=alt)
-    tr = p.workload.ZipfTrace(SMALL_ROWS, alpha=1.05, seed=5)
+    tr = p.workload.ZipfTrace(SMALL_ROWS, alpha=alpha, seed=seed)
     n = 4000
     trace = np.ascontiguousarray(tr.batches(1, n)[0].T.astype(np.int32))
     last = None
@@ -91,5 +92,5 @@ def test_three_layer_sequential_equals_compiled_reference_driven_slowly():
     assert st["perfect"] == perfect_ref, (st, perfect_ref)
     # the trace exercised the whole path: evictions fed C3 in groups of 50, C3 evicted (second chance),
     # alternative keys answered from C1, rows came back at C2's precision
-    assert st["evict"] > 2000 and st["c3_evicted"] > 500 and st["c3_c1"] > 300 and st["c2"] > 1000, st
+    assert st["evict"] > 2000 and st["c3_evicted"] > 500 and st["c3_c1"] > min_c3 and st["c2"] > 1000, st
     assert st["stale"] < 400, st

@@ -41,13 +41,13 @@ def _trace(n, seed, alpha=1.05):
     return np.ascontiguousarray(tr.batches(1, n)[0].T.astype(np.int32))        # [n, 26]
 
 
-def _run_pin(variant, fixture_tables, n, seed, alpha=1.05):
+def _run_pin(variant, fixture_tables, n, seed, alpha=1.05, fresh=False):
     if not (ref_driver.available(variant) and tiers.shim_available()):
         pytest.skip("oracle/_ref not built (run oracle/build_ref.py where /root/reference exists)")
     _tables, raw, dec = fixture_tables
     v = VARIANTS[variant]
     ref_driver.write_fixture(variant, {prec: raw[prec] for prec in PRECS})
-    ref = ref_driver.RefCache(variant)
+    ref = ref_driver.RefCache(variant, fresh_copy=fresh)       # fresh: a private, empty instance of the library
     trace = _trace(n, seed, alpha)
     _sec, out = ref.drive(trace, want_out=True)                                 # [n, 26, 36]
     perfect_ref = int(C.c_int.in_dll(ref.lib, "perfectHit").value)
@@ -105,6 +105,16 @@ def test_seq_flush_rule_equals_compiled_reference(fixture_tables):
         pytest.skip("variant not configured")
     r = _run_pin("test_c1_flush_d36", fixture_tables, 6000, seed=8, alpha=2.5)
     assert r["flush"] > 0, r
+
+
+@pytest.mark.parametrize("variant,seed,alpha", [
+    ("test_c2_8_4_small_d36", 21, 0.7), ("test_c2_8_4_small_d36", 22, 1.4), ("test_c2_32_8_small_d36", 23, 0.7),
+    ("test_c2_16_4_small_d36", 24, 1.4), ("test_c1_fp32_d36", 25, 0.7), ("test_c1_8_d36", 26, 1.4)])
+def test_more_traces_on_fresh_library_instances(fixture_tables, variant, seed, alpha):
+    """Other seeds and skews (flatter: more evictions; steeper: more promotions) through private copies of the
+    compiled reference, each starting from an empty cache."""
+    r = _run_pin(variant, fixture_tables, 4000, seed=seed, alpha=alpha, fresh=True)
+    assert r["evict"] > 100 and r["stale"] < 200, r
 
 
 # ---- batch-granular policy vs the sequential restatement ------------------------------------------
