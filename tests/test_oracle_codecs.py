@@ -42,3 +42,34 @@ def test_round_trip_error_bounds():
     d = codecs.dequantize_rows(p, 4)
     assert d.shape == t.shape and set(np.unique(d)).issubset(set(codecs.LUT4.tolist()))
     assert (np.sign(d) == np.sign(np.where(np.abs(t) < 0.00025, np.sign(d), t))).all()
+
+
+def test_product_host_codecs_equal_the_reference_on_the_golden_vector(golden_dir):
+    """ev-store-dlrm_b200/codecs.py (what writes the backing-store rows the GPU decodes) against the reference's own
+    quantisers on the golden vector -- dense range, out-of-range values, bucket edges, signed zeros -- and against the
+    oracle's dequantisers on every code the quantisers can emit."""
+    import importlib
+    import os
+
+    import numpy as np
+    pc = importlib.import_module("ev-store-dlrm_b200").codecs
+    from oracle import codecs as oc
+    with np.load(os.path.join(golden_dir, "codecs.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    x = g["x"].astype(np.float32)
+    n = len(x) - len(x) % 2
+    t = x[:n].reshape(-1, 2)
+    assert np.array_equal(pc.encode_table(t, 16).reshape(-1).astype(np.int64), g["q16"][:n])
+    assert np.array_equal(pc.encode_table(t, 8).reshape(-1).astype(np.int64), g["q8"][:n])
+    packed = pc.encode_table(t, 4).reshape(-1)
+    assert np.array_equal(np.stack([packed >> 4, packed & 15], axis=1).reshape(-1).astype(np.int64), np.minimum(g["q4"][:n], 15))
+    for prec in (16, 8, 4):
+        raw = pc.encode_table(t, prec)
+        assert np.array_equal(raw, oc.quantize_table(t, prec))
+        assert np.array_equal(pc.decode_rows(raw, prec), oc.dequantize_rows(raw, prec))
+    # every 16-bit and 8-bit code, every nibble pair
+    all16 = np.arange(65536, dtype=np.uint16).reshape(-1, 2)
+    assert np.array_equal(pc.decode_rows(all16, 16), oc.dequantize_rows(all16, 16))
+    all8 = np.arange(256, dtype=np.uint8).reshape(-1, 2)
+    assert np.array_equal(pc.decode_rows(all8, 8), oc.dequantize_rows(all8, 8))
+    assert np.array_equal(pc.decode_rows(all8, 4), oc.dequantize_rows(all8, 4))
