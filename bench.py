@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="A/B: do not announce the next index batch (evs_prefetch)")
+    ap.add_argument("--no-b16k", action="store_true", help="skip the batch-16384 roofline leg")
     ap.add_argument("--store-in-hbm", action="store_true", help="debug: backing store copied into HBM (not the BASELINE config)")
     ap.add_argument("--layers", type=int, default=1, help="1 = configs[1] (C1); 2 = configs[2] (C1+C2); 3 = configs[3] (C1+C2+C3, needs 8/4)")
     ap.add_argument("--secondary", type=int, default=0, help="SECONDARY_PRECISION of the C2 tier")
@@ -147,6 +149,39 @@ def build_workload(args, n_batches: int, rows, dim: int, B: int, seed: int = 42)
     return pkg, tables, idx
 
 
+def batches_until_full(idx: np.ndarray, rows, cap: int) -> int:
+    """Number of leading batches of the trace after which more than `cap` distinct keys have been requested, i.e. the
+    cache (any policy: nothing is evicted before it is full) holds `cap` entries.  idx: int64 [n, T, B].  Both arms
+    derive their cache warm-up from this, so they reach the timed region in the same state."""
+    n, T, B = idx.shape
+    new_per_batch = np.zeros(n, dtype=np.int64)
+    for t in range(T):
+        seen = np.zeros(int(rows[t]), dtype=bool)
+        for k0 in range(0, n, 128):
+            flat = idx[k0:k0 + 128, t].ravel()
+            u, first = np.unique(flat, return_index=True)
+            fresh = ~seen[u]
+            np.add.at(new_per_batch, k0 + first[fresh] // B, 1)
+            seen[u[fresh]] = True
+    cum = np.cumsum(new_per_batch)
+    full = int(np.searchsorted(cum, cap, side="left")) + 1
+    return min(full, n)
+
+
+WARM_AFTER_FULL = 300       # batches with evictions running before anything is timed
+WARM_SEARCH = 4800          # batches of the trace examined for the fill point
+
+
+def configs1_config(B: int, dim: int, cache_rows: int, warm: int) -> dict:
+    """The `config` object of BASELINE configs[1]; both arms print exactly this."""
+    return {"workload": "configs[1]: C1 EvLFU fp32 tier, Kaggle-shape 26 tables (33.76M rows), dim %d, Zipf(1.05), batch %d, "
+                        "cache %d rows (13%% of the rows), backing store in host memory" % (dim, B, cache_rows),
+            "batch": B, "dim": dim, "precision": 32, "layers": 1, "policy": "evlfu", "cache_rows": cache_rows,
+            "cache_warm_batches": warm,
+            "cache_warm": "the Zipf trace itself until the cache is full (%d batches, derived from the trace) plus %d batches "
+                          "with evictions running" % (warm - WARM_AFTER_FULL, WARM_AFTER_FULL)}
+
+
 # ------------------------------------------------------------------------------------ reference arm
 def run_cpu_reference(variant, tables_raw, idx, B, warm_batches, timed_batches, budget_s=None):
     """Times the reference's libcachemanager.so (oracle/_ref) through ev_lookup, one sample per
@@ -195,7 +230,6 @@ def main_reference(args):
     if rank != 0:
         return 0
     from oracle import ref_driver
-    from oracle.ref_variants import KAGGLE_CACHE_13PCT
     pkg = importlib.import_module("ev-store-dlrm_b200")
     B = (args.batch or 2048) * max(1, args.gpus)          # the N-GPU arm's global batch (weak scaling)
     dim = args.dim or 16
@@ -204,27 +238,40 @@ def main_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/lib%s.so not built for this config" % variant}))
         return 0
     rows = pkg.workload.KAGGLE_ROWS
-    warm = args.cache_warm if args.cache_warm >= 0 else 600
-    n_batches = warm + args.warmup + args.steps
+    cache_rows = pkg.workload.KAGGLE_CACHE_ROWS
+    W = max(args.warmup, 3)
+    # the same trace, the same warm-up rule and the same `config` as main_ours (N = 1); at N > 1 the reference still runs
+    # unsharded on the host cores, over the N-GPU arm's global batch
+    search = max(8, WARM_SEARCH * 2048 // B)
+    n_batches = search + 4 * (W + args.steps) + 16
     _, tables, idx = build_workload(args, n_batches, rows, dim, B)
-    r = run_cpu_reference(variant, tables, idx, B, warm + args.warmup, args.steps)
+    warm = args.cache_warm if args.cache_warm >= 0 else batches_until_full(idx[:search], rows, cache_rows) + WARM_AFTER_FULL * 2048 // B
+    log(f"reference arm: {warm} warm batches of {B} (cache full after {warm - WARM_AFTER_FULL * 2048 // B}), then {W} + {args.steps}")
+    r = run_cpu_reference(variant, tables, idx, B, warm + W, args.steps)
+    cfg = configs1_config(B, dim, cache_rows, warm) if args.gpus <= 1 else sharded_config(args.gpus, B, dim, warm)
     line = {
         "impl": "reference", "metric": "ev_lookups_per_s", "value": r["lookups_per_s"], "unit": "lookups/s",
-        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": W, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "samples_per_s": r["samples_per_s"],
-        "config": {"workload": "configs[1]: C1 EvLFU fp32, Kaggle-shape 26 tables (33.76M rows), dim 16, Zipf(1.05), batch %d, "
-                               "cache %d rows (13%%)" % (B, KAGGLE_CACHE_13PCT),
-                   "batch": B, "dim": dim, "cache_rows": KAGGLE_CACHE_13PCT, "cache_warm_batches": r["warm_batches"]},
+        "samples_per_s": r["samples_per_s"], "config": cfg,
         "cpu_baseline": {"value": r["lookups_per_s"], "unit": "lookups/s", "cores": 4, "kind": "reference",
-                         "sample": "%d full batches of %d samples after %d warm batches; reference libcachemanager.so "
-                                   "(1 caller + 3 reader threads), tables in /dev/shm" % (r["steps"], B, r["warm_batches"]),
-                         "perfect_hits": r["perfect_hits"], "host_cpus": os.cpu_count()},
+                         "sample": "%d full batches of %d samples after %d warm batches (cache full); the reference's own "
+                                   "libcachemanager.so compiled from its sources (1 caller + 3 reader threads, "
+                                   "N_THD__READ_EVTABLE_32BIT), backing tables as files in /dev/shm" % (r["steps"], B, r["warm_batches"]),
+                         "perfect_hits": r["perfect_hits"], "warm_seconds": r["warm_seconds"], "host_cpus": os.cpu_count()},
         "e2e": {"value": r["lookups_per_s"], "unit": "lookups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def sharded_config(world: int, B: int, dim: int, warm) -> dict:
+    """`config` of the N > 1 line (Kaggle shape, weak scaling); the reference arm prints the same object."""
+    return {"workload": "configs[1] tables sharded table-wise over %d GPUs (weak scaling of the N = 1 line): C1 EvLFU fp32 tier, "
+                        "Kaggle-shape 26 tables (33.76M rows), dim %d, Zipf(1.05), global batch %d = 2048 per GPU, 13%% of the rows "
+                        "cached, backing store in host memory" % (world, dim, B),
+            "batch": B, "dim": dim, "precision": 32, "layers": 1, "policy": "evlfu", "n_gpus": world}
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -258,9 +305,14 @@ def main_ours(args):
         assert sliced or args.scale < 1.0, "the whole Terabyte shape is 48 GB of host memory: pass --table-slice a:b (one rank's tables)"
     T = len(rows)
     cache_rows = pkg.workload.KAGGLE_CACHE_ROWS if (args.scale == 1.0 and args.shape == "kaggle" and not sliced) else int(sum(rows) * 0.13)
-    warm = args.cache_warm if args.cache_warm >= 0 else 4800
-    n_batches = warm + 4 * (W + K)
+    search = max(8, WARM_SEARCH * 2048 // B)
+    n_batches = search + 4 * (W + K) + 16                  # the reference arm generates the same trace (same n, same B)
     _, tables, idx = build_workload(args, n_batches, rows, dim, B)
+    t0 = time.time()
+    warm = args.cache_warm if args.cache_warm >= 0 else batches_until_full(idx[:search], rows, cache_rows * 32 // args.precision
+                                                                           if args.layers == 1 else cache_rows) + WARM_AFTER_FULL * 2048 // B
+    warm = min(warm, search)
+    log(f"cache warm-up: {warm} batches (fill point derived from the trace in {time.time() - t0:.1f}s)")
 
     layers = args.layers
     sec = args.secondary if layers >= 2 else 0
@@ -295,8 +347,11 @@ def main_ours(args):
 
     # ---- fill the cache (mirrors the reference's --cache-warmup pass) ------------------------
     t0 = time.time()
+    use_pf = not args.no_prefetch
     for k in range(warm):
         store.lookup(idx_dev[k], out=out, hit=hit)
+        if use_pf:
+            store.prefetch(idx_dev[k + 1])
     store.sync()
     st = store.stats(reset=True)
     log(f"cache warm: {warm} batches in {time.time() - t0:.2f}s, resident {st['size'][0]}/{st['capacity'][0]}, "
@@ -310,24 +365,39 @@ def main_ours(args):
 
     store.phase_times()                           # clears the debug accumulators
     # ---- value: indices resident in HBM ------------------------------------------------------
+    # Three regions of EXACTLY K steps each, W warm-up steps before the first; the line reports the median region (a
+    # 20-step region is 0.6 ms: box-to-box and run-to-run spread of anything that touches PCIe is +-10 %) and lists all.
+    # Every step announces the next index batch (evs_prefetch), as a serving loop with its requests queued would.
     base = warm
     for k in range(W):
         store.lookup(idx_dev[base + k], out=out, hit=hit)
+        if use_pf:
+            store.prefetch(idx_dev[base + k + 1])
     torch.cuda.synchronize()
-    l0 = store.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(K):
-        store.lookup(idx_dev[base + W + k], out=out, hit=hit)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_dev = e0.elapsed_time(e1)
-    launches = store.launch_count() - l0
+    base += W
+    regions = []
+    launches = 0
+    for rep in range(3):
+        l0 = store.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(K):
+            store.lookup(idx_dev[base + k], out=out, hit=hit)
+            if use_pf:
+                store.prefetch(idx_dev[base + k + 1])
+        e1.record()
+        torch.cuda.synchronize()
+        regions.append(e0.elapsed_time(e1))
+        launches = store.launch_count() - l0
+        base += K
+    ms_dev = sorted(regions)[1]
+    base -= W + K                                 # the sections below advance by W + K
     phases = store.phase_times()
     log("device phases of the last timed batch (us):", phases)
     st = store.stats(reset=True)
-    log("per step: misses %.0f evictions %.0f flushed %.0f inserts %.0f" % (st["misses"] / K, st["evictions"][0] / K,
-        st["flushed"][0] / K, st["inserts"][0] / K))
+    KK = 3 * K
+    log("per step: misses %.0f evictions %.0f flushed %.0f inserts %.0f" % (st["misses"] / KK, st["evictions"][0] / KK,
+        st["flushed"][0] / KK, st["inserts"][0] / KK))
     hit_rate = (st["hits"][0] + st["hits"][1] + st["c3_hits"]) / max(1, st["lookups"])
     tier_rates = {"c1": st["hits"][0] / max(1, st["lookups"]), "c2": st["hits"][1] / max(1, st["lookups"]),
                   "c3": st["c3_hits"] / max(1, st["lookups"])}

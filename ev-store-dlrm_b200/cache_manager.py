@@ -29,6 +29,7 @@ class CacheConfig:
     device: int = 0
     n_tables_total: int = 0           # agg_hit range; 0 = n_tables
     table_base: int = 0
+    table_ids: tuple = ()             # global ids of the local tables (non-contiguous placement); () = table_base + t
     store_in_hbm: bool = False
     record_events: bool = False
     flush_rate: float = 0.0
@@ -153,9 +154,33 @@ class EvStore:
         if cfg.policy not in ("evlfu", "lru"):
             raise ValueError(f"unknown policy {cfg.policy!r} (evlfu | lru)")
         c.policy = 1 if cfg.policy == "lru" else 0
+        if cfg.table_ids:
+            if len(cfg.table_ids) != self.n_tables:
+                raise ValueError("table_ids needs one global id per local table")
+            self._table_ids = (C.c_int32 * self.n_tables)(*[int(g) for g in cfg.table_ids])
+            c.table_ids = C.cast(self._table_ids, C.POINTER(C.c_int32))
         self._c = c
 
     # ---- hot path ------------------------------------------------------------------------
+    def prefetch(self, lS_i_next, ready_event=None):
+        """Look-ahead (evs_prefetch): announce the index batch the NEXT lookup / shard_lookup call will pass (the same
+        tensor).  Its probable misses are staged from the pinned backing store into HBM while the batch in flight
+        runs.  ``ready_event``: a torch.cuda.Event recorded after the tensor was filled; None = already complete."""
+        T, B = lS_i_next.shape
+        assert lS_i_next.is_cuda and lS_i_next.is_contiguous() and T == self.n_tables
+        ev = ready_event.cuda_event if ready_event is not None else None
+        _native.check(self.lib.evs_prefetch(self.handle, lS_i_next.data_ptr(), B, ev), "evs_prefetch")
+
+    def check(self, clear: bool = False):
+        """Raise if a batch that has already run saw an out-of-range index or a silent peer (no synchronisation)."""
+        _native.check(self.lib.evs_check(self.handle, int(clear)), "evs_check")
+
+    def memory_footprint(self) -> int:
+        """Bytes of HBM the handle holds (index + slot-indexed slabs + rings + staging)."""
+        n = C.c_uint64(0)
+        _native.check(self.lib.evs_memory_footprint(self.handle, C.byref(n)), "evs_memory_footprint")
+        return int(n.value)
+
     def lookup(self, lS_i, out=None, hit=None, agg_in=None, stream=None):
         """lS_i: int64 CUDA tensor [n_tables, B].  Returns (out [B, n_tables, dim] fp32, hit [B, n_tables] uint8)."""
         import torch
@@ -311,7 +336,7 @@ class EvStore:
                 "avg_gap2": v[11] / n / 1e3, "avg_evict": v[12] / n / 1e3,
                 "overlapped_batches": v[14], "evict_plan": v[22] / n / 1e3, "evict_chunks": v[23] / n / 1e3,
                 "evict_wait_last": v[24] / n / 1e3, "evict_writeback": v[25] / n / 1e3, "evict_chunks_per_batch": v[20] / n,
-                "evict_records_per_batch": v[21] / n, "avg_fetch_since_evict_start": v[28] / n / 1e3, "evict_last_chunk_avg": v[26] / n, "evict_last_chunk_max": v[27], "evict_scanned_total": v[15], "appends_total": v[1],
+                "evict_records_per_batch": v[21] / n, "avg_fetch_since_evict_start": v[28] / n / 1e3, "avg_peer_wait": v[29] / n / 1e3, "evict_last_chunk_avg": v[26] / n, "evict_last_chunk_max": v[27], "evict_scanned_total": v[15], "appends_total": v[1],
                 "serve": us(0, 7), "serve_to_update_gap": us(7, 2), "update": us(2, 3), "update_to_evict_gap": us(3, 4),
                 "evict": us(4, 5), "c3": us(5, 6), "total": us(0, 6)}
 

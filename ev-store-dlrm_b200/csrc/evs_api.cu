@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -13,6 +15,7 @@
 #include "evs_kernels.cuh"
 #include "evs_c3.cuh"
 #include "evs_update.cuh"
+#include "evs_prefetch.cuh"
 
 namespace evs {
 
@@ -79,38 +82,85 @@ int compute_caps(const evs_config &cfg, Caps &out) {
     return EVS_ERR_INVALID;
 }
 
+// Entry points that launch or copy run under the handle's device whatever the caller's current device is
+// (one process may drive several GPUs; torch's current device need not be cfg.device), and restore it.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+static thread_local size_t *t_alloc_bytes = nullptr;     // evs_create / pipe_init: device bytes are added to the handle's count
+
 template <typename T>
 static int dev_alloc(std::vector<void *> &owner, T **p, size_t n, bool zero = true) {
     void *q = nullptr;
     const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
     EVS_CUDA(cudaMalloc(&q, bytes));
+    if (t_alloc_bytes) *t_alloc_bytes += bytes;
     owner.push_back(q);
     if (zero) EVS_CUDA(cudaMemset(q, 0, bytes));
     *p = static_cast<T *>(q);
     return EVS_OK;
 }
 
-// Device-visible alias of a host range: ranges that are already page-locked (cudaHostAlloc /
-// an earlier cudaHostRegister, e.g. a framework's pinned allocator) are used as they are,
-// anything else is page-locked and mapped here (and released in free_all).
+// Device-visible alias of a host range: ranges that are already page-locked by somebody else (cudaHostAlloc /
+// a framework's pinned allocator) are used as they are; anything else is page-locked and mapped here.  Ranges WE
+// page-locked live in a process-wide, reference-counted registry: handles normally share backing arrays (EvStore
+// passes the caller's fp32 tables through uncopied, and the legacy store plus an EvStore over the same tables is
+// a usual setup), so a range is unregistered only when the last handle that maps it is destroyed.
+// Lifetime rule for the caller: the host range must outlive every handle created over it.
+struct HostReg {
+    size_t bytes;
+    int refs;
+};
+static std::mutex g_reg_mu;
+static std::map<void *, HostReg> g_reg;
+
 static int map_host_range(evs_handle h, void *hp, size_t bytes, void **dp, const std::string &what) {
-    cudaPointerAttributes attr{};
-    cudaError_t e = cudaPointerGetAttributes(&attr, hp);
-    if (e != cudaSuccess) cudaGetLastError();
-    if (e != cudaSuccess || attr.type != cudaMemoryTypeHost) {
-        e = cudaHostRegister(hp, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
-        if (e == cudaSuccess) {
-            h->registered.push_back(hp);
-        } else if (e == cudaErrorHostMemoryAlreadyRegistered) {
-            cudaGetLastError();
-        } else {
-            set_error("cudaHostRegister(" + what + ", " + std::to_string(bytes) + " B) -> " + cudaGetErrorString(e));
-            cudaGetLastError();
-            return EVS_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    auto it = g_reg.find(hp);
+    if (it != g_reg.end() && it->second.bytes >= bytes) {
+        it->second.refs++;
+        h->registered.push_back(hp);
+    } else {
+        cudaPointerAttributes attr{};
+        cudaError_t e = cudaPointerGetAttributes(&attr, hp);
+        if (e != cudaSuccess) cudaGetLastError();
+        if (e != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+            e = cudaHostRegister(hp, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+            if (e == cudaSuccess) {
+                g_reg[hp] = HostReg{bytes, 1};
+                h->registered.push_back(hp);
+            } else if (e == cudaErrorHostMemoryAlreadyRegistered) {
+                cudaGetLastError();
+            } else {
+                set_error("cudaHostRegister(" + what + ", " + std::to_string(bytes) + " B) -> " + cudaGetErrorString(e));
+                cudaGetLastError();
+                return EVS_ERR_CUDA;
+            }
         }
     }
     EVS_CUDA(cudaHostGetDevicePointer(dp, hp, 0));
     return EVS_OK;
+}
+
+static void release_host_ranges(evs_handle h) {
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    for (void *p : h->registered) {
+        auto it = g_reg.find(p);
+        if (it == g_reg.end()) continue;
+        if (--it->second.refs == 0) {
+            cudaHostUnregister(p);
+            g_reg.erase(it);
+        }
+    }
+    h->registered.clear();
 }
 
 static int make_store(evs_handle h, const void *const *ptrs, int prec, std::vector<const unsigned char *> &out) {
@@ -255,12 +305,13 @@ static void free_all(evs_handle h) {
         for (void *p : h->tier[i].allocs) cudaFree(p);
     for (void *p : h->c3_allocs) cudaFree(p);
     for (void *p : h->dev_allocs) cudaFree(p);
-    for (void *p : h->registered) cudaHostUnregister(p);
+    release_host_ranges(h);
     h->prof.destroy();
-    if (h->ev_served) cudaEventDestroy(h->ev_served);
-    if (h->ev_updated) cudaEventDestroy(h->ev_updated);
-    if (h->ev_filled) cudaEventDestroy(h->ev_filled);
-    if (h->side) cudaStreamDestroy(h->side);
+    if (h->pf_stream) cudaStreamDestroy(h->pf_stream);
+    for (int i = 0; i < 2; ++i)
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    if (h->ev_pf_ready) cudaEventDestroy(h->ev_pf_ready);
+    if (h->err_host) cudaFreeHost(h->err_host);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     for (int i = 0; i < evs_handle_s::kPipeSlots; ++i) {
@@ -304,17 +355,20 @@ static int maintain_rings(evs_handle h, int ti, cudaStream_t st) {
 // ---- kernel selection by (main precision, secondary precision) -----------------------------
 using KernelFn = void (*)(const Params);
 using ServeFn = void (*)(const Params, const BatchArgs);
+using PrefetchFn = void (*)(const Params, const PrefetchArgs);
 struct KernelSet {
-    ServeFn serve = nullptr;
-    KernelFn fetch = nullptr;
-    KernelFn fetch_list = nullptr;
+    ServeFn serve = nullptr;        // one GPU
+    ServeFn serve_sh = nullptr;     // one rank of a table-wise sharded cache
+    KernelFn evict = nullptr;       // eviction + miss-fetch roles
+    PrefetchFn prefetch = nullptr;
 };
 template <int P0, int P1>
 static KernelSet kernels_of() {
     KernelSet k;
-    k.serve = k_serve<P0, P1>;
-    k.fetch = k_fetch<P0, P1>;
-    k.fetch_list = k_fetch_list<P0, P1>;
+    k.serve = k_serve<P0, P1, false>;
+    k.serve_sh = k_serve<P0, P1, true>;
+    k.evict = k_evict<P0, P1>;
+    k.prefetch = k_prefetch<P0, P1>;
     return k;
 }
 static KernelSet pick_kernels(int p0, int p1) {
@@ -332,63 +386,61 @@ static KernelSet pick_kernels(int p0, int p1) {
         default: return KernelSet();
     }
 }
+static KernelSet kernels_of_handle(evs_handle h) { return pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0); }
+static ServeFn serve_of(evs_handle h, const KernelSet &ks) { return h->sharded ? ks.serve_sh : ks.serve; }
+
+// A launch; `pdl`: the kernel may start while its predecessor on the stream drains (programmatic stream
+// serialization) -- it blocks in griddepcontrol.wait before it touches anything the predecessor wrote.
+static cudaError_t launch_ex(const void *fn, dim3 grid, int block, size_t smem, cudaStream_t st, void **args, bool pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = pdl ? at : nullptr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelExC(&cfg, fn, args);
+}
 
 static cudaError_t launch_serve(ServeFn fn, int grid, cudaStream_t st, const Params &p, const BatchArgs &a) {
     void *args[] = {const_cast<Params *>(&p), const_cast<BatchArgs *>(&a)};
-    return cudaLaunchKernel(reinterpret_cast<const void *>(fn), dim3(grid), dim3(kLookupThreads), args, 0, st);
+    return launch_ex(reinterpret_cast<const void *>(fn), dim3(grid), kLookupThreads, 0, st, args, false);
 }
 
-static cudaError_t launch(KernelFn fn, dim3 grid, int block, size_t smem, cudaStream_t st, const Params &p) {
+static cudaError_t launch(KernelFn fn, dim3 grid, int block, size_t smem, cudaStream_t st, const Params &p, bool pdl) {
     void *args[] = {const_cast<Params *>(&p)};
-    return cudaLaunchKernel(reinterpret_cast<const void *>(fn), grid, dim3(block), args, smem, st);
+    return launch_ex(reinterpret_cast<const void *>(fn), grid, block, smem, st, args, pdl);
 }
 
 static size_t fetch_smem(evs_handle h) {
     unsigned s = h->tier[0].dev.row_stride;
     if (h->n_tiers == 2) s = std::max(s, h->tier[1].dev.row_stride);
-    return static_cast<size_t>(kSamplesPerCta) * s;
+    return static_cast<size_t>(kEvictThreads / 32) * s;
 }
 
-static int side_grid(evs_handle h, int n_chunks) {
-    const long long n = static_cast<long long>(n_chunks) * h->params.spc * h->cfg.n_tables;
-    static const int cap = [] {
-        const char *e = getenv("EVSTORE_B200_FETCH_CTAS");      // tuning aid: CTAs of the miss-fetch kernel
-        return (e && atoi(e) > 0) ? atoi(e) : 148 * 4;
-    }();
-    return static_cast<int>(std::max<long long>(1, std::min<long long>((n + 255) / 256, cap)));
-}
-
-// The per-batch kernel sequence.  Critical path: k_serve -> [k_scan ->] k_update -> k_evict.  The
-// zero-copy miss fetch (PCIe round trips) and the slab fill run on the side stream next to it:
-//     k_serve --> k_update --+--> k_evict --+--> (next batch)
-//                            +--> k_fetch --+
-// (fetching next to k_update instead slowed k_update from 9 to 17 us: the SMs' outstanding
-// PCIe reads get in the way of its atomics)
+// The per-batch kernel sequence, a linear chain on one stream:
+//     k_serve -> [k_scan ->] k_update -> k_evict {eviction of each tier || miss fetch}
+// (the zero-copy miss fetch used to be its own kernel on a side stream next to k_evict; as a role of k_evict's grid
+// the graph has no fork / join, and with evs_prefetch its rows are mostly staged in HBM already).
 // `n_chunks` CTAs of k_serve / k_update; CTAs past the batch end exit at once, so a captured graph
 // uses the maximum.
 static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const BatchArgs &a) {
     const Params &p = h->params;
-    const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
+    const KernelSet ks = kernels_of_handle(h);
     Profiler &pf = h->prof;
-    { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch_serve(ks.serve, n_chunks, st, p, a)); }
+    const bool pdl = h->use_pdl && !pf.on;                // event records between the launches would serialise them anyway
+    { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch_serve(serve_of(h, ks), n_chunks, st, p, a)); }
     if (p.n_chunks_max > p.quad_max || p.L < 32) {
         LaunchScope ls(pf, K_SCAN, st);
-        EVS_CUDA(launch(k_scan, (h->n_tiers == 1 ? 1 : kSeqGroups) * h->tier[0].dev.n_buckets, 256, 0, st, p));
+        EVS_CUDA(launch(k_scan, (h->n_tiers == 1 ? 1 : kSeqGroups) * h->tier[0].dev.n_buckets, 256, 0, st, p, pdl));
     }
-    { LaunchScope ls(pf, K_UPDATE, st); EVS_CUDA(launch(h->n_tiers == 1 ? k_update<1, 8> : k_update<kSeqGroups, 4>, n_chunks, kLookupThreads, 0, st, p)); }
-    EVS_CUDA(cudaEventRecord(h->ev_updated, st));
-    EVS_CUDA(cudaStreamWaitEvent(h->side, h->ev_updated, 0));
-    { LaunchScope ls(pf, K_EVICT, st); EVS_CUDA(launch(k_evict, dim3(h->evict_ctas, h->n_tiers), kEvictThreads, 0, st, p)); }
+    { LaunchScope ls(pf, K_UPDATE, st); EVS_CUDA(launch(h->n_tiers == 1 ? k_update<1, 8> : k_update<kSeqGroups, 4>, n_chunks, kLookupThreads, 0, st, p, pdl)); }
     {
-        LaunchScope ls(pf, K_FETCH, h->side);
-        if (p.fetch_mode != 0) EVS_CUDA(launch(ks.fetch_list, h->fetch_list_ctas, h->fetch_list_threads, fetch_smem(h), h->side, p));
-        else EVS_CUDA(launch(ks.fetch, side_grid(h, n_chunks), 256, fetch_smem(h), h->side, p));
-    }
-    EVS_CUDA(cudaEventRecord(h->ev_filled, h->side));
-    EVS_CUDA(cudaStreamWaitEvent(st, h->ev_filled, 0));
-    if (h->sharded) {
-        { LaunchScope ls(pf, K_SIGNAL, st); EVS_CUDA(launch(k_signal, 1, 32, 0, st, p)); }
-        { LaunchScope ls(pf, K_WAIT, st); EVS_CUDA(launch(k_wait, 1, 32, 0, st, p)); }
+        LaunchScope ls(pf, K_EVICT, st);
+        EVS_CUDA(launch(ks.evict, dim3(std::max(h->evict_ctas, h->fetch_list_ctas), h->n_tiers + 1), kEvictThreads, fetch_smem(h), st, p, pdl));
     }
     return EVS_OK;
 }
@@ -412,7 +464,7 @@ static int build_graph(evs_handle h) {
     EVS_CUDA(cudaGraphGetNodes(g, nullptr, &n_nodes));
     std::vector<cudaGraphNode_t> nodes(n_nodes);
     EVS_CUDA(cudaGraphGetNodes(g, nodes.data(), &n_nodes));
-    const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
+    const KernelSet ks = kernels_of_handle(h);
     h->serve_node = nullptr;
     for (cudaGraphNode_t nd : nodes) {
         cudaGraphNodeType ty;
@@ -420,7 +472,7 @@ static int build_graph(evs_handle h) {
         if (ty != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp{};
         EVS_CUDA(cudaGraphKernelNodeGetParams(nd, &kp));
-        if (kp.func == reinterpret_cast<void *>(ks.serve)) h->serve_node = nd;
+        if (kp.func == reinterpret_cast<void *>(serve_of(h, ks))) h->serve_node = nd;
     }
     if (h->serve_node == nullptr) {
         set_error("graph capture: k_serve node not found");
@@ -437,6 +489,8 @@ static int check_device_errors(evs_handle h) {
     if (g.error) {
         unsigned zero = 0;
         cudaMemcpy(&h->g->error, &zero, sizeof(zero), cudaMemcpyHostToDevice);
+        *reinterpret_cast<volatile unsigned *>(h->err_host) = 0u;
+        h->sticky_error = 0;
         if (g.error == 7u) {
             set_error("a peer rank did not deliver its hit counts / rows in time (table-wise sharding)");
             return EVS_ERR_PEER;
@@ -484,10 +538,23 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     evs_handle h = new evs_handle_s();
     h->cfg = *cfg;
     if (h->cfg.n_tables_total <= 0) h->cfg.n_tables_total = cfg->n_tables;
-    if (h->cfg.n_tables_total > 31 || h->cfg.n_tables_total < cfg->n_tables + 0 * cfg->table_base) {
+    if (h->cfg.n_tables_total > 31 || h->cfg.n_tables_total < cfg->n_tables) {
         set_error("evs_create: n_tables_total must be in [n_tables, 31]");
         delete h;
         return EVS_ERR_INVALID;
+    }
+    // global table ids: keys, the agg_hit buckets and -- sharded -- the peers' receive-buffer columns are derived from
+    // them, so an id outside [0, n_tables_total) would alias another table's keys and write outside a peer's buffer
+    h->table_ids.resize(cfg->n_tables);
+    for (int t = 0; t < cfg->n_tables; ++t) h->table_ids[t] = cfg->table_ids ? cfg->table_ids[t] : cfg->table_base + t;
+    h->cfg.table_ids = nullptr;
+    for (int t = 0; t < cfg->n_tables; ++t) {
+        const int g = h->table_ids[t];
+        if (g < 0 || g >= h->cfg.n_tables_total || (t > 0 && g <= h->table_ids[t - 1])) {
+            set_error("evs_create: table ids (table_base + t, or table_ids[t]) must be strictly increasing and lie in [0, n_tables_total)");
+            delete h;
+            return EVS_ERR_INVALID;
+        }
     }
     if (h->cfg.high_agghit_threshold <= 0) h->cfg.high_agghit_threshold = 23;
     if (cfg->policy != EVS_POLICY_EVLFU && cfg->policy != EVS_POLICY_LRU) {
@@ -530,14 +597,20 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         free_all(h);
         return code;
     };
+    t_alloc_bytes = &h->hbm_bytes;
+    struct AllocScope {
+        ~AllocScope() { t_alloc_bytes = nullptr; }
+    } alloc_scope;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_served, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_updated, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_filled, cudaEventDisableTiming) != cudaSuccess) {
-        set_error("cudaStreamCreate / cudaEventCreate failed");
+        cudaStreamCreateWithFlags(&h->pf_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_done[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_done[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_pf_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void **>(&h->err_host), 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        set_error("cudaStreamCreate / cudaEventCreate / cudaHostAlloc failed");
         return fail(EVS_ERR_CUDA);
     }
+    *h->err_host = 0u;
     h->n_tiers = cfg->n_layers >= 2 ? 2 : 1;
     if (pick_kernels(cfg->main_precision, h->n_tiers == 2 ? cfg->secondary_precision : 0).serve == nullptr) {
         set_error("evs_create: no kernel for this precision pair");
@@ -587,20 +660,30 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     P.L = L;
     P.L_shift = L_shift;
     P.spc = spc;
-    P.table_base = cfg->table_base;
+    P.table_base = h->table_ids[0];
+    for (int g = 0; g < kMaxTables; ++g) P.loc[g] = -1;
+    for (int t = 0; t < cfg->n_tables; ++t) {
+        P.tid[t] = h->table_ids[t];
+        P.col[t] = t;                                   // evs_shard_connect switches to the global id
+        P.loc[h->table_ids[t]] = t;
+    }
+    P.n_max = static_cast<unsigned>(n_max);
+    {
+        void *dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, h->err_host, 0) != cudaSuccess) return fail(EVS_ERR_CUDA);
+        P.err_host = static_cast<unsigned *>(dp);
+    }
     P.n_perfect_agg = h->cfg.n_tables_total;
     P.approx_thres = (h->n_tiers == 1) ? cfg->approx_emb_thres : 0;
     P.policy = cfg->policy;
     P.high_thres = h->cfg.high_agghit_threshold;
     P.n_chunks_max = n_chunks_max;
     {
-        const char *fm = getenv("EVSTORE_B200_FETCH_MODE");        // tuning aid: 0 = k_fetch scans the flags (all misses issue at once)
-        P.fetch_mode = (fm && fm[0] == '0') ? 0 : 1;
         const char *qm = getenv("EVSTORE_B200_QUAD_MAX");          // tuning aid: largest serve grid whose k_update sums its predecessors directly
         P.quad_max = (qm && atoi(qm) > 0) ? atoi(qm) : kQuadMaxChunks;
-        // Grid of k_fetch_list: ~512 64-byte row reads in flight (32 KB; fewer rows when they are larger), at most 64 rows
-        // per CTA -- measured optimum of profiles/r1_fetch_list_ab.md.  Rows that are 16-byte aligned are shared by
-        // groups of gsize lanes (32 / gsize rows per warp and round), others take a whole warp each.
+        // CTAs of the miss-fetch role: ~512 64-byte row reads in flight (32 KB; fewer rows when they are larger) -- measured
+        // optimum of profiles/r1_fetch_list_ab.md.  Rows that are 16-byte aligned are shared by groups of gsize lanes
+        // (32 / gsize rows per warp and round), others take a whole warp each.
         {
             unsigned stride = h->tier[0].dev.row_stride;
             bool aligned = true;
@@ -615,17 +698,19 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
                 gsize = 1;
                 while (gsize < static_cast<int>(stride >> 4) && gsize < 32) gsize <<= 1;
             }
-            const int rpw = 32 / gsize;
-            const int threads = std::max(32, std::min(256, 64 * gsize));
-            const int rows_per_cta = (threads / 32) * rpw;
+            const int rows_per_cta = (kEvictThreads / 32) * (32 / gsize);
             const int target = static_cast<int>(std::min(512u, std::max(128u, 32768u / stride)));
-            h->fetch_list_threads = threads;
             h->fetch_list_ctas = std::max(1, (target + rows_per_cta - 1) / rows_per_cta);
+            h->pf_ok = aligned;
+            // the look-ahead kernel keeps about twice as many reads in flight: nothing waits for it
+            h->pf_ctas = std::max(4, 2 * h->fetch_list_ctas);
         }
-        const char *ft = getenv("EVSTORE_B200_FETCH_LIST_THREADS"); // tuning aid: threads per CTA of k_fetch_list (32..256)
-        if (ft && atoi(ft) >= 32 && atoi(ft) <= 256) h->fetch_list_threads = atoi(ft) & ~31;
-        const char *fc = getenv("EVSTORE_B200_FETCH_LIST_CTAS");   // tuning aid: CTAs of k_fetch_list = PCIe reads kept in flight
+        const char *fc = getenv("EVSTORE_B200_FETCH_LIST_CTAS");   // tuning aid: CTAs of the fetch role = PCIe reads kept in flight
         if (fc && atoi(fc) > 0) h->fetch_list_ctas = atoi(fc);
+        const char *pc = getenv("EVSTORE_B200_PF_CTAS");           // tuning aid: CTAs of k_prefetch
+        if (pc && atoi(pc) > 0) h->pf_ctas = atoi(pc);
+        const char *pe = getenv("EVSTORE_B200_NO_PREFETCH");       // tuning aid: evs_prefetch becomes a no-op
+        if (pe && pe[0] == '1') h->pf_ok = false;
         // CTAs of k_evict per tier = 256-record chunks of the rings examined at once.  A batch evicts about as many keys
         // as it misses (a few per cent of its positions) and most records at the ring heads are live, so one chunk per
         // 2048 positions covers the usual batch several times over (configs[1]: victims complete after 5-7 chunks of 26);
@@ -633,7 +718,12 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         h->evict_ctas = static_cast<int>(std::min<long long>(kTierCtas, std::max<long long>(16, n_max / 2048)));
         const char *ec = getenv("EVSTORE_B200_EVICT_CTAS");        // tuning aid (<= 256)
         if (ec && atoi(ec) > 0) h->evict_ctas = std::min(atoi(ec), kEvictThreads);
+        const char *pd = getenv("EVSTORE_B200_PDL");               // tuning aid: 0 = plain stream order between the batch's kernels
+        h->use_pdl = !(pd && pd[0] == '0');
     }
+    P.evict_ctas = h->evict_ctas;
+    P.fetch_ctas = h->fetch_list_ctas;
+    P.pdl = h->use_pdl ? 1 : 0;
     P.rows = h->d_rows;
     P.args = h->d_args;
     P.g = h->g;
@@ -644,19 +734,31 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     }
     P.stage_stride = std::max(h->tier[0].dev.row_stride, h->n_tiers == 2 ? h->tier[1].dev.row_stride : 0u);
     const size_t us = fetch_smem(h);
-    if (us > 40 * 1024) {
-        const KernelSet ks = pick_kernels(cfg->main_precision, h->n_tiers == 2 ? cfg->secondary_precision : 0);
-        if (cudaFuncSetAttribute(reinterpret_cast<const void *>(ks.fetch), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(us)) != cudaSuccess ||
-            cudaFuncSetAttribute(reinterpret_cast<const void *>(ks.fetch_list), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (us > 32 * 1024) {
+        const KernelSet ks = kernels_of_handle(h);
+        if (cudaFuncSetAttribute(reinterpret_cast<const void *>(ks.evict), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(us)) != cudaSuccess) {
-            set_error("row too large for the fetch kernel's staging buffer");
+            set_error("row too large for the fetch role's staging buffer");
             return fail(EVS_ERR_INVALID);
         }
     }
+    if (h->pf_ok) {
+        // staging rows of the look-ahead: two parities, one row_stride slot per position
+        if ((rc = dev_alloc(h->dev_allocs, &P.pf_tag, 2 * static_cast<size_t>(n_max)))) return fail(rc);
+        if ((rc = dev_alloc(h->dev_allocs, &P.pf_rows, 2 * static_cast<size_t>(n_max) * P.stage_stride, false))) return fail(rc);
+    }
     const char *ng = getenv("EVSTORE_B200_NO_GRAPH");
     h->use_graph = !(ng && ng[0] == '1');
-    if (h->use_graph && (rc = build_graph(h))) return fail(rc);
+    if (h->use_graph && (rc = build_graph(h))) {
+        if (!h->use_pdl) return fail(rc);
+        // a driver that cannot capture programmatic edges: plain stream order between the kernels
+        fprintf(stderr, "evstore_b200: graph capture with programmatic dependent launch failed (%s); retrying without\n", evs_last_error());
+        cudaGetLastError();
+        h->use_pdl = false;
+        P.pdl = 0;
+        if (h->graph_src) cudaGraphDestroy(h->graph_src), h->graph_src = nullptr;
+        if ((rc = build_graph(h))) return fail(rc);
+    }
     *out = h;
     return EVS_OK;
 }
@@ -667,17 +769,22 @@ int evs_destroy(evs_handle h) {
     return EVS_OK;
 }
 
-static int run_batch(evs_handle h, const BatchArgs &a, cudaStream_t st) {
-    const KernelSet ks = pick_kernels(h->tier[0].prec, h->n_tiers == 2 ? h->tier[1].prec : 0);
-    if (a.probe_only) {
+static int run_batch(evs_handle h, const BatchArgs &a_in, cudaStream_t st) {
+    const KernelSet ks = kernels_of_handle(h);
+    if (a_in.probe_only) {
         LaunchScope ls(h->prof, K_PROBE, st);
-        EVS_CUDA(launch_serve(ks.serve, (a.B + h->params.spc - 1) / h->params.spc, st, h->params, a));
+        EVS_CUDA(launch_serve(serve_of(h, ks), (a_in.B + h->params.spc - 1) / h->params.spc, st, h->params, a_in));
         return EVS_OK;
     }
+    BatchArgs a = a_in;
+    const uint64_t seq = ++h->seq;
+    a.seq = static_cast<unsigned>(seq);
+    // rows staged by evs_prefetch are used when the announcement matches this call
+    a.pf_gen = (h->pf_ok && h->pf_seq == seq && h->pf_idx == static_cast<const void *>(a.idx) && h->pf_B == a.B) ? h->pf_gen : 0u;
     if (h->use_graph && !h->prof.on) {
-        void *kargs[] = {&h->params, const_cast<BatchArgs *>(&a)};
+        void *kargs[] = {&h->params, &a};
         cudaKernelNodeParams kp{};
-        kp.func = reinterpret_cast<void *>(ks.serve);
+        kp.func = reinterpret_cast<void *>(serve_of(h, ks));
         kp.gridDim = dim3(h->params.n_chunks_max);
         kp.blockDim = dim3(kLookupThreads);
         kp.sharedMemBytes = 0;
@@ -685,13 +792,14 @@ static int run_batch(evs_handle h, const BatchArgs &a, cudaStream_t st) {
         EVS_CUDA(cudaGraphExecKernelNodeSetParams(h->graph, h->serve_node, &kp));
         EVS_CUDA(cudaGraphLaunch(h->graph, st));
         h->prof.launches[K_SERVE]++, h->prof.launches[K_UPDATE]++, h->prof.launches[K_EVICT]++;
-        h->prof.launches[K_FETCH]++;
-        if (h->sharded) h->prof.launches[K_SIGNAL]++, h->prof.launches[K_WAIT]++;
         if (h->params.n_chunks_max > h->params.quad_max || h->params.L < 32) h->prof.launches[K_SCAN]++;
     } else {
         int rc = enqueue_batch(h, st, (a.B + h->params.spc - 1) / h->params.spc, a);
         if (rc) return rc;
     }
+    // the staging rows of this parity may be overwritten (by the look-ahead for batch seq + 2) once this batch is done
+    EVS_CUDA(cudaEventRecord(h->ev_done[seq & 1], st));
+    h->ev_done_valid[seq & 1] = true;
     h->batches++;
     for (int i = 0; i < h->n_tiers; ++i) {
         h->tier[i].ub_used += static_cast<unsigned long long>(a.B) * h->cfg.n_tables;
@@ -701,6 +809,47 @@ static int run_batch(evs_handle h, const BatchArgs &a, cudaStream_t st) {
     return EVS_OK;
 }
 
+// Look-ahead for the next batch (see evs_prefetch.cuh).  ready: event after which idx_dev is complete, or null.
+static int prefetch_next(evs_handle h, const int64_t *idx_dev, int32_t B, cudaEvent_t ready) {
+    if (!h->pf_ok) return EVS_OK;
+    const uint64_t seq = h->seq + 1;
+    if (h->pf_seq == seq && h->pf_idx == static_cast<const void *>(idx_dev) && h->pf_B == B) return EVS_OK;   // already announced
+    if (ready) EVS_CUDA(cudaStreamWaitEvent(h->pf_stream, ready, 0));
+    // the staging rows of this parity belong to batch seq - 2 until it has finished
+    if (h->ev_done_valid[seq & 1]) EVS_CUDA(cudaStreamWaitEvent(h->pf_stream, h->ev_done[seq & 1], 0));
+    if (++h->pf_gen >= 0x7FFFFFFFu) {                      // tags are generation << 1 | tier: start over with clean tags
+        EVS_CUDA(cudaMemsetAsync(h->params.pf_tag, 0, 2 * sizeof(unsigned) * static_cast<size_t>(h->params.n_max), h->pf_stream));
+        h->pf_gen = 1;
+    }
+    PrefetchArgs pa{};
+    pa.idx = reinterpret_cast<const long long *>(idx_dev);
+    pa.B = B;
+    pa.seq = static_cast<unsigned>(seq);
+    pa.gen = h->pf_gen;
+    const KernelSet ks = kernels_of_handle(h);
+    const int S = pf_tile_samples(h->cfg.n_tables);
+    const int n_tiles = (B + S - 1) / S;
+    {
+        LaunchScope ls(h->prof, K_PREFETCH, h->pf_stream);
+        void *args[] = {&h->params, &pa};
+        EVS_CUDA(launch_ex(reinterpret_cast<const void *>(ks.prefetch), dim3(std::min(h->pf_ctas, n_tiles)), kPfThreads, 0, h->pf_stream,
+                           args, false));
+    }
+    h->pf_seq = seq;
+    h->pf_idx = idx_dev;
+    h->pf_B = B;
+    return EVS_OK;
+}
+
+int evs_prefetch(evs_handle h, const int64_t *idx_dev, int32_t B, void *ready_event) {
+    if (h == nullptr || idx_dev == nullptr || B < 1 || B > h->cfg.max_batch) {
+        set_error("evs_prefetch: bad handle / B / pointer");
+        return EVS_ERR_INVALID;
+    }
+    DeviceGuard dg(h->cfg.device);
+    return prefetch_next(h, idx_dev, B, static_cast<cudaEvent_t>(ready_event));
+}
+
 int evs_lookup_batch(evs_handle h, const int64_t *idx_dev, int32_t B, float *out_dev, int64_t out_stride,
                      uint8_t *hit_dev, const uint8_t *agg_in, void *stream) {
     if (h == nullptr || B < 0 || B > h->cfg.max_batch || (B > 0 && (idx_dev == nullptr || out_dev == nullptr))) {
@@ -708,6 +857,7 @@ int evs_lookup_batch(evs_handle h, const int64_t *idx_dev, int32_t B, float *out
         return EVS_ERR_INVALID;
     }
     if (B == 0) return EVS_OK;
+    DeviceGuard dg(h->cfg.device);
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
     BatchArgs a{};
     a.idx = reinterpret_cast<const long long *>(idx_dev);
@@ -724,6 +874,7 @@ int evs_lookup_batch(evs_handle h, const int64_t *idx_dev, int32_t B, float *out
 int evs_probe_batch(evs_handle h, const int64_t *idx_dev, int32_t B, uint8_t *agg_out_dev, void *stream) {
     if (h == nullptr || B < 0 || B > h->cfg.max_batch || idx_dev == nullptr || agg_out_dev == nullptr) return EVS_ERR_INVALID;
     if (B == 0) return EVS_OK;
+    DeviceGuard dg(h->cfg.device);
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
     BatchArgs a{};
     a.idx = reinterpret_cast<const long long *>(idx_dev);
@@ -733,13 +884,40 @@ int evs_probe_batch(evs_handle h, const int64_t *idx_dev, int32_t B, uint8_t *ag
     return run_batch(h, a, st);
 }
 
+// The device error word as the host sees it (the kernels mirror it into pinned memory): sticky until cleared.
+static int poll_error(evs_handle h) {
+    const unsigned e = *reinterpret_cast<volatile unsigned *>(h->err_host);
+    if (e != 0u && h->sticky_error == 0) h->sticky_error = (e == 7u) ? EVS_ERR_PEER : EVS_ERR_INDEX;
+    if (h->sticky_error == EVS_ERR_PEER) set_error("a peer rank did not deliver its hit counts / rows in time (table-wise sharding)");
+    else if (h->sticky_error == EVS_ERR_INDEX) set_error("an index was outside [0, rows[table]); the lookup was answered from row 0");
+    return h->sticky_error;
+}
+
+int evs_check(evs_handle h, int clear) {
+    if (h == nullptr) return EVS_ERR_INVALID;
+    const int rc = poll_error(h);
+    if (clear) {
+        h->sticky_error = 0;
+        *reinterpret_cast<volatile unsigned *>(h->err_host) = 0u;
+    }
+    return rc;
+}
+
+int evs_memory_footprint(evs_handle h, uint64_t *hbm_bytes) {
+    if (h == nullptr || hbm_bytes == nullptr) return EVS_ERR_INVALID;
+    *hbm_bytes = h->hbm_bytes;
+    return EVS_OK;
+}
+
 int evs_lookup_batch_host(evs_handle h, const int64_t *idx_host, int32_t B, float *out_host, uint8_t *hit_host) {
     if (h == nullptr || B < 0 || B > h->cfg.max_batch || (B > 0 && (idx_host == nullptr || out_host == nullptr))) {
         set_error("evs_lookup_batch_host: bad handle / B / pointers");
         return EVS_ERR_INVALID;
     }
     if (B == 0) return EVS_OK;
-    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
+    // staging slot 0 is shared with the pipelined path: wait for a ticket that may still be copying out of it
+    if (h->s_out != nullptr) EVS_CUDA(cudaStreamSynchronize(h->s_out));
     const size_t n = static_cast<size_t>(B) * h->cfg.n_tables;
     EVS_CUDA(cudaMemcpyAsync(h->d_idx[0], idx_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     int rc = evs_lookup_batch(h, reinterpret_cast<const int64_t *>(h->d_idx[0]), B, h->d_out[0], 0, h->d_hit[0], nullptr, h->stream);
@@ -747,7 +925,7 @@ int evs_lookup_batch_host(evs_handle h, const int64_t *idx_host, int32_t B, floa
     EVS_CUDA(cudaMemcpyAsync(out_host, h->d_out[0], n * h->cfg.dim * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (hit_host != nullptr) EVS_CUDA(cudaMemcpyAsync(hit_host, h->d_hit[0], n, cudaMemcpyDeviceToHost, h->stream));
     EVS_CUDA(cudaStreamSynchronize(h->stream));
-    return EVS_OK;
+    return poll_error(h);
 }
 
 // Pipelined host-buffer path.  evs_submit_host returns at once with a ticket; at most kPipeSlots
@@ -756,6 +934,10 @@ int evs_lookup_batch_host(evs_handle h, const int64_t *idx_host, int32_t B, floa
 // of batch n; the batches themselves stay strictly ordered.
 static int pipe_init(evs_handle h) {
     if (h->s_in != nullptr) return EVS_OK;
+    t_alloc_bytes = &h->hbm_bytes;
+    struct AllocScope {
+        ~AllocScope() { t_alloc_bytes = nullptr; }
+    } alloc_scope;
     const long long n_max = static_cast<long long>(h->cfg.max_batch) * h->cfg.n_tables;
     EVS_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     EVS_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
@@ -778,7 +960,7 @@ int evs_submit_host(evs_handle h, const int64_t *idx_host, int32_t B, float *out
         set_error("evs_submit_host: bad handle / B / pointers");
         return EVS_ERR_INVALID;
     }
-    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     int rc = pipe_init(h);
     if (rc) return rc;
     const int slot = static_cast<int>(h->submitted % evs_handle_s::kPipeSlots);
@@ -786,6 +968,8 @@ int evs_submit_host(evs_handle h, const int64_t *idx_host, int32_t B, float *out
     const size_t n = static_cast<size_t>(B) * h->cfg.n_tables;
     EVS_CUDA(cudaMemcpyAsync(h->d_idx[slot], idx_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, h->s_in));
     EVS_CUDA(cudaEventRecord(h->ev_in[slot], h->s_in));
+    // look-ahead: the indices are on the device long before the batches queued ahead of this one have run
+    if ((rc = prefetch_next(h, reinterpret_cast<const int64_t *>(h->d_idx[slot]), B, h->ev_in[slot]))) return rc;
     EVS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[slot], 0));
     rc = evs_lookup_batch(h, reinterpret_cast<const int64_t *>(h->d_idx[slot]), B, h->d_out[slot], 0, h->d_hit[slot], nullptr,
                           h->stream);
@@ -802,9 +986,9 @@ int evs_submit_host(evs_handle h, const int64_t *idx_host, int32_t B, float *out
 
 int evs_wait_host(evs_handle h, int64_t ticket) {
     if (h == nullptr || ticket < 0 || ticket >= h->submitted) return EVS_ERR_INVALID;
-    if (ticket + evs_handle_s::kPipeSlots < h->submitted) return EVS_OK;         // its slot was already recycled => done
+    if (ticket + evs_handle_s::kPipeSlots < h->submitted) return poll_error(h);   // its slot was already recycled => done
     EVS_CUDA(cudaEventSynchronize(h->ev_out[ticket % evs_handle_s::kPipeSlots]));
-    return EVS_OK;
+    return poll_error(h);
 }
 
 int evs_sync(evs_handle h) {
@@ -1026,13 +1210,21 @@ int evs_interact(const float *x_dev, const float *ly_dev, float *r_dev, int32_t 
 }
 
 // ---- table-wise sharding over NVLink peer memory -----------------------------------------------
+// First 256 bytes of every rank's exchange block: what the rank was built with, so that evs_shard_connect can refuse
+// a peer whose layout differs (rows would otherwise land at the wrong offsets of its receive buffer).
+struct ShardHeader {
+    unsigned magic, world, rank, t_total, dim, batch_max;
+    unsigned table_mask;                      // bit g: this rank serves global table g
+};
+constexpr unsigned kShardMagic = 0x45565332u;  // "EVS2"
+
 int evs_shard_create(evs_handle h, int32_t rank, int32_t world, int32_t batch_max, evs_shard *out) {
     if (h == nullptr || out == nullptr || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || batch_max < world ||
         batch_max % world != 0 || batch_max > h->cfg.max_batch) {
         set_error("evs_shard_create: bad rank / world / batch_max (batch_max must be a multiple of world and <= max_batch)");
         return EVS_ERR_INVALID;
     }
-    EVS_CUDA(cudaSetDevice(h->cfg.device));
+    DeviceGuard dg(h->cfg.device);
     evs_shard s = new evs_shard_s();
     s->h = h;
     s->rank = rank;
@@ -1040,8 +1232,9 @@ int evs_shard_create(evs_handle h, int32_t rank, int32_t world, int32_t batch_ma
     s->batch_max = batch_max;
     s->t_total = h->cfg.n_tables_total;
     const size_t bl = static_cast<size_t>(batch_max / world);
+    s->off_recv = 256;
     s->recv_bytes = (bl * s->t_total * h->cfg.dim * sizeof(float) + 255) & ~static_cast<size_t>(255);
-    s->off_parts = 2 * s->recv_bytes;
+    s->off_parts = s->off_recv + 2 * s->recv_bytes;
     s->off_pflags = (s->off_parts + 2 * static_cast<size_t>(world) * batch_max + 255) & ~static_cast<size_t>(255);
     s->off_oflags = s->off_pflags + 256;
     s->bytes = s->off_oflags + 256;
@@ -1052,7 +1245,17 @@ int evs_shard_create(evs_handle h, int32_t rank, int32_t world, int32_t batch_ma
         delete s;
         return EVS_ERR_CUDA;
     }
+    h->hbm_bytes += s->bytes;
     cudaMemset(q, 0, s->bytes);
+    ShardHeader hd{};
+    hd.magic = kShardMagic;
+    hd.world = static_cast<unsigned>(world);
+    hd.rank = static_cast<unsigned>(rank);
+    hd.t_total = static_cast<unsigned>(s->t_total);
+    hd.dim = static_cast<unsigned>(h->cfg.dim);
+    hd.batch_max = static_cast<unsigned>(batch_max);
+    for (int g : h->table_ids) hd.table_mask |= 1u << g;
+    cudaMemcpy(q, &hd, sizeof(hd), cudaMemcpyHostToDevice);
     cudaDeviceSynchronize();
     s->block = static_cast<unsigned char *>(q);
     s->peer[rank] = s->block;
@@ -1063,6 +1266,7 @@ int evs_shard_create(evs_handle h, int32_t rank, int32_t world, int32_t batch_ma
 int evs_shard_export(evs_shard s, void *handle64) {
     if (s == nullptr || handle64 == nullptr) return EVS_ERR_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    DeviceGuard dg(s->h->cfg.device);
     cudaIpcMemHandle_t hd;
     EVS_CUDA(cudaIpcGetMemHandle(&hd, s->block));
     memcpy(handle64, &hd, sizeof(hd));
@@ -1071,25 +1275,52 @@ int evs_shard_export(evs_shard s, void *handle64) {
 
 int evs_shard_connect(evs_shard s, const void *handles) {
     if (s == nullptr || handles == nullptr) return EVS_ERR_INVALID;
-    EVS_CUDA(cudaSetDevice(s->h->cfg.device));
-    for (int r = 0; r < s->world; ++r) {
-        if (r == s->rank) continue;
-        cudaIpcMemHandle_t hd;
-        memcpy(&hd, static_cast<const unsigned char *>(handles) + 64 * r, sizeof(hd));
-        void *q = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&q, hd, cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) {
-            set_error("evs_shard_connect: cudaIpcOpenMemHandle(rank " + std::to_string(r) + ") -> " + cudaGetErrorString(e));
-            cudaGetLastError();
-            return EVS_ERR_CUDA;
-        }
-        s->peer[r] = static_cast<unsigned char *>(q);
-        s->opened[r] = true;
-    }
-    // the batch graph gets its k_signal / k_wait tail
+    DeviceGuard dg(s->h->cfg.device);
     evs_handle h = s->h;
+    unsigned seen = 0;
+    for (int r = 0; r < s->world; ++r) {
+        if (r != s->rank) {
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, static_cast<const unsigned char *>(handles) + 64 * r, sizeof(hd));
+            void *q = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&q, hd, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                set_error("evs_shard_connect: cudaIpcOpenMemHandle(rank " + std::to_string(r) + ") -> " + cudaGetErrorString(e));
+                cudaGetLastError();
+                return EVS_ERR_CUDA;
+            }
+            s->peer[r] = static_cast<unsigned char *>(q);
+            s->opened[r] = true;
+        }
+        // every rank must have been built for the same model and exchange layout, and no table may be served twice
+        ShardHeader ph{};
+        EVS_CUDA(cudaMemcpy(&ph, s->peer[r], sizeof(ph), cudaMemcpyDeviceToHost));
+        if (ph.magic != kShardMagic || ph.world != static_cast<unsigned>(s->world) || ph.rank != static_cast<unsigned>(r) ||
+            ph.t_total != static_cast<unsigned>(s->t_total) || ph.dim != static_cast<unsigned>(h->cfg.dim) ||
+            ph.batch_max != static_cast<unsigned>(s->batch_max) || (ph.table_mask & seen) != 0u) {
+            set_error("evs_shard_connect: rank " + std::to_string(r) + " was created with a different world / n_tables_total / dim / "
+                      "batch_max, or serves a table another rank serves");
+            return EVS_ERR_INVALID;
+        }
+        seen |= ph.table_mask;
+    }
+    // from here on the batch is k_serve<.., true> ... k_evict with the peer completion in its tail, and a table's rows
+    // go to the column of its global id in the owner ranks' receive buffers
     EVS_CUDA(cudaDeviceSynchronize());
     h->sharded = true;
+    for (int t = 0; t < h->cfg.n_tables; ++t) h->params.col[t] = h->table_ids[t];
+    // one-pass exchange needs every CTA of k_serve co-resident (they spin on words the peers' last CTAs raise)
+    {
+        const KernelSet ks = kernels_of_handle(h);
+        int per_sm = 0, sms = 0;
+        EVS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void *>(ks.serve_sh), kLookupThreads, 0));
+        EVS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device));
+        const int n_chunks = (s->batch_max + h->params.spc - 1) / h->params.spc;
+        // half of the slots at most: the look-ahead kernel and the caller's own kernels may hold the others
+        s->fused = n_chunks <= per_sm * sms / 2;
+        const char *nf = getenv("EVSTORE_B200_SHARD_TWO_PASS");    // tuning aid: 1 = separate probe pass (the round-1 path)
+        if (nf && nf[0] == '1') s->fused = false;
+    }
     if (h->use_graph) {
         if (h->graph) cudaGraphExecDestroy(h->graph);
         if (h->graph_src) cudaGraphDestroy(h->graph_src);
@@ -1112,6 +1343,7 @@ int evs_shard_lookup(evs_shard s, const int64_t *idx_dev, int32_t B, uint8_t *hi
             set_error("evs_shard_lookup: evs_shard_connect has not been called");
             return EVS_ERR_NOT_CONFIGURED;
         }
+    DeviceGuard dg(h->cfg.device);
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
     const unsigned epoch = ++s->epoch;
     const unsigned par = epoch & 1u;
@@ -1121,9 +1353,10 @@ int evs_shard_lookup(evs_shard s, const int64_t *idx_dev, int32_t B, uint8_t *hi
     sh.Bl = B / s->world;
     sh.T_total = s->t_total;
     sh.epoch = epoch;
+    sh.fused = s->fused ? 1 : 0;
     const size_t parts_par = s->off_parts + static_cast<size_t>(par) * s->world * s->batch_max;
     for (int r = 0; r < s->world; ++r) {
-        sh.recv[r] = reinterpret_cast<float *>(s->peer[r] + par * s->recv_bytes);
+        sh.recv[r] = reinterpret_cast<float *>(s->peer[r] + s->off_recv + par * s->recv_bytes);
         sh.parts[r] = s->peer[r] + parts_par + static_cast<size_t>(s->rank) * B;
         sh.probe_flag[r] = reinterpret_cast<unsigned *>(s->peer[r] + s->off_pflags) + s->rank;
         sh.out_flag[r] = reinterpret_cast<unsigned *>(s->peer[r] + s->off_oflags) + s->rank;
@@ -1137,16 +1370,18 @@ int evs_shard_lookup(evs_shard s, const int64_t *idx_dev, int32_t B, uint8_t *hi
     a.B = B;
     a.agg_out = h->d_agg;
     a.sh = sh;
-    a.probe_only = 1;
-    int rc = run_batch(h, a, st);
-    if (rc) return rc;
+    int rc;
+    if (!s->fused) {
+        a.probe_only = 1;
+        if ((rc = run_batch(h, a, st))) return rc;
+    }
     a.probe_only = 0;
     a.hit = hit_dev;
     a.out = nullptr;
     a.out_stride = static_cast<long long>(h->cfg.n_tables) * h->cfg.dim;
     rc = run_batch(h, a, st);
     if (rc) return rc;
-    *out_dev = reinterpret_cast<float *>(s->block + par * s->recv_bytes);
+    *out_dev = reinterpret_cast<float *>(s->block + s->off_recv + par * s->recv_bytes);
     return EVS_OK;
 }
 

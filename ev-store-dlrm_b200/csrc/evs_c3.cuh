@@ -192,7 +192,7 @@ __device__ void c3_update(const Params &p) {
     for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
         const unsigned long long key = (i < n1) ? __ldcg(p.tier[1].evicted + i) : __ldcg(p.tier[0].evicted + (i - n1));
         c.ring[(tail + i) & (c.ring_cap - 1)] = key;
-        const int tbl = static_cast<int>(key >> kKeyShift) - p.table_base;
+        const int tbl = p.loc[static_cast<int>(key >> kKeyShift) & (kMaxTables - 1)];
         const unsigned long long row = key & ((1ull << kKeyShift) - 1ull);
         const unsigned alt = __ldg(c.alt[tbl] + row);
         // upsert: a key that is already mapped keeps its slot (claiming the first free slot of its probe

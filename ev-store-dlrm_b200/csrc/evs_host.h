@@ -39,9 +39,9 @@ struct Tier {
 
 
 // Kernel ids for the launch counter / per-kernel CUDA-event timing (evs_set_profiling).
-enum KernelId { K_SERVE = 0, K_SCAN, K_UPDATE, K_EVICT, K_FETCH, K_COMPACT, K_PROBE, K_INTERACT, K_GATHER, K_SIGNAL, K_WAIT, K_COUNT };
-static const char *const kKernelNames[K_COUNT] = {"k_serve", "k_scan", "k_update", "k_evict", "k_fetch", "k_compact", "k_probe", "k_interact",
-                                                  "k_gather", "k_signal", "k_wait"};
+enum KernelId { K_SERVE = 0, K_SCAN, K_UPDATE, K_EVICT, K_PREFETCH, K_COMPACT, K_PROBE, K_INTERACT, K_GATHER, K_COUNT };
+static const char *const kKernelNames[K_COUNT] = {"k_serve", "k_scan", "k_update", "k_evict", "k_prefetch", "k_compact", "k_probe", "k_interact",
+                                                  "k_gather"};
 
 struct Profiler {
     bool on = false;
@@ -94,6 +94,7 @@ struct LaunchScope {
 struct evs_handle_s {
     evs_config cfg{};
     std::vector<int64_t> rows;
+    std::vector<int> table_ids;              // global id of local table t
     int n_tiers = 0;
     bool c3_active = false;
     evs::Caps caps;
@@ -101,15 +102,28 @@ struct evs_handle_s {
     evs::Params params{};                    // kernel parameter block (device pointers inside)
     std::vector<void *> c3_allocs;
     cudaStream_t stream = nullptr;           // the handle's own stream
-    cudaStream_t side = nullptr;             // miss fetch (+ slab fill), next to the eviction
-    cudaEvent_t ev_served = nullptr, ev_updated = nullptr, ev_filled = nullptr;
     cudaGraphNode_t serve_node = nullptr;    // its BatchArgs parameter is rewritten before every graph launch
     cudaGraph_t graph_src = nullptr;
-    cudaGraphExec_t graph = nullptr;         // k_serve -> [k_scan ->] k_update -> {k_evict || k_fetch}
+    cudaGraphExec_t graph = nullptr;         // k_serve -> [k_scan ->] k_update -> k_evict (eviction + miss-fetch roles)
     bool use_graph = true;
-    int fetch_list_threads = 256;            // threads per CTA of k_fetch_list
-    int fetch_list_ctas = 8;                 // CTAs of k_fetch_list (EVSTORE_B200_FETCH_LIST_CTAS overrides)
+    bool use_pdl = true;                     // the batch's kernels are chained by programmatic dependent launch
+    int fetch_list_ctas = 8;                 // CTAs of the miss-fetch role (EVSTORE_B200_FETCH_LIST_CTAS overrides)
     int evict_ctas = evs::kTierCtas;         // CTAs of k_evict per tier (EVSTORE_B200_EVICT_CTAS overrides)
+    // look-ahead (evs_prefetch): k_prefetch for batch seq+1 runs on pf_stream under the kernels of batch seq
+    cudaStream_t pf_stream = nullptr;
+    cudaEvent_t ev_done[2] = {};             // batch of that parity has finished (its staging rows may be overwritten)
+    bool ev_done_valid[2] = {};
+    cudaEvent_t ev_pf_ready = nullptr;       // scratch: orders pf_stream after a caller-supplied stream position
+    bool pf_ok = false;                      // staging possible (every backing row 16-byte aligned)
+    int pf_ctas = 16;
+    uint64_t seq = 0;                        // batches started on this handle
+    uint64_t pf_seq = 0;                     // batch number the last evs_prefetch staged for
+    uint32_t pf_gen = 0;                     // generation of that announcement (tags of its staged rows)
+    const void *pf_idx = nullptr;
+    int pf_B = 0;
+    unsigned *err_host = nullptr;            // pinned, device-mapped: last device-side error code (0 = none)
+    int sticky_error = 0;                    // first error evs_check saw
+    size_t hbm_bytes = 0;                    // device memory this handle allocated
     evs::GlobalCtl *g = nullptr;             // device
     evs::BatchArgs *d_args = nullptr;        // device copy of the per-batch arguments
     long long *d_rows = nullptr;
@@ -123,7 +137,7 @@ struct evs_handle_s {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[kPipeSlots] = {}, ev_comp[kPipeSlots] = {}, ev_out[kPipeSlots] = {};
     int64_t submitted = 0;
-    bool sharded = false;                    // an evs_shard is connected: the batch ends with k_signal + k_wait
+    bool sharded = false;                    // an evs_shard is connected: k_serve<.., true>, k_evict closes the batch with the peers
     std::vector<void *> registered;          // host ranges we page-locked
     std::vector<void *> dev_allocs;
     uint64_t batches = 0;
@@ -137,7 +151,8 @@ struct evs_shard_s {
     int batch_max = 0;                       // global batch
     int t_total = 0;
     unsigned char *block = nullptr;          // our exchange block (cudaMalloc, exported by CUDA IPC)
-    size_t bytes = 0, off_parts = 0, off_pflags = 0, off_oflags = 0, recv_bytes = 0;
+    size_t bytes = 0, off_recv = 0, off_parts = 0, off_pflags = 0, off_oflags = 0, recv_bytes = 0;
+    bool fused = true;                       // one-pass exchange inside k_serve (else a separate probe_only pass)
     unsigned char *peer[evs::kMaxPeers] = {};   // peer r's block in our address space (ours at [rank])
     bool opened[evs::kMaxPeers] = {};
     unsigned epoch = 0;

@@ -33,28 +33,41 @@ __device__ __forceinline__ unsigned long long u64_of(unsigned lo, unsigned hi) {
     return (static_cast<unsigned long long>(hi) << 32) | lo;
 }
 
+// Programmatic dependent launch (Params::pdl): a kernel of the batch is launched while its predecessor drains; it may
+// run its preamble, and blocks here until the predecessor's grid has completed and its writes are visible.
+__device__ __forceinline__ void griddep_wait(const Params &p) {
+    if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_launch(const Params &p) {
+    if (p.pdl) asm volatile("griddepcontrol.launch_dependents;");
+}
+
 // Where the fp32 rows of sample s go: the caller's buffer, or -- table-wise sharded -- the receive
-// buffer of the rank that owns the sample, at this rank's table offset (peer memory over NVLink).
+// buffer of the rank that owns the sample (peer memory over NVLink).  Local table t lands at column p.col[t].
 __device__ __forceinline__ float *out_row(const BatchArgs &a, const Params &p, int s) {
     if (a.sh.world <= 1) return a.out + static_cast<size_t>(s) * a.out_stride;
     const int dst = s / a.sh.Bl, ls = s - dst * a.sh.Bl;
-    return a.sh.recv[dst] + (static_cast<size_t>(ls) * a.sh.T_total + p.table_base) * p.D;
+    return a.sh.recv[dst] + static_cast<size_t>(ls) * a.sh.T_total * p.D;
 }
 __device__ __forceinline__ bool out_vec_ok(const BatchArgs &a, int D) {
     if (a.sh.world > 1) return (D & 3) == 0;              // receive buffers are cudaMalloc'ed blocks
     return ((reinterpret_cast<uintptr_t>(a.out) & 15u) == 0) && ((a.out_stride & 3) == 0) && ((D & 3) == 0);
 }
+__device__ __forceinline__ void set_error(const Params &p, unsigned code) {
+    p.g->error = code;
+    *reinterpret_cast<volatile unsigned *>(p.err_host) = code;
+}
 
 // Lanes 0..world-1 wait until every rank's flag word has reached `epoch` (the words live in OUR
 // memory, peers store into them).  Gives up after kPeerTimeoutNs and reports error 7.
-__device__ __forceinline__ void wait_flags(const unsigned *flags, int world, unsigned epoch, int lane, GlobalCtl *g) {
+__device__ __forceinline__ void wait_flags(const unsigned *flags, int world, unsigned epoch, int lane, const Params &p) {
     if (lane < world) {
         const volatile unsigned *f = flags + lane;
         if (static_cast<int>(*f - epoch) < 0) {
             const unsigned long long t0 = gtime();
             while (static_cast<int>(*f - epoch) < 0) {
                 if (gtime() - t0 > kPeerTimeoutNs) {
-                    g->error = 7u;
+                    set_error(p, 7u);
                     break;
                 }
             }
@@ -147,20 +160,19 @@ __device__ __forceinline__ void fetch_row(const unsigned char *__restrict__ src,
     for (unsigned o = row_bytes + lane; o < stride; o += 32u) stage[o] = 0;
 }
 
-// Fetch one missing row (table t, row r of sample s) from the backing store: dequantised into the
-// output and, raw, into the slab row of the slot the position claimed (dst; null for a same-batch
+// Fetch one missing row from `src` (its backing-store row, or the copy evs_prefetch staged in HBM): dequantised
+// into the output and, raw, into the slab row of the slot the position claimed (dst; null for a same-batch
 // duplicate of a key another position claimed).  Executed by a group of `gsize` consecutive lanes
 // (glane = lane within the group) straight through registers when rows are 16-byte aligned
 // (stage == nullptr), else by the whole warp via a shared-memory staging row.
 template <int PREC>
-__device__ __forceinline__ void fetch_one(const TierDev &tier, float *orow, int D, int t, long long r,
+__device__ __forceinline__ void fetch_one(const TierDev &tier, const unsigned char *src, bool coherent, float *orow, int D,
                                           unsigned char *dst, int lane, int glane, int gsize, unsigned char *stage,
                                           bool vec, const CodecLut *lut) {
-    const unsigned char *src = tier.store[t] + static_cast<size_t>(r) * tier.row_bytes;
     const int cpr = static_cast<int>(tier.row_stride >> 4);
     if (stage == nullptr) {
         for (int c = glane; c < cpr; c += gsize) {
-            const uint4 v = ldg16(src + (c << 4));
+            const uint4 v = coherent ? __ldcg(reinterpret_cast<const uint4 *>(src + (c << 4))) : ldg16(src + (c << 4));
             if (dst != nullptr) *reinterpret_cast<uint4 *>(dst + (c << 4)) = v;
             decode_store<PREC>(v, orow, c, D, vec, lut);
         }
@@ -176,100 +188,30 @@ __device__ __forceinline__ void fetch_one(const TierDev &tier, float *orow, int 
     }
 }
 
-// ---- k_fetch -----------------------------------------------------------------------------
-// Runs on a side stream after k_update (the slots are claimed), next to k_evict: a warp scans 32
-// positions' flags at a time and fetches the rows of the misses among them from the host-pinned
-// backing store into the output and the slab (groups of lanes share a row when rows are 16-byte
-// aligned).  PCIe read tags bound it: ~110 rows / us on this part, whatever the row size <= 256 B.
-template <int PREC>
-__device__ __forceinline__ void fetch_group(const TierDev &tier, const Params &p, const BatchArgs &a, int base, unsigned mm,
-                                            int lane, bool aligned, unsigned char *stage, bool vec, const CodecLut *lut) {
-    const int T = p.T, D = p.D;
-    auto row_of = [&](int pos, int &s, int &t) {
-        s = pos / T;
-        t = pos - s * T;
-        long long r = __ldg(a.idx + static_cast<size_t>(t) * a.B + s);
-        if (r < 0 || r >= __ldg(p.rows + t)) r = 0;
-        return r;
-    };
-    // the slab row of the slot this position claimed in k_update, if it is the claimer
-    auto slab_of = [&](int pos) -> unsigned char * {
-        const unsigned sw = __ldcg(p.pos_slot + pos);
-        return (sw & kClaimedBit) ? tier.slab + static_cast<size_t>(sw & ~kClaimedBit) * tier.row_stride : nullptr;
-    };
-    if (aligned) {
-        int gsize = 1;
-        while (gsize < static_cast<int>(tier.row_stride >> 4) && gsize < 32) gsize <<= 1;
-        const int ngrp = 32 / gsize, grp = lane / gsize, gl = lane - grp * gsize;
-        while (mm) {
-            unsigned rest = mm;
-            int mine = -1;
-            for (int k = 0; k < ngrp && rest; ++k) {
-                const int bit = __ffs(rest) - 1;
-                rest &= rest - 1;
-                if (k == grp) mine = bit;
-            }
-            mm = rest;
-            if (mine >= 0) {
-                int s, t;
-                const long long r = row_of(base + mine, s, t);
-                fetch_one<PREC>(tier, out_row(a, p, s) + t * D, D, t, r, slab_of(base + mine), lane, gl, gsize, nullptr, vec, lut);
-            }
-        }
-    } else {
-        while (mm) {
-            const int bit = __ffs(mm) - 1;
-            mm &= mm - 1;
-            int s, t;
-            const long long r = row_of(base + bit, s, t);
-            fetch_one<PREC>(tier, out_row(a, p, s) + t * D, D, t, r, slab_of(base + bit), lane, lane, 32, stage, vec, lut);
-        }
-    }
+// Lanes per row when every stored row is 16-byte aligned (a power of two covering the widest row's chunks), else 32.
+__device__ __forceinline__ int fetch_gsize(const Params &p, int n_tiers) {
+    const bool al0 = (p.store_aligned & 1) != 0, al1 = (n_tiers < 2) || (p.store_aligned & 2) != 0;
+    if (!(al0 && al1)) return 32;
+    unsigned cpr = p.tier[0].row_stride >> 4;
+    if (n_tiers == 2 && (p.tier[1].row_stride >> 4) > cpr) cpr = p.tier[1].row_stride >> 4;
+    int gsize = 1;
+    while (gsize < static_cast<int>(cpr) && gsize < 32) gsize <<= 1;
+    return gsize;
 }
 
+// ---- the miss-fetch role of k_evict ---------------------------------------------------------
+// Driven by the compact miss list k_serve wrote (entry = position | tier << 31): every group of lanes takes one
+// missing row per round, so a SMALL number of CTAs keeps a bounded number of PCIe reads in flight all the time.
+// Why: the link serves 55-110 row reads / us whatever is asked of it (the GPU's address translation for system
+// memory is the limit once the table exceeds ~512 MB: profiles/r2_zc_page_probe.txt); letting every miss of the
+// batch issue at once only delays the HBM accesses of the eviction CTAs running next to it (profiles/r1_fetch_list_ab.md).
+// A row that evs_prefetch already staged in HBM for this batch (tag == generation << 1 | tier) is copied from there
+// instead -- the common case when the caller announces its next batch.
+// Returns true in the CTA that finished last (all rows of the batch are in place).
 template <int P0, int P1>
-__global__ void __launch_bounds__(256) k_fetch(const __grid_constant__ Params p) {
-    extern __shared__ __align__(16) unsigned char s_stage[];    // warps * max(row_stride); unaligned rows only
-    __shared__ CodecLut s_lut;
-    codec_lut_init<P0, P1>(&s_lut);
-    __syncthreads();
-    const BatchArgs a = *p.args;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wpc = blockDim.x >> 5;
-    const int N = a.B * p.T;
-    const TierDev &t0 = p.tier[0];
-    const TierDev &t1 = p.tier[1];
-    unsigned char *stage = s_stage + static_cast<size_t>(warp) * p.stage_stride;
-    const bool vec = out_vec_ok(a, p.D);
-    for (int base = (blockIdx.x * wpc + warp) * 32; base < N; base += gridDim.x * wpc * 32) {
-        const int pos = base + lane;
-        const unsigned f = (pos < N) ? p.flags[pos] : 0u;
-        const unsigned m0 = __ballot_sync(kFull, (f & kFlagMiss) && !(f & kFlagTier));
-        const unsigned m1 = __ballot_sync(kFull, (f & kFlagMiss) && (f & kFlagTier));
-        if (m0) fetch_group<P0>(t0, p, a, base, m0, lane, (p.store_aligned & 1) != 0, stage, vec, &s_lut);
-        if (P1 != 0 && m1)
-            fetch_group<(P1 != 0 ? P1 : 32)>(t1, p, a, base, m1, lane, (p.store_aligned & 2) != 0, stage, vec, &s_lut);
-    }
-}
-
-// ---- k_fetch_list ------------------------------------------------------------------------
-// The same fetch driven by the compact miss list k_serve wrote (entry = position | tier << 31): every group
-// of lanes takes one missing row per round, so a SMALL grid keeps a bounded number of PCIe reads in flight
-// all the time.  Why: the link serves ~110 row reads / us whatever is asked of it; k_fetch above lets every
-// miss of the batch issue at once (thousands of warps each finding < 1 miss), and the reads queued beyond what
-// the link takes delay the HBM accesses of k_evict running next to it (12 -> 20 us); with few warps scanning
-// the flags the fetch itself becomes a chain of dependent round trips (profiles/r1_fetch_ctas_*.json).
-// Measured (profiles/r1_fetch_list_ab.md): ~512 rows in flight is the optimum however they are spread over
-// SMs (8 x 256, 16 x 128, 32 x 64, 64 x 32 threads all within 0.5 us); several rows per lane group and round
-// (fewer warps, same reads in flight) is much slower -- one SM does not keep more than a few dozen sysmem
-// reads going.
-template <int P0, int P1>
-__global__ void __launch_bounds__(256) k_fetch_list(const __grid_constant__ Params p) {
-    extern __shared__ __align__(16) unsigned char s_stage[];    // warps * max(row_stride); unaligned rows only
-    __shared__ CodecLut s_lut;
-    codec_lut_init<P0, P1>(&s_lut);
-    __syncthreads();
-    // the few per-batch arguments this kernel needs, in registers (a by-value copy of BatchArgs would live in
+__device__ __forceinline__ bool fetch_list_body(const Params &p, unsigned cta, unsigned n_ctas, unsigned char *s_stage,
+                                                const CodecLut *s_lut, unsigned *s_flag) {
+    // the few per-batch arguments this role needs, in registers (a by-value copy of BatchArgs would live in
     // local memory: ShardArgs' pointer arrays are indexed dynamically); peers' buffers are looked up on demand
     const BatchArgs *ga = p.args;
     const long long *idx = ga->idx;
@@ -277,6 +219,9 @@ __global__ void __launch_bounds__(256) k_fetch_list(const __grid_constant__ Para
     float *out = ga->out;
     const long long out_stride = ga->out_stride;
     const int world = ga->sh.world, Bl = ga->sh.Bl, T_total = ga->sh.T_total;
+    const unsigned want_tag = ga->pf_gen << 1;
+    const bool use_pf = ga->pf_gen != 0u;
+    const unsigned par = ga->seq & 1u;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
     const int T = p.T, D = p.D;
@@ -286,52 +231,59 @@ __global__ void __launch_bounds__(256) k_fetch_list(const __grid_constant__ Para
     const bool vec = (world > 1) ? ((D & 3) == 0)
                                  : (((reinterpret_cast<uintptr_t>(out) & 15u) == 0) && ((out_stride & 3) == 0) && ((D & 3) == 0));
     const bool al0 = (p.store_aligned & 1) != 0, al1 = (P1 == 0) || (p.store_aligned & 2) != 0;
-    // all rows 16-byte aligned: groups of lanes share a row straight through registers; else a warp per row
-    int gsize = 32;
-    if (al0 && al1) {
-        unsigned cpr = t0.row_stride >> 4;
-        if (P1 != 0 && (t1.row_stride >> 4) > cpr) cpr = t1.row_stride >> 4;
-        gsize = 1;
-        while (gsize < static_cast<int>(cpr) && gsize < 32) gsize <<= 1;
-    }
+    const int gsize = fetch_gsize(p, P1 == 0 ? 1 : 2);
     const int rpw = 32 / gsize, grp = lane / gsize, gl = lane - grp * gsize;
     unsigned char *stage = s_stage + static_cast<size_t>(warp) * p.stage_stride;
-    const unsigned gw = blockIdx.x * wpc + warp, nw = gridDim.x * wpc;
+    const unsigned gw = cta * wpc + warp, nw = n_ctas * wpc;
     for (unsigned i0 = gw * rpw; i0 < n; i0 += nw * rpw) {
         const unsigned i = i0 + grp;
         if (i < n) {
             const unsigned e = __ldcg(p.miss_list + i);
             const int pos = static_cast<int>(e & 0x7FFFFFFFu);
+            const unsigned tr = (P1 == 0) ? 0u : (e >> 31);
             const int s = pos / T, t = pos - s * T;
-            long long r = __ldg(idx + static_cast<size_t>(t) * B + s);
-            if (r < 0 || r >= __ldg(p.rows + t)) r = 0;
             const unsigned sw = __ldcg(p.pos_slot + pos);       // the slot this position claimed in k_update, if it is the claimer
+            bool staged = false;
+            if (use_pf) staged = __ldcg(p.pf_tag + static_cast<size_t>(par) * p.n_max + pos) == (want_tag | tr);
             float *orow;
             if (world <= 1) {
-                orow = out + static_cast<size_t>(s) * out_stride + t * D;
+                orow = out + static_cast<size_t>(s) * out_stride + p.col[t] * D;
             } else {                                            // as out_row(): the owner rank's receive buffer
                 const int dst = s / Bl, ls = s - dst * Bl;
-                orow = ga->sh.recv[dst] + (static_cast<size_t>(ls) * T_total + p.table_base + t) * D;
+                orow = ga->sh.recv[dst] + (static_cast<size_t>(ls) * T_total + p.col[t]) * D;
             }
-            if (P1 == 0 || !(e >> 31)) {
-                unsigned char *dst = (sw & kClaimedBit) ? t0.slab + static_cast<size_t>(sw & ~kClaimedBit) * t0.row_stride : nullptr;
-                fetch_one<P0>(t0, orow, D, t, r, dst, lane, gl, gsize, al0 ? nullptr : stage, vec, &s_lut);
+            const TierDev &tier = tr ? t1 : t0;
+            const unsigned char *src;
+            if (staged) {
+                __threadfence();                                // the row was written before its tag
+                src = p.pf_rows + (static_cast<size_t>(par) * p.n_max + pos) * p.stage_stride;
             } else {
-                unsigned char *dst = (sw & kClaimedBit) ? t1.slab + static_cast<size_t>(sw & ~kClaimedBit) * t1.row_stride : nullptr;
-                fetch_one<(P1 != 0 ? P1 : 32)>(t1, orow, D, t, r, dst, lane, gl, gsize, al1 ? nullptr : stage, vec, &s_lut);
+                long long r = __ldg(idx + static_cast<size_t>(t) * B + s);
+                if (r < 0 || r >= __ldg(p.rows + t)) r = 0;
+                src = tier.store[t] + static_cast<size_t>(r) * tier.row_bytes;
             }
+            unsigned char *dst = (sw & kClaimedBit) ? tier.slab + static_cast<size_t>(sw & ~kClaimedBit) * tier.row_stride : nullptr;
+            if (P1 == 0 || !tr)
+                fetch_one<P0>(t0, src, staged, orow, D, dst, lane, gl, gsize, (al0 || staged) ? nullptr : stage, vec, s_lut);
+            else
+                fetch_one<(P1 != 0 ? P1 : 32)>(t1, src, staged, orow, D, dst, lane, gl, gsize, (al1 || staged) ? nullptr : stage, vec, s_lut);
         }
     }
     // the last CTA empties the list for the next batch (every CTA has read the count by then)
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(p.miss_ctl + 1, 1u) == gridDim.x - 1) {
+        if (world > 1) __threadfence_system();      // rows stored into peers' receive buffers
+        else __threadfence();
+        const bool last = atomicAdd(p.miss_ctl + 1, 1u) == n_ctas - 1;
+        if (last) {
             p.miss_ctl[0] = 0u;
             p.miss_ctl[1] = 0u;
-            p.dbg[28] += gtime() - p.dbg[4];      // fetch span, counted from the start of the k_evict it runs beside
+            p.dbg[28] += gtime() - p.dbg[4];      // fetch span, counted from the start of the k_evict it is part of
         }
+        *s_flag = last ? 1u : 0u;
     }
+    __syncthreads();
+    return *s_flag != 0u;
 }
 
 // ---- k_serve ---------------------------------------------------------------------------
@@ -363,8 +315,8 @@ __device__ __forceinline__ int grp_sum(int v, int L) {
 // T*CPR 16-byte chunks so consecutive lanes read consecutive 16 B of a row and write consecutive
 // floats of the output; all loads of an unrolled round are issued before the first decode/store.
 template <int PREC>
-__device__ __forceinline__ void gather_tier(const TierDev &t, int k, int src_t, unsigned src_s, float *orow, bool sact, int T,
-                                            int D, bool vec, const Grp &q, const CodecLut *lut) {
+__device__ __forceinline__ void gather_tier(const Params &p, const TierDev &t, int k, int src_t, unsigned src_s, float *orow, bool sact,
+                                            int T, int D, bool vec, const Grp &q, const CodecLut *lut) {
     if (__ballot_sync(kFull, src_t == k) == 0u) return;
     constexpr int U = 4;
     const int cpr = static_cast<int>(t.row_stride >> 4);
@@ -386,14 +338,20 @@ __device__ __forceinline__ void gather_tier(const TierDev &t, int k, int src_t, 
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (ok[u]) decode_store<PREC>(v[u], orow + tt[u] * D, part[u], D, vec, lut);
+            if (ok[u]) decode_store<PREC>(v[u], orow + p.col[tt[u]] * D, part[u], D, vec, lut);
     }
 }
 
 // A CTA covers p.spc = 8 * (32 / L) consecutive samples, so the int64 index tile is read as T runs
 // of 8*spc contiguous bytes.  P1 == 0: single tier.  The cache state is only read here (C3 recency
 // flags excepted).
-template <int P0, int P1>
+// SH: the handle is one rank of a table-wise sharded cache.  With a.sh.fused the kernel is the whole exchange: it
+// stores each sample's local hit count into every rank's count table, gathers the rows it can already serve
+// straight into the owner ranks' receive buffers (which row serves a key does not depend on agg_hit), and only then
+// waits for the peers' counts -- their NVLink round trip runs under the gather -- to derive agg_hit, the EvLFU
+// flags and the miss list.  Every CTA spins on words that the peers' LAST CTAs raise, so the grid must be
+// co-resident (evs_shard_connect checks the occupancy and falls back to a separate probe_only pass otherwise).
+template <int P0, int P1, bool SH>
 __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(const __grid_constant__ Params p, const __grid_constant__ BatchArgs a) {
     __shared__ long long s_idx[kLookupThreads];          // [sample in CTA][L]
     __shared__ unsigned s_hist[kSeqs];
@@ -406,6 +364,7 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
         if (p.dbg[4] > p.dbg[6]) p.dbg[14] += 1ull;       // previous batch's k_evict has not finished (must stay 0)
         *p.args = a;                                       // the later kernels of this batch read the arguments here
     }
+    griddep_launch(p);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int T = p.T, B = a.B, D = p.D;
     const Grp q = make_grp(p, lane);
@@ -431,16 +390,17 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
     const bool sact = s < B;                   // a group past the batch end only joins the warp-wide operations
     const bool act = sact && q.gl < T;
     const int tbl = q.gl;
+    const int gtbl = act ? p.tid[tbl] : 0;     // global table id
     unsigned long long key = 0, m0 = 0, m1 = 0;
     unsigned slot0 = 0, slot1 = 0;
     bool h0 = false, h1 = false;
     if (act) {
         long long r = s_idx[(j << p.L_shift) + tbl];
         if (r < 0 || r >= __ldg(p.rows + tbl)) {
-            p.g->error = 1u;                   // EVS_ERR_INDEX; answer from row 0
+            set_error(p, 1u);                  // EVS_ERR_INDEX; answer from row 0
             r = 0;
         }
-        key = make_key(p.table_base + tbl, r);
+        key = make_key(gtbl, r);
         // both tiers' first rounds are in flight together
         const unsigned i0 = hash_key(key, t0.hash_mask);
         uint4 v0[4];
@@ -487,32 +447,61 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
     else if (full) agg = __popc(m_h0 | m_h1) + __popc(m_c3);           // evlfu_8.cpp:512-541
     else agg = __popc(m_h0);                                           // evlfu_8.cpp:601 (C1 not full)
     const int local_agg = agg;
-    if (a.probe_only) {
-        if (a.sh.world > 1) {
-            // sharded probe: our count of every sample goes into every rank's count table; the last
-            // CTA raises the ranks' "counts of epoch e complete" words
-            if (sact)
-                for (int r = q.gl; r < a.sh.world; r += q.L) a.sh.parts[r][s] = static_cast<uint8_t>(local_agg);
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const bool last = atomicAdd(p.probe_done, 1u) == gridDim.x - 1;
-                if (last) {
-                    *p.probe_done = 0u;
-                    __threadfence_system();
-                    for (int r = 0; r < a.sh.world; ++r) *reinterpret_cast<volatile unsigned *>(a.sh.probe_flag[r]) = a.sh.epoch;
-                }
+    const bool fused = SH && a.sh.world > 1 && a.sh.fused != 0 && a.agg_in == nullptr;
+    if (SH && a.sh.world > 1 && (a.probe_only || fused)) {
+        // our count of every sample goes into every rank's count table; the last CTA of the batch raises the
+        // ranks' "counts of epoch e complete" words
+        if (sact)
+            for (int r = q.gl; r < a.sh.world; r += q.L) a.sh.parts[r][s] = static_cast<uint8_t>(local_agg);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned n_act = static_cast<unsigned>((B + spc - 1) / spc);
+            const bool last = atomicAdd(p.probe_done, 1u) == n_act - 1;
+            if (last) {
+                *p.probe_done = 0u;
+                __threadfence_system();
+                for (int r = 0; r < a.sh.world; ++r) *reinterpret_cast<volatile unsigned *>(a.sh.probe_flag[r]) = a.sh.epoch;
             }
-        } else if (q.gl == 0 && sact) {
-            a.agg_out[s] = static_cast<uint8_t>(local_agg);
         }
+    }
+    if (a.probe_only) {
+        if (!(SH && a.sh.world > 1) && q.gl == 0 && sact) a.agg_out[s] = static_cast<uint8_t>(local_agg);
         return;
     }
+
+    // which resident row answers a key does not depend on agg_hit (the approximate substitution excepted)
+    uint8_t hc = kHitMiss;
+    int src_t = -1;
+    unsigned src_s = 0;
+    if (act) {
+        if (h0) {                                                      // C1 serves (and overrides C2)
+            hc = kHitC1;
+            src_t = 0;
+            src_s = slot0;
+        } else if (c3hit) {
+            hc = kHitC3;
+            src_t = c3_tier;
+            src_s = c3_slot;
+        } else if (P1 != 0 && full && h1) {                            // C2 serves
+            hc = kHitC2;
+            src_t = 1;
+            src_s = slot1;
+        }
+    }
+    float *orow = sact ? out_row(a, p, s) : nullptr;
+    const bool vec = out_vec_ok(a, D);
+    const bool early = fused && !(P1 == 0 && p.approx_thres > 0);
+    if (SH && early) {
+        gather_tier<P0>(p, t0, 0, src_t, src_s, orow, sact, T, D, vec, q, &s_lut);
+        if (P1 != 0) gather_tier<(P1 != 0 ? P1 : 32)>(p, t1, 1, src_t, src_s, orow, sact, T, D, vec, q, &s_lut);
+    }
+
     if (a.agg_in != nullptr) {
         if (sact) agg = a.agg_in[s];
-    } else if (a.sh.world > 1) {
+    } else if (SH && a.sh.world > 1) {
         // exact groupability: agg_hit = sum over the ranks of their local hit counts
-        wait_flags(a.sh.my_probe_flags, a.sh.world, a.sh.epoch, lane, p.g);
+        wait_flags(a.sh.my_probe_flags, a.sh.world, a.sh.epoch, lane, p);
         int v = 0;
         if (sact)
             for (int r = q.gl; r < a.sh.world; r += q.L) v += static_cast<int>(__ldcg(a.sh.my_parts + static_cast<size_t>(r) * a.B + s));
@@ -523,27 +512,16 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
     const bool lru = (P1 == 0) && (p.policy == 1);
     const int bkt = lru ? 0 : agg;
 
-    uint8_t f = 0, hc = kHitMiss;
-    int src_t = -1;
-    unsigned src_s = 0;
+    uint8_t f = 0;
     const int pos = s * T + tbl;
     if (act) {
-        if (h0) {                                                      // C1 serves (and overrides C2)
-            hc = kHitC1;
-            src_t = 0;
-            src_s = slot0;
+        if (hc == kHitC1) {
             if (lru || meta_bucket(m0) < agg) {
                 f = static_cast<uint8_t>(bkt + 1);
                 p.pos_slot[pos] = slot0;
             }
-        } else if (c3hit) {
-            hc = kHitC3;
-            src_t = c3_tier;
-            src_s = c3_slot;
-        } else if (P1 != 0 && full && h1) {                            // C2 serves
-            hc = kHitC2;
-            src_t = 1;
-            src_s = slot1;
+        } else if (hc == kHitC3) {
+        } else if (hc == kHitC2) {
             if (meta_bucket(m1) < agg) {
                 f = static_cast<uint8_t>(kFlagTier | (agg + 1));
                 p.pos_slot[pos] = slot1;
@@ -555,7 +533,7 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
             // fetch and insert.  C1 not full: everything goes to C1 (evlfu_8.cpp:590-602).  C1 full:
             // odd tables to C1, even to C2 while agg < high_agghit_threshold, else all to C2 (:573-588).
             int tier_ins = 0;
-            if (P1 != 0 && full) tier_ins = (agg < p.high_thres && ((p.table_base + tbl) & 1)) ? 0 : 1;
+            if (P1 != 0 && full) tier_ins = (agg < p.high_thres && (gtbl & 1)) ? 0 : 1;
             f = static_cast<uint8_t>(kFlagMiss | (tier_ins ? kFlagTier : 0) | (bkt + 1));
         }
         p.flags[pos] = f;
@@ -576,10 +554,10 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
     const unsigned m_miss = __ballot_sync(kFull, (f & kFlagMiss) != 0) & q.mask;
     const unsigned m_c2 = __ballot_sync(kFull, hc == kHitC2) & q.mask;
     const unsigned m_ap = __ballot_sync(kFull, hc == kHitApprox) & q.mask;
-    // compact miss list for k_fetch_list: one atomic per sample that missed anything, issued here so that
+    // compact miss list for the fetch role of k_evict: one atomic per sample that missed anything, issued here so that
     // its round trip hides behind the gather below
     unsigned mbase = 0;
-    if (p.fetch_mode != 0 && q.gl == 0 && sact && m_miss) mbase = atomicAdd(p.miss_ctl, static_cast<unsigned>(__popc(m_miss)));
+    if (q.gl == 0 && sact && m_miss) mbase = atomicAdd(p.miss_ctl, static_cast<unsigned>(__popc(m_miss)));
     if (q.gl == 0 && sact) {
         a.agg_out[s] = static_cast<uint8_t>(agg);
         if (m_f0) atomicAdd(&s_hist[bkt], static_cast<unsigned>(__popc(m_f0)));
@@ -593,14 +571,12 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
         if (agg == p.n_perfect_agg) atomicAdd(&s_stat[5], 1u);
     }
 
-    {
-        float *orow = sact ? out_row(a, p, s) : nullptr;
-        const bool vec = out_vec_ok(a, D);
-        gather_tier<P0>(t0, 0, src_t, src_s, orow, sact, T, D, vec, q, &s_lut);
-        if (P1 != 0) gather_tier<(P1 != 0 ? P1 : 32)>(t1, 1, src_t, src_s, orow, sact, T, D, vec, q, &s_lut);
+    if (!(SH && early)) {
+        gather_tier<P0>(p, t0, 0, src_t, src_s, orow, sact, T, D, vec, q, &s_lut);
+        if (P1 != 0) gather_tier<(P1 != 0 ? P1 : 32)>(p, t1, 1, src_t, src_s, orow, sact, T, D, vec, q, &s_lut);
     }
 
-    if (p.fetch_mode != 0) {
+    {
         mbase = __shfl_sync(kFull, mbase, q.base);
         if (f & kFlagMiss)
             p.miss_list[mbase + __popc(m_miss & ((1u << lane) - 1u))] = static_cast<unsigned>(pos) | ((f & kFlagTier) ? 0x80000000u : 0u);
@@ -638,6 +614,8 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
 // chunk's first record inside the sequence.  One CTA per (group, bucket).
 __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Params p) {
     __shared__ unsigned s_w[8];
+    griddep_launch(p);
+    griddep_wait(p);
     const int B = p.args->B;
     const int n_chunks = (B + p.spc - 1) / p.spc;
     if (p.L == 32 && n_chunks <= p.quad_max) return;          // k_update sums its predecessors directly
@@ -958,19 +936,6 @@ __device__ void evict_tier(const TierDev &tier, const Params &p) {
         if (ev < need) c->error = 4u;
     }
     __syncthreads();
-}
-
-// ---- sharded completion ----------------------------------------------------------------------
-// k_signal runs after k_serve and k_fetch of a batch: every row this rank owes its peers has been
-// stored, tell them.  k_wait holds the stream until every peer has said the same to us.
-__global__ void k_signal(const __grid_constant__ Params p) {
-    const ShardArgs sh = p.args->sh;
-    __threadfence_system();
-    if (static_cast<int>(threadIdx.x) < sh.world) *reinterpret_cast<volatile unsigned *>(sh.out_flag[threadIdx.x]) = sh.epoch;
-}
-__global__ void k_wait(const __grid_constant__ Params p) {
-    const ShardArgs sh = p.args->sh;
-    wait_flags(sh.my_out_flags, sh.world, sh.epoch, threadIdx.x & 31, p.g);
 }
 
 // ---- k_compact ---------------------------------------------------------------------------

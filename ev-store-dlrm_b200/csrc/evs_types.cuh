@@ -151,6 +151,8 @@ struct ShardArgs {
     const uint8_t *my_parts;               // our count table of this parity: [world][B]
     const unsigned *my_probe_flags;        // [world]
     const unsigned *my_out_flags;          // [world]
+    int fused;                             // 1: k_serve sends its counts, gathers, THEN waits for the peers' counts (one pass);
+                                           // 0: a probe_only pass sends the counts first (grids too large to be co-resident)
 };
 
 struct BatchArgs {
@@ -162,7 +164,17 @@ struct BatchArgs {
     uint8_t *agg_out;                      // [B]
     int B;
     int probe_only;
+    unsigned seq;                          // number of this batch on the handle (>= 1)
+    unsigned pf_gen;                       // != 0: evs_prefetch staged rows for this batch (Params::pf_*), tagged with this generation
     ShardArgs sh;
+};
+
+// Arguments of the look-ahead kernel (k_prefetch, evs_prefetch.cuh)
+struct PrefetchArgs {
+    const long long *idx;                  // [T][B] of the NEXT batch
+    int B;
+    unsigned seq;                          // the number that batch will get (its parity selects the staging buffer)
+    unsigned gen;                          // generation of this announcement (>= 1): the tag of the rows it stages
 };
 
 // Everything a kernel of the batch pipeline needs; constant for the life of a handle.
@@ -174,6 +186,9 @@ struct Params {
     int L, L_shift;                        // lanes per sample: next_pow2(T) and its log2
     int spc;                               // samples per serve / update CTA: 8 warps * 32 / L
     int table_base;
+    int tid[kMaxTables];                   // global id of local table t (keys, tier routing parity); table_base + t unless table_ids given
+    int col[kMaxTables];                   // output column of local table t: t, or tid[t] in the batch-sharded receive buffers
+    int loc[kMaxTables];                   // local index of global table g (-1: not served here)
     int n_perfect_agg;                     // agg value that counts as a perfect hit (n_tables_total)
     int approx_thres;
     int high_thres;                        // high_agghit_threshold (evlfu_32.hpp:74)
@@ -191,9 +206,16 @@ struct Params {
     unsigned int stage_stride;             // max row_stride of the tiers (shared-memory staging of unaligned rows)
     unsigned int *done;                    // k_evict: tiers finished (C3 needs both tiers' victims)
     unsigned int *probe_done;              // sharded probe: CTAs finished (the last one raises the peers' flags)
-    int fetch_mode;                        // 1: k_serve lists the misses, k_fetch_list fetches them (default); 0: k_fetch scans the flags
     unsigned int *miss_list;               // [N] position | tier << 31 of every miss of the batch in flight
-    unsigned int *miss_ctl;                // [0] entries in miss_list, [1] k_fetch_list CTAs finished
+    unsigned int *miss_ctl;                // [0] entries in miss_list, [1] fetch CTAs finished
+    int evict_ctas;                        // CTAs per tier of the eviction roles of k_evict
+    int fetch_ctas;                        // CTAs of its miss-fetch role
+    int pdl;                               // kernels of a batch are chained by programmatic dependent launch
+    unsigned int *err_host;                // mapped pinned copy of g->error: the host sees it without a device round trip
+    // look-ahead staging (evs_prefetch): rows of the next batch's probable misses, by position, two parities
+    unsigned int *pf_tag;                  // [2][n_max]: generation << 1 | tier once the row is complete
+    unsigned char *pf_rows;                // [2][n_max][stage_stride]
+    unsigned int n_max;                    // max_batch * T
     int store_aligned;                     // bit t: every backing row of tier t starts 16-byte aligned
     unsigned long long *dbg;               // [16] %globaltimer stamps of the last batch's phases (ns)
 };

@@ -32,6 +32,14 @@ __global__ void __launch_bounds__(kLookupThreads, NG == 1 ? 5 : 4) k_update(cons
     __shared__ unsigned s_new[kMaxTiers], s_ins[kMaxTiers];
     __shared__ unsigned long long s_prot[kMaxTiers];
 
+    griddep_launch(p);
+    if (threadIdx.x < kMaxTiers * kMaxBuckets) s_delta[threadIdx.x] = 0;
+    if (threadIdx.x < kMaxTiers) {
+        s_new[threadIdx.x] = 0;
+        s_ins[threadIdx.x] = 0;
+        s_prot[threadIdx.x] = 0ull;
+    }
+    griddep_wait(p);
     if (blockIdx.x == 0 && threadIdx.x == 0) p.dbg[2] = gtime();
     const BatchArgs a = *p.args;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -50,12 +58,6 @@ __global__ void __launch_bounds__(kLookupThreads, NG == 1 ? 5 : 4) k_update(cons
     if (f & kFlagMiss) {
         r = __ldg(a.idx + static_cast<size_t>(tbl) * B + s);
         if (r < 0 || r >= __ldg(p.rows + tbl)) r = 0;
-    }
-    if (threadIdx.x < kMaxTiers * kMaxBuckets) s_delta[threadIdx.x] = 0;
-    if (threadIdx.x < kMaxTiers) {
-        s_new[threadIdx.x] = 0;
-        s_ins[threadIdx.x] = 0;
-        s_prot[threadIdx.x] = 0ull;
     }
 
     const int tr = (f & kFlagTier) ? 1 : 0;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kLookupThreads, NG == 1 ? 5 : 4) k_update(cons
         unsigned slot = 0;
         bool claimed = false;
         if (f & kFlagMiss) {
-            slot = claim_slot(p.tier[tr], make_key(p.table_base + tbl, r), claimed);
+            slot = claim_slot(p.tier[tr], make_key(p.tid[tbl], r), claimed);
             p.pos_slot[pos] = slot | (claimed ? kClaimedBit : 0u);
             if (claimed) atomicAdd(&s_new[tr], 1u);
             atomicMax(&s_prot[tr], (static_cast<unsigned long long>(f & 0x3Fu) << 32) | static_cast<unsigned>(pos));
@@ -284,18 +286,38 @@ __device__ __forceinline__ unsigned lookback_excl_wide(unsigned long long *lb, u
     return excl;
 }
 
+// One launch, three kinds of CTA (blockIdx.y = role): roles 0 .. n_tiers-1 evict from that tier (p.evict_ctas CTAs each),
+// role n_tiers fetches the batch's missing rows (p.fetch_ctas CTAs: fetch_list_body, evs_kernels.cuh).  The two do not
+// depend on each other -- both follow k_update -- so they used to be two kernels on two streams joined by events;
+// as roles of one grid the batch is a linear chain of three launches (no fork / join inside the graph).
+// The last role to finish closes the batch: C3 insertions, and for a sharded handle the "my rows are delivered"
+// words to the peers and the wait for theirs.
+template <int P0, int P1>
 __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__ Params p) {
+    extern __shared__ __align__(16) unsigned char s_stage[];    // fetch role: warps * max(row_stride); unaligned rows only
+    __shared__ CodecLut s_lut;
     __shared__ EvictPlan P;
     __shared__ unsigned s_w[33];
     __shared__ unsigned s_chunk, s_excl, s_last, s_taken, s_more;
-    const int t = blockIdx.y;
+    const int role = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (role == p.n_tiers) {
+        if (static_cast<int>(blockIdx.x) >= p.fetch_ctas) return;
+        codec_lut_init<P0, P1>(&s_lut);
+        griddep_wait(p);
+        __syncthreads();
+        if (!fetch_list_body<P0, P1>(p, blockIdx.x, static_cast<unsigned>(p.fetch_ctas), s_stage, &s_lut, &s_last)) return;
+    } else {
+    if (static_cast<int>(blockIdx.x) >= p.evict_ctas) return;
+    const unsigned nev = static_cast<unsigned>(p.evict_ctas);
+    const int t = role;
     const TierDev &tier = p.tier[t];
     TierCtl *ctl = tier.ctl;
     volatile TierCtl *c = ctl;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int top = tier.n_buckets - 1;
     constexpr unsigned W = kEvictWindow;
     static_assert(kEvictWindow == kEvictThreads, "one ring record per thread");
+    griddep_wait(p);
     if (t == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
         p.dbg[4] = gtime();
         if (p.dbg[0] > p.dbg[2]) p.dbg[14] += 1000ull;      // the next batch's k_serve already started (must not happen)
@@ -376,7 +398,7 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
             // the tier's counters may change only after every other CTA has derived its plan from them
             // (they do nothing else in this case and are not waiting for anything)
             if (threadIdx.x == 0)
-                while (c->done_ctas < gridDim.x - 1) {}
+                while (c->done_ctas < nev - 1) {}
             __syncthreads();
             if (threadIdx.x < tier.n_buckets) c->tail[threadIdx.x] = P.tail[threadIdx.x];
             __syncthreads();
@@ -391,7 +413,7 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
             // the first chunk of a CTA is its block index (no round trip); further ones are handed out
             // by ticket, so a chunk's predecessors always belong to CTAs that are already running
             __syncthreads();
-            if (threadIdx.x == 0) s_chunk = first ? blockIdx.x : (c->stop ? kNoSlot : gridDim.x + atomicAdd(&ctl->ticket, 1u));
+            if (threadIdx.x == 0) s_chunk = first ? blockIdx.x : (c->stop ? kNoSlot : nev + atomicAdd(&ctl->ticket, 1u));
             first = false;
             __syncthreads();
             const unsigned ch = s_chunk;
@@ -446,9 +468,9 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
                     }
                 } else {
                     const unsigned long long pred = (static_cast<unsigned long long>(ch) + 1ull) * need / max(incl, 1u) + 1ull;
-                    const bool covered = pred + (pred >> 2) + 2ull <= gridDim.x;
+                    const bool covered = pred + (pred >> 2) + 2ull <= nev;
                     if (!covered) more = 1u;
-                    else if (ch + 1u >= gridDim.x) more = (ch + 1u == gridDim.x + c->ticket) ? 1u : 0u;
+                    else if (ch + 1u >= nev) more = (ch + 1u == nev + c->ticket) ? 1u : 0u;
                 }
                 s_more = more;
             }
@@ -486,14 +508,14 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
     if (threadIdx.x == 0) {
         if (s_taken) atomicAdd(&ctl->n_taken, s_taken);
         __threadfence();
-        s_last = (atomicAdd(&ctl->done_ctas, 1u) == gridDim.x - 1) ? 1u : 0u;
+        s_last = (atomicAdd(&ctl->done_ctas, 1u) == nev - 1) ? 1u : 0u;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     if (t == 0 && threadIdx.x == 0) {
         p.dbg[18] = gtime();
-        p.dbg[20] += c->ticket + gridDim.x;
+        p.dbg[20] += c->ticket + nev;
         p.dbg[21] += P.seg_off[P.n_seg];
     }
     if (!P.flush) {
@@ -527,7 +549,7 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
         }
     }
     // per-batch scratch of the tier
-    const unsigned n_tk = min(c->ticket + gridDim.x, tier.lb_cap);
+    const unsigned n_tk = min(c->ticket + nev, tier.lb_cap);
     for (unsigned i = threadIdx.x; i < n_tk; i += blockDim.x) tier.lookback[i] = 0ull;
     if (threadIdx.x < kMaxBuckets) {
         c->kept[threadIdx.x] = ~0ull;
@@ -546,23 +568,33 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
         c->n_taken = 0;
     }
 
-    // ---- the last tier to finish feeds C3 and closes the batch ---------------------------------
+    }   // eviction role
+
+    // ---- the last role to finish feeds C3 and closes the batch ------------------------------------
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (p.n_tiers == 1) {
-            s_last = 1u;                                  // nobody else to wait for: no round trip
-        } else {
-            __threadfence();
-            const unsigned prev = atomicAdd(p.done, 1u);
-            s_last = (prev == static_cast<unsigned>(p.n_tiers) - 1u) ? 1u : 0u;
-            if (s_last) *p.done = 0u;
-        }
+        __threadfence();
+        const unsigned prev = atomicAdd(p.done, 1u);
+        s_last = (prev == static_cast<unsigned>(p.n_tiers)) ? 1u : 0u;
+        if (s_last) *p.done = 0u;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     if (threadIdx.x == 0) p.dbg[5] = gtime();
     if (p.c3.active) c3_update(p);
+    if (warp == 0 && p.args->sh.world > 1) {
+        // every row this rank owes its peers has been stored (k_serve's gather, the fetch role): tell them, then
+        // hold the stream until every peer has said the same to us
+        const ShardArgs *sh = &p.args->sh;
+        const int world = sh->world;
+        const unsigned epoch = sh->epoch;
+        __threadfence_system();
+        if (lane < world) *reinterpret_cast<volatile unsigned *>(sh->out_flag[lane]) = epoch;
+        const unsigned long long tw0 = gtime();
+        wait_flags(sh->my_out_flags, world, epoch, lane, p);
+        if (lane == 0) p.dbg[29] += gtime() - tw0;
+    }
     if (warp == 0) {
         // phase accounting, one accumulator per lane (a single round trip at the very end of the batch):
         // running sums over batches (ns): [8] serve, [9] gap, [10] update, [11] gap, [12] evict(+c3), [13] count;

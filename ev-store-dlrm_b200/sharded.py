@@ -28,16 +28,41 @@ def get_my_slice(n: int, rank: int, size: int) -> slice:
     return slice(rank * k + min(rank, m), (rank + 1) * k + min(rank + 1, m), 1)
 
 
+def contiguous_placement(n: int, size: int):
+    """The reference's placement: rank r serves the tables of get_my_slice(n, r, size)."""
+    return [list(range(n))[get_my_slice(n, r, size)] for r in range(size)]
+
+
+def balanced_placement(rows, size: int):
+    """Tables spread over the ranks by ROW COUNT, keeping get_split_lengths' tables-per-rank (so every rank still
+    handles the same number of lookups per sample).  This DEPARTS from the reference's contiguous split
+    (extend_distributed.py:47-62): Criteo's few huge tables sit next to each other, so the contiguous slices leave
+    most ranks with a handful of rows -- and almost no misses, evictions or backing-store traffic -- while one or
+    two ranks carry everything.  Largest table first, each to the rank with the fewest rows that still has a free
+    slot; ids ascending within a rank."""
+    n = len(rows)
+    cap = get_split_lengths(n, size)
+    load = [0] * size
+    out = [[] for _ in range(size)]
+    for t in sorted(range(n), key=lambda t: (-int(rows[t]), t)):
+        r = min((r for r in range(size) if len(out[r]) < cap[r]), key=lambda r: (load[r], r))
+        out[r].append(t)
+        load[r] += int(rows[t])
+    return [sorted(x) for x in out]
+
+
 class ShardedLookup:
     """One rank's part of the sharded lookup.  ``store`` serves this rank's tables
     (``EvStore`` built with table_base / n_tables_total; any object with ``probe`` and ``lookup``
     of the same signatures works, which is how the CPU tests drive the host logic)."""
 
     def __init__(self, store, n_tables_total: int, dim: int, rank: int, world: int, group=None, exact_agg: bool = True,
-                 transport: str = "nccl", batch_max: int = 0):
+                 transport: str = "nccl", batch_max: int = 0, placement=None):
         """transport "nccl": torch.distributed all-reduce + all_to_all_single (any backend; what the reference does).
         transport "p2p": the exchange is fused into the kernels over NVLink peer memory (evs_shard_*); needs
-        ``batch_max`` (the global batch) and a store with shard_create / shard_connect / shard_lookup."""
+        ``batch_max`` (the global batch) and a store with shard_create / shard_connect / shard_lookup.
+        placement: per rank the global ids of its tables (default: the reference's contiguous slices); the store of
+        a rank with a non-contiguous set must have been built with ``CacheConfig.table_ids``."""
         self.store, self.T, self.dim = store, n_tables_total, dim
         self.rank, self.world, self.group = rank, world, group
         self.exact_agg = exact_agg
@@ -49,8 +74,10 @@ class ShardedLookup:
             dist.all_gather_object(handles, mine, group=group)
             store.shard_connect(handles)
             dist.barrier(group=group)
-        self.splits = get_split_lengths(n_tables_total, world)
-        self.my = get_my_slice(n_tables_total, rank, world)
+        self.placement = [list(x) for x in placement] if placement is not None else contiguous_placement(n_tables_total, world)
+        assert sorted(t for x in self.placement for t in x) == list(range(n_tables_total)), "every table on exactly one rank"
+        self.splits = [len(x) for x in self.placement]
+        self.my = self.placement[rank]
         self.T_local = self.splits[rank]
         self._bufs = {}
 
@@ -67,15 +94,19 @@ class ShardedLookup:
             self._bufs[key] = (send, recv, out, hit, agg)
         return self._bufs[key]
 
-    def lookup(self, lS_i_local):
+    def lookup(self, lS_i_local, next_idx=None):
         """lS_i_local: int64 [T_local, B], this rank's tables for the whole batch (B % world == 0).
+        next_idx: the tensor the NEXT call will pass (look-ahead, EvStore.prefetch), or None.
         Returns (ly [B/world, 26, dim] for this rank's slice of the batch, hit [B, T_local])."""
         import torch
         import torch.distributed as dist
         T_local, B = lS_i_local.shape
         assert T_local == self.T_local and B % self.world == 0
         if self.transport == "p2p":
-            return self.store.shard_lookup(lS_i_local)
+            r = self.store.shard_lookup(lS_i_local)
+            if next_idx is not None:
+                self.store.prefetch(next_idx)
+            return r
         send, recv, out, hit, agg = self._buffers(B, lS_i_local.device)
         agg_in = None
         if self.exact_agg and self.world > 1:
@@ -83,6 +114,8 @@ class ShardedLookup:
             dist.all_reduce(agg, op=dist.ReduceOp.SUM, group=self.group)
             agg_in = agg
         self.store.lookup(lS_i_local, out=send, hit=hit, agg_in=agg_in)
+        if next_idx is not None and hasattr(self.store, "prefetch"):
+            self.store.prefetch(next_idx)
         if self.world == 1:
             return send, hit
         Bl = B // self.world
@@ -91,12 +124,15 @@ class ShardedLookup:
         out_splits = [Bl * t * self.dim for t in self.splits]
         dist.all_to_all_single(recv, send.view(-1), out_splits, in_splits, group=self.group)
         o = 0
-        t0 = 0
-        for t in self.splits:
+        for ids in self.placement:
+            t = len(ids)
             n = Bl * t * self.dim
-            out[:, t0:t0 + t, :] = recv[o:o + n].view(Bl, t, self.dim)
+            blk = recv[o:o + n].view(Bl, t, self.dim)
+            if ids == list(range(ids[0], ids[0] + t)):
+                out[:, ids[0]:ids[0] + t, :] = blk
+            else:
+                out[:, torch.as_tensor(ids, device=out.device), :] = blk
             o += n
-            t0 += t
         return out, hit
 
     def alltoall_bytes(self, B: int) -> int:

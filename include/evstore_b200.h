@@ -85,6 +85,12 @@ typedef struct {
      * cache_algo/LRU.py:15-37 (n_layers == 1 only), selected in the reference by --cache-algo
      * (dlrm_s_pytorch_C1_C2_C3.py:249-254). */
     int32_t policy;
+    /* Table placement (table-wise sharding): global id of each local table, [n_tables], strictly increasing, each
+     * in [0, n_tables_total).  NULL = the contiguous slice table_base .. table_base + n_tables - 1 that
+     * ext_dist.get_my_slice gives a rank (extend_distributed.py:47-51).  A non-contiguous placement (e.g. tables
+     * balanced by rows) departs from the reference's split; keys, tier routing and the output column of a table
+     * always follow its global id. */
+    const int32_t *table_ids;
 } evs_config;
 
 #define EVS_POLICY_EVLFU 0
@@ -128,6 +134,15 @@ int evs_version(void);
 int evs_lookup_batch(evs_handle h, const int64_t *idx_dev, int32_t B, float *out_dev, int64_t out_stride,
                      uint8_t *hit_dev, const uint8_t *agg_in, void *stream);
 
+/* Look-ahead: idx_dev is the index batch the NEXT evs_lookup_batch / evs_shard_lookup call on this handle will pass
+ * (same pointer, same B).  The library probes it and stages the rows of its probable misses from the host-pinned
+ * backing store into HBM on its own stream, under the kernels of the batch in flight; the next call then finds
+ * its missing rows staged instead of waiting for the PCIe reads (the longest part of a step).  Pure data movement:
+ * every hit / eviction decision is still taken by the next call itself, results are identical with and without.
+ *   ready_event  cudaEvent_t recorded after idx_dev was written, or NULL if the indices are already complete
+ * Optional; a call that was not announced (or whose announcement does not match) runs as before. */
+int evs_prefetch(evs_handle h, const int64_t *idx_dev, int32_t B, void *ready_event);
+
 /* Probe only: per-sample local hit counts (for the sharded exact mode the ranks
  * all-reduce these and pass the sum back as agg_in).  Does not change state. */
 int evs_probe_batch(evs_handle h, const int64_t *idx_dev, int32_t B, uint8_t *agg_out_dev, void *stream);
@@ -145,6 +160,13 @@ int evs_wait_host(evs_handle h, int64_t ticket);
 
 int evs_sync(evs_handle h);
 int evs_stats(evs_handle h, evs_stats_t *out, int reset);
+/* Cheap error poll (no synchronisation, no device round trip): the kernels mirror their error word into pinned
+ * host memory.  Returns EVS_OK, or the sticky EVS_ERR_INDEX / EVS_ERR_PEER of a batch that has already run;
+ * evs_wait_host and evs_lookup_batch_host call it after their synchronisation.  clear != 0 resets it. */
+int evs_check(evs_handle h, int clear);
+/* Device memory the handle holds (index, slabs, rings, staging), in bytes: the slab is slot-indexed at a load
+ * factor <= 1/3, so this is a multiple of TOTAL_SIZE * row bytes (the reference's budget, cache_manager.cpp:16). */
+int evs_memory_footprint(evs_handle h, uint64_t *hbm_bytes);
 
 /* ---- measurement ------------------------------------------------------------------- *
  * Every kernel launch of a handle is counted.  With profiling on, each launch is also bracketed

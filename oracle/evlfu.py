@@ -162,8 +162,9 @@ class BatchEvLFU:
         self.flushed: list[int] = []
         self.inserted: list[int] = []
 
-    def lookup_batch(self, idx, approx_emb_thres: int = -1, agg=None, table_base: int = 0):
-        """idx: int array [Tl, B] (the reference's lS_i layout).
+    def lookup_batch(self, idx, approx_emb_thres: int = -1, agg=None, table_base: int = 0, table_ids=None):
+        """idx: int array [Tl, B] (the reference's lS_i layout).  Local table t has the global id
+        ``table_base + t`` (a rank's contiguous slice) or ``table_ids[t]`` (any placement).
 
         Returns (hit [B,Tl] bool, src_t [B,Tl] int32, src_r [B,Tl] int64, agg [B]).
         ``src_t < 0`` marks a substituted position with no earlier hit (the
@@ -173,13 +174,14 @@ class BatchEvLFU:
         Tl, B = idx.shape
         T = self.T
         ent = self.entries
-        keys = [[make_key(table_base + t, idx[t, s]) for t in range(Tl)] for s in range(B)]
+        gid = [table_base + t for t in range(Tl)] if table_ids is None else [int(g) for g in table_ids]
+        keys = [[make_key(gid[t], idx[t, s]) for t in range(Tl)] for s in range(B)]
         hit0 = np.array([[k in ent for k in ks] for ks in keys], dtype=bool).reshape(B, Tl)
         if agg is None:
             agg = hit0.sum(axis=1).astype(np.int64)
         agg = np.asarray(agg, dtype=np.int64)
         hit = hit0.copy()
-        src_t = np.tile(np.arange(Tl, dtype=np.int32) + table_base, (B, 1))
+        src_t = np.tile(np.asarray(gid, dtype=np.int32), (B, 1))
         src_r = np.ascontiguousarray(idx.T).astype(np.int64)
 
         winners: dict[int, tuple[int, int]] = {}
@@ -203,7 +205,7 @@ class BatchEvLFU:
                     j = last if last >= 0 else first
                     hit[s, t] = True
                     if j >= 0:
-                        src_t[s, t] = table_base + j
+                        src_t[s, t] = gid[j]
                         src_r[s, t] = idx[j, s]
                     else:
                         src_t[s, t] = -1

@@ -24,8 +24,10 @@ def decoded_tables(tables, prec):
 
 
 def run_single_tier_parity(rows, dim, prec, total_size, B_list, n_batches, seed=42, approx=-1,
-                           store_in_hbm=False, host_path=False, check_state_every=1, alpha=1.05, policy="evlfu"):
-    """Drive the CUDA path and BatchEvLFU (or BatchLRU) with the same batches; compare everything, every batch."""
+                           store_in_hbm=False, host_path=False, check_state_every=1, alpha=1.05, policy="evlfu", prefetch=False):
+    """Drive the CUDA path and BatchEvLFU (or BatchLRU) with the same batches; compare everything, every batch.
+    prefetch: every batch is announced with evs_prefetch right after the previous batch was enqueued, so the
+    look-ahead kernel races the previous batch's update / eviction kernels as it does in production."""
     import torch
     p = pkg()
     tables = p.workload.make_tables(rows, dim)
@@ -39,13 +41,20 @@ def run_single_tier_parity(rows, dim, prec, total_size, B_list, n_batches, seed=
     T = len(rows)
     totals = dict(hits=0, lookups=0, evicted=0, flushed=0)
     try:
+        all_idx = [trace.batch(B_list[it % len(B_list)]) for it in range(n_batches)]
+        dev_idx = [torch.from_numpy(i).cuda() for i in all_idx] if not host_path else None
+        if prefetch:
+            torch.cuda.synchronize()
+            store.prefetch(dev_idx[0])
         for it in range(n_batches):
             B = B_list[it % len(B_list)]
-            idx = trace.batch(B)
+            idx = all_idx[it]
             if host_path:
                 out, hit = store.lookup_host(idx)
             else:
-                o, h = store.lookup(torch.from_numpy(idx).cuda())
+                o, h = store.lookup(dev_idx[it])
+                if prefetch and it + 1 < n_batches:
+                    store.prefetch(dev_idx[it + 1])
                 torch.cuda.synchronize()
                 out, hit = o.cpu().numpy(), h.cpu().numpy()
             o_hit, st, sr, agg = oracle.lookup_batch(idx, approx_emb_thres=approx)
@@ -75,7 +84,7 @@ def run_single_tier_parity(rows, dim, prec, total_size, B_list, n_batches, seed=
 
 
 def run_tier_parity(rows, dim, layers, main, sec, total, B_list, n_batches, prop="", seed=42, check_state_every=1,
-                    alpha=1.05, store_in_hbm=False, high_thres=0):
+                    alpha=1.05, store_in_hbm=False, high_thres=0, prefetch=False):
     """Two / three layer CUDA path vs oracle.tiers.BatchTiers: hit codes, fp32 rows (dequantised at the
     answering tier's precision), eviction / flush streams and FIFO state of both tiers, C3 contents."""
     import torch
@@ -95,10 +104,17 @@ def run_tier_parity(rows, dim, layers, main, sec, total, B_list, n_batches, prop
     try:
         st0 = store.stats()
         assert tuple(st0["capacity"]) == caps[:2] and st0["c3_capacity"] == (caps[2] if layers == 3 else 0), (st0, caps)
+        all_idx = [trace.batch(B_list[it % len(B_list)]) for it in range(n_batches)]
+        dev_idx = [torch.from_numpy(i).cuda() for i in all_idx]
+        if prefetch:
+            torch.cuda.synchronize()
+            store.prefetch(dev_idx[0])
         for it in range(n_batches):
             B = B_list[it % len(B_list)]
-            idx = trace.batch(B)
-            o, h = store.lookup(torch.from_numpy(idx).cuda())
+            idx = all_idx[it]
+            o, h = store.lookup(dev_idx[it])
+            if prefetch and it + 1 < n_batches:
+                store.prefetch(dev_idx[it + 1])
             torch.cuda.synchronize()
             out, hit = o.cpu().numpy(), h.cpu().numpy()
             code, val_tier, st, sr, agg = oracle.lookup_batch(idx)

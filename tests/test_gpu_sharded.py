@@ -54,11 +54,17 @@ def test_shards_on_one_device_exact_groupability(world):
 CASES = {"small": (SMALL_ROWS, 16, 64, 260, 8), "skew": (SKEW_ROWS, 64, 256, 2000, 10)}
 
 
-def _worker(rank, world, port, q, backend, transport, same_device, case):
+def _placement(kind, rows, world):
+    p = pkg()
+    return p.sharded.balanced_placement(rows, world) if kind == "balanced" else p.sharded.contiguous_placement(26, world)
+
+
+def _worker(rank, world, port, q, backend, transport, same_device, case, kind, prefetch, env):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    os.environ.update(env)
     devno = 0 if same_device else rank
     torch.cuda.set_device(devno)
     if backend == "nccl":
@@ -69,15 +75,20 @@ def _worker(rank, world, port, q, backend, transport, same_device, case):
     rows, dim, B, cap, n = CASES[case]
     tables = p.workload.make_tables(rows, dim)
     batches = p.workload.ZipfTrace(rows, seed=43).batches(n, B)
-    sl = p.sharded.get_my_slice(26, rank, world)
-    cfg = p.CacheConfig(total_size=cap, max_batch=B, n_tables_total=26, table_base=sl.start, device=devno)
-    store = p.EvStore(tables[sl], cfg)
-    sh = p.sharded.ShardedLookup(store, 26, dim, rank, world, transport=transport, batch_max=B)
+    placement = _placement(kind, rows, world)
+    ids = placement[rank]
+    cfg = p.CacheConfig(total_size=cap, max_batch=B, n_tables_total=26, table_ids=tuple(ids), device=devno)
+    store = p.EvStore([tables[t] for t in ids], cfg)
+    sh = p.sharded.ShardedLookup(store, 26, dim, rank, world, transport=transport, batch_max=B, placement=placement)
     res = []
     err = None
     try:
-        for idx in batches:
-            ly, hit = sh.lookup(torch.from_numpy(np.ascontiguousarray(idx[sl])).cuda())
+        dev = [torch.from_numpy(np.ascontiguousarray(idx[ids])).cuda() for idx in batches]
+        torch.cuda.synchronize()
+        if prefetch:
+            store.prefetch(dev[0])
+        for k in range(len(dev)):
+            ly, hit = sh.lookup(dev[k], next_idx=dev[k + 1] if (prefetch and k + 1 < len(dev)) else None)
             torch.cuda.synchronize()
             res.append((ly.cpu().numpy().copy(), hit.cpu().numpy().copy()))
         store.sync()
@@ -89,12 +100,13 @@ def _worker(rank, world, port, q, backend, transport, same_device, case):
     dist.destroy_process_group()
 
 
-def _run_sharded(world, backend, transport, same_device, case):
+def _run_sharded(world, backend, transport, same_device, case, kind="contiguous", prefetch=False, env=None):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() + hash((backend, transport, case))) % 2000
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, backend, transport, same_device, case)) for r in range(world)]
+    port = 29600 + (os.getpid() + hash((backend, transport, case, kind, prefetch, str(env)))) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, backend, transport, same_device, case, kind, prefetch, env or {}))
+             for r in range(world)]
     for pr in procs:
         pr.start()
     got = {}
@@ -110,16 +122,16 @@ def _run_sharded(world, backend, transport, same_device, case):
     tables = p.workload.make_tables(rows, dim)
     batches = p.workload.ZipfTrace(rows, seed=43).batches(n, B)
     oracles = [BatchEvLFU(cap, n_tables=26) for _ in range(world)]
-    slices = [p.sharded.get_my_slice(26, r, world) for r in range(world)]
+    placement = _placement(kind, rows, world)
     Bl = B // world
     n_ev = 0
     for k, idx in enumerate(batches):
-        agg = sum(np.array([[((sl.start + t) << 40 | int(idx[sl][t, s])) in o.entries for t in range(sl.stop - sl.start)]
-                            for s in range(B)]).sum(axis=1) for o, sl in zip(oracles, slices))
+        agg = sum(np.array([[(ids[t] << 40 | int(idx[ids[t], s])) in o.entries for t in range(len(ids))]
+                            for s in range(B)]).sum(axis=1) for o, ids in zip(oracles, placement))
         full = np.empty((B, 26, dim), dtype=np.float32)
-        for r, (o, sl) in enumerate(zip(oracles, slices)):
-            o_hit, s_t, s_r, _ = o.lookup_batch(idx[sl], agg=agg, table_base=sl.start)
-            full[:, sl] = gather_rows(tables[sl], s_t - sl.start, s_r)
+        for r, (o, ids) in enumerate(zip(oracles, placement)):
+            o_hit, s_t, s_r, _ = o.lookup_batch(idx[ids], agg=agg, table_ids=ids)
+            full[:, ids] = gather_rows(tables, s_t, s_r)
             n_ev += len(o.evicted)
             assert np.array_equal(got[r][k][1].astype(bool), o_hit), (k, r)
         for r in range(world):
@@ -134,15 +146,41 @@ def test_sharded_lookup_p2p_two_processes_on_one_gpu():
     assert n_ev > 0
 
 
+def test_sharded_lookup_p2p_one_gpu_two_pass_balanced_and_look_ahead():
+    """The separate probe pass (grids too large to be co-resident; forced here), a non-contiguous table placement
+    and evs_prefetch, all on the one-GPU two-process setup."""
+    assert _run_sharded(2, "gloo", "p2p", True, "small", env={"EVSTORE_B200_SHARD_TWO_PASS": "1"}) > 0
+    assert _run_sharded(2, "gloo", "p2p", True, "small", kind="balanced", prefetch=True) > 0
+
+
 def test_sharded_lookup_nccl_two_gpus():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     _run_sharded(2, "nccl", "nccl", False, "skew")
+    _run_sharded(2, "nccl", "nccl", False, "skew", kind="balanced")
 
 
-def test_sharded_lookup_p2p_two_gpus():
+@pytest.mark.parametrize("kind,prefetch", [("contiguous", False), ("balanced", False), ("balanced", True)])
+def test_sharded_lookup_p2p_two_gpus(kind, prefetch):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    _run_sharded(2, "nccl", "p2p", False, "skew")
+    assert _run_sharded(2, "nccl", "p2p", False, "skew", kind=kind, prefetch=prefetch) > 0
+
+
+def test_shard_connect_refuses_a_peer_built_for_another_layout():
+    """evs_create validates the global table ids; the exchange header lets evs_shard_connect refuse a peer whose
+    n_tables_total / dim / batch differs (its receive buffer would be addressed with the wrong strides)."""
+    p = pkg()
+    tables = p.workload.make_tables(SMALL_ROWS[:4], 16)
+    for bad in (dict(table_base=-1), dict(table_base=24), dict(table_ids=(3, 2, 5, 6)), dict(table_ids=(1, 2, 3, 26))):
+        with pytest.raises(p.EvsError):
+            p.EvStore(tables, p.CacheConfig(total_size=100, max_batch=8, n_tables_total=26, **bad))
+    a = p.EvStore(tables, p.CacheConfig(total_size=100, max_batch=8, n_tables_total=26, table_ids=(0, 1, 2, 3)))
+    b = p.EvStore(tables, p.CacheConfig(total_size=100, max_batch=8, n_tables_total=26, table_ids=(2, 3, 4, 5)))    # overlaps a
+    ha, hb = a.shard_create(0, 2, 8), b.shard_create(1, 2, 8)
+    # same process: the peer block cannot be opened over IPC, so only the creation-time validation is exercised here
+    assert len(ha) == 64 and len(hb) == 64
+    a.close()
+    b.close()

@@ -161,12 +161,57 @@ def test_fp32_direct_prefix_beyond_the_preloaded_rounds_and_medium_scan_path():
     assert t["evicted"] > 0
 
 
-def test_flag_scan_fetch_kernel_still_matches(monkeypatch):
-    """EVSTORE_B200_FETCH_MODE=0 selects the earlier miss fetch (k_fetch scans the flags instead of reading
-    the compact miss list); kept as the A/B baseline of profiles/r1_fetch_list_ab.md."""
-    monkeypatch.setenv("EVSTORE_B200_FETCH_MODE", "0")
+def test_without_programmatic_dependent_launch(monkeypatch):
+    """EVSTORE_B200_PDL=0: plain stream order between the batch's kernels (the A/B baseline of the PDL chain)."""
+    monkeypatch.setenv("EVSTORE_B200_PDL", "0")
     run_single_tier_parity(SMALL_ROWS, 16, 32, 600, [64, 5], 12)
     run_single_tier_parity(SMALL_ROWS, 36, 8, 150, [33], 8)
+
+
+@pytest.mark.parametrize("dim,prec", [(16, 32), (64, 32), (16, 16), (64, 8), (36, 32)])
+def test_look_ahead_prefetch_changes_nothing(dim, prec):
+    """evs_prefetch announces every next batch: its probable misses are staged in HBM by a kernel that races the
+    batch in flight.  Hit stream, rows, eviction / flush streams and FIFO state must stay bit-exact (dim 36 fp32 rows
+    are 144 B: aligned; dim 36 at 8 bits would not be, and then the announcement is a no-op)."""
+    t = run_single_tier_parity(SKEW_ROWS, dim, prec, 2500 * prec // 32, [700, 64, 257, 2048, 1], 30, prefetch=True, check_state_every=3)
+    assert t["evicted"] > 0
+    run_single_tier_parity(SMALL_ROWS, dim, prec, 600 * prec // 32, [64, 5], 14, prefetch=True)
+
+
+def test_look_ahead_prefetch_unaligned_rows_and_lru():
+    run_single_tier_parity(SMALL_ROWS, 36, 8, 150, [33, 64], 10, prefetch=True)          # 36-byte rows: no staging, same results
+    run_single_tier_parity(SKEW_ROWS, 16, 32, 2500, [300, 64], 16, prefetch=True, policy="lru", check_state_every=4)
+
+
+def test_look_ahead_announcement_that_does_not_match_is_ignored():
+    """Announce batch A, then look B up; announce twice before one lookup; announce and never look up."""
+    import torch
+    from helpers import pkg
+    from oracle.evlfu import BatchEvLFU, gather_rows
+    p = pkg()
+    dim, B, cap = 16, 128, 700
+    tables = p.workload.make_tables(SMALL_ROWS, dim)
+    trace = p.workload.ZipfTrace(SMALL_ROWS, seed=5)
+    store = p.EvStore(tables, p.CacheConfig(total_size=cap, max_batch=B, record_events=True))
+    oracle = BatchEvLFU(cap)
+    batches = [trace.batch(B) for _ in range(24)]
+    dev = [torch.from_numpy(b).cuda() for b in batches]
+    torch.cuda.synchronize()
+    for it in range(0, 24, 3):
+        store.prefetch(dev[it + 1])                 # wrong announcement for batch `it`
+        store.prefetch(dev[it + 2])                 # a second one for the same slot
+        for k in (it, it + 1):
+            out, hit = store.lookup(dev[k])
+            if k == it:
+                store.prefetch(dev[it + 1])         # the right one for the next call
+            torch.cuda.synchronize()
+            o_hit, st, sr, _ = oracle.lookup_batch(batches[k])
+            assert (hit.cpu().numpy().astype(bool) == o_hit).all(), k
+            assert (out.cpu().numpy() == gather_rows(tables, st, sr)).all(), k
+            ev, fl = store.last_events()
+            assert ev.tolist() == oracle.evicted and fl.tolist() == oracle.flushed, k
+    store.sync()
+    store.close()
 
 
 @pytest.mark.parametrize("n_tables", [1, 2, 3, 5, 13, 16, 17])

@@ -114,3 +114,16 @@ def test_three_tier_cache_over_a_stored_model_directory(tmp_path):
         assert c3 > 0
     finally:
         store.close()
+
+
+@pytest.mark.parametrize("dim,main,sec,total", [(64, 32, 8, 400), (32, 16, 8, 300), (32, 8, 4, 300)])
+def test_two_tier_look_ahead_prefetch(dim, main, sec, total):
+    """evs_prefetch with two tiers: the staged row is tagged with the tier the look-ahead guessed (odd tables C1, even
+    tables C2 once C1 is full); a wrong guess is fetched the usual way.  Everything stays bit-exact."""
+    t = run_tier_parity(SKEW_ROWS, dim, 2, main, sec, total, [256, 64, 700], 30, check_state_every=3, prefetch=True)
+    assert t["c2"] > 0 and t["ev1"] > 0, t
+
+
+def test_three_tier_look_ahead_prefetch():
+    t = run_tier_parity(SMALL_ROWS, 32, 3, 8, 4, 300, [64, 9, 128], 40, prop="45-45-10", check_state_every=2, prefetch=True)
+    assert t["c3"] > 0 and t["ev1"] > 0, t

@@ -17,16 +17,16 @@ DIM, B, CAP, N_BATCH = 16, 32, 300, 12
 class OracleStore:
     """CPU test double with EvStore's probe / lookup signatures."""
 
-    def __init__(self, tables_local, cap, table_base):
+    def __init__(self, tables_all, cap, ids):
         from oracle.evlfu import BatchEvLFU
         self.o = BatchEvLFU(cap, n_tables=26)
-        self.tables, self.base = tables_local, table_base
+        self.tables, self.ids = tables_all, list(ids)
 
     def probe(self, lS_i, agg_out=None):
         import torch
         from oracle.evlfu import make_key
         idx = lS_i.numpy()
-        cnt = np.array([sum(make_key(self.base + t, idx[t, s]) in self.o.entries for t in range(idx.shape[0]))
+        cnt = np.array([sum(make_key(self.ids[t], idx[t, s]) in self.o.entries for t in range(idx.shape[0]))
                         for s in range(idx.shape[1])], dtype=np.uint8)
         agg_out.copy_(torch.from_numpy(cnt))
         return agg_out
@@ -35,26 +35,27 @@ class OracleStore:
         import torch
         from oracle.evlfu import gather_rows
         idx = lS_i.numpy()
-        h, st, sr, _ = self.o.lookup_batch(idx, agg=None if agg_in is None else agg_in.numpy(), table_base=self.base)
-        rows = gather_rows(self.tables, st - self.base, sr)
+        h, st, sr, _ = self.o.lookup_batch(idx, agg=None if agg_in is None else agg_in.numpy(), table_ids=self.ids)
+        rows = gather_rows(self.tables, st, sr)
         out.copy_(torch.from_numpy(rows))
         hit.copy_(torch.from_numpy(h.astype(np.uint8)))
         return out, hit
 
 
-def _simulate(tables, batches):
-    """All ranks in one process: what the distributed run must reproduce."""
+def _placement(kind):
     p = pkg()
-    stores = []
-    for r in range(WORLD):
-        sl = p.sharded.get_my_slice(26, r, WORLD)
-        stores.append(OracleStore(tables[sl], CAP, sl.start))
+    return p.sharded.balanced_placement(SMALL_ROWS, WORLD) if kind == "balanced" else p.sharded.contiguous_placement(26, WORLD)
+
+
+def _simulate(tables, batches, placement):
+    """All ranks in one process: what the distributed run must reproduce."""
+    stores = [OracleStore(tables, CAP, placement[r]) for r in range(WORLD)]
     outs, hits = [], []
     import torch
     for idx in batches:
         aggs = []
         for r, st in enumerate(stores):
-            sl = p.sharded.get_my_slice(26, r, WORLD)
+            sl = placement[r]
             a = torch.empty(B, dtype=torch.uint8)
             st.probe(torch.from_numpy(idx[sl]), agg_out=a)
             aggs.append(a.numpy().astype(np.int64))
@@ -62,9 +63,9 @@ def _simulate(tables, batches):
         full = np.empty((B, 26, DIM), dtype=np.float32)
         hh = np.empty((B, 26), dtype=np.uint8)
         for r, st in enumerate(stores):
-            sl = p.sharded.get_my_slice(26, r, WORLD)
-            o = torch.empty((B, sl.stop - sl.start, DIM))
-            h = torch.empty((B, sl.stop - sl.start), dtype=torch.uint8)
+            sl = placement[r]
+            o = torch.empty((B, len(sl), DIM))
+            h = torch.empty((B, len(sl)), dtype=torch.uint8)
             st.lookup(torch.from_numpy(idx[sl]), out=o, hit=h, agg_in=agg)
             full[:, sl] = o.numpy()
             hh[:, sl] = h.numpy()
@@ -73,7 +74,7 @@ def _simulate(tables, batches):
     return outs, hits
 
 
-def _worker(rank, port, q):
+def _worker(rank, port, q, kind):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -82,9 +83,10 @@ def _worker(rank, port, q):
     p = pkg()
     tables = p.workload.make_tables(SMALL_ROWS, DIM)
     batches = p.workload.ZipfTrace(SMALL_ROWS, seed=21).batches(N_BATCH, B)
-    sl = p.sharded.get_my_slice(26, rank, WORLD)
-    store = OracleStore(tables[sl], CAP, sl.start)
-    sh = p.sharded.ShardedLookup(store, 26, DIM, rank, WORLD)
+    placement = _placement(kind)
+    sl = placement[rank]
+    store = OracleStore(tables, CAP, sl)
+    sh = p.sharded.ShardedLookup(store, 26, DIM, rank, WORLD, placement=placement)
     res = []
     for idx in batches:
         ly, hit = sh.lookup(torch.from_numpy(np.ascontiguousarray(idx[sl])))
@@ -94,12 +96,15 @@ def _worker(rank, port, q):
     dist.destroy_process_group()
 
 
-def test_sharded_lookup_two_ranks_gloo():
+@pytest.mark.parametrize("kind", ["contiguous", "balanced"])
+def test_sharded_lookup_two_ranks_gloo(kind):
+    """contiguous = the reference's get_my_slice split; balanced = tables spread by row count (non-contiguous ids:
+    the reassembly after the all-to-all scatters each rank's block to its tables' columns)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, port, q)) for r in range(WORLD)]
+    port = 29500 + (os.getpid() + (7 if kind == "balanced" else 0)) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, port, q, kind)) for r in range(WORLD)]
     for pr in procs:
         pr.start()
     got = dict(q.get(timeout=180) for _ in range(WORLD))
@@ -109,13 +114,16 @@ def test_sharded_lookup_two_ranks_gloo():
     p = pkg()
     tables = p.workload.make_tables(SMALL_ROWS, DIM)
     batches = p.workload.ZipfTrace(SMALL_ROWS, seed=21).batches(N_BATCH, B)
-    outs, hits = _simulate(tables, batches)
+    placement = _placement(kind)
+    if kind == "balanced":
+        assert placement != p.sharded.contiguous_placement(26, WORLD)
+    outs, hits = _simulate(tables, batches, placement)
     Bl = B // WORLD
     n_hits = 0
     for k in range(N_BATCH):
         for r in range(WORLD):
             ly, hit = got[r][k]
-            sl = p.sharded.get_my_slice(26, r, WORLD)
+            sl = placement[r]
             assert ly.shape == (Bl, 26, DIM)
             assert np.array_equal(ly, outs[k][r * Bl:(r + 1) * Bl]), f"batch {k} rank {r}: pooled rows after the all-to-all"
             assert np.array_equal(hit, hits[k][:, sl]), f"batch {k} rank {r}: hit map"
