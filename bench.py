@@ -53,10 +53,15 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink table cardinalities (debug only; invalidates the number)")
     ap.add_argument("--cache-warm", type=int, default=-1, help="untimed batches that fill the cache before warm-up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=150.0, help="time budget of the CPU baseline's warm-up")
     ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="A/B: do not announce the next index batch (evs_prefetch)")
     ap.add_argument("--no-b16k", action="store_true", help="skip the batch-16384 roofline leg")
+    ap.add_argument("--op", default="", choices=["", "interact", "embedding_bag"],
+                    help="time one of the tensor ops either side of the cache alone (bench_ops.py) instead of the lookup path")
+    ap.add_argument("--no-ops", action="store_true", help="skip the interact / embedding_bag legs of the default line")
+    ap.add_argument("--no-configs4", action="store_true", help="N = 1: skip the Terabyte-shape (configs[4]) leg (48 GB of pinned host memory)")
+    ap.add_argument("--only-main", action="store_true", help="N > 1: only the main leg (no contiguous-placement and configs[4] legs)")
     ap.add_argument("--store-in-hbm", action="store_true", help="debug: backing store copied into HBM (not the BASELINE config)")
     ap.add_argument("--layers", type=int, default=1, help="1 = configs[1] (C1); 2 = configs[2] (C1+C2); 3 = configs[3] (C1+C2+C3, needs 8/4)")
     ap.add_argument("--secondary", type=int, default=0, help="SECONDARY_PRECISION of the C2 tier")
@@ -155,14 +160,12 @@ def batches_until_full(idx: np.ndarray, rows, cap: int) -> int:
     derive their cache warm-up from this, so they reach the timed region in the same state."""
     n, T, B = idx.shape
     new_per_batch = np.zeros(n, dtype=np.int64)
+    batch_of = np.repeat(np.arange(n, dtype=np.int32), B)[::-1]
     for t in range(T):
-        seen = np.zeros(int(rows[t]), dtype=bool)
-        for k0 in range(0, n, 128):
-            flat = idx[k0:k0 + 128, t].ravel()
-            u, first = np.unique(flat, return_index=True)
-            fresh = ~seen[u]
-            np.add.at(new_per_batch, k0 + first[fresh] // B, 1)
-            seen[u[fresh]] = True
+        # first batch that requests each row: written in reverse trace order, so the earliest batch is the write that stays
+        first = np.full(int(rows[t]), n, dtype=np.int32)
+        first[idx[:, t].ravel()[::-1]] = batch_of
+        new_per_batch += np.bincount(first[first < n], minlength=n)
     cum = np.cumsum(new_per_batch)
     full = int(np.searchsorted(cum, cap, side="left")) + 1
     return min(full, n)
@@ -179,7 +182,9 @@ def configs1_config(B: int, dim: int, cache_rows: int, warm: int) -> dict:
             "batch": B, "dim": dim, "precision": 32, "layers": 1, "policy": "evlfu", "cache_rows": cache_rows,
             "cache_warm_batches": warm,
             "cache_warm": "the Zipf trace itself until the cache is full (%d batches, derived from the trace) plus %d batches "
-                          "with evictions running" % (warm - WARM_AFTER_FULL, WARM_AFTER_FULL)}
+                          "with evictions running" % (warm - WARM_AFTER_FULL, WARM_AFTER_FULL),
+            "l2": "no flush: index + slab working set (%.2f GB) exceeds the 126 MB L2 and every step reads a distinct index batch"
+                  % (cache_rows * (dim * 4 + 32) / 1e9)}
 
 
 # ------------------------------------------------------------------------------------ reference arm
@@ -243,12 +248,12 @@ def main_reference(args):
     # the same trace, the same warm-up rule and the same `config` as main_ours (N = 1); at N > 1 the reference still runs
     # unsharded on the host cores, over the N-GPU arm's global batch
     search = max(8, WARM_SEARCH * 2048 // B)
-    n_batches = search + 4 * (W + args.steps) + 16
+    n_batches = search + 4 * W + 8 * args.steps + 32
     _, tables, idx = build_workload(args, n_batches, rows, dim, B)
     warm = args.cache_warm if args.cache_warm >= 0 else batches_until_full(idx[:search], rows, cache_rows) + WARM_AFTER_FULL * 2048 // B
     log(f"reference arm: {warm} warm batches of {B} (cache full after {warm - WARM_AFTER_FULL * 2048 // B}), then {W} + {args.steps}")
     r = run_cpu_reference(variant, tables, idx, B, warm + W, args.steps)
-    cfg = configs1_config(B, dim, cache_rows, warm) if args.gpus <= 1 else sharded_config(args.gpus, B, dim, warm)
+    cfg = configs1_config(B, dim, cache_rows, warm) if args.gpus <= 1 else sharded_config(args.gpus, B, dim, args.transport)
     line = {
         "impl": "reference", "metric": "ev_lookups_per_s", "value": r["lookups_per_s"], "unit": "lookups/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": W, "ms_per_step": r["ms_per_step"],
@@ -266,12 +271,18 @@ def main_reference(args):
     return 0
 
 
-def sharded_config(world: int, B: int, dim: int, warm) -> dict:
+def sharded_config(world: int, B: int, dim: int, transport: str = "p2p") -> dict:
     """`config` of the N > 1 line (Kaggle shape, weak scaling); the reference arm prints the same object."""
     return {"workload": "configs[1] tables sharded table-wise over %d GPUs (weak scaling of the N = 1 line): C1 EvLFU fp32 tier, "
                         "Kaggle-shape 26 tables (33.76M rows), dim %d, Zipf(1.05), global batch %d = 2048 per GPU, 13%% of the rows "
                         "cached, backing store in host memory" % (world, dim, B),
-            "batch": B, "dim": dim, "precision": 32, "layers": 1, "policy": "evlfu", "n_gpus": world}
+            "batch": B, "dim": dim, "precision": 32, "layers": 1, "policy": "evlfu", "n_gpus": world,
+            "parallelism": "table-wise x%d, exchange %s" % (world, "fused into the kernels over NVLink peer memory (evs_shard_*)"
+                                                            if transport == "p2p" else "NCCL all-reduce + all_to_all_single"),
+            "transport": transport,
+            "placement": "tables spread over the ranks by row count (sharded.balanced_placement; departs from ext_dist.get_my_slice, "
+                         "whose contiguous slices are reported under placement_contiguous)",
+            "l2": "no flush: index + slab working set exceeds the 126 MB L2 and every step reads a distinct index batch"}
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -306,7 +317,7 @@ def main_ours(args):
     T = len(rows)
     cache_rows = pkg.workload.KAGGLE_CACHE_ROWS if (args.scale == 1.0 and args.shape == "kaggle" and not sliced) else int(sum(rows) * 0.13)
     search = max(8, WARM_SEARCH * 2048 // B)
-    n_batches = search + 4 * (W + K) + 16                  # the reference arm generates the same trace (same n, same B)
+    n_batches = search + 4 * W + 8 * K + 32                # the reference arm generates the same trace (same n, same B)
     _, tables, idx = build_workload(args, n_batches, rows, dim, B)
     t0 = time.time()
     warm = args.cache_warm if args.cache_warm >= 0 else batches_until_full(idx[:search], rows, cache_rows * 32 // args.precision
@@ -458,23 +469,24 @@ def main_ours(args):
     alg_bytes = B * T * bpl
     # The roofline kernel is k_serve: the fused probe + dequantise + gather kernel is the only HBM-bandwidth-bound
     # kernel of the step and the one SURVEY.md 8(d)'s bytes-per-lookup figure describes (and the north-star's 50 %
-    # target names).  The kernels that take more of the step at this batch size are not bandwidth bound: k_fetch by
-    # the PCIe small-read rate (~110 M rows/s), k_update / k_evict by chains of dependent accesses;
+    # target names).  The kernels that take more of the step at this batch size are not bandwidth bound: k_update / k_evict
+    # are chains of dependent accesses, the miss fetch (a role of k_evict, and the look-ahead k_prefetch) is bound by the
+    # PCIe small-read rate;
     # they are listed under "per_kernel" with their share and named in "dominant_by_time".
     serve_ev_us = per_kernel["k_serve"]["avg_us"]
     # in-kernel %globaltimer span (first CTA start to last CTA end) averaged over the timed batches; the CUDA-event
     # figure additionally holds ~6 us of launch and drain
     serve_us = phases["avg_serve"]
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
-    # same command (profiles/r1_traffic.json, written by tools/ncu_summary.py); null when no capture is committed
+    # same command (profiles/r2_traffic.json, written by tools/ncu_summary.py); null when no capture is committed
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if tj.get("batch") == B and tj.get("dim") == dim and tj.get("precision") == prec and layers == 1:
             traffic = tj["dram_bytes_per_launch"].get("k_serve")
     except Exception:
         pass
-    n_miss = st["misses"] / max(1, K)
+    n_miss = st["misses"] / max(1, 3 * K)
     roofline = {
         "bound": "hbm", "kernel": "k_serve", "achieved": alg_bytes / (serve_ev_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": alg_bytes / (serve_ev_us * 1e-6) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
@@ -485,10 +497,80 @@ def main_ours(args):
         "k_serve": {"event_avg_us": serve_ev_us, "in_kernel_avg_us": serve_us,
                     "achieved": alg_bytes / (serve_us * 1e-6) / 1e9, "frac": alg_bytes / (serve_us * 1e-6) / 1e9 / peak},
         "dominant_by_time": {"kernel": dom, "share": per_kernel[dom]["share"], "avg_us": per_kernel[dom]["avg_us"],
-                             "bound": ("pcie small-read rate: %.0f zero-copy row reads per launch at ~110 rows/us" % n_miss) if dom == "k_fetch"
+                             "bound": ("k_evict = eviction roles (latency: dependent HBM / L2 accesses) + miss-fetch role (%.0f missing rows per "
+                                       "launch: staged by the look-ahead, else zero-copy PCIe reads at 55-110 rows/us)" % n_miss) if dom == "k_evict"
                              else "latency: chains of dependent HBM / L2 accesses, not bandwidth"},
         "step_frac": lookups * bpl / (ms_dev * 1e-3) / 1e9 / peak, "per_kernel": per_kernel, "phases_us": phases,
     }
+
+    footprint = store.memory_footprint()
+    # ---- the same cache at batch 16384: where k_serve reaches its bandwidth regime ---------------------------------
+    # (configs[1] is quoted at batch 2048, where 8 MB per launch is latency-bound whatever the kernel does; the
+    # north-star's ">= 50 % of HBM peak on the fused probe + dequantise + gather kernel" is a statement about the
+    # kernel at a batch that fills the machine, reported here from the same run)
+    b16 = None
+    if (not args.no_b16k and B == 2048 and layers == 1 and args.scale == 1.0 and not sliced):
+        try:
+            store.close()
+            store = None
+            B2, K2 = 16384, min(K, 50)
+            n2 = warm // 8 + W + 2 * K2 + 2
+            assert n2 * 8 <= idx.shape[0]
+            idx2 = np.ascontiguousarray(idx[:n2 * 8].reshape(n2, 8, T, B).transpose(0, 2, 1, 3)).reshape(n2, T, B2)
+            idx2_dev = torch.from_numpy(idx2).to(dev)
+            cfg2 = pkg.CacheConfig(n_layers=1, main_precision=prec, total_size=total_size, max_batch=B2, device=local_rank, policy=args.policy)
+            st2 = pkg.EvStore(tables, cfg2, stores=stores)
+            out2 = torch.empty((B2, T, dim), dtype=torch.float32, device=dev)
+            hit2 = torch.empty((B2, T), dtype=torch.uint8, device=dev)
+            k = 0
+            for _ in range(warm // 8 + W):
+                st2.lookup(idx2_dev[k], out=out2, hit=hit2)
+                st2.prefetch(idx2_dev[k + 1])
+                k += 1
+            torch.cuda.synchronize()
+            st2.phase_times()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K2):
+                st2.lookup(idx2_dev[k], out=out2, hit=hit2)
+                st2.prefetch(idx2_dev[k + 1])
+                k += 1
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1)
+            ph2 = st2.phase_times()
+            st2.kernel_times(reset=True)
+            st2.set_profiling(True)
+            for _ in range(K2):
+                st2.lookup(idx2_dev[k], out=out2, hit=hit2)
+                k += 1
+            torch.cuda.synchronize()
+            kt2 = st2.kernel_times(reset=True)
+            st2.set_profiling(False)
+            ev_us = 1e3 * kt2["k_serve"][0] / max(1, kt2["k_serve"][1])
+            ab2 = B2 * T * bpl
+            b16 = {"batch": B2, "steps": K2, "ms_per_step": ms2 / K2, "lookups_per_s": K2 * B2 * T / (ms2 * 1e-3),
+                   "algorithmic_bytes_per_launch": ab2, "k_serve_event_us": ev_us, "frac": ab2 / (ev_us * 1e-6) / 1e9 / peak,
+                   "achieved": ab2 / (ev_us * 1e-6) / 1e9, "k_serve_in_kernel_us": ph2["avg_serve"],
+                   "in_kernel_frac": ab2 / (ph2["avg_serve"] * 1e-6) / 1e9 / peak,
+                   "per_kernel_us": {n: 1e3 * ms / max(1, timed) for n, (ms, timed, _l) in kt2.items() if timed}}
+            st2.close()
+            del idx2_dev, out2, hit2
+        except Exception as e:
+            log("batch-16384 leg failed:", repr(e))
+    roofline["batch16384"] = b16
+
+    # ---- the two tensor ops either side of the cache, alone, against the HBM roofline (bench.py --op ... for more) ----
+    ops = None
+    if not args.no_ops and args.scale == 1.0:
+        try:
+            from bench_ops import bench_embedding_bag, bench_interact
+            ops = {"interact_d16": bench_interact(pkg, dev, B=16384, d=16, K=30, peak=peak),
+                   "interact_d64": bench_interact(pkg, dev, B=16384, d=64, K=30, peak=peak),
+                   "embedding_bag_d64": bench_embedding_bag(pkg, dev, B=16384, P=10, d=64, K=30, peak=peak)}
+            torch.cuda.empty_cache()
+        except Exception as e:
+            log("op legs failed:", repr(e))
 
     # ---- CPU baseline: the reference's own library on this host -------------------------------
     cpu = None
@@ -498,14 +580,28 @@ def main_ours(args):
             from oracle import ref_driver
             variant = "bench_c1_fp32_d16"
             if ref_driver.available(variant):
-                # ~10-30 s of CPU work: the reference does ~25 k samples/s => 12 batches/s
-                warm_b = int(args.cpu_baseline_seconds * 8)
-                r = run_cpu_reference(variant, tables, idx, B, warm_b, 40, budget_s=args.cpu_baseline_seconds)
+                # the same warm-up as the GPU arm (until the cache is full, + evictions running), bounded by a time budget
+                r = run_cpu_reference(variant, tables, idx, B, warm + W, 40, budget_s=args.cpu_baseline_seconds)
                 cpu = {"value": r["lookups_per_s"], "unit": "lookups/s", "cores": 4, "kind": "reference",
-                       "sample": "%d batches of %d samples timed after %d warm batches (cache only partly full); reference "
-                                 "libcachemanager.so, 1 caller + 3 reader threads, tables in /dev/shm"
-                                 % (r["steps"], B, r["warm_batches"]),
+                       "sample": "%d batches of %d samples timed after %d warm batches in %.0f s (%s); the reference's own "
+                                 "libcachemanager.so, 1 caller + 3 reader threads, backing tables as files in /dev/shm"
+                                 % (r["steps"], B, r["warm_batches"], r["warm_seconds"],
+                                    "the GPU arm's warm-up: cache full" if r["warm_batches"] >= warm + W else "time budget reached: cache only partly full"),
                        "samples_per_s": r["samples_per_s"], "host_cpus": os.cpu_count()}
+                # leg (ii) of SURVEY 8(d): the sequential Python EvLFU (restated EvLFU_C1.py, in-RAM rows), one core
+                try:
+                    from oracle.evlfu import SeqEvLFU
+                    seq = SeqEvLFU(cache_rows, n_tables=T)
+                    tr = np.ascontiguousarray(idx[:3].transpose(0, 2, 1).reshape(-1, T))
+                    n_py = min(4000, tr.shape[0])
+                    t0 = time.perf_counter()
+                    for i in range(n_py):
+                        seq.request(tr[i])
+                    dt = time.perf_counter() - t0
+                    cpu["python_evlfu"] = {"value": n_py * T / dt, "unit": "lookups/s", "cores": 1, "kind": "port",
+                                           "sample": "%d requests through oracle.evlfu.SeqEvLFU (EvLFU_C1.py restated; policy only, rows not copied), cold cache" % n_py}
+                except Exception as e:
+                    log("python EvLFU leg failed:", repr(e))
             else:
                 log("cpu_baseline: oracle/_ref not built")
         except Exception as e:                          # the baseline must not take the GPU number down
@@ -513,12 +609,31 @@ def main_ours(args):
     if cpu is None:
         cpu = {"value": None, "unit": "lookups/s", "cores": 0, "kind": "reference", "sample": "not run"}
 
+    std_cfg = (layers == 1 and prec == 32 and args.policy == "evlfu" and args.shape == "kaggle" and not sliced and args.scale == 1.0
+               and not args.store_in_hbm)
+    # ---- configs[4] on one GPU: the N = 1 point of the Terabyte-shape scaling series (bench_sharded.py runs it at N > 1) ----
+    configs4 = None
+    if std_cfg and B == 2048 and not args.no_configs4:
+        try:
+            if store is not None:
+                store.close()
+                store = None
+            del tables, idx, idx_dev, idx_host, stores
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            from bench_sharded import run_one_leg
+            ver = {}
+            configs4 = run_one_leg(pkg, log, args, 0, 1, local_rank, "terabyte", "balanced", "configs4", min(K, 50), False, ver)
+        except Exception as e:
+            log("configs[4] leg failed:", repr(e))
     line = {
         "metric": "ev_lookups_per_s", "value": value, "unit": "lookups/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if prec == 32 else f"u{prec}->f32", "data": "synthetic",
         "samples_per_s": value / T, "hit_rate": hit_rate, "hit_rate_by_tier": tier_rates, "perfect_hit_rate": perfect_rate,
-        "config": {"workload": ("%s: C1 %s fp%d tier" % ("configs[1]" if args.shape == "kaggle" else "configs[4], one GPU",
+        "config": configs1_config(B, dim, cache_rows, warm) if std_cfg else
+                  {"workload": ("%s: C1 %s fp%d tier" % ("configs[1]" if args.shape == "kaggle" else "configs[4], one GPU",
                                                           "EvLFU" if args.policy == "evlfu" else "LRU (cache_algo/LRU.py, comparison policy)", prec) if layers == 1 else
                                 "configs[%d]: C1 %d-bit + C2 %d-bit%s, TOTAL_SIZE %d fp32-row units%s" % (
                                     layers, prec, sec, " + C3" if layers == 3 else "", total_size, (" split " + args.prop) if args.prop else ""))
@@ -528,17 +643,20 @@ def main_ours(args):
                                      + ((" tables %s only (one rank's shard, local agg_hit)," % args.table_slice) if sliced else ""),
                                      T, sum(rows) / 1e6, dim, B, cache_rows),
                    "layers": layers, "secondary_precision": sec, "policy": args.policy,
-                   "batch": B, "dim": dim, "precision": prec, "cache_rows": cache_rows, "cache_fill": fill,
-                   "cache_warm_batches": warm,
-                   "l2": "no flush: index+slab working set (%.2f GB) exceeds the 126 MB L2 and every step reads a distinct index batch"
-                         % ((cache_rows * (dim * prec // 8 + 32)) / 1e9)},
+                   "batch": B, "dim": dim, "precision": prec, "cache_rows": cache_rows, "cache_warm_batches": warm,
+                   "l2": "no flush: index + slab working set exceeds the 126 MB L2 and every step reads a distinct index batch"},
+        "cache": {"fill": fill, "hbm_bytes": footprint, "budget_bytes": cache_rows * dim * prec // 8,
+                  "note": "hbm_bytes = index (load factor <= 1/3) + slot-indexed slab + bucket rings + look-ahead staging; budget_bytes "
+                          "= cache rows x row bytes, the reference's TOTAL_SIZE accounting (cache_manager.cpp:16)"},
+        "value_regions_ms": regions, "look_ahead": use_pf, "configs4": configs4, "ops": ops,
         "e2e": {"value": e2e_value, "unit": "lookups/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / K, "api": "evs_submit_host/evs_wait_host (4 batches in flight)",
                 "sync_call_value": lookups / e2e_sync_s, "sync_call_ms_per_step": 1e3 * e2e_sync_s / K},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    store.close()
+    if store is not None:
+        store.close()
     return 0
 
 
@@ -554,4 +672,7 @@ def _guard_stdout():
 if __name__ == "__main__":
     a = parse_args()
     _guard_stdout()
+    if a.op:
+        from bench_ops import main_ops
+        sys.exit(main_ops(a))
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

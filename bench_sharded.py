@@ -1,31 +1,229 @@
 """bench.py --gpus N (N > 1): the lookup path table-wise sharded over the GPUs of one box.
 
-One process per GPU (torchrun), NCCL.  Rank r owns the tables get_my_slice(26, r, N)
-(extend_distributed.py:47-62), looks the whole global batch up in them (probe -> all-reduce of the
-per-sample hit counts -> batch-granular EvLFU with the exact agg_hit), and an all-to-all turns the
-pooled rows [B, T_local*d] into [B/N, 26*d] (dlrm_s_pytorch.py:564-570).
+One process per GPU (torchrun).  Rank r owns a set of tables, looks the whole global batch up in them (batch-granular
+EvLFU with the EXACT agg_hit: the sum of the ranks' per-sample hit counts) and the pooled rows [B, T_local*d] end up
+batch-sharded, [B/N, 26*d] (DLRM_Net.distributed_forward, dlrm_s_pytorch.py:529-586; ext_dist.alltoall,
+extend_distributed.py:541-576).  The exchange is part of the kernels (peer-memory stores over NVLink + epoch words,
+evs_shard_*); --transport nccl selects all-reduce + all_to_all_single instead.
 
-Weak scaling: the global batch is 2048*N samples, so every rank handles (26/N tables) x (2048*N
-samples) = 53 248 lookups per step whatever N is, and ends with the 2048 samples of its batch slice.
-Default shape: the Kaggle tables of configs[1] (so the N = 1 line of bench.py is the same workload,
-unsharded, and the reference arm is comparable); --shape terabyte selects configs[4] (dim 64,
-MLPerf cardinalities capped at 40 M).
+Legs of one run (every rank 53 248 lookups per step whatever N is -- weak scaling):
+  main        Kaggle-shape tables of configs[1] (so the N = 1 line of bench.py is the same workload unsharded), global
+              batch 2048*N, tables placed by ROW COUNT (sharded.balanced_placement; departs from get_my_slice)  -> `value`
+  contiguous  the same with the reference's contiguous get_my_slice placement                               -> "placement_contiguous"
+  configs4    BASELINE configs[4]: Criteo-Terabyte shape (dim 64, cardinalities capped at 40 M, 48 GB of backing
+              rows in pinned host memory), same placement rule                                              -> "configs4"
+Every leg is VERIFIED on untimed steps: each rank all-gathers the index batch and checks every row it received
+against the closed-form backing table of its key (workload.synth_rows); one more leg replays a scaled-down shard
+against the batch-granular oracle (hit maps, eviction counts).  A mismatch makes the run exit non-zero.
 """
 from __future__ import annotations
 
 import importlib
 import json
 import os
+import sys
 import time
 
 import numpy as np
+
+
+def _max_over_ranks(x: float, dev, world) -> float:
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return float(x)
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(vals, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t)
+    return [float(v) for v in t.tolist()]
+
+
+def _barrier(world):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+class Leg:
+    """One sharded cache over one table shape: build, fill, verify, time."""
+
+    def __init__(self, pkg, log, rank, world, local_rank, all_rows, dim, prec, Bl, placement_kind, transport, label):
+        import torch
+        self.pkg, self.log, self.rank, self.world, self.label = pkg, log, rank, world, label
+        self.dev = torch.device("cuda", local_rank)
+        self.all_rows, self.dim, self.prec = list(all_rows), dim, prec
+        self.T = len(all_rows)
+        self.Bl, self.B = Bl, Bl * world
+        self.placement = (pkg.sharded.balanced_placement(all_rows, world) if placement_kind == "balanced"
+                          else pkg.sharded.contiguous_placement(self.T, world))
+        self.ids = self.placement[rank]
+        self.rows = [all_rows[t] for t in self.ids]
+        self.T_local = len(self.ids)
+        # the reference's 13 % operating point (cache_manager.cpp:16), each rank caching 13 % of its own rows
+        self.cache_rows = max(1024, int(sum(self.rows) * 0.13))
+        t0 = time.time()
+        self.pinned = [pkg.workload.synth_table_pinned(t, all_rows[t], dim, self.dev) for t in self.ids]
+        assert prec == 32, "the sharded bench serves the fp32 tier"
+        stores = {32: [q.numpy() for q in self.pinned]}
+        self.trace = pkg.workload.ZipfTrace(self.rows, alpha=1.05, seed=42 + self.ids[0], perm_seed=7 + self.ids[0])
+        cfg = pkg.CacheConfig(n_layers=1, main_precision=prec, total_size=self.cache_rows, max_batch=self.B, device=local_rank,
+                              n_tables_total=self.T, table_ids=tuple(self.ids))
+        self.store = pkg.EvStore.from_raw_stores(self.rows, dim, cfg, stores)
+        self.sh = pkg.sharded.ShardedLookup(self.store, self.T, dim, rank, world, transport=transport, batch_max=self.B,
+                                            placement=self.placement)
+        log(f"[{label} rank {rank}] tables {self.ids}: {sum(self.rows) / 1e6:.2f} M rows, {sum(p.numel() * 4 for p in self.pinned) / 1e9:.2f} GB pinned, "
+            f"cache {self.cache_rows} rows, HBM {self.store.memory_footprint() / 1e9:.2f} GB, built in {time.time() - t0:.1f}s")
+
+    def batches(self, n):
+        import torch
+        return torch.from_numpy(self.trace.batches(n, self.B))
+
+    def fill(self, warm_max):
+        import torch
+        import torch.distributed as dist
+        t0 = time.time()
+        done = 0
+        full = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        while done < warm_max:
+            n = min(200, warm_max - done)
+            idx = self.batches(n + 1).to(self.dev)
+            for k in range(n):
+                self.sh.lookup(idx[k], next_idx=idx[k + 1])
+            done += n
+            st = self.store.stats()
+            full[0] = 1 if st["size"][0] >= st["capacity"][0] else 0
+            if self.world > 1:
+                dist.all_reduce(full, op=dist.ReduceOp.MIN)
+            if int(full.item()) == 1:
+                break
+        # evictions running on every rank before anything is timed
+        idx = self.batches(101).to(self.dev)
+        for k in range(100):
+            self.sh.lookup(idx[k], next_idx=idx[k + 1])
+        done += 100
+        st = self.store.stats(reset=True)
+        self.store.check()
+        self.log(f"[{self.label} rank {self.rank}] cache warm: {done} batches in {time.time() - t0:.1f}s, resident {st['size'][0]}/{st['capacity'][0]}, "
+                 f"hit rate so far {st['hits'][0] / max(1, st['lookups']):.3f}")
+        return done
+
+    def verify(self, idx_dev, n_steps=2):
+        """Untimed: every row this rank received == the closed-form backing row of its key (bit-exact), and the hit map
+        agrees with it (a hit and a miss both deliver the backing row).  Returns (ok, rows checked)."""
+        import torch
+        import torch.distributed as dist
+        ok, checked = True, 0
+        tmax = max(len(x) for x in self.placement)
+        for k in range(n_steps):
+            ly, hit = self.sh.lookup(idx_dev[k], next_idx=idx_dev[k + 1])
+            mine = torch.zeros((tmax, self.B), dtype=torch.int64, device=self.dev)
+            mine[:self.T_local] = idx_dev[k]
+            if self.world > 1:
+                allidx = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(allidx, mine)
+            else:
+                allidx = [mine]
+            s0 = self.rank * self.Bl
+            for r, ids in enumerate(self.placement):
+                for j, t in enumerate(ids):
+                    want = self.pkg.workload.synth_rows(t, allidx[r][j, s0:s0 + self.Bl], self.dim, self.all_rows[t])
+                    good = bool(torch.equal(ly[:, t, :], want))
+                    ok = ok and good
+                    checked += self.Bl
+                    if not good:
+                        self.log(f"[{self.label} rank {self.rank}] VERIFY FAILED: table {t} from rank {r}, step {k}: "
+                                 f"{int((ly[:, t, :] != want).any(dim=1).sum())} of {self.Bl} rows differ")
+            torch.cuda.synchronize()
+        self.store.check()
+        return ok, checked
+
+    def timed(self, idx_dev, base, W, K, reps=3):
+        """`reps` regions of exactly K steps (barrier + synchronize on both sides, device time, max over ranks)."""
+        import torch
+        for k in range(W):
+            self.sh.lookup(idx_dev[base + k], next_idx=idx_dev[base + k + 1])
+        base += W
+        regions = []
+        launches = 0
+        for _ in range(reps):
+            _barrier(self.world)
+            l0 = self.store.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(K):
+                self.sh.lookup(idx_dev[base + k], next_idx=idx_dev[base + k + 1])
+            e1.record()
+            _barrier(self.world)
+            regions.append(_max_over_ranks(e0.elapsed_time(e1), self.dev, self.world))
+            launches = self.store.launch_count() - l0
+            base += K
+        return regions, base, launches
+
+    def close(self):
+        self.store.close()
+        self.pinned = None
+
+
+def verify_policy_small(pkg, log, rank, world, local_rank, transport):
+    """A scaled-down shard against the batch-granular oracle: per-rank hit maps, eviction counts and resident sizes
+    (the full-size caches are checked for delivered VALUES; this checks the policy under the sharded exchange)."""
+    import torch
+    import torch.distributed as dist
+    from oracle.evlfu import BatchEvLFU, make_key
+    dev = torch.device("cuda", local_rank)
+    rows = [3, 5, 4000, 2500, 7, 4, 60, 9, 3, 300, 50, 3500, 40, 4, 80, 3000, 5, 45, 30, 4, 3800, 6, 5, 600, 11, 400]
+    dim, Bl, cap, n = 16, 64, 500, 14
+    B = Bl * world
+    placement = pkg.sharded.balanced_placement(rows, world)
+    ids = placement[rank]
+    lrows = [rows[t] for t in ids]
+    tables = [pkg.workload.synth_rows(t, np.arange(rows[t]), dim, rows[t]) for t in ids]
+    cfg = pkg.CacheConfig(total_size=cap, max_batch=B, n_tables_total=26, table_ids=tuple(ids), device=local_rank, record_events=True)
+    store = pkg.EvStore(tables, cfg)
+    sh = pkg.sharded.ShardedLookup(store, 26, dim, rank, world, transport=transport, batch_max=B, placement=placement)
+    oracle = BatchEvLFU(cap, n_tables=26)
+    trace = pkg.workload.ZipfTrace(lrows, seed=91 + ids[0], perm_seed=3 + ids[0])
+    batches = trace.batches(n + 1, B)
+    dev_idx = [torch.from_numpy(np.ascontiguousarray(b)).to(dev) for b in batches]
+    ok = True
+    n_ev = 0
+    for k in range(n):
+        ly, hit = sh.lookup(dev_idx[k], next_idx=dev_idx[k + 1])
+        idx = batches[k]
+        local = np.array([sum(make_key(ids[t], idx[t, s]) in oracle.entries for t in range(len(ids))) for s in range(B)], dtype=np.int32)
+        agg = torch.from_numpy(local).to(dev)
+        if world > 1:
+            dist.all_reduce(agg)
+        o_hit, _st, _sr, _ = oracle.lookup_batch(idx, agg=agg.cpu().numpy(), table_ids=ids)
+        torch.cuda.synchronize()
+        ev, _fl = store.last_events()
+        good = bool(np.array_equal(hit.cpu().numpy().astype(bool), o_hit)) and ev.tolist() == oracle.evicted
+        if not good:
+            log(f"[policy check rank {rank}] batch {k}: hit map / eviction stream differs from the oracle")
+        ok = ok and good
+        n_ev += len(oracle.evicted)
+    st = store.stats()
+    ok = ok and st["size"][0] == len(oracle.entries) and n_ev > 0
+    store.close()
+    return ok
 
 
 def main_sharded(args):
     import torch
     import torch.distributed as dist
 
-    from bench import ClockSampler, bytes_per_lookup, log, measured_peak_hbm
+    from bench import log
 
     world = int(os.environ["WORLD_SIZE"])
     rank = int(os.environ["RANK"])
@@ -34,195 +232,202 @@ def main_sharded(args):
     dev = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=dev)
     pkg = importlib.import_module("ev-store-dlrm_b200")
-
-    shape = getattr(args, "shape", "kaggle")
-    all_rows = pkg.workload.TERABYTE_ROWS if shape == "terabyte" else pkg.workload.KAGGLE_ROWS
-    if args.scale != 1.0:
-        all_rows = pkg.workload.scaled_rows(all_rows, args.scale)
-    dim = args.dim or (64 if shape == "terabyte" else 16)
-    prec = args.precision
-    T = len(all_rows)
-    Bl = args.batch or 2048
-    B = Bl * world
-    K, W = args.steps, max(args.warmup, 3)
-    sl = pkg.sharded.get_my_slice(T, rank, world)
-    rows = all_rows[sl]
-    T_local = len(rows)
-    # the reference's 13 % operating point (cache_manager.cpp:16), each rank caching 13 % of its own rows
-    cache_rows = max(1024, int(sum(rows) * 0.13))
-
-    t0 = time.time()
-    tables = [pkg.workload.make_table(sl.start + t, r, dim) for t, r in enumerate(rows)]
-    raw = [pkg.codecs.encode_table(t, prec) for t in tables]
-    pinned = [torch.from_numpy(r).pin_memory() for r in raw]
-    stores = {prec: [q.numpy() for q in pinned]}
-    del raw
-    trace = pkg.workload.ZipfTrace(rows, alpha=1.05, seed=42 + sl.start, perm_seed=7 + sl.start)
-    log(f"[rank {rank}] tables {sl.start}..{sl.stop - 1}: {sum(rows) / 1e6:.2f} M rows, {sum(t.nbytes for t in tables) / 1e9:.2f} GB, "
-        f"cache {cache_rows} rows, built in {time.time() - t0:.1f}s")
-    cfg = pkg.CacheConfig(n_layers=1, main_precision=prec, total_size=cache_rows * prec // 32, max_batch=B, device=local_rank,
-                          n_tables_total=T, table_base=sl.start)
-    store = pkg.EvStore(tables, cfg, stores=stores)
-    del tables
-    transport = getattr(args, "transport", "p2p")
-    sh = pkg.sharded.ShardedLookup(store, T, dim, rank, world, transport=transport, batch_max=B)
-
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
 
-    # ---- fill the cache ------------------------------------------------------------------------
-    t0 = time.time()
-    warm_max = args.cache_warm if args.cache_warm >= 0 else 6000
-    done = 0
-    full = torch.zeros(1, dtype=torch.int32, device=dev)
-    while done < warm_max:
-        n = min(200, warm_max - done)
-        idx = torch.from_numpy(trace.batches(n, B)).to(dev)
-        for k in range(n):
-            sh.lookup(idx[k])
-        done += n
-        st = store.stats()
-        full[0] = 1 if st["size"][0] >= st["capacity"][0] else 0
-        dist.all_reduce(full, op=dist.ReduceOp.MIN)
-        if int(full.item()) == 1:
-            break
-    st = store.stats(reset=True)
-    log(f"[rank {rank}] cache warm: {done} batches in {time.time() - t0:.1f}s, resident {st['size'][0]}/{st['capacity'][0]}, "
-        f"hit rate so far {st['hits'][0] / max(1, st['lookups']):.3f}")
+    K = args.steps
+    transport = getattr(args, "transport", "p2p")
 
-    n_batches = 3 * (W + K) + 8
-    idx_host = torch.from_numpy(trace.batches(n_batches, B)).pin_memory()        # [n, T_local, B]
+    def shape_rows(shape):
+        r = pkg.workload.TERABYTE_ROWS if shape == "terabyte" else pkg.workload.KAGGLE_ROWS
+        return pkg.workload.scaled_rows(r, args.scale) if args.scale != 1.0 else r
+
+    verified = {}
+    # ---- policy under the sharded exchange, against the oracle (scaled-down shard) -----------------------------------
+    okp = verify_policy_small(pkg, log, rank, world, local_rank, transport)
+    verified["policy_vs_oracle_scaled_shard"] = bool(_sum_over_ranks([0.0 if okp else 1.0], dev, world)[0] == 0.0)
+
+    def run_leg(shape, placement_kind, label, K_leg, full_report):
+        return run_one_leg(pkg, log, args, rank, world, local_rank, shape, placement_kind, label, K_leg, full_report, verified)
+
+    shape = getattr(args, "shape", "kaggle")
+    main = run_leg(shape, "balanced", "main", K, True)
+    legs = {}
+    if not getattr(args, "only_main", False):
+        legs["placement_contiguous"] = run_leg(shape, "contiguous", "contiguous", min(K, 50), False)
+        if shape == "kaggle" and args.scale == 1.0:
+            legs["configs4"] = run_leg("terabyte", "balanced", "configs4", min(K, 50), False)
+    return finish_sharded(pkg, log, args, rank, world, dev, main, legs, verified, shape_rows(shape))
+
+
+def configs4_text(world, B):
+    return ("configs[4]: Criteo-Terabyte shape, 26 tables (187.77M rows, capped at 40M), dim 64, 48 GB of fp32 backing rows in pinned host "
+            "memory, C1 EvLFU fp32 tier caching 13 %% of each rank's rows, Zipf(1.05), table-wise sharded over %d GPU%s (tables placed by "
+            "row count), global batch %d, exact agg_hit" % (world, "" if world == 1 else "s", B))
+
+
+def run_one_leg(pkg, log, args, rank, world, local_rank, shape, placement_kind, label, K_leg, full_report, verified):
+    """Build, fill, verify and time one sharded cache; returns the leg's report (identical on every rank where it matters)."""
+    import torch
+    from bench import ClockSampler, bytes_per_lookup, measured_peak_hbm
+    dev = torch.device("cuda", local_rank)
+    prec = args.precision
+    Bl = args.batch or 2048
+    B = Bl * world
+    W = max(args.warmup, 3)
+    transport = getattr(args, "transport", "p2p")
+    peak, peak_src = measured_peak_hbm()
+
+    def shape_rows(shape):
+        r = pkg.workload.TERABYTE_ROWS if shape == "terabyte" else pkg.workload.KAGGLE_ROWS
+        return pkg.workload.scaled_rows(r, args.scale) if args.scale != 1.0 else r
+
+    dim = args.dim or (64 if shape == "terabyte" else 16)
+    leg = Leg(pkg, log, rank, world, local_rank, shape_rows(shape), dim, prec, Bl, placement_kind, transport, label)
+    warm_done = leg.fill(args.cache_warm if args.cache_warm >= 0 else 24000)
+    n_batches = (4 if full_report else 3) * K_leg + 2 * W + 8
+    idx_host = leg.batches(n_batches).pin_memory()                   # [n, T_local, B]
     idx_dev = idx_host.to(dev, non_blocking=True)
     torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0 and not args.no_clocks:
+    ok, checked = leg.verify(idx_dev, 2)
+    ok_all = bool(_sum_over_ranks([0.0 if ok else 1.0], dev, world)[0] == 0.0)
+    verified[label] = ok_all
+    leg.store.phase_times()
+    sampler = None
+    if full_report and rank == 0 and not args.no_clocks:
+        sampler = ClockSampler(local_rank)
         sampler.start()
         time.sleep(0.3)
+    regions, base, launches = leg.timed(idx_dev, 2, W, K_leg)
+    ms_dev = sorted(regions)[1]
+    ph = leg.store.phase_times()
+    st = leg.store.stats(reset=True)
+    tot = _sum_over_ranks([st["hits"][0], st["lookups"], st["misses"]], dev, world)
+    T = leg.T
+    lookups = K_leg * B * T
+    res = {"value": lookups / (ms_dev * 1e-3), "samples_per_s": K_leg * B / (ms_dev * 1e-3), "ms_per_step": ms_dev / K_leg,
+           "value_regions_ms": regions, "hit_rate": tot[0] / max(1.0, tot[1]), "misses_per_step_all_ranks": tot[2] / (3 * K_leg + W),
+           "cache_warm_batches": warm_done, "rows_verified_per_rank": checked, "verified": ok_all, "dim": dim,
+           "placement": placement_kind, "tables_per_rank": [len(x) for x in leg.placement],
+           "rows_per_rank_M": [round(sum(leg.all_rows[t] for t in x) / 1e6, 2) for x in leg.placement],
+           # where rank 0 waits for its peers (in-kernel %globaltimer, averaged over the timed steps): inside k_serve for their
+           # hit counts (part of avg_serve) and at the end of k_evict for their rows
+           "rank0_phases_us": {"serve_incl_wait_for_counts": ph["avg_serve"], "update": ph["avg_update"],
+                               "evict_incl_fetch_and_wait_for_rows": ph["avg_evict"], "wait_for_peer_rows": ph["avg_peer_wait"],
+                               "fetch_role_since_evict_start": ph["avg_fetch_since_evict_start"]},
+           "nvlink_bytes_per_rank_per_step": leg.sh.alltoall_bytes(B)}
+    res["nvlink_GBps_per_rank"] = res["nvlink_bytes_per_rank_per_step"] / (res["ms_per_step"] * 1e-3) / 1e9
+    res["nvlink_frac_of_peer_copy_peak"] = res["nvlink_GBps_per_rank"] / 770.0
+    clocks = None
+    if full_report:
+        # ---- e2e: pinned host indices in, this rank's pooled rows out to pinned host memory -----------------
+        out_host = [torch.empty((Bl, T, dim), dtype=torch.float32).pin_memory() for _ in range(2)]
+        idx_stage = [torch.empty((leg.T_local, B), dtype=torch.int64, device=dev) for _ in range(2)]
 
-    def max_over_ranks(x: float) -> float:
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        def e2e_step(k):
+            # the look-ahead for step k + 1 is announced as soon as its indices are on their way (ready event)
+            idx_stage[k % 2].copy_(idx_host[base + k], non_blocking=True)
+            ly, _ = leg.sh.lookup(idx_stage[k % 2])
+            out_host[k % 2].copy_(ly, non_blocking=True)
 
-    # ---- value: index batches resident in HBM ------------------------------------------------------
-    base = 0
-    for k in range(W):
-        sh.lookup(idx_dev[base + k])
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
-    l0 = store.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(K):
-        sh.lookup(idx_dev[base + W + k])
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms_dev = max_over_ranks(e0.elapsed_time(e1))
-    launches = store.launch_count() - l0
-    st = store.stats(reset=True)
-    lookups = K * B * T                                   # whole job: every rank's tables
-    value = lookups / (ms_dev * 1e-3)
-    hits = torch.tensor([st["hits"][0], st["lookups"], st["misses"]], dtype=torch.float64, device=dev)
-    dist.all_reduce(hits)
-    hit_rate = float(hits[0] / max(1.0, float(hits[1])))
+        for k in range(W):
+            e2e_step(k)
+        _barrier(world)
+        t0 = time.perf_counter()
+        for k in range(W, W + K_leg):
+            e2e_step(k)
+        torch.cuda.synchronize()
+        e2e_s = _max_over_ranks(time.perf_counter() - t0, dev, world)
+        _barrier(world)
+        res["e2e"] = {"value": lookups / e2e_s, "unit": "lookups/s", "h2d_bytes_per_step": leg.T_local * B * 8 * world,
+                      "d2h_bytes_per_step": Bl * T * dim * 4 * world, "ms_per_step": 1e3 * e2e_s / K_leg,
+                      "api": "ShardedLookup.lookup (%s) on pinned host indices, pooled rows copied back to pinned host memory" % transport}
+        clocks = sampler.stop() if sampler is not None else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        # ---- per-kernel CUDA-event times on every rank's shard (plain launches), rank 0 reported ----------------
+        leg.store.kernel_times(reset=True)
+        leg.store.set_profiling(True)
+        for k in range(K_leg):
+            leg.sh.lookup(idx_dev[2 + W + (k % (3 * K_leg))])
+        torch.cuda.synchronize()
+        kt = leg.store.kernel_times(reset=True)
+        leg.store.set_profiling(False)
+        _barrier(world)
+        per_kernel = {n: {"avg_us": 1e3 * ms / max(1, timed), "launches": timed} for n, (ms, timed, _l) in kt.items() if timed}
+        tot_us = sum(v["avg_us"] * v["launches"] for v in per_kernel.values())
+        for v in per_kernel.values():
+            v["share"] = v["avg_us"] * v["launches"] / max(tot_us, 1e-9)
+        dom = max(per_kernel, key=lambda n: per_kernel[n]["share"])
+        bpl = bytes_per_lookup(dim, prec)
+        alg_bytes = B * leg.T_local * bpl
+        sv = per_kernel["k_serve"]["avg_us"]
+        res["roofline"] = {"bound": "hbm", "kernel": "k_serve", "achieved": alg_bytes / (sv * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": alg_bytes / (sv * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                           "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_lookup": bpl, "kernel_avg_us": sv,
+                           "note": "rank 0's launch; under the fused exchange k_serve also waits for the peers' hit counts and stores its rows over NVLink",
+                           "dominant_by_time": {"kernel": dom, "share": per_kernel[dom]["share"], "avg_us": per_kernel[dom]["avg_us"]},
+                           "per_kernel_rank0": per_kernel}
+        res["gpu_launches"] = int(launches) * world
+        res["clocks"] = clocks
+    if "configs4" == label:
+        res["workload"] = configs4_text(world, B)
+    leg.close()
+    del idx_dev, idx_host
+    torch.cuda.empty_cache()
+    return res
 
-    # ---- e2e: pinned host indices in, this rank's pooled rows out to pinned host memory -----------------
-    base += W + K
-    out_host = [torch.empty((Bl, T, dim), dtype=torch.float32).pin_memory() for _ in range(2)]
-    idx_stage = [torch.empty((T_local, B), dtype=torch.int64, device=dev) for _ in range(2)]
-    for k in range(W):
-        idx_stage[k % 2].copy_(idx_host[base + k], non_blocking=True)
-        ly, _ = sh.lookup(idx_stage[k % 2])
-        out_host[k % 2].copy_(ly, non_blocking=True)
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = time.perf_counter()
-    for k in range(K):
-        idx_stage[k % 2].copy_(idx_host[base + W + k], non_blocking=True)
-        ly, _ = sh.lookup(idx_stage[k % 2])
-        out_host[k % 2].copy_(ly, non_blocking=True)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    dist.barrier()
-    e2e_value = lookups / e2e_s
 
-    clocks = sampler.stop() if (rank == 0 and not args.no_clocks) else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+def finish_sharded(pkg, log, args, rank, world, dev, main, legs, verified, rows_main):
+    import torch
+    import torch.distributed as dist
+    from bench import sharded_config
+    Bl = args.batch or 2048
+    B = Bl * world
+    K, W = args.steps, max(args.warmup, 3)
+    transport = getattr(args, "transport", "p2p")
+    if "configs4" in legs:
+        legs["configs4"]["workload"] = configs4_text(world, B)
+    # ---- the NCCL all-to-all alone, for scale (what the fused exchange replaces) ----------------------------------------
+    a2a = None
+    try:
+        dim = main["dim"]
+        T = 26
+        pl = pkg.sharded.balanced_placement(rows_main, world)
+        T_local = len(pl[rank])
+        send = torch.empty((B, T_local, dim), dtype=torch.float32, device=dev)
+        recv = torch.empty((Bl * T * dim,), dtype=torch.float32, device=dev)
+        in_splits = [Bl * T_local * dim] * world
+        out_splits = [Bl * len(x) * dim for x in pl]
+        for _ in range(5):
+            dist.all_to_all_single(recv, send.view(-1), out_splits, in_splits)
+        _barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            dist.all_to_all_single(recv, send.view(-1), out_splits, in_splits)
+        e1.record()
+        torch.cuda.synchronize()
+        a2a_ms = _max_over_ranks(e0.elapsed_time(e1), dev, world) / 50
+        a2a_bytes = B * T_local * dim * 4 * (world - 1) // world
+        a2a = {"bytes_sent_per_rank": a2a_bytes, "ms": a2a_ms, "achieved_GBps": a2a_bytes / (a2a_ms * 1e-3) / 1e9, "peak_GBps": 770.0,
+               "peak_source": "B200_PROFILING.md measured peer copy per direction", "frac": a2a_bytes / (a2a_ms * 1e-3) / 1e9 / 770.0}
+    except Exception as e:
+        log("all-to-all leg failed:", repr(e))
 
-    # ---- the all-to-all alone (NVLink share of the step) ---------------------------------------------
-    send = torch.empty((B, T_local, dim), dtype=torch.float32, device=dev)
-    recv = torch.empty((Bl * T * dim,), dtype=torch.float32, device=dev)
-    in_splits = [Bl * T_local * dim] * world
-    out_splits = [Bl * t * dim for t in sh.splits]
-    for _ in range(5):
-        dist.all_to_all_single(recv, send.view(-1), out_splits, in_splits)
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0.record()
-    for _ in range(50):
-        dist.all_to_all_single(recv, send.view(-1), out_splits, in_splits)
-    e1.record()
-    torch.cuda.synchronize()
-    a2a_ms = max_over_ranks(e0.elapsed_time(e1)) / 50
-    a2a_bytes = sh.alltoall_bytes(B)
-
-    # ---- roofline: per-kernel CUDA-event times on rank 0's shard ----------------------------------------
-    base += W + K
-    store.kernel_times(reset=True)
-    store.set_profiling(True)
-    for k in range(K):
-        sh.lookup(idx_dev[base + (k % (W + K))])
-    torch.cuda.synchronize()
-    kt = store.kernel_times(reset=True)
-    store.set_profiling(False)
-    dist.barrier()
-    per_kernel = {n: {"avg_us": 1e3 * ms / max(1, timed), "launches": timed} for n, (ms, timed, _l) in kt.items() if timed}
-    tot_us = sum(v["avg_us"] * v["launches"] for v in per_kernel.values())
-    for v in per_kernel.values():
-        v["share"] = v["avg_us"] * v["launches"] / max(tot_us, 1e-9)
-    dom = max(per_kernel, key=lambda n: per_kernel[n]["share"])
-    peak, peak_src = measured_peak_hbm()
-    bpl = bytes_per_lookup(dim, prec)
-    alg_bytes = B * T_local * bpl                                   # what one launch of a rank's kernel covers
-    # as in bench.py: the HBM-bound kernel of the step is k_serve (rank 0's launch; under p2p it also waits for the
-    # peers' hit counts and stores its rows over NVLink); the kernel with the largest share is named beside it
-    dom_us = per_kernel["k_serve"]["avg_us"] if "k_serve" in per_kernel else per_kernel[dom]["avg_us"]
-    roofline = {"bound": "hbm", "kernel": "k_serve" if "k_serve" in per_kernel else dom,
-                "achieved": alg_bytes / (dom_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg_bytes / (dom_us * 1e-6) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_lookup": bpl, "kernel_avg_us": dom_us,
-                "dominant_by_time": {"kernel": dom, "share": per_kernel[dom]["share"], "avg_us": per_kernel[dom]["avg_us"]},
-                "per_kernel_rank0": per_kernel,
-                "alltoall_nccl_alone": {"bytes_sent_per_rank": a2a_bytes, "ms": a2a_ms, "achieved_GBps": a2a_bytes / (a2a_ms * 1e-3) / 1e9,
-                             "peak_GBps": 770.0, "peak_source": "B200_PROFILING.md measured peer copy per direction",
-                             "frac": a2a_bytes / (a2a_ms * 1e-3) / 1e9 / 770.0}}
-
+    all_ok = all(verified.values())
     if rank == 0:
+        roof = main.pop("roofline")
+        roof["alltoall_nccl_alone"] = a2a
+        cfg = sharded_config(world, B, main["dim"], transport)
         line = {
-            "metric": "ev_lookups_per_s", "value": value, "unit": "lookups/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if prec == 32 else f"u{prec}->f32", "data": "synthetic", "samples_per_s": value / T,
-            "hit_rate": hit_rate,
-            "config": {"workload": "%s-shape 26 tables (%.2fM rows), dim %d, C1 EvLFU fp%d tier, Zipf(1.05), table-wise sharded over %d "
-                                   "GPUs (13 %% of each rank's rows cached), global batch %d = %d per GPU, exact agg_hit; exchange: %s"
-                                   % (shape, sum(all_rows) / 1e6, dim, prec, world, B, Bl,
-                                      "fused into the kernels (peer-memory stores over NVLink + epoch flags, evs_shard_*)"
-                                      if transport == "p2p" else "NCCL all-reduce of the hit counts + all_to_all_single of the pooled rows"),
-                       "batch": B, "dim": dim, "precision": prec, "parallelism": "table-wise x%d + all-to-all" % world,
-                       "transport": transport,
-                       "cache_warm_batches": done,
-                       "l2": "no flush: index+slab working set exceeds the 126 MB L2 and every step reads a distinct index batch"},
-            "e2e": {"value": e2e_value, "unit": "lookups/s", "h2d_bytes_per_step": T_local * B * 8 * world,
-                    "d2h_bytes_per_step": Bl * T * dim * 4 * world, "ms_per_step": 1e3 * e2e_s / K,
-                    "api": "ShardedLookup.lookup (%s) on pinned host indices, pooled rows copied back to pinned host memory" % transport},
-            "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline,
+            "metric": "ev_lookups_per_s", "value": main["value"], "unit": "lookups/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "samples_per_s": main["samples_per_s"], "hit_rate": main["hit_rate"],
+            "config": cfg, "e2e": main.pop("e2e"), "gpu_launches": main.pop("gpu_launches"), "clocks": main.pop("clocks"),
+            "roofline": roof, "verified": all_ok, "verified_legs": verified, "main": main,
             "cpu_baseline": {"value": None, "unit": "lookups/s", "cores": 0, "kind": "reference", "sample": "reported at N = 1 only"},
         }
+        line.update(legs)
         print(json.dumps(line), flush=True)
     dist.barrier()
-    store.close()
     dist.destroy_process_group()
-    return 0
+    return 0 if all_ok else 3

@@ -207,6 +207,18 @@ class EvStore:
         _native.check(self.lib.evs_probe_batch(self.handle, lS_i.data_ptr(), B, agg_out.data_ptr(), st), "evs_probe_batch")
         return agg_out
 
+    # raw-pointer forms of the two hot calls: what a C / cgo caller does, and what a Python serving loop that has
+    # its buffers set up uses to keep the per-batch host cost at the two library calls
+    def lookup_ptr(self, idx_ptr: int, B: int, out_ptr: int, out_stride: int = 0, hit_ptr: int = 0, stream: int = 0):
+        rc = self.lib.evs_lookup_batch(self.handle, idx_ptr, B, out_ptr, out_stride, hit_ptr or None, None, stream or None)
+        if rc:
+            _native.check(rc, "evs_lookup_batch")
+
+    def prefetch_ptr(self, idx_ptr: int, B: int):
+        rc = self.lib.evs_prefetch(self.handle, idx_ptr, B, None)
+        if rc:
+            _native.check(rc, "evs_prefetch")
+
     def lookup_host(self, idx: np.ndarray, out: np.ndarray | None = None, hit: np.ndarray | None = None):
         """idx: int64 host array [n_tables, B] (numpy or a pinned torch tensor's numpy view)."""
         idx = np.ascontiguousarray(idx, dtype=np.int64)

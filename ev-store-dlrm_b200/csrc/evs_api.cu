@@ -405,9 +405,9 @@ static cudaError_t launch_ex(const void *fn, dim3 grid, int block, size_t smem, 
     return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
-static cudaError_t launch_serve(ServeFn fn, int grid, cudaStream_t st, const Params &p, const BatchArgs &a) {
+static cudaError_t launch_serve(ServeFn fn, int grid, cudaStream_t st, const Params &p, const BatchArgs &a, bool pdl = false) {
     void *args[] = {const_cast<Params *>(&p), const_cast<BatchArgs *>(&a)};
-    return launch_ex(reinterpret_cast<const void *>(fn), dim3(grid), kLookupThreads, 0, st, args, false);
+    return launch_ex(reinterpret_cast<const void *>(fn), dim3(grid), kLookupThreads, 0, st, args, pdl);
 }
 
 static cudaError_t launch(KernelFn fn, dim3 grid, int block, size_t smem, cudaStream_t st, const Params &p, bool pdl) {
@@ -432,7 +432,9 @@ static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const Batc
     const KernelSet ks = kernels_of_handle(h);
     Profiler &pf = h->prof;
     const bool pdl = h->use_pdl && !pf.on;                // event records between the launches would serialise them anyway
-    { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch_serve(serve_of(h, ks), n_chunks, st, p, a)); }
+    // outside a graph the chain continues across batches: k_serve is a programmatic dependent of whatever kernel precedes
+    // it on the stream (the previous batch's k_evict in a serving loop)
+    { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch_serve(serve_of(h, ks), n_chunks, st, p, a, pdl && !h->capturing)); }
     if (p.n_chunks_max > p.quad_max || p.L < 32) {
         LaunchScope ls(pf, K_SCAN, st);
         EVS_CUDA(launch(k_scan, (h->n_tiers == 1 ? 1 : kSeqGroups) * h->tier[0].dev.n_buckets, 256, 0, st, p, pdl));
@@ -453,7 +455,9 @@ static int build_graph(evs_handle h) {
     memcpy(saved, h->prof.launches, sizeof(saved));
     EVS_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     BatchArgs none{};
+    h->capturing = true;
     int rc = enqueue_batch(h, h->stream, h->params.n_chunks_max, none);
+    h->capturing = false;
     cudaError_t e = cudaStreamEndCapture(h->stream, &g);
     memcpy(h->prof.launches, saved, sizeof(saved));
     h->prof.on = was_on;
@@ -699,16 +703,24 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
                 while (gsize < static_cast<int>(stride >> 4) && gsize < 32) gsize <<= 1;
             }
             const int rows_per_cta = (kEvictThreads / 32) * (32 / gsize);
-            const int target = static_cast<int>(std::min(512u, std::max(128u, 32768u / stride)));
+            // the link serves ~65 row reads / us whatever the row size up to 256 B once ~512-768 are in flight
+            // (profiles/r2_zc_inflight.txt); the fetch role runs next to the eviction roles and keeps fewer
+            const int target = static_cast<int>(std::min(512u, std::max(256u, 65536u / stride)));
             h->fetch_list_ctas = std::max(1, (target + rows_per_cta - 1) / rows_per_cta);
             h->pf_ok = aligned;
-            // the look-ahead kernel keeps about twice as many reads in flight: nothing waits for it
-            h->pf_ctas = std::max(4, 2 * h->fetch_list_ctas);
+            // the look-ahead kernel: nothing waits for it, so it keeps the link saturated (measured optimum for 64-byte
+            // rows: 16 CTAs = 1024 rows; 8 or 12 leave rows unstaged, 32 slow k_update's atomics down)
+            const int pf_target = stride <= 64 ? 1024 : 768;
+            h->pf_ctas = std::max(4, (pf_target + rows_per_cta - 1) / rows_per_cta);
         }
         const char *fc = getenv("EVSTORE_B200_FETCH_LIST_CTAS");   // tuning aid: CTAs of the fetch role = PCIe reads kept in flight
         if (fc && atoi(fc) > 0) h->fetch_list_ctas = atoi(fc);
         const char *pc = getenv("EVSTORE_B200_PF_CTAS");           // tuning aid: CTAs of k_prefetch
         if (pc && atoi(pc) > 0) h->pf_ctas = atoi(pc);
+        const char *pm = getenv("EVSTORE_B200_PF_MODE");           // experiments: 1 = probe + L2 warm-up only (no staging)
+        h->pf_mode = (pm && pm[0] == '1') ? 1 : 0;
+        const char *pw = getenv("EVSTORE_B200_PF_WAIT");           // experiments: 1 = stream-event wait for the staging buffer as well
+        h->pf_wait_mode = (pw && pw[0] == '1') ? 1 : 0;
         const char *pe = getenv("EVSTORE_B200_NO_PREFETCH");       // tuning aid: evs_prefetch becomes a no-op
         if (pe && pe[0] == '1') h->pf_ok = false;
         // CTAs of k_evict per tier = 256-record chunks of the rings examined at once.  A batch evicts about as many keys
@@ -798,8 +810,10 @@ static int run_batch(evs_handle h, const BatchArgs &a_in, cudaStream_t st) {
         if (rc) return rc;
     }
     // the staging rows of this parity may be overwritten (by the look-ahead for batch seq + 2) once this batch is done
-    EVS_CUDA(cudaEventRecord(h->ev_done[seq & 1], st));
-    h->ev_done_valid[seq & 1] = true;
+    if (h->pf_wait_mode == 1) {
+        EVS_CUDA(cudaEventRecord(h->ev_done[seq & 1], st));
+        h->ev_done_valid[seq & 1] = true;
+    }
     h->batches++;
     for (int i = 0; i < h->n_tiers; ++i) {
         h->tier[i].ub_used += static_cast<unsigned long long>(a.B) * h->cfg.n_tables;
@@ -815,8 +829,9 @@ static int prefetch_next(evs_handle h, const int64_t *idx_dev, int32_t B, cudaEv
     const uint64_t seq = h->seq + 1;
     if (h->pf_seq == seq && h->pf_idx == static_cast<const void *>(idx_dev) && h->pf_B == B) return EVS_OK;   // already announced
     if (ready) EVS_CUDA(cudaStreamWaitEvent(h->pf_stream, ready, 0));
-    // the staging rows of this parity belong to batch seq - 2 until it has finished
-    if (h->ev_done_valid[seq & 1]) EVS_CUDA(cudaStreamWaitEvent(h->pf_stream, h->ev_done[seq & 1], 0));
+    // (the staging rows of this parity belong to batch seq - 2 until its fetch role has finished: k_prefetch waits for that
+    // on the device -- GlobalCtl::fetch_done_seq -- so that nothing is released at a batch boundary)
+    if (h->pf_wait_mode == 1 && h->ev_done_valid[seq & 1]) EVS_CUDA(cudaStreamWaitEvent(h->pf_stream, h->ev_done[seq & 1], 0));
     if (++h->pf_gen >= 0x7FFFFFFFu) {                      // tags are generation << 1 | tier: start over with clean tags
         EVS_CUDA(cudaMemsetAsync(h->params.pf_tag, 0, 2 * sizeof(unsigned) * static_cast<size_t>(h->params.n_max), h->pf_stream));
         h->pf_gen = 1;
@@ -826,6 +841,7 @@ static int prefetch_next(evs_handle h, const int64_t *idx_dev, int32_t B, cudaEv
     pa.B = B;
     pa.seq = static_cast<unsigned>(seq);
     pa.gen = h->pf_gen;
+    pa.mode = h->pf_mode;
     const KernelSet ks = kernels_of_handle(h);
     const int S = pf_tile_samples(h->cfg.n_tables);
     const int n_tiles = (B + S - 1) / S;
@@ -1036,9 +1052,10 @@ int evs_stats(evs_handle h, evs_stats_t *out, int reset) {
         out->c3_capacity = h->params.c3.cap;
     }
     if (reset) {
-        const unsigned err = g.error;
+        const unsigned err = g.error, fds = g.fetch_done_seq;
         memset(&g, 0, sizeof(g));
         g.error = err;
+        g.fetch_done_seq = fds;
         EVS_CUDA(cudaMemcpy(h->g, &g, sizeof(g), cudaMemcpyHostToDevice));
     }
     return EVS_OK;

@@ -106,6 +106,7 @@ struct evs_handle_s {
     cudaGraph_t graph_src = nullptr;
     cudaGraphExec_t graph = nullptr;         // k_serve -> [k_scan ->] k_update -> k_evict (eviction + miss-fetch roles)
     bool use_graph = true;
+    bool capturing = false;                  // enqueue_batch is being captured into the graph
     bool use_pdl = true;                     // the batch's kernels are chained by programmatic dependent launch
     int fetch_list_ctas = 8;                 // CTAs of the miss-fetch role (EVSTORE_B200_FETCH_LIST_CTAS overrides)
     int evict_ctas = evs::kTierCtas;         // CTAs of k_evict per tier (EVSTORE_B200_EVICT_CTAS overrides)
@@ -116,6 +117,7 @@ struct evs_handle_s {
     cudaEvent_t ev_pf_ready = nullptr;       // scratch: orders pf_stream after a caller-supplied stream position
     bool pf_ok = false;                      // staging possible (every backing row 16-byte aligned)
     int pf_ctas = 16;
+    int pf_mode = 0, pf_wait_mode = 0;       // experiment switches (EVSTORE_B200_PF_MODE / _PF_WAIT)
     uint64_t seq = 0;                        // batches started on this handle
     uint64_t pf_seq = 0;                     // batch number the last evs_prefetch staged for
     uint32_t pf_gen = 0;                     // generation of that announcement (tags of its staged rows)

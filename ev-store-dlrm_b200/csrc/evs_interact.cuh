@@ -1,10 +1,18 @@
 // Pairwise-dot feature interaction (dlrm_s_pytorch_C1_C2_C3.py:625-658, op "dot",
-// arch_interaction_itself = 0):  T = [x ; ly] in [B, n_f+1, d],  Z = T T^t,
+// arch_interaction_itself = 0):  T = [x ; ly] in [B, n_f+1, d],  Z = T T^t  (torch.bmm at :632),
 // R = [x, Z[i][j] for i > j in row-major order]  ->  [B, d + (n_f+1) n_f / 2].
 //
-// 2*(n_f+1)^2*d FLOP against (n_f+1)*d*4 + (d + pairs)*4 bytes per sample is 7-11 FLOP/B,
-// far below the tensor-core ridge, so this is an fp32 FMA kernel bound by HBM: one warp per
-// sample, T staged in shared memory (padded rows), each lane owns every 32nd (i, j) pair.
+// k_interact_mma -- the tensor-core path (n_f + 1 <= 32, d <= 128): one warp per sample.
+//   * T is staged in shared memory with 128-bit loads (rows padded to 32, d padded to a multiple of 8, row stride
+//     = 4 mod 8 floats so that the fragment reads below are bank-conflict free);
+//   * Z = T T^t as 32x32xd on the tensor cores with mma.sync.m16n8k8 TF32: T serves as the row-major A operand and,
+//     unchanged, as the "column-major" B operand (B[k][n] = T[n][k]), so a lane loads 8 values per k-step and uses
+//     them for both.  Only the 6 of 8 accumulator tiles that touch the strict lower triangle are computed;
+//   * fp32 accuracy from TF32 hardware: every operand is split hi + lo (cvt.rna.tf32) and a tile is the sum of
+//     hi*hi + hi*lo + lo*hi (the "3xTF32" scheme; the dropped lo*lo term is 2^-22 relative).  The kernel is bound
+//     by HBM (7-11 FLOP/B), so the 3x tensor work is free;
+//   * the accumulators go back through shared memory so that the 351 packed outputs are written as consecutive floats.
+// k_interact (fp32 FMA) remains for shapes outside those limits.
 #pragma once
 #include "evs_host.h"
 
@@ -49,9 +57,141 @@ __global__ void __launch_bounds__(kInteractWarps * 32) k_interact(const float *_
     }
 }
 
+// ---- tensor-core path -------------------------------------------------------------------------------------------
+constexpr int kMmaWarps = 8;
+
+__device__ __forceinline__ unsigned to_tf32(float v) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+// D += A(16x8, row) * B(8x8, col), TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// ld: floats between rows of the staged T (>= Dp, a multiple of 4, = 4 mod 8); per-warp region = 32 * max(ld, 33) floats
+__global__ void __launch_bounds__(kMmaWarps * 32) k_interact_mma(const float *__restrict__ x, const float *__restrict__ ly,
+                                                                 float *__restrict__ r, int B, int n_f, int D, int Dp, int ld) {
+    extern __shared__ __align__(16) float s_t[];
+    __shared__ unsigned char s_pi[512], s_pj[512];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nt = n_f + 1;
+    const int n_pairs = nt * (nt - 1) / 2;
+    const int out_w = D + n_pairs;
+    // (i, j) of packed pair pr = i(i-1)/2 + j, 0 <= j < i, once per CTA
+    for (int pr = threadIdx.x; pr < n_pairs; pr += blockDim.x) {
+        int i = static_cast<int>((1.0f + sqrtf(1.0f + 8.0f * static_cast<float>(pr))) * 0.5f);
+        while (i * (i - 1) / 2 > pr) --i;
+        while ((i + 1) * i / 2 <= pr) ++i;
+        s_pi[pr] = static_cast<unsigned char>(i);
+        s_pj[pr] = static_cast<unsigned char>(pr - i * (i - 1) / 2);
+    }
+    __syncthreads();
+    const int region = 32 * (ld > 33 ? ld : 33);
+    float *t = s_t + static_cast<size_t>(warp) * region;
+    const int g = lane >> 2, tq = lane & 3;
+    const bool vec = ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(ly) & 15u) == 0);
+    for (int s = blockIdx.x * kMmaWarps + warp; s < B; s += gridDim.x * kMmaWarps) {
+        const float *xs = x + static_cast<size_t>(s) * D;
+        const float *ls = ly + static_cast<size_t>(s) * n_f * D;
+        float *rs = r + static_cast<size_t>(s) * out_w;
+        // ---- stage T = [x ; ly], zero the K padding ------------------------------------------------------------
+        if (vec) {
+            const int d4 = D >> 2;
+            const int n4 = nt * d4;
+            for (int e = lane; e < n4; e += 32) {
+                const int row = e / d4, c4 = e - row * d4;
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(row == 0 ? xs : ls + static_cast<size_t>(row - 1) * D) + c4);
+                *reinterpret_cast<float4 *>(t + row * ld + (c4 << 2)) = v;
+            }
+        } else {
+            for (int e = lane; e < nt * D; e += 32) {
+                const int row = e / D, c = e - row * D;
+                t[row * ld + c] = __ldg(row == 0 ? xs + c : ls + static_cast<size_t>(row - 1) * D + c);
+            }
+        }
+        if (Dp > D)
+            for (int e = lane; e < nt * (Dp - D); e += 32) {
+                const int row = e / (Dp - D), c = D + (e - row * (Dp - D));
+                t[row * ld + c] = 0.0f;
+            }
+        __syncwarp();
+        // ---- Z = T T^t on the tensor cores (rows >= nt hold stale data: they only reach outputs nobody reads) ----
+        float acc[6][4];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][k] = 0.0f;
+        for (int k0 = 0; k0 < Dp; k0 += 8) {
+            unsigned hi[4][2], lo[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float v = t[(g + 8 * j) * ld + k0 + tq + 4 * h];
+                    hi[j][h] = to_tf32(v);
+                    lo[j][h] = to_tf32(v - __uint_as_float(hi[j][h]));
+                }
+            // tile (m, n): rows 16m .. 16m+15 (A from row groups 2m, 2m+1), cols 8n .. 8n+7 (B from row group n)
+#define EVS_TILE(ti, m, n)                                                                                           \
+    mma_tf32(acc[ti], hi[2 * m][0], hi[2 * m + 1][0], hi[2 * m][1], hi[2 * m + 1][1], hi[n][0], hi[n][1]);              \
+    mma_tf32(acc[ti], hi[2 * m][0], hi[2 * m + 1][0], hi[2 * m][1], hi[2 * m + 1][1], lo[n][0], lo[n][1]);              \
+    mma_tf32(acc[ti], lo[2 * m][0], lo[2 * m + 1][0], lo[2 * m][1], lo[2 * m + 1][1], hi[n][0], hi[n][1]);
+            EVS_TILE(0, 0, 0)
+            EVS_TILE(1, 0, 1)
+            EVS_TILE(2, 1, 0)
+            EVS_TILE(3, 1, 1)
+            EVS_TILE(4, 1, 2)
+            EVS_TILE(5, 1, 3)
+#undef EVS_TILE
+        }
+        __syncwarp();                                   // every lane has read its last fragment: T may be overwritten
+        // ---- accumulators -> Z[32][33] in the same shared-memory region --------------------------------------------
+        {
+            const int tm[6] = {0, 0, 1, 1, 1, 1}, tn[6] = {0, 1, 0, 1, 2, 3};
+#pragma unroll
+            for (int ti = 0; ti < 6; ++ti) {
+                const int row = 16 * tm[ti] + g, col = 8 * tn[ti] + 2 * tq;
+                t[row * 33 + col] = acc[ti][0];
+                t[row * 33 + col + 1] = acc[ti][1];
+                t[(row + 8) * 33 + col] = acc[ti][2];
+                t[(row + 8) * 33 + col + 1] = acc[ti][3];
+            }
+        }
+        __syncwarp();
+        // ---- R = [x, strict lower triangle row-major], consecutive lanes write consecutive floats ----------------
+        for (int e = lane; e < D; e += 32) rs[e] = __ldg(xs + e);
+        for (int pr = lane; pr < n_pairs; pr += 32) rs[D + pr] = t[s_pi[pr] * 33 + s_pj[pr]];
+        __syncwarp();
+    }
+}
+
 inline int launch_interact(const float *x, const float *ly, float *r, int B, int n_f, int D, cudaStream_t st) {
     if (B < 0 || n_f < 1 || D < 1 || x == nullptr || ly == nullptr || r == nullptr) return EVS_ERR_INVALID;
     if (B == 0) return EVS_OK;
+    static const bool force_fma = [] {
+        const char *e = getenv("EVSTORE_B200_INTERACT_FMA");     // A/B aid: 1 = the fp32 FMA kernel for every shape
+        return e && e[0] == '1';
+    }();
+    if (n_f + 1 <= 32 && D <= 128 && !force_fma) {
+        const int Dp = (D + 7) & ~7;
+        int ld = Dp + 4;                                        // = 4 mod 8: conflict-free fragment reads
+        const size_t smem = static_cast<size_t>(kMmaWarps) * 32 * std::max(ld, 33) * sizeof(float);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_interact_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) {
+                set_error(std::string("k_interact_mma smem: ") + cudaGetErrorString(e));
+                return EVS_ERR_CUDA;
+            }
+        }
+        const int ctas = std::min((B + kMmaWarps - 1) / kMmaWarps, 148 * 8);
+        k_interact_mma<<<ctas, kMmaWarps * 32, smem, st>>>(x, ly, r, B, n_f, D, Dp, ld);
+        EVS_CUDA(cudaGetLastError());
+        return EVS_OK;
+    }
     const size_t smem = static_cast<size_t>(kInteractWarps) * (n_f + 1) * (D + 1) * sizeof(float);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_interact, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

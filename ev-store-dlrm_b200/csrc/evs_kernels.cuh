@@ -279,6 +279,8 @@ __device__ __forceinline__ bool fetch_list_body(const Params &p, unsigned cta, u
             p.miss_ctl[0] = 0u;
             p.miss_ctl[1] = 0u;
             p.dbg[28] += gtime() - p.dbg[4];      // fetch span, counted from the start of the k_evict it is part of
+            // the staging rows of this batch's parity are free: the look-ahead for batch seq + 2 may overwrite them
+            *reinterpret_cast<volatile unsigned *>(&p.g->fetch_done_seq) = ga->seq;
         }
         *s_flag = last ? 1u : 0u;
     }
@@ -358,6 +360,10 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
     __shared__ unsigned s_stat[8];           // hits C1, hits C2, C3, approx, misses, perfect
     __shared__ CodecLut s_lut;
 
+    // Launched without a graph, k_serve is programmatically dependent on the previous batch's k_evict (which lets its
+    // dependents go at once): the launch latency of this kernel runs under that kernel's tail.  Nothing -- not even
+    // the caller's index batch, whose producer may be the kernel before us -- is touched before the wait.
+    griddep_wait(p);
     const unsigned long long t_start = gtime();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.dbg[0] = t_start;

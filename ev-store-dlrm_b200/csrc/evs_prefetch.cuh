@@ -43,6 +43,30 @@ __global__ void __launch_bounds__(kPfThreads) k_prefetch(const __grid_constant__
     unsigned *tags = p.pf_tag + static_cast<size_t>(par) * p.n_max;
     unsigned char *rows = p.pf_rows + static_cast<size_t>(par) * p.n_max * p.stage_stride;
     const int full = (P1 != 0) ? static_cast<int>(*reinterpret_cast<volatile unsigned *>(&t0.ctl->full_at_start)) : 0;
+    // The staging rows of this parity belong to batch seq - 2 until its miss-fetch role has finished.  The wait is a
+    // device-side spin on a word that role sets, not a stream dependency: a stream wait would release this kernel at the
+    // very moment the next batch's k_serve becomes runnable, and the two launches then queue behind each other.
+    if (a.seq > 2u) {
+        __shared__ int s_go;
+        if (threadIdx.x == 0) {
+            const volatile unsigned *f = &p.g->fetch_done_seq;
+            int go = 1;
+            if (static_cast<int>(*f - (a.seq - 2u)) < 0) {
+                const unsigned long long t0 = gtime();
+                while (static_cast<int>(*f - (a.seq - 2u)) < 0) {
+                    if (gtime() - t0 > 20000000ull) {           // 20 ms: give the look-ahead up, the batch fetches for itself
+                        go = 0;
+                        break;
+                    }
+                    __nanosleep(200);
+                }
+            }
+            s_go = go;
+        }
+        __syncthreads();
+        if (!s_go) return;
+        __threadfence();
+    }
     const int S = pf_tile_samples(T);
     const int n_tiles = (B + S - 1) / S;
     const int gsize = fetch_gsize(p, P1 == 0 ? 1 : 2);
@@ -114,7 +138,7 @@ __global__ void __launch_bounds__(kPfThreads) k_prefetch(const __grid_constant__
         }
         __syncthreads();
         // ---- fetch: a group of lanes per row, 16 bytes per lane --------------------------------------------------
-        const unsigned n = min(s_n, static_cast<unsigned>(kPfListCap));
+        const unsigned n = (a.mode == 1) ? 0u : min(s_n, static_cast<unsigned>(kPfListCap));
         for (unsigned k0 = warp * rpw; k0 < n; k0 += (kPfThreads / 32) * rpw) {
             const unsigned k = k0 + grp;
             const bool on = k < n;

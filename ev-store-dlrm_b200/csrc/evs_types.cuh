@@ -124,7 +124,7 @@ struct C3Dev {
 struct GlobalCtl {
     unsigned long long lookups, samples, hits[2], c3_hits, approx_subst, misses, perfect_hits, batches;
     unsigned int error;                    // 1 = index out of range, 7 = a peer did not answer in time
-    unsigned int pad;
+    unsigned int fetch_done_seq;           // number of the last batch whose miss-fetch role has finished (it no longer reads its staging rows)
 };
 constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;   // spin-waits on peer flags give up after 4 s
 
@@ -175,6 +175,7 @@ struct PrefetchArgs {
     int B;
     unsigned seq;                          // the number that batch will get (its parity selects the staging buffer)
     unsigned gen;                          // generation of this announcement (>= 1): the tag of the rows it stages
+    int mode;                              // 0 = probe + stage; 1 = probe and L2 warm-up only (experiments)
 };
 
 // Everything a kernel of the batch pipeline needs; constant for the life of a handle.

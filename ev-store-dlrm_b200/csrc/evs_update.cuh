@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
     __shared__ unsigned s_chunk, s_excl, s_last, s_taken, s_more;
     const int role = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    griddep_launch(p);                  // the next batch's k_serve may be made resident: it waits for this grid to finish
     if (role == p.n_tiers) {
         if (static_cast<int>(blockIdx.x) >= p.fetch_ctas) return;
         codec_lut_init<P0, P1>(&s_lut);

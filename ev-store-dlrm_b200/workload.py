@@ -94,3 +94,49 @@ def make_alt_keys(rows, seed: int = 11):
         alt_row = perm[alt_rank]
         out.append((alt_row * 100 + (t + 1)).astype(np.uint32))
     return out
+
+
+# ---- closed-form tables ------------------------------------------------------------------------------------
+# value(table, row, col) is a pure function, so ANY process can say what a backing row holds without owning the
+# table: a rank of a table-wise sharded run checks the rows it RECEIVED from its peers against it
+# (bench_sharded.py "verified"), and a 40 M x 64 table is generated on the GPU in a second instead of by a host RNG.
+# Integer mixing in int64 with 32-bit masks (no overflow anywhere), then k / 2^24 -> U(-bound, bound) in float32:
+# every step is exact or a single IEEE rounding, so numpy, torch-CPU and torch-CUDA give identical bits.
+def _synth_bound(rows: int) -> float:
+    return float(np.float32(min(1.0 / np.sqrt(rows), 0.6499)))
+
+
+def synth_rows(table_id: int, row_ids, dim: int, rows_in_table: int):
+    """fp32 [n, dim] rows of the closed-form table `table_id`; row_ids: int64 numpy array or torch tensor (any device)."""
+    is_np = isinstance(row_ids, np.ndarray)
+    if is_np:
+        r = row_ids.astype(np.int64).reshape(-1, 1)
+        c = np.arange(dim, dtype=np.int64).reshape(1, -1)
+    else:
+        import torch
+        r = row_ids.to(torch.int64).reshape(-1, 1)
+        c = torch.arange(dim, dtype=torch.int64, device=row_ids.device).reshape(1, -1)
+    x = ((r * 73856093) ^ (c * 19349663) ^ (int(table_id) * 83492791 + 12345)) & 0xFFFFFFFF
+    x = ((x ^ (x >> 16)) * 0x45D9F3B) & 0xFFFFFFFF
+    x = ((x ^ (x >> 16)) * 0x45D9F3B) & 0xFFFFFFFF
+    x = (x ^ (x >> 16)) >> 8                                   # 24 bits
+    b = _synth_bound(rows_in_table)
+    if is_np:
+        u = x.astype(np.float32) * np.float32(1.0 / 16777216.0)
+        return (u * np.float32(2.0) - np.float32(1.0)) * np.float32(b)
+    import torch
+    u = x.to(torch.float32) * (1.0 / 16777216.0)
+    return (u * 2.0 - 1.0) * b
+
+
+def synth_table_pinned(table_id: int, rows: int, dim: int, device, chunk_rows: int = 1 << 21):
+    """The whole closed-form table as a pinned host tensor [rows, dim] fp32, generated on `device` chunk by chunk."""
+    import torch
+    out = torch.empty((rows, dim), dtype=torch.float32, pin_memory=True)
+    for r0 in range(0, rows, chunk_rows):
+        r1 = min(rows, r0 + chunk_rows)
+        ids = torch.arange(r0, r1, dtype=torch.int64, device=device)
+        out[r0:r1].copy_(synth_rows(table_id, ids, dim, rows), non_blocking=True)
+    if torch.device(device).type == "cuda":
+        torch.cuda.synchronize(device)
+    return out

@@ -59,3 +59,62 @@ def test_kaggle_shape_full_size_properties():
     assert len(keys) == cap and len(np.unique(keys)) == cap
     assert checked >= 125
     store.close()
+
+
+def _follow_full_size(layers_cfg, n_compare, B=2048, prefetch=True):
+    """The CUDA path next to the C restatement of the batch-granular oracle (oracle/evlfu_batch.c, pinned to
+    oracle/evlfu.py by tests/test_oracle_c_batch.py) at the BASELINE sizes: the oracle follows every batch of the
+    warm-up (the cache fills to its 4 389 135 entries and the rings wrap), then hit maps, agg_hit, eviction streams
+    (order included) and n_perfect are compared batch by batch, and the whole FIFO state at the end."""
+    import torch
+    from oracle.evlfu_c import CBatchEvLFU
+    p = pkg()
+    rows, dim = p.workload.KAGGLE_ROWS, 16
+    cap = p.workload.KAGGLE_CACHE_ROWS
+    tables = p.workload.make_tables(rows, dim)
+    # the fill point of the trace (bench.py uses the same rule), then evictions for a while, then the compared batches
+    import bench
+    n_search = 4200
+    idx = p.workload.ZipfTrace(rows, seed=42).batches(n_search + n_compare + 2, B)
+    warm = min(n_search, bench.batches_until_full(idx[:n_search], rows, cap) + 150)
+    store = p.EvStore(tables, p.CacheConfig(total_size=cap, max_batch=B, record_events=True, **layers_cfg))
+    oracle = CBatchEvLFU(cap, n_tables=26, max_keys_per_batch=B * 26)
+    d_idx = torch.from_numpy(idx[:warm + n_compare + 1]).cuda()
+    out = torch.empty((B, 26, dim), dtype=torch.float32, device="cuda")
+    hit = torch.empty((B, 26), dtype=torch.uint8, device="cuda")
+    for k in range(warm):
+        store.lookup(d_idx[k], out=out, hit=hit)
+        if prefetch:
+            store.prefetch(d_idx[k + 1])
+        oracle.lookup_batch(idx[k])
+    torch.cuda.synchronize()
+    assert oracle.size == cap and store.stats()["size"][0] == cap
+    n_ev = 0
+    for k in range(warm, warm + n_compare):
+        store.lookup(d_idx[k], out=out, hit=hit)
+        if prefetch:
+            store.prefetch(d_idx[k + 1])
+        o_hit, _st, _sr, _agg = oracle.lookup_batch(idx[k])
+        torch.cuda.synchronize()
+        assert np.array_equal(hit.cpu().numpy().astype(bool), o_hit), f"hit map, batch {k}"
+        ev, fl = store.last_events()
+        assert ev.tolist() == oracle.evicted, f"eviction stream, batch {k}: {len(ev)} vs {len(oracle.evicted)} keys"
+        assert fl.tolist() == oracle.flushed, f"flush stream, batch {k}"
+        n_ev += len(oracle.evicted)
+        if (k - warm) % 50 == 0:
+            o = out.cpu().numpy()
+            for t in range(26):
+                assert np.array_equal(o[:, t], tables[t][idx[k, t]]), f"batch {k} table {t}: row differs from the backing store"
+    state, n_perfect = store.dump_state()
+    assert n_perfect == oracle.n_perfect
+    assert state == oracle.state(), "resident FIFO state after the compared batches"
+    store.close()
+    oracle.close()
+    return n_ev, warm
+
+
+def test_kaggle_shape_full_size_eviction_order_equals_the_oracle():
+    """configs[1] at full size: 33.76 M rows, cache 4 389 135, batch 2048 -- bit-exact against the oracle for 200 batches
+    after the cache has filled and evicted for 150 batches, with the look-ahead on."""
+    n_ev, warm = _follow_full_size({}, 200)
+    assert n_ev > 200 * 800 and warm > 1000, (n_ev, warm)

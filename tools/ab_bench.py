@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2048)
     ap.add_argument("--dim", type=int, default=16)
     ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warm", type=int, default=4800)
+    ap.add_argument("--warm", type=int, default=2700)
     ap.add_argument("--repeat", type=int, default=2)
     a = ap.parse_args()
     import torch
@@ -33,7 +33,7 @@ def main():
     pkg = importlib.import_module("ev-store-dlrm_b200")
     rows = pkg.workload.KAGGLE_ROWS
     B, T = a.batch, len(rows)
-    n_batches = a.warm + 10 + a.steps * a.repeat
+    n_batches = a.warm + 12 + a.steps * a.repeat
     _, tables, idx = bench.build_workload(a, n_batches, rows, a.dim, B)
     pinned = [torch.from_numpy(t).pin_memory() for t in tables]
     stores = {32: [q.numpy() for q in pinned]}
@@ -45,6 +45,8 @@ def main():
     hit = torch.empty((B, T), dtype=torch.uint8, device=dev)
     for var in a.variants:
         env = dict(kv.split("=", 1) for kv in var.split(",") if kv and kv != "default")
+        pf = env.pop("PF", "1") == "1"               # pseudo-variables: PF=0 no look-ahead announcements, PTR=1 raw-pointer calls
+        ptr = env.pop("PTR", "0") == "1"
         saved = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:
@@ -58,6 +60,8 @@ def main():
                     os.environ[k] = v
         for k in range(a.warm + 10):
             store.lookup(idx_dev[k], out=out, hit=hit)
+            if pf:
+                store.prefetch(idx_dev[k + 1])
         store.sync()
         store.stats(reset=True)
         store.phase_times()
@@ -66,9 +70,24 @@ def main():
             base = a.warm + 10 + r * a.steps
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ptrs = [idx_dev[base + k].data_ptr() for k in range(a.steps + 1)]
+            op, hp, sp, os_ = out.data_ptr(), hit.data_ptr(), stream.cuda_stream, out.stride(0)
+            if pf:
+                store.prefetch(idx_dev[base])
+            torch.cuda.synchronize()
             e0.record()
-            for k in range(a.steps):
-                store.lookup(idx_dev[base + k], out=out, hit=hit)
+            t0 = time.perf_counter()
+            if ptr:
+                for k in range(a.steps):
+                    store.lookup_ptr(ptrs[k], B, op, os_, hp, sp)
+                    if pf:
+                        store.prefetch_ptr(ptrs[k + 1], B)
+            else:
+                for k in range(a.steps):
+                    store.lookup(idx_dev[base + k], out=out, hit=hit)
+                    if pf:
+                        store.prefetch(idx_dev[base + k + 1])
+            host_us = 1e6 * (time.perf_counter() - t0) / a.steps
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / a.steps
@@ -86,7 +105,7 @@ def main():
         store.set_profiling(False)
         keys = ("avg_serve", "avg_gap1", "avg_update", "avg_gap2", "avg_evict", "evict_plan", "evict_chunks", "evict_wait_last",
                 "evict_writeback", "avg_fetch_since_evict_start", "evict_chunks_per_batch", "evict_last_chunk_avg", "evict_last_chunk_max")
-        print(json.dumps({"variant": var, "us_per_step": 1e3 * best, "lookups_per_s": B * T / (best * 1e-3),
+        print(json.dumps({"variant": var, "us_per_step": 1e3 * best, "host_us_per_step": host_us, "lookups_per_s": B * T / (best * 1e-3),
                           "evictions_per_step": st["evictions"][0] / (a.steps * a.repeat),
                           "phases_us": {k: round(ph[k], 3) for k in keys if k in ph}, "kernel_event_us": kt}), flush=True)
         store.close()
