@@ -314,6 +314,7 @@ def run_one_leg(pkg, log, args, rank, world, local_rank, shape, placement_kind, 
            # hit counts (part of avg_serve) and at the end of k_evict for their rows
            "rank0_phases_us": {"serve_incl_wait_for_counts": ph["avg_serve"], "update": ph["avg_update"],
                                "evict_incl_fetch_and_wait_for_rows": ph["avg_evict"], "wait_for_peer_rows": ph["avg_peer_wait"],
+                                   "wait_for_peer_counts_cta0": ph["avg_count_wait_cta0"],
                                "fetch_role_since_evict_start": ph["avg_fetch_since_evict_start"]},
            "nvlink_bytes_per_rank_per_step": leg.sh.alltoall_bytes(B)}
     res["nvlink_GBps_per_rank"] = res["nvlink_bytes_per_rank_per_step"] / (res["ms_per_step"] * 1e-3) / 1e9

@@ -348,7 +348,7 @@ class EvStore:
                 "avg_gap2": v[11] / n / 1e3, "avg_evict": v[12] / n / 1e3,
                 "overlapped_batches": v[14], "evict_plan": v[22] / n / 1e3, "evict_chunks": v[23] / n / 1e3,
                 "evict_wait_last": v[24] / n / 1e3, "evict_writeback": v[25] / n / 1e3, "evict_chunks_per_batch": v[20] / n,
-                "evict_records_per_batch": v[21] / n, "avg_fetch_since_evict_start": v[28] / n / 1e3, "avg_peer_wait": v[29] / n / 1e3, "evict_last_chunk_avg": v[26] / n, "evict_last_chunk_max": v[27], "evict_scanned_total": v[15], "appends_total": v[1],
+                "evict_records_per_batch": v[21] / n, "avg_fetch_since_evict_start": v[28] / n / 1e3, "avg_peer_wait": v[29] / n / 1e3, "avg_count_wait_cta0": v[30] / n / 1e3, "evict_last_chunk_avg": v[26] / n, "evict_last_chunk_max": v[27], "evict_scanned_total": v[15], "appends_total": v[1],
                 "serve": us(0, 7), "serve_to_update_gap": us(7, 2), "update": us(2, 3), "update_to_evict_gap": us(3, 4),
                 "evict": us(4, 5), "c3": us(5, 6), "total": us(0, 6)}
 

@@ -435,7 +435,7 @@ static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const Batc
     // outside a graph the chain continues across batches: k_serve is a programmatic dependent of whatever kernel precedes
     // it on the stream (the previous batch's k_evict in a serving loop)
     { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch_serve(serve_of(h, ks), n_chunks, st, p, a, pdl && !h->capturing)); }
-    if (p.n_chunks_max > p.quad_max || p.L < 32) {
+    if (p.n_chunks_max > p.quad_max || p.L < kDirectMinLanes) {
         LaunchScope ls(pf, K_SCAN, st);
         EVS_CUDA(launch(k_scan, (h->n_tiers == 1 ? 1 : kSeqGroups) * h->tier[0].dev.n_buckets, 256, 0, st, p, pdl));
     }
@@ -804,7 +804,7 @@ static int run_batch(evs_handle h, const BatchArgs &a_in, cudaStream_t st) {
         EVS_CUDA(cudaGraphExecKernelNodeSetParams(h->graph, h->serve_node, &kp));
         EVS_CUDA(cudaGraphLaunch(h->graph, st));
         h->prof.launches[K_SERVE]++, h->prof.launches[K_UPDATE]++, h->prof.launches[K_EVICT]++;
-        if (h->params.n_chunks_max > h->params.quad_max || h->params.L < 32) h->prof.launches[K_SCAN]++;
+        if (h->params.n_chunks_max > h->params.quad_max || h->params.L < kDirectMinLanes) h->prof.launches[K_SCAN]++;
     } else {
         int rc = enqueue_batch(h, st, (a.B + h->params.spc - 1) / h->params.spc, a);
         if (rc) return rc;

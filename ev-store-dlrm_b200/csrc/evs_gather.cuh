@@ -91,22 +91,36 @@ __global__ void __launch_bounds__(256) k_gather(const unsigned char *__restrict_
                 float acc[EPC];
 #pragma unroll
                 for (int i = 0; i < EPC; ++i) acc[i] = 0.0f;
-                for (long long j = j0; j < j1; ++j) {
-                    long long r = __ldg(idx + j);
-                    if (r < 0 || r >= rows) {
-                        *err = 1u;
-                        r = 0;
+                // U rows of the bag per round: the index loads, then the row loads, are all issued before the first
+                // add, so a bag costs ceil(P / U) dependent round trips instead of P; the sum still runs in ascending j
+                constexpr int U = 5;
+                for (long long jb = j0; jb < j1; jb += U) {
+                    long long rr[U];
+                    uint4 v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        rr[u] = (jb + u < j1) ? __ldg(idx + jb + u) : 0;
+                        if (rr[u] < 0 || rr[u] >= rows) {
+                            *err = 1u;
+                            rr[u] = 0;
+                        }
                     }
-                    const uint4 v = gather_ldg16(table + static_cast<size_t>(r) * row_bytes + (c << 4));
-                    float x[EPC];
-                    decode_regs<PREC>(v, x, &s_lut);
-                    if (psw != nullptr) {
-                        const float w = __ldg(psw + j);
 #pragma unroll
-                        for (int i = 0; i < EPC; ++i) acc[i] = __fadd_rn(acc[i], __fmul_rn(w, x[i]));
-                    } else {
+                    for (int u = 0; u < U; ++u)
+                        if (jb + u < j1) v[u] = gather_ldg16(table + static_cast<size_t>(rr[u]) * row_bytes + (c << 4));
 #pragma unroll
-                        for (int i = 0; i < EPC; ++i) acc[i] = __fadd_rn(acc[i], x[i]);
+                    for (int u = 0; u < U; ++u) {
+                        if (jb + u >= j1) break;
+                        float x[EPC];
+                        decode_regs<PREC>(v[u], x, &s_lut);
+                        if (psw != nullptr) {
+                            const float w = __ldg(psw + jb + u);
+#pragma unroll
+                            for (int i = 0; i < EPC; ++i) acc[i] = __fadd_rn(acc[i], __fmul_rn(w, x[i]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < EPC; ++i) acc[i] = __fadd_rn(acc[i], x[i]);
+                        }
                     }
                 }
 #pragma unroll

@@ -72,12 +72,25 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], unsigned a0, unsigned a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// ld: floats between rows of the staged T (>= Dp, a multiple of 4, = 4 mod 8); per-warp region = 32 * max(ld, 33) floats
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ld: floats between rows of the staged T (>= Dp, a multiple of 4, = 4 mod 8).  A warp owns two buffers of `region`
+// floats (region >= 32 * ld and >= 32 * 33): while it computes sample s out of one, cp.async fills the other with the
+// T of its next sample, so a warp always has a sample's worth of HBM reads in flight; the grid is sized to what is
+// resident at once and every warp walks the batch with the grid's stride.
 __global__ void __launch_bounds__(kMmaWarps * 32) k_interact_mma(const float *__restrict__ x, const float *__restrict__ ly,
-                                                                 float *__restrict__ r, int B, int n_f, int D, int Dp, int ld) {
+                                                                 float *__restrict__ r, int B, int n_f, int D, int Dp, int ld, int region) {
     extern __shared__ __align__(16) float s_t[];
     __shared__ unsigned char s_pi[512], s_pj[512];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const int nt = n_f + 1;
     const int n_pairs = nt * (nt - 1) / 2;
     const int out_w = D + n_pairs;
@@ -90,22 +103,20 @@ __global__ void __launch_bounds__(kMmaWarps * 32) k_interact_mma(const float *__
         s_pj[pr] = static_cast<unsigned char>(pr - i * (i - 1) / 2);
     }
     __syncthreads();
-    const int region = 32 * (ld > 33 ? ld : 33);
-    float *t = s_t + static_cast<size_t>(warp) * region;
+    float *buf0 = s_t + static_cast<size_t>(warp) * 2 * region;
     const int g = lane >> 2, tq = lane & 3;
     const bool vec = ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(ly) & 15u) == 0);
-    for (int s = blockIdx.x * kMmaWarps + warp; s < B; s += gridDim.x * kMmaWarps) {
+    const int d4 = D >> 2, n4 = nt * d4;
+    const int stride = gridDim.x * wpc;
+
+    // stage T = [x ; ly] of sample s into t (asynchronously when rows are 16-byte aligned)
+    auto stage = [&](int s, float *t) {
         const float *xs = x + static_cast<size_t>(s) * D;
         const float *ls = ly + static_cast<size_t>(s) * n_f * D;
-        float *rs = r + static_cast<size_t>(s) * out_w;
-        // ---- stage T = [x ; ly], zero the K padding ------------------------------------------------------------
         if (vec) {
-            const int d4 = D >> 2;
-            const int n4 = nt * d4;
             for (int e = lane; e < n4; e += 32) {
                 const int row = e / d4, c4 = e - row * d4;
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(row == 0 ? xs : ls + static_cast<size_t>(row - 1) * D) + c4);
-                *reinterpret_cast<float4 *>(t + row * ld + (c4 << 2)) = v;
+                cp_async16(t + row * ld + (c4 << 2), (row == 0 ? xs : ls + static_cast<size_t>(row - 1) * D) + (c4 << 2));
             }
         } else {
             for (int e = lane; e < nt * D; e += 32) {
@@ -113,12 +124,32 @@ __global__ void __launch_bounds__(kMmaWarps * 32) k_interact_mma(const float *__
                 t[row * ld + c] = __ldg(row == 0 ? xs + c : ls + static_cast<size_t>(row - 1) * D + c);
             }
         }
-        if (Dp > D)
+        cp_async_commit();
+    };
+
+    int s = blockIdx.x * wpc + warp;
+    int cur = 0;
+    if (s < B) stage(s, buf0);
+    for (; s < B; s += stride) {
+        float *t = buf0 + cur * region;
+        const int s_next = s + stride;
+        if (s_next < B) {
+            stage(s_next, buf0 + (cur ^ 1) * region);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        float *rs = r + static_cast<size_t>(s) * out_w;
+        if (Dp > D) {
             for (int e = lane; e < nt * (Dp - D); e += 32) {
                 const int row = e / (Dp - D), c = D + (e - row * (Dp - D));
                 t[row * ld + c] = 0.0f;
             }
-        __syncwarp();
+            __syncwarp();
+        }
+        // x goes to the head of the output row
+        for (int e = lane; e < D; e += 32) rs[e] = t[e];
         // ---- Z = T T^t on the tensor cores (rows >= nt hold stale data: they only reach outputs nobody reads) ----
         float acc[6][4];
 #pragma unroll
@@ -149,7 +180,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) k_interact_mma(const float *__
 #undef EVS_TILE
         }
         __syncwarp();                                   // every lane has read its last fragment: T may be overwritten
-        // ---- accumulators -> Z[32][33] in the same shared-memory region --------------------------------------------
+        // ---- accumulators -> Z[32][33] in the same buffer ---------------------------------------------------------
         {
             const int tm[6] = {0, 0, 1, 1, 1, 1}, tn[6] = {0, 1, 0, 1, 2, 3};
 #pragma unroll
@@ -162,10 +193,10 @@ __global__ void __launch_bounds__(kMmaWarps * 32) k_interact_mma(const float *__
             }
         }
         __syncwarp();
-        // ---- R = [x, strict lower triangle row-major], consecutive lanes write consecutive floats ----------------
-        for (int e = lane; e < D; e += 32) rs[e] = __ldg(xs + e);
+        // ---- strict lower triangle row-major behind x, consecutive lanes write consecutive floats ------------------
         for (int pr = lane; pr < n_pairs; pr += 32) rs[D + pr] = t[s_pi[pr] * 33 + s_pj[pr]];
         __syncwarp();
+        cur ^= 1;
     }
 }
 
@@ -178,8 +209,17 @@ inline int launch_interact(const float *x, const float *ly, float *r, int B, int
     }();
     if (n_f + 1 <= 32 && D <= 128 && !force_fma) {
         const int Dp = (D + 7) & ~7;
-        int ld = Dp + 4;                                        // = 4 mod 8: conflict-free fragment reads
-        const size_t smem = static_cast<size_t>(kMmaWarps) * 32 * std::max(ld, 33) * sizeof(float);
+        const int ld = Dp + 4;                                  // = 4 mod 8: conflict-free fragment reads
+        const int region = 32 * std::max(ld, 33);
+        // two buffers per warp; fewer warps per CTA when the rows are wide, so that several CTAs stay resident
+        const int warps = (static_cast<size_t>(kMmaWarps) * 2 * region * sizeof(float) > 72 * 1024) ? 4 : kMmaWarps;
+        const size_t smem = static_cast<size_t>(warps) * 2 * region * sizeof(float);
+        static int sms = 0;
+        if (sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(k_interact_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
             if (e != cudaSuccess) {
@@ -187,8 +227,10 @@ inline int launch_interact(const float *x, const float *ly, float *r, int B, int
                 return EVS_ERR_CUDA;
             }
         }
-        const int ctas = std::min((B + kMmaWarps - 1) / kMmaWarps, 148 * 8);
-        k_interact_mma<<<ctas, kMmaWarps * 32, smem, st>>>(x, ly, r, B, n_f, D, Dp, ld);
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_interact_mma, warps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const int ctas = std::min((B + warps - 1) / warps, per_sm * sms);
+        k_interact_mma<<<ctas, warps * 32, smem, st>>>(x, ly, r, B, n_f, D, Dp, ld, region);
         EVS_CUDA(cudaGetLastError());
         return EVS_OK;
     }

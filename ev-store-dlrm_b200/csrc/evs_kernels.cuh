@@ -21,6 +21,7 @@ namespace evs {
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kEvictThreads = 256;         // small CTAs: they must fit on SMs that k_fetch occupies
 constexpr int kEvictPerThread = 4;           // ring records one thread examines per window
+constexpr int kDirectMinLanes = 8;           // k_update sums its predecessors' counts itself when a sample has at least this many lanes
 constexpr int kQuadMaxChunks = 512;          // above this a k_scan launch replaces the direct prefix sums (B = 16384: 150 -> 141 us)
 
 __device__ __forceinline__ uint4 ldg16(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
@@ -459,9 +460,11 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
         // ranks' "counts of epoch e complete" words
         if (sact)
             for (int r = q.gl; r < a.sh.world; r += q.L) a.sh.parts[r][s] = static_cast<uint8_t>(local_agg);
-        __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
+            // one system-scope fence per CTA (cumulative over the CTA's stores, which the barrier ordered before it):
+            // the other warps go on to the gather while the counts travel
+            __threadfence_system();
             const unsigned n_act = static_cast<unsigned>((B + spc - 1) / spc);
             const bool last = atomicAdd(p.probe_done, 1u) == n_act - 1;
             if (last) {
@@ -507,7 +510,9 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
         if (sact) agg = a.agg_in[s];
     } else if (SH && a.sh.world > 1) {
         // exact groupability: agg_hit = sum over the ranks of their local hit counts
+        const unsigned long long tw0 = (blockIdx.x == 0 && threadIdx.x == 0) ? gtime() : 0ull;
         wait_flags(a.sh.my_probe_flags, a.sh.world, a.sh.epoch, lane, p);
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.dbg[30] += gtime() - tw0;      // CTA 0's wait for the peers' counts
         int v = 0;
         if (sact)
             for (int r = q.gl; r < a.sh.world; r += q.L) v += static_cast<int>(__ldcg(a.sh.my_parts + static_cast<size_t>(r) * a.B + s));
@@ -624,7 +629,7 @@ __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Params p) 
     griddep_wait(p);
     const int B = p.args->B;
     const int n_chunks = (B + p.spc - 1) / p.spc;
-    if (p.L == 32 && n_chunks <= p.quad_max) return;          // k_update sums its predecessors directly
+    if (p.L >= kDirectMinLanes && n_chunks <= p.quad_max) return;          // k_update sums its predecessors directly
     const int nb = p.tier[0].n_buckets;
     const int grp = blockIdx.x / nb, b = blockIdx.x - grp * nb;
     unsigned *h = p.hist + static_cast<size_t>(grp * kMaxBuckets + b) * p.n_chunks_max;

@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(kLookupThreads, NG == 1 ? 5 : 4) k_update(cons
         const unsigned *h[NG];
 #pragma unroll
         for (int g = 0; g < NG; ++g) h[g] = p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max;
-        const bool direct = !(q.L < 32 || n_chunks > p.quad_max);
+        // direct: the lanes of a sample's group sum the counts of the earlier chunks themselves (groups of >= 8 lanes)
+        const bool direct = q.L >= kDirectMinLanes && n_chunks <= p.quad_max;
         const int nc = static_cast<int>(blockIdx.x);
         unsigned base[kSeqGroups] = {0, 0, 0};
         unsigned x[NG][XU];
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kLookupThreads, NG == 1 ? 5 : 4) k_update(cons
             } else {
 #pragma unroll
                 for (int u = 0; u < XU; ++u) {
-                    const int c = u * 32 + lane;
+                    const int c = u * q.L + q.gl;
                     if (c < nc) x[g][u] = __ldcg(h[g] + c);
                 }
             }
@@ -132,23 +133,23 @@ __global__ void __launch_bounds__(kLookupThreads, NG == 1 ? 5 : 4) k_update(cons
 #pragma unroll
                 for (int u = 0; u < XU; ++u) acc[g] += x[g][u];
             }
-            for (int c0 = XU * 32; c0 < nc; c0 += 128) {       // the rest: 4 loads per lane, group and round
+            for (int c0 = XU * q.L; c0 < nc; c0 += 4 * q.L) {       // the rest: 4 loads per lane, group and round
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     if (!msk[g]) continue;
                     unsigned y[4] = {0, 0, 0, 0};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int c = c0 + u * 32 + lane;
+                        const int c = c0 + u * q.L + q.gl;
                         if (c < nc) y[u] = __ldcg(h[g] + c);
                     }
                     acc[g] += y[0] + y[1] + y[2] + y[3];
                 }
             }
+            // every lane of the group is here (`any` is uniform within a group), other groups of the warp may not be
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) acc[g] += __shfl_xor_sync(kFull, acc[g], d);
+                for (int d = q.L >> 1; d > 0; d >>= 1) acc[g] += __shfl_xor_sync(q.mask, acc[g], d);
                 base[g] = acc[g];
             }
         }
