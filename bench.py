@@ -334,15 +334,19 @@ def main_ours(args):
                           total_size=total_size, max_batch=B, device=local_rank, store_in_hbm=args.store_in_hbm, policy=args.policy)
     alt = pkg.workload.make_alt_keys(rows) if layers == 3 else None
     t0 = time.time()
-    stores = None
-    if os.environ.get("EVS_BENCH_PINNED_ALLOC", "1") == "1":
-        # backing store in cudaHostAlloc memory (torch's pinned allocator) instead of page-locking numpy's pages
-        stores, keep = {}, []
-        for pr in [prec] + ([sec] if layers >= 2 else []):
+    # backing store in host memory: evs_host_alloc rows (mapped into the device with large pages: about twice the zero-copy row
+    # rate of cudaHostAlloc memory over a 2 GB table, profiles/r2_zc_vmm_probe.txt); EVS_BENCH_STORE=pinned selects torch's
+    # pinned allocator instead (A/B)
+    stores, keep = {}, []
+    store_mem = os.environ.get("EVS_BENCH_STORE", "mapped")
+    for pr in [prec] + ([sec] if layers >= 2 else []):
+        if store_mem == "mapped":
+            stores[pr] = [pkg.to_host_rows(pkg.codecs.encode_table(t, pr), device=local_rank) for t in tables]
+        else:
             pinned = [torch.from_numpy(pkg.codecs.encode_table(t, pr)).pin_memory() for t in tables]
             keep.append(pinned)
             stores[pr] = [q.numpy() for q in pinned]
-        log(f"backing store copied to pinned allocations in {time.time() - t0:.1f}s")
+    log(f"backing store copied to {store_mem} host allocations in {time.time() - t0:.1f}s")
     store = pkg.EvStore(tables, cfg, stores=stores, alt_keys=alt)
     log(f"EvStore created in {time.time() - t0:.1f}s (cache {cache_rows} rows, backing store host-pinned zero-copy)")
 
@@ -388,14 +392,23 @@ def main_ours(args):
     base += W
     regions = []
     launches = 0
+    # The serving loop has its requests queued, so it hands the library GROUP batches per call (evs_lookup_batches: one
+    # captured graph per 4 batches, the batches still strictly ordered on the device) and announces the first batch of
+    # the next call; every batch is a full pass of the hot path over its own index batch.
+    GROUP = max(1, int(os.environ.get("EVS_BENCH_GROUP", "4")))
+    import ctypes as C
+    out_ptrs = (C.c_void_p * GROUP)(*([out.data_ptr()] * GROUP))
+    hit_ptrs = (C.c_void_p * GROUP)(*([hit.data_ptr()] * GROUP))
     for rep in range(3):
         l0 = store.launch_count()
+        calls = [(k, min(GROUP, K - k), (C.c_void_p * GROUP)(*[idx_dev[base + k + j].data_ptr() for j in range(GROUP)]))
+                 for k in range(0, K, GROUP)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for k in range(K):
-            store.lookup(idx_dev[base + k], out=out, hit=hit)
+        for k, n, ips in calls:
+            store.lookup_many_ptr(n, ips, B, out_ptrs, out.stride(0), hit_ptrs, bench_stream.cuda_stream)
             if use_pf:
-                store.prefetch(idx_dev[base + k + 1])
+                store.prefetch(idx_dev[base + k + n])
         e1.record()
         torch.cuda.synchronize()
         regions.append(e0.elapsed_time(e1))
@@ -648,7 +661,7 @@ def main_ours(args):
         "cache": {"fill": fill, "hbm_bytes": footprint, "budget_bytes": cache_rows * dim * prec // 8,
                   "note": "hbm_bytes = index (load factor <= 1/3) + slot-indexed slab + bucket rings + look-ahead staging; budget_bytes "
                           "= cache rows x row bytes, the reference's TOTAL_SIZE accounting (cache_manager.cpp:16)"},
-        "value_regions_ms": regions, "look_ahead": use_pf, "configs4": configs4, "ops": ops,
+        "value_regions_ms": regions, "look_ahead": use_pf, "batches_per_call": GROUP, "configs4": configs4, "ops": ops,
         "e2e": {"value": e2e_value, "unit": "lookups/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / K, "api": "evs_submit_host/evs_wait_host (4 batches in flight)",
                 "sync_call_value": lookups / e2e_sync_s, "sync_call_ms_per_step": 1e3 * e2e_sync_s / K},

@@ -73,16 +73,21 @@ class Leg:
         # the reference's 13 % operating point (cache_manager.cpp:16), each rank caching 13 % of its own rows
         self.cache_rows = max(1024, int(sum(self.rows) * 0.13))
         t0 = time.time()
-        self.pinned = [pkg.workload.synth_table_pinned(t, all_rows[t], dim, self.dev) for t in self.ids]
         assert prec == 32, "the sharded bench serves the fp32 tier"
-        stores = {32: [q.numpy() for q in self.pinned]}
+        # backing rows in evs_host_alloc memory (host memory mapped into this rank's device with large pages)
+        if os.environ.get("EVS_BENCH_STORE", "mapped") == "mapped":
+            self.pinned = [pkg.workload.synth_table_mapped(t, all_rows[t], dim, self.dev) for t in self.ids]
+            stores = {32: self.pinned}
+        else:
+            self.pinned = [pkg.workload.synth_table_pinned(t, all_rows[t], dim, self.dev) for t in self.ids]
+            stores = {32: [q.numpy() for q in self.pinned]}
         self.trace = pkg.workload.ZipfTrace(self.rows, alpha=1.05, seed=42 + self.ids[0], perm_seed=7 + self.ids[0])
         cfg = pkg.CacheConfig(n_layers=1, main_precision=prec, total_size=self.cache_rows, max_batch=self.B, device=local_rank,
                               n_tables_total=self.T, table_ids=tuple(self.ids))
         self.store = pkg.EvStore.from_raw_stores(self.rows, dim, cfg, stores)
         self.sh = pkg.sharded.ShardedLookup(self.store, self.T, dim, rank, world, transport=transport, batch_max=self.B,
                                             placement=self.placement)
-        log(f"[{label} rank {rank}] tables {self.ids}: {sum(self.rows) / 1e6:.2f} M rows, {sum(p.numel() * 4 for p in self.pinned) / 1e9:.2f} GB pinned, "
+        log(f"[{label} rank {rank}] tables {self.ids}: {sum(self.rows) / 1e6:.2f} M rows, {sum(self.rows) * dim * 4 / 1e9:.2f} GB of host rows, "
             f"cache {self.cache_rows} rows, HBM {self.store.memory_footprint() / 1e9:.2f} GB, built in {time.time() - t0:.1f}s")
 
     def batches(self, n):

@@ -51,8 +51,8 @@ class EvsStats(C.Structure):
 
 # every symbol include/evstore_b200.h declares
 SYMBOLS = [
-    "evs_create", "evs_destroy", "evs_last_error", "evs_version", "evs_lookup_batch", "evs_prefetch", "evs_probe_batch", "evs_check",
-    "evs_memory_footprint",
+    "evs_create", "evs_destroy", "evs_last_error", "evs_version", "evs_lookup_batch", "evs_lookup_batches", "evs_lookup_bags", "evs_prefetch", "evs_probe_batch", "evs_check",
+    "evs_memory_footprint", "evs_host_alloc", "evs_host_free",
     "evs_lookup_batch_host", "evs_submit_host", "evs_wait_host", "evs_sync", "evs_stats", "evs_last_events", "evs_dump_state", "evs_dump_c3",
     "evs_interact", "evs_embedding_bag", "evs_embedding_bag_status", "evs_store_ptr", "evs_shard_create", "evs_shard_export",
     "evs_shard_connect", "evs_shard_lookup", "evs_shard_destroy", "evs_set_profiling", "evs_kernel_times", "evs_launch_count", "evs_phase_times", "evs_legacy_configure", "evs_legacy_handle", "ev_lookup", "get_ev_values", "print_perfect_hit",
@@ -82,12 +82,20 @@ def load_library(path: str | None = None):
     lib.evs_version.restype = C.c_int
     lib.evs_lookup_batch.argtypes = [vp, vp, i32, vp, i64, vp, vp, vp]
     lib.evs_lookup_batch.restype = C.c_int
+    lib.evs_lookup_batches.argtypes = [vp, i32, vp, i32, vp, i64, vp, vp]
+    lib.evs_lookup_batches.restype = C.c_int
+    lib.evs_lookup_bags.argtypes = [vp, vp, vp, i32, i64, i32, vp, i64, vp, vp]
+    lib.evs_lookup_bags.restype = C.c_int
     lib.evs_prefetch.argtypes = [vp, vp, i32, vp]
     lib.evs_prefetch.restype = C.c_int
     lib.evs_check.argtypes = [vp, C.c_int]
     lib.evs_check.restype = C.c_int
     lib.evs_memory_footprint.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.evs_memory_footprint.restype = C.c_int
+    lib.evs_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64, i32]
+    lib.evs_host_alloc.restype = C.c_int
+    lib.evs_host_free.argtypes = [vp]
+    lib.evs_host_free.restype = C.c_int
     lib.evs_probe_batch.argtypes = [vp, vp, i32, vp, vp]
     lib.evs_probe_batch.restype = C.c_int
     lib.evs_lookup_batch_host.argtypes = [vp, vp, i32, vp, vp]

@@ -75,6 +75,30 @@ def _tensor_from_ptr(ptr, shape, device):
     return torch.as_tensor(_DevArray(ptr, shape), device=device)
 
 
+def host_rows(shape, dtype=np.float32, device: int = 0) -> np.ndarray:
+    """An uninitialised host array for backing rows from ``evs_host_alloc``: host memory the device maps with large
+    pages, so that the zero-copy miss fetch over a multi-GB table runs at about twice the row rate of page-locked
+    numpy / cudaHostAlloc memory.  Fill it like any array (``np.copyto``, ``np.fromfile`` into it, ...); it is freed
+    when the array and every view of it are gone (destroy the EvStore built over it first)."""
+    import weakref
+    lib = _native.load_library()
+    shape = tuple(int(x) for x in (shape if hasattr(shape, "__len__") else (shape,)))
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    ptr = C.c_void_p()
+    _native.check(lib.evs_host_alloc(C.byref(ptr), max(nbytes, 1), int(device)), "evs_host_alloc")
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(ptr.value)
+    weakref.finalize(buf, lib.evs_host_free, ptr.value)        # the numpy array below keeps `buf` alive
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+
+def to_host_rows(array: np.ndarray, device: int = 0) -> np.ndarray:
+    """Copy of ``array`` in ``host_rows`` memory."""
+    out = host_rows(array.shape, array.dtype, device)
+    np.copyto(out, array)
+    return out
+
+
 class _ShapeOnly:
     """Stands in for an fp32 table whose rows are only available quantised / on disk."""
 
@@ -197,6 +221,60 @@ class EvStore:
                                        agg_in.data_ptr() if agg_in is not None else None, st)
         _native.check(rc, "evs_lookup_batch")
         return out, hit
+
+    def lookup_bags(self, lS_o, lS_i, max_per_bag: int = 10, out=None, stream=None):
+        """Pooled lookup (evs_lookup_bags): lS_i / lS_o are the per-table index and offset tensors of apply_emb
+        (lS_i[t] int64 CUDA [nnz_t], lS_o[t] int64 CUDA [B], nn.EmbeddingBag's offsets).  Returns (pooled fp32
+        [B, n_tables, dim], hit: list of n_tables uint8 tensors [nnz_t])."""
+        import torch
+        T = self.n_tables
+        assert len(lS_i) == T and len(lS_o) == T
+        B = int(lS_o[0].numel())
+        dev = lS_i[0].device
+        nnz_t = [int(x.numel()) for x in lS_i]
+        base = np.concatenate([[0], np.cumsum(nnz_t)]).astype(np.int64)
+        idx = torch.cat([x.reshape(-1).to(torch.int64) for x in lS_i]) if base[-1] > 0 else torch.zeros(1, dtype=torch.int64, device=dev)
+        off = torch.cat([lS_o[t].reshape(-1).to(torch.int64) + int(base[t]) for t in range(T)] +
+                        [torch.tensor([int(base[-1])], dtype=torch.int64, device=dev)])
+        if out is None:
+            out = torch.empty((B, T, self.dim), dtype=torch.float32, device=dev)
+        hit = torch.empty((max(int(base[-1]), 1),), dtype=torch.uint8, device=dev)
+        st = _stream_handle(stream, dev)
+        rc = self.lib.evs_lookup_bags(self.handle, idx.data_ptr(), off.data_ptr(), B, int(base[-1]), int(max_per_bag),
+                                      out.data_ptr(), out.stride(0), hit.data_ptr(), st)
+        _native.check(rc, "evs_lookup_bags")
+        return out, [hit[int(base[t]):int(base[t + 1])] for t in range(T)]
+
+    def lookup_many(self, lS_i_list, outs=None, hits=None, stream=None):
+        """Consecutive batches in one call (evs_lookup_batches): the same results as ``lookup`` on each in turn, but groups
+        of 4 batches reach the device as one captured graph and their misses are staged by the look-ahead.
+        lS_i_list: int64 CUDA tensors [n_tables, B] (same B).  outs / hits: one tensor per batch, or a single tensor every
+        batch overwrites (a caller that consumes only the last), or None.  Returns (outs, hits) as lists."""
+        import torch
+        n = len(lS_i_list)
+        T, B = lS_i_list[0].shape
+        dev = lS_i_list[0].device
+        assert all(x.is_cuda and x.dtype == torch.int64 and x.is_contiguous() and x.shape == (T, B) for x in lS_i_list) and T == self.n_tables
+        if outs is None:
+            outs = [torch.empty((B, T, self.dim), dtype=torch.float32, device=dev) for _ in range(n)]
+        elif torch.is_tensor(outs):
+            outs = [outs] * n
+        if hits is None:
+            hits = [torch.empty((B, T), dtype=torch.uint8, device=dev) for _ in range(n)]
+        elif torch.is_tensor(hits):
+            hits = [hits] * n
+        ip = (C.c_void_p * n)(*[x.data_ptr() for x in lS_i_list])
+        op = (C.c_void_p * n)(*[x.data_ptr() for x in outs])
+        hp = (C.c_void_p * n)(*[x.data_ptr() for x in hits])
+        st = _stream_handle(stream, dev)
+        _native.check(self.lib.evs_lookup_batches(self.handle, n, ip, B, op, outs[0].stride(0), hp, st), "evs_lookup_batches")
+        return outs, hits
+
+    def lookup_many_ptr(self, n: int, idx_ptrs, B: int, out_ptrs, out_stride: int, hit_ptrs, stream: int = 0):
+        """Raw form: idx_ptrs / out_ptrs / hit_ptrs are ctypes arrays of n device pointers (built once by a serving loop)."""
+        rc = self.lib.evs_lookup_batches(self.handle, n, idx_ptrs, B, out_ptrs, out_stride, hit_ptrs, stream or None)
+        if rc:
+            _native.check(rc, "evs_lookup_batches")
 
     def probe(self, lS_i, agg_out=None, stream=None):
         import torch

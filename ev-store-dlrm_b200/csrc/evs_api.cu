@@ -16,6 +16,7 @@
 #include "evs_c3.cuh"
 #include "evs_update.cuh"
 #include "evs_prefetch.cuh"
+#include "evs_bags.cuh"
 
 namespace evs {
 
@@ -124,6 +125,7 @@ static std::map<void *, HostReg> g_reg;
 
 static int map_host_range(evs_handle h, void *hp, size_t bytes, void **dp, const std::string &what) {
     std::lock_guard<std::mutex> lk(g_reg_mu);
+    h->n_ranges++;
     auto it = g_reg.find(hp);
     if (it != g_reg.end() && it->second.bytes >= bytes) {
         it->second.refs++;
@@ -132,6 +134,12 @@ static int map_host_range(evs_handle h, void *hp, size_t bytes, void **dp, const
         cudaPointerAttributes attr{};
         cudaError_t e = cudaPointerGetAttributes(&attr, hp);
         if (e != cudaSuccess) cudaGetLastError();
+        if (e == cudaSuccess && attr.type == cudaMemoryTypeManaged) {
+            // evs_host_alloc memory (managed, resident in host memory, mapped into the device): the same address on both sides
+            *dp = hp;
+            h->n_ranges_managed++;
+            return EVS_OK;
+        }
         if (e != cudaSuccess || attr.type != cudaMemoryTypeHost) {
             e = cudaHostRegister(hp, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
             if (e == cudaSuccess) {
@@ -295,12 +303,12 @@ static int build_c3(evs_handle h) {
     return EVS_OK;
 }
 
+static void destroy_graphs(evs_handle h);
 static void free_all(evs_handle h) {
     if (h == nullptr) return;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
-    if (h->graph) cudaGraphExecDestroy(h->graph);
-    if (h->graph_src) cudaGraphDestroy(h->graph_src);
+    destroy_graphs(h);
     for (int i = 0; i < EVS_MAX_TIERS; ++i)
         for (void *p : h->tier[i].allocs) cudaFree(p);
     for (void *p : h->c3_allocs) cudaFree(p);
@@ -326,10 +334,10 @@ static void free_all(evs_handle h) {
 
 // Keep every bucket ring from overflowing: the host only tracks an upper bound of the
 // occupancy and looks at the real head/tail when that bound gets close to the ring size.
-static int maintain_rings(evs_handle h, int ti, cudaStream_t st) {
+static int maintain_rings(evs_handle h, int ti, cudaStream_t st, int ahead = 2) {
     Tier &tr = h->tier[ti];
     const unsigned long long n_max = static_cast<unsigned long long>(h->cfg.max_batch) * h->cfg.n_tables;
-    if (tr.ub_used + 2 * n_max <= tr.dev.ring_cap) return EVS_OK;
+    if (tr.ub_used + static_cast<unsigned long long>(ahead) * n_max <= tr.dev.ring_cap) return EVS_OK;
     TierCtl ctl;
     EVS_CUDA(cudaStreamSynchronize(st));
     EVS_CUDA(cudaMemcpy(&ctl, tr.dev.ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
@@ -427,14 +435,14 @@ static size_t fetch_smem(evs_handle h) {
 // the graph has no fork / join, and with evs_prefetch its rows are mostly staged in HBM already).
 // `n_chunks` CTAs of k_serve / k_update; CTAs past the batch end exit at once, so a captured graph
 // uses the maximum.
-static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const BatchArgs &a) {
+static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const BatchArgs &a, bool serve_pdl) {
     const Params &p = h->params;
     const KernelSet ks = kernels_of_handle(h);
     Profiler &pf = h->prof;
     const bool pdl = h->use_pdl && !pf.on;                // event records between the launches would serialise them anyway
-    // outside a graph the chain continues across batches: k_serve is a programmatic dependent of whatever kernel precedes
-    // it on the stream (the previous batch's k_evict in a serving loop)
-    { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch_serve(serve_of(h, ks), n_chunks, st, p, a, pdl && !h->capturing)); }
+    // serve_pdl: k_serve is a programmatic dependent of the kernel that precedes it -- the previous batch's k_evict, on the
+    // stream of a serving loop or inside a graph of several batches (never the first node of a graph)
+    { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch_serve(serve_of(h, ks), n_chunks, st, p, a, pdl && serve_pdl)); }
     if (p.n_chunks_max > p.quad_max || p.L < kDirectMinLanes) {
         LaunchScope ls(pf, K_SCAN, st);
         EVS_CUDA(launch(k_scan, (h->n_tiers == 1 ? 1 : kSeqGroups) * h->tier[0].dev.n_buckets, 256, 0, st, p, pdl));
@@ -447,43 +455,82 @@ static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const Batc
     return EVS_OK;
 }
 
-static int build_graph(evs_handle h) {
+// Capture `nb` consecutive batches into one graph.  Only the BatchArgs parameter of the k_serve nodes changes between
+// launches; the nodes are told apart by the marker the capture puts into BatchArgs::seq.
+constexpr unsigned kSeqMarker = 0xE5000000u;
+static int build_graph_n(evs_handle h, int nb, cudaGraph_t *src_out, cudaGraphExec_t *exec_out, cudaGraphNode_t *serve_nodes) {
     cudaGraph_t g = nullptr;
     const bool was_on = h->prof.on;
     h->prof.on = false;                                   // no event records inside the capture
     unsigned long long saved[K_COUNT];
     memcpy(saved, h->prof.launches, sizeof(saved));
     EVS_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    BatchArgs none{};
     h->capturing = true;
-    int rc = enqueue_batch(h, h->stream, h->params.n_chunks_max, none);
+    int rc = EVS_OK;
+    for (int i = 0; i < nb && rc == EVS_OK; ++i) {
+        BatchArgs none{};
+        none.seq = kSeqMarker + static_cast<unsigned>(i);
+        rc = enqueue_batch(h, h->stream, h->params.n_chunks_max, none, i > 0);
+    }
     h->capturing = false;
     cudaError_t e = cudaStreamEndCapture(h->stream, &g);
     memcpy(h->prof.launches, saved, sizeof(saved));
     h->prof.on = was_on;
     if (rc) return rc;
     EVS_CUDA(e);
-    // find the k_serve node: its BatchArgs parameter is the only thing that changes between launches
     size_t n_nodes = 0;
     EVS_CUDA(cudaGraphGetNodes(g, nullptr, &n_nodes));
     std::vector<cudaGraphNode_t> nodes(n_nodes);
     EVS_CUDA(cudaGraphGetNodes(g, nodes.data(), &n_nodes));
     const KernelSet ks = kernels_of_handle(h);
-    h->serve_node = nullptr;
+    for (int i = 0; i < nb; ++i) serve_nodes[i] = nullptr;
     for (cudaGraphNode_t nd : nodes) {
         cudaGraphNodeType ty;
         EVS_CUDA(cudaGraphNodeGetType(nd, &ty));
         if (ty != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp{};
         EVS_CUDA(cudaGraphKernelNodeGetParams(nd, &kp));
-        if (kp.func == reinterpret_cast<void *>(serve_of(h, ks))) h->serve_node = nd;
+        if (kp.func != reinterpret_cast<void *>(serve_of(h, ks)) || kp.kernelParams == nullptr) continue;
+        const unsigned mark = static_cast<const BatchArgs *>(kp.kernelParams[1])->seq - kSeqMarker;
+        if (mark < static_cast<unsigned>(nb)) serve_nodes[mark] = nd;
     }
-    if (h->serve_node == nullptr) {
-        set_error("graph capture: k_serve node not found");
-        return EVS_ERR_CUDA;
+    for (int i = 0; i < nb; ++i)
+        if (serve_nodes[i] == nullptr) {
+            set_error("graph capture: k_serve node not found");
+            cudaGraphDestroy(g);
+            return EVS_ERR_CUDA;
+        }
+    EVS_CUDA(cudaGraphInstantiate(exec_out, g, 0));
+    *src_out = g;                                         // kept: the node handles belong to it
+    return EVS_OK;
+}
+
+static void destroy_graphs(evs_handle h) {
+    if (h->graph) cudaGraphExecDestroy(h->graph);
+    if (h->graph_src) cudaGraphDestroy(h->graph_src);
+    if (h->ggraph) cudaGraphExecDestroy(h->ggraph);
+    if (h->ggraph_src) cudaGraphDestroy(h->ggraph_src);
+    h->graph = h->ggraph = nullptr;
+    h->graph_src = h->ggraph_src = nullptr;
+}
+
+// The single-batch graph, and -- for evs_lookup_batches -- one of kGroup batches: a graph-to-graph boundary costs
+// ~5 us on the device, a kernel boundary inside a graph (programmatic edge) under 1 us.
+static int build_graph(evs_handle h) {
+    int rc = build_graph_n(h, 1, &h->graph_src, &h->graph, &h->serve_node);
+    if (rc) return rc;
+    const char *gg = getenv("EVSTORE_B200_GROUP");        // tuning aid: batches per group graph (1 = none)
+    h->group = evs_handle_s::kGroup;
+    if (gg && atoi(gg) >= 1) h->group = std::min(atoi(gg), static_cast<int>(evs_handle_s::kGroup));
+    if (h->group > 1) {
+        rc = build_graph_n(h, h->group, &h->ggraph_src, &h->ggraph, h->gserve);
+        if (rc) {                                         // not fatal: batches then go one graph each
+            cudaGetLastError();
+            h->group = 1;
+            h->ggraph = nullptr;
+            h->ggraph_src = nullptr;
+        }
     }
-    EVS_CUDA(cudaGraphInstantiate(&h->graph, g, 0));
-    h->graph_src = g;                                     // kept: the node handle belongs to it
     return EVS_OK;
 }
 
@@ -705,12 +752,16 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
             const int rows_per_cta = (kEvictThreads / 32) * (32 / gsize);
             // the link serves ~65 row reads / us whatever the row size up to 256 B once ~512-768 are in flight
             // (profiles/r2_zc_inflight.txt); the fetch role runs next to the eviction roles and keeps fewer
-            const int target = static_cast<int>(std::min(512u, std::max(256u, 65536u / stride)));
+            // (r2: backing rows in evs_host_alloc memory take ~4x as many before the rate levels off, and the fetch role only
+            // reads what the look-ahead did not stage)
+            const bool big_pages = h->n_ranges > 0 && h->n_ranges_managed == h->n_ranges;
+            const int target = big_pages ? static_cast<int>(std::min(2048u, std::max(512u, 131072u / stride)))
+                                         : static_cast<int>(std::min(512u, std::max(256u, 65536u / stride)));
             h->fetch_list_ctas = std::max(1, (target + rows_per_cta - 1) / rows_per_cta);
             h->pf_ok = aligned;
             // the look-ahead kernel: nothing waits for it, so it keeps the link saturated (measured optimum for 64-byte
             // rows: 16 CTAs = 1024 rows; 8 or 12 leave rows unstaged, 32 slow k_update's atomics down)
-            const int pf_target = stride <= 64 ? 1024 : 768;
+            const int pf_target = big_pages ? (stride <= 64 ? 2048 : 1024) : (stride <= 64 ? 1024 : 768);
             h->pf_ctas = std::max(4, (pf_target + rows_per_cta - 1) / rows_per_cta);
         }
         const char *fc = getenv("EVSTORE_B200_FETCH_LIST_CTAS");   // tuning aid: CTAs of the fetch role = PCIe reads kept in flight
@@ -768,7 +819,7 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         cudaGetLastError();
         h->use_pdl = false;
         P.pdl = 0;
-        if (h->graph_src) cudaGraphDestroy(h->graph_src), h->graph_src = nullptr;
+        destroy_graphs(h);
         if ((rc = build_graph(h))) return fail(rc);
     }
     *out = h;
@@ -779,6 +830,24 @@ int evs_destroy(evs_handle h) {
     if (h == nullptr) return EVS_ERR_INVALID;
     free_all(h);
     return EVS_OK;
+}
+
+static int set_serve_params(evs_handle h, cudaGraphExec_t exec, cudaGraphNode_t node, BatchArgs &a) {
+    const KernelSet ks = kernels_of_handle(h);
+    void *kargs[] = {&h->params, &a};
+    cudaKernelNodeParams kp{};
+    kp.func = reinterpret_cast<void *>(serve_of(h, ks));
+    kp.gridDim = dim3(h->params.n_chunks_max);
+    kp.blockDim = dim3(kLookupThreads);
+    kp.sharedMemBytes = 0;
+    kp.kernelParams = kargs;
+    EVS_CUDA(cudaGraphExecKernelNodeSetParams(exec, node, &kp));
+    return EVS_OK;
+}
+
+static void count_batch_launches(evs_handle h) {
+    h->prof.launches[K_SERVE]++, h->prof.launches[K_UPDATE]++, h->prof.launches[K_EVICT]++;
+    if (h->params.n_chunks_max > h->params.quad_max || h->params.L < kDirectMinLanes) h->prof.launches[K_SCAN]++;
 }
 
 static int run_batch(evs_handle h, const BatchArgs &a_in, cudaStream_t st) {
@@ -794,19 +863,14 @@ static int run_batch(evs_handle h, const BatchArgs &a_in, cudaStream_t st) {
     // rows staged by evs_prefetch are used when the announcement matches this call
     a.pf_gen = (h->pf_ok && h->pf_seq == seq && h->pf_idx == static_cast<const void *>(a.idx) && h->pf_B == a.B) ? h->pf_gen : 0u;
     if (h->use_graph && !h->prof.on) {
-        void *kargs[] = {&h->params, &a};
-        cudaKernelNodeParams kp{};
-        kp.func = reinterpret_cast<void *>(serve_of(h, ks));
-        kp.gridDim = dim3(h->params.n_chunks_max);
-        kp.blockDim = dim3(kLookupThreads);
-        kp.sharedMemBytes = 0;
-        kp.kernelParams = kargs;
-        EVS_CUDA(cudaGraphExecKernelNodeSetParams(h->graph, h->serve_node, &kp));
+        int rc = set_serve_params(h, h->graph, h->serve_node, a);
+        if (rc) return rc;
         EVS_CUDA(cudaGraphLaunch(h->graph, st));
-        h->prof.launches[K_SERVE]++, h->prof.launches[K_UPDATE]++, h->prof.launches[K_EVICT]++;
-        if (h->params.n_chunks_max > h->params.quad_max || h->params.L < kDirectMinLanes) h->prof.launches[K_SCAN]++;
+        count_batch_launches(h);
     } else {
-        int rc = enqueue_batch(h, st, (a.B + h->params.spc - 1) / h->params.spc, a);
+        // outside a graph the chain continues across batches: k_serve is a programmatic dependent of whatever kernel
+        // precedes it on the stream (the previous batch's k_evict in a serving loop)
+        int rc = enqueue_batch(h, st, (a.B + h->params.spc - 1) / h->params.spc, a, true);
         if (rc) return rc;
     }
     // the staging rows of this parity may be overwritten (by the look-ahead for batch seq + 2) once this batch is done
@@ -823,37 +887,87 @@ static int run_batch(evs_handle h, const BatchArgs &a_in, cudaStream_t st) {
     return EVS_OK;
 }
 
+// Launch k_prefetch for batch number `seq` with generation `gen` on the look-ahead stream.  The kernel itself waits (on the
+// device) until the staging rows of its parity are free, i.e. until the miss-fetch role of batch seq - 2 has finished.
+static int launch_prefetch(evs_handle h, const int64_t *idx_dev, int32_t B, uint64_t seq, uint32_t gen) {
+    PrefetchArgs pa{};
+    pa.idx = reinterpret_cast<const long long *>(idx_dev);
+    pa.B = B;
+    pa.seq = static_cast<unsigned>(seq);
+    pa.gen = gen;
+    pa.mode = h->pf_mode;
+    const KernelSet ks = kernels_of_handle(h);
+    const int S = pf_tile_samples(h->cfg.n_tables);
+    const int n_tiles = (B + S - 1) / S;
+    LaunchScope ls(h->prof, K_PREFETCH, h->pf_stream);
+    void *args[] = {&h->params, &pa};
+    EVS_CUDA(launch_ex(reinterpret_cast<const void *>(ks.prefetch), dim3(std::min(h->pf_ctas, n_tiles)), kPfThreads, 0, h->pf_stream,
+                       args, false));
+    return EVS_OK;
+}
+
+// The next announcement's generation (tags are generation << 1 | tier: start over with clean tags before they wrap).
+static int next_pf_gen(evs_handle h, uint32_t *gen) {
+    if (++h->pf_gen >= 0x7FFFFFFFu) {
+        EVS_CUDA(cudaStreamSynchronize(h->stream));
+        EVS_CUDA(cudaMemsetAsync(h->params.pf_tag, 0, 2 * sizeof(unsigned) * static_cast<size_t>(h->params.n_max), h->pf_stream));
+        h->pf_gen = 1;
+    }
+    *gen = h->pf_gen;
+    return EVS_OK;
+}
+
 // Look-ahead for the next batch (see evs_prefetch.cuh).  ready: event after which idx_dev is complete, or null.
 static int prefetch_next(evs_handle h, const int64_t *idx_dev, int32_t B, cudaEvent_t ready) {
     if (!h->pf_ok) return EVS_OK;
     const uint64_t seq = h->seq + 1;
     if (h->pf_seq == seq && h->pf_idx == static_cast<const void *>(idx_dev) && h->pf_B == B) return EVS_OK;   // already announced
     if (ready) EVS_CUDA(cudaStreamWaitEvent(h->pf_stream, ready, 0));
-    // (the staging rows of this parity belong to batch seq - 2 until its fetch role has finished: k_prefetch waits for that
-    // on the device -- GlobalCtl::fetch_done_seq -- so that nothing is released at a batch boundary)
     if (h->pf_wait_mode == 1 && h->ev_done_valid[seq & 1]) EVS_CUDA(cudaStreamWaitEvent(h->pf_stream, h->ev_done[seq & 1], 0));
-    if (++h->pf_gen >= 0x7FFFFFFFu) {                      // tags are generation << 1 | tier: start over with clean tags
-        EVS_CUDA(cudaMemsetAsync(h->params.pf_tag, 0, 2 * sizeof(unsigned) * static_cast<size_t>(h->params.n_max), h->pf_stream));
-        h->pf_gen = 1;
-    }
-    PrefetchArgs pa{};
-    pa.idx = reinterpret_cast<const long long *>(idx_dev);
-    pa.B = B;
-    pa.seq = static_cast<unsigned>(seq);
-    pa.gen = h->pf_gen;
-    pa.mode = h->pf_mode;
-    const KernelSet ks = kernels_of_handle(h);
-    const int S = pf_tile_samples(h->cfg.n_tables);
-    const int n_tiles = (B + S - 1) / S;
-    {
-        LaunchScope ls(h->prof, K_PREFETCH, h->pf_stream);
-        void *args[] = {&h->params, &pa};
-        EVS_CUDA(launch_ex(reinterpret_cast<const void *>(ks.prefetch), dim3(std::min(h->pf_ctas, n_tiles)), kPfThreads, 0, h->pf_stream,
-                           args, false));
-    }
+    uint32_t gen = 0;
+    int rc = next_pf_gen(h, &gen);
+    if (rc) return rc;
+    if ((rc = launch_prefetch(h, idx_dev, B, seq, gen))) return rc;
     h->pf_seq = seq;
     h->pf_idx = idx_dev;
     h->pf_B = B;
+    return EVS_OK;
+}
+
+// kGroup batches in ONE graph launch (evs_lookup_batches).  The batches stay strictly ordered -- the graph is the same
+// linear chain of kernels -- but only the first k_serve pays a graph-to-graph boundary; the others follow their
+// predecessor's k_evict over a programmatic edge.  The look-ahead kernels of batches 1 .. kGroup-1 are enqueued on the
+// look-ahead stream AFTER the graph (each waits on the device for the batch two before it, which is then already queued).
+static int run_group(evs_handle h, BatchArgs *a, int n, cudaStream_t st) {
+    const uint64_t seq0 = h->seq + 1;
+    uint32_t gens[evs_handle_s::kGroup] = {};
+    for (int i = 0; i < n; ++i) {
+        a[i].seq = static_cast<unsigned>(seq0 + i);
+        if (i == 0) {
+            a[i].pf_gen = (h->pf_ok && h->pf_seq == seq0 && h->pf_idx == static_cast<const void *>(a[i].idx) && h->pf_B == a[i].B) ? h->pf_gen : 0u;
+        } else if (h->pf_ok) {
+            int rc = next_pf_gen(h, &gens[i]);
+            if (rc) return rc;
+            a[i].pf_gen = gens[i];
+        }
+        int rc = set_serve_params(h, h->ggraph, h->gserve[i], a[i]);
+        if (rc) return rc;
+    }
+    EVS_CUDA(cudaGraphLaunch(h->ggraph, st));
+    h->seq += n;
+    for (int i = 0; i < n; ++i) count_batch_launches(h);
+    if (h->pf_ok) {
+        for (int i = 1; i < n; ++i) {
+            int rc = launch_prefetch(h, reinterpret_cast<const int64_t *>(a[i].idx), a[i].B, seq0 + i, gens[i]);
+            if (rc) return rc;
+        }
+        h->pf_seq = seq0 + n - 1;
+        h->pf_idx = a[n - 1].idx;
+        h->pf_B = a[n - 1].B;
+    }
+    h->batches += n;
+    for (int i = 0; i < h->n_tiers; ++i)
+        for (int k = 0; k < n; ++k) h->tier[i].ub_used += static_cast<unsigned long long>(a[k].B) * h->cfg.n_tables;
     return EVS_OK;
 }
 
@@ -885,6 +999,123 @@ int evs_lookup_batch(evs_handle h, const int64_t *idx_dev, int32_t B, float *out
     a.B = B;
     a.probe_only = 0;
     return run_batch(h, a, st);
+}
+
+int evs_lookup_batches(evs_handle h, int32_t n, const int64_t *const *idx_dev, int32_t B, float *const *out_dev, int64_t out_stride,
+                       uint8_t *const *hit_dev, void *stream) {
+    if (h == nullptr || n < 0 || B < 1 || B > h->cfg.max_batch || (n > 0 && (idx_dev == nullptr || out_dev == nullptr))) {
+        set_error("evs_lookup_batches: bad handle / n / B / pointers");
+        return EVS_ERR_INVALID;
+    }
+    for (int i = 0; i < n; ++i)
+        if (idx_dev[i] == nullptr || out_dev[i] == nullptr) {
+            set_error("evs_lookup_batches: null batch pointer");
+            return EVS_ERR_INVALID;
+        }
+    DeviceGuard dg(h->cfg.device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    const int G = h->group;
+    const unsigned long long n_max = static_cast<unsigned long long>(h->cfg.max_batch) * h->cfg.n_tables;
+    int i = 0;
+    while (i < n) {
+        bool grouped = h->use_graph && !h->prof.on && !h->sharded && G > 1 && h->ggraph != nullptr && n - i >= G && h->pf_wait_mode == 0;
+        if (grouped) {
+            // every bucket ring must take the whole group's appends (the host tracks an upper bound of the occupancy)
+            for (int t = 0; t < h->n_tiers && grouped; ++t) {
+                if (h->tier[t].ub_used + static_cast<unsigned long long>(G + 1) * n_max > h->tier[t].dev.ring_cap) {
+                    int rc = maintain_rings(h, t, st, G + 1);
+                    if (rc) return rc;
+                    grouped = h->tier[t].ub_used + static_cast<unsigned long long>(G + 1) * n_max <= h->tier[t].dev.ring_cap;
+                }
+            }
+        }
+        if (grouped) {
+            BatchArgs a[evs_handle_s::kGroup];
+            for (int k = 0; k < G; ++k) {
+                a[k] = BatchArgs{};
+                a[k].idx = reinterpret_cast<const long long *>(idx_dev[i + k]);
+                a[k].out = out_dev[i + k];
+                a[k].out_stride = out_stride > 0 ? out_stride : static_cast<long long>(h->cfg.n_tables) * h->cfg.dim;
+                a[k].hit = hit_dev ? hit_dev[i + k] : nullptr;
+                a[k].agg_out = h->d_agg;
+                a[k].B = B;
+            }
+            int rc = run_group(h, a, G, st);
+            if (rc) return rc;
+            i += G;
+        } else {
+            // one graph per batch; the batch after it is announced so that its misses are staged as inside a group
+            int rc = evs_lookup_batch(h, idx_dev[i], B, out_dev[i], out_stride, hit_dev ? hit_dev[i] : nullptr, nullptr, st);
+            if (rc) return rc;
+            if (i + 1 < n && (rc = prefetch_next(h, idx_dev[i + 1], B, nullptr))) return rc;
+            i += 1;
+        }
+    }
+    return EVS_OK;
+}
+
+// Bags (pooling factor > 1) on the cached path: see evs_bags.cuh.
+int evs_lookup_bags(evs_handle h, const int64_t *idx_dev, const int64_t *off_dev, int32_t B, int64_t nnz, int32_t max_per_bag,
+                    float *out_dev, int64_t out_stride, uint8_t *hit_dev, void *stream) {
+    if (h == nullptr || B < 0 || nnz < 0 || max_per_bag < 1 || max_per_bag > kMaxPerBag || off_dev == nullptr ||
+        (B > 0 && out_dev == nullptr) || (nnz > 0 && idx_dev == nullptr)) {
+        set_error("evs_lookup_bags: bad handle / B / nnz / max_per_bag (1..32) / pointers");
+        return EVS_ERR_INVALID;
+    }
+    if (static_cast<long long>(B) * max_per_bag > h->cfg.max_batch) {
+        set_error("evs_lookup_bags: B * max_per_bag slices exceed max_batch (create the handle with max_batch >= B * max_per_bag)");
+        return EVS_ERR_INVALID;
+    }
+    if (h->sharded) {
+        set_error("evs_lookup_bags: not available on a rank of a table-wise sharded cache");
+        return EVS_ERR_INVALID;
+    }
+    if (B == 0) return EVS_OK;
+    DeviceGuard dg(h->cfg.device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    const int T = h->cfg.n_tables, D = h->cfg.dim, P = max_per_bag;
+    if (h->bag_idx == nullptr) {                              // slice scratch, on first use
+        t_alloc_bytes = &h->hbm_bytes;
+        struct AllocScope {
+            ~AllocScope() { t_alloc_bytes = nullptr; }
+        } alloc_scope;
+        const long long n_max = static_cast<long long>(h->cfg.max_batch) * T;
+        int rc;
+        if ((rc = dev_alloc(h->dev_allocs, &h->bag_idx, n_max))) return rc;
+        if ((rc = dev_alloc(h->dev_allocs, &h->bag_rows, n_max * D))) return rc;
+        if ((rc = dev_alloc(h->dev_allocs, &h->bag_hit, n_max))) return rc;
+    }
+    const int Bv = B * P;
+    const long long total = static_cast<long long>(Bv) * T;
+    {
+        LaunchScope ls(h->prof, K_BAGS, st);
+        k_bags_expand<<<static_cast<unsigned>(std::min<long long>((total + 255) / 256, 148 * 8)), 256, 0, st>>>(
+            h->params, reinterpret_cast<const long long *>(idx_dev), reinterpret_cast<const long long *>(off_dev), B, P, nnz, h->bag_idx);
+        EVS_CUDA(cudaGetLastError());
+    }
+    BatchArgs a{};
+    a.idx = h->bag_idx;
+    a.out = h->bag_rows;
+    a.out_stride = static_cast<long long>(T) * D;
+    a.hit = h->bag_hit;
+    a.agg_out = h->d_agg;
+    a.B = Bv;
+    a.bags = 1;
+    int rc = run_batch(h, a, st);
+    if (rc) return rc;
+    {
+        LaunchScope ls(h->prof, K_BAGS, st);
+        const long long os = out_stride > 0 ? out_stride : static_cast<long long>(T) * D;
+        const bool vec = (D & 3) == 0 && (os & 3) == 0 && (reinterpret_cast<uintptr_t>(out_dev) & 15u) == 0;
+        const long long items = static_cast<long long>(B) * T * (vec ? D / 4 : D);
+        const unsigned grid = static_cast<unsigned>(std::min<long long>((items + 255) / 256, 148 * 16));
+        if (vec)
+            k_bags_pool<true><<<grid, 256, 0, st>>>(h->bag_rows, h->bag_hit, reinterpret_cast<const long long *>(off_dev), B, P, T, D, out_dev, os, hit_dev);
+        else
+            k_bags_pool<false><<<grid, 256, 0, st>>>(h->bag_rows, h->bag_hit, reinterpret_cast<const long long *>(off_dev), B, P, T, D, out_dev, os, hit_dev);
+        EVS_CUDA(cudaGetLastError());
+    }
+    return EVS_OK;
 }
 
 int evs_probe_batch(evs_handle h, const int64_t *idx_dev, int32_t B, uint8_t *agg_out_dev, void *stream) {
@@ -1339,10 +1570,7 @@ int evs_shard_connect(evs_shard s, const void *handles) {
         if (nf && nf[0] == '1') s->fused = false;
     }
     if (h->use_graph) {
-        if (h->graph) cudaGraphExecDestroy(h->graph);
-        if (h->graph_src) cudaGraphDestroy(h->graph_src);
-        h->graph = nullptr;
-        h->graph_src = nullptr;
+        destroy_graphs(h);
         int rc = build_graph(h);
         if (rc) return rc;
     }
@@ -1446,6 +1674,41 @@ int evs_embedding_bag_status(void) {
         set_error("evs_embedding_bag: an index was outside [0, rows)");
         return EVS_ERR_INDEX;
     }
+    return EVS_OK;
+}
+
+// ---- host memory for backing rows -------------------------------------------------------------
+// cudaHostAlloc / cudaHostRegister memory is mapped into the device with 4 KB entries whatever the host pages behind it:
+// once the random rows of a batch's misses spread over more than ~512 MB the zero-copy read rate halves
+// (profiles/r2_zc_page_probe.txt).  Managed memory whose preferred location is the CPU and that is `accessed by` the
+// device stays in host memory, is never migrated, and is mapped with large pages: 240 instead of 120-140 row reads / us over
+// a 2 GB table (profiles/r2_zc_vmm_probe.txt).  The host reads and writes it like any allocation.
+int evs_host_alloc(void **ptr, uint64_t bytes, int32_t device) {
+    if (ptr == nullptr || bytes == 0) return EVS_ERR_INVALID;
+    *ptr = nullptr;
+    DeviceGuard dg(device);
+    void *p = nullptr;
+    cudaError_t e = cudaMallocManaged(&p, bytes, cudaMemAttachGlobal);
+    if (e != cudaSuccess) {
+        set_error(std::string("evs_host_alloc: cudaMallocManaged(") + std::to_string(bytes) + " B) -> " + cudaGetErrorString(e));
+        cudaGetLastError();
+        return EVS_ERR_CUDA;
+    }
+    e = cudaMemAdvise(p, bytes, cudaMemAdviseSetPreferredLocation, cudaCpuDeviceId);
+    if (e == cudaSuccess) e = cudaMemAdvise(p, bytes, cudaMemAdviseSetAccessedBy, device);
+    if (e != cudaSuccess) {
+        set_error(std::string("evs_host_alloc: cudaMemAdvise -> ") + cudaGetErrorString(e));
+        cudaGetLastError();
+        cudaFree(p);
+        return EVS_ERR_CUDA;
+    }
+    *ptr = p;
+    return EVS_OK;
+}
+
+int evs_host_free(void *ptr) {
+    if (ptr == nullptr) return EVS_OK;
+    EVS_CUDA(cudaFree(ptr));
     return EVS_OK;
 }
 

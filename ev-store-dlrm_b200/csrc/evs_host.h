@@ -39,9 +39,9 @@ struct Tier {
 
 
 // Kernel ids for the launch counter / per-kernel CUDA-event timing (evs_set_profiling).
-enum KernelId { K_SERVE = 0, K_SCAN, K_UPDATE, K_EVICT, K_PREFETCH, K_COMPACT, K_PROBE, K_INTERACT, K_GATHER, K_COUNT };
+enum KernelId { K_SERVE = 0, K_SCAN, K_UPDATE, K_EVICT, K_PREFETCH, K_COMPACT, K_PROBE, K_INTERACT, K_GATHER, K_BAGS, K_COUNT };
 static const char *const kKernelNames[K_COUNT] = {"k_serve", "k_scan", "k_update", "k_evict", "k_prefetch", "k_compact", "k_probe", "k_interact",
-                                                  "k_gather"};
+                                                  "k_gather", "k_bags"};
 
 struct Profiler {
     bool on = false;
@@ -105,6 +105,12 @@ struct evs_handle_s {
     cudaGraphNode_t serve_node = nullptr;    // its BatchArgs parameter is rewritten before every graph launch
     cudaGraph_t graph_src = nullptr;
     cudaGraphExec_t graph = nullptr;         // k_serve -> [k_scan ->] k_update -> k_evict (eviction + miss-fetch roles)
+    // evs_lookup_batches: kGroup consecutive batches captured in one graph
+    static constexpr int kGroup = 4;
+    int group = 1;
+    cudaGraph_t ggraph_src = nullptr;
+    cudaGraphExec_t ggraph = nullptr;
+    cudaGraphNode_t gserve[kGroup] = {};
     bool use_graph = true;
     bool capturing = false;                  // enqueue_batch is being captured into the graph
     bool use_pdl = true;                     // the batch's kernels are chained by programmatic dependent launch
@@ -130,6 +136,10 @@ struct evs_handle_s {
     evs::BatchArgs *d_args = nullptr;        // device copy of the per-batch arguments
     long long *d_rows = nullptr;
     uint8_t *d_agg = nullptr;                // [max_batch]
+    // evs_lookup_bags: the batch's slices (allocated on first use): indices [T][B*P], rows [B*P][T][D], hit codes [B*P][T]
+    long long *bag_idx = nullptr;
+    float *bag_rows = nullptr;
+    uint8_t *bag_hit = nullptr;
     // staging for the host-buffer paths: slot 0 serves the synchronous call, all kPipeSlots the
     // pipelined one (H2D of batch n+1 and D2H of batch n-1 overlap the kernels of batch n)
     static constexpr int kPipeSlots = 4;
@@ -141,6 +151,7 @@ struct evs_handle_s {
     int64_t submitted = 0;
     bool sharded = false;                    // an evs_shard is connected: k_serve<.., true>, k_evict closes the batch with the peers
     std::vector<void *> registered;          // host ranges we page-locked
+    int n_ranges = 0, n_ranges_managed = 0;  // host ranges mapped / of them evs_host_alloc (managed) memory
     std::vector<void *> dev_allocs;
     uint64_t batches = 0;
     evs::Profiler prof;

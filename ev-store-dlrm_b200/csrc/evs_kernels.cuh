@@ -358,7 +358,7 @@ template <int P0, int P1, bool SH>
 __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(const __grid_constant__ Params p, const __grid_constant__ BatchArgs a) {
     __shared__ long long s_idx[kLookupThreads];          // [sample in CTA][L]
     __shared__ unsigned s_hist[kSeqs];
-    __shared__ unsigned s_stat[8];           // hits C1, hits C2, C3, approx, misses, perfect
+    __shared__ unsigned s_stat[8];           // hits C1, hits C2, C3, approx, misses, perfect, positions without a key (bags)
     __shared__ CodecLut s_lut;
 
     // Launched without a graph, k_serve is programmatically dependent on the previous batch's k_evict (which lets its
@@ -395,12 +395,15 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
     const int j = warp * (32 >> p.L_shift) + q.g;     // sample within the CTA
     const int s = s0 + j;
     const bool sact = s < B;                   // a group past the batch end only joins the warp-wide operations
-    const bool act = sact && q.gl < T;
+    bool act = sact && q.gl < T;
     const int tbl = q.gl;
     const int gtbl = act ? p.tid[tbl] : 0;     // global table id
     unsigned long long key = 0, m0 = 0, m1 = 0;
     unsigned slot0 = 0, slot1 = 0;
     bool h0 = false, h1 = false;
+    // bags: a negative index = this slice has no key for the table (the bag is shorter): nothing to probe, count or serve
+    const bool absent = act && a.bags != 0 && s_idx[(j << p.L_shift) + tbl] < 0;
+    if (absent) act = false;
     if (act) {
         long long r = s_idx[(j << p.L_shift) + tbl];
         if (r < 0 || r >= __ldg(p.rows + tbl)) {
@@ -549,6 +552,9 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
         }
         p.flags[pos] = f;
         if (a.hit != nullptr) a.hit[pos] = hc;
+    } else if (absent) {
+        p.flags[pos] = 0;
+        if (a.hit != nullptr) a.hit[pos] = kHitAbsent;
     }
     if (P1 == 0 && p.approx_thres > 0) {
         // value of the latest earlier hit in table order, else of the first hit
@@ -565,6 +571,7 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
     const unsigned m_miss = __ballot_sync(kFull, (f & kFlagMiss) != 0) & q.mask;
     const unsigned m_c2 = __ballot_sync(kFull, hc == kHitC2) & q.mask;
     const unsigned m_ap = __ballot_sync(kFull, hc == kHitApprox) & q.mask;
+    const unsigned m_abs = __ballot_sync(kFull, absent) & q.mask;
     // compact miss list for the fetch role of k_evict: one atomic per sample that missed anything, issued here so that
     // its round trip hides behind the gather below
     unsigned mbase = 0;
@@ -580,6 +587,7 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
         if (m_ap) atomicAdd(&s_stat[3], static_cast<unsigned>(__popc(m_ap)));
         if (m_miss) atomicAdd(&s_stat[4], static_cast<unsigned>(__popc(m_miss)));
         if (agg == p.n_perfect_agg) atomicAdd(&s_stat[5], 1u);
+        if (m_abs) atomicAdd(&s_stat[6], static_cast<unsigned>(__popc(m_abs)));
     }
 
     if (!(SH && early)) {
@@ -605,7 +613,7 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
         atomicMax(&p.dbg[1], t_end);
         GlobalCtl *g = p.g;
         const int ns = min(spc, B - s0);
-        atomicAdd(&g->lookups, static_cast<unsigned long long>(ns) * T);
+        atomicAdd(&g->lookups, static_cast<unsigned long long>(ns) * T - s_stat[6]);
         atomicAdd(&g->samples, static_cast<unsigned long long>(ns));
         if (s_stat[0]) atomicAdd(&g->hits[0], static_cast<unsigned long long>(s_stat[0]));
         if (s_stat[1]) atomicAdd(&g->hits[1], static_cast<unsigned long long>(s_stat[1]));

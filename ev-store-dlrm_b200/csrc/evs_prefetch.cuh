@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kPfThreads) k_prefetch(const __grid_constant__
                 tt[u] = ok[u] ? e / ns : 0;
                 ss[u] = s_base + (e - tt[u] * ns);
                 long long r = ok[u] ? __ldg(a.idx + static_cast<size_t>(tt[u]) * B + ss[u]) : 0;
+                if (r < 0) ok[u] = false;                   // no key at this position (a slice of ragged bags), or an index error
                 if (r < 0 || r >= __ldg(p.rows + tt[u])) r = 0;
                 key[u] = make_key(p.tid[tt[u]], r);
                 i0[u] = hash_key(key[u], t0.hash_mask);

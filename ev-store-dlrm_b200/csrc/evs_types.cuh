@@ -46,6 +46,7 @@ constexpr uint8_t kFlagTier = 0x40;
 
 // hit[p] codes (nonzero == answered without touching the backing store)
 constexpr uint8_t kHitMiss = 0, kHitC1 = 1, kHitC2 = 2, kHitC3 = 3, kHitApprox = 4;
+constexpr uint8_t kHitAbsent = 255;               // bags: no key at this position of the slice (evs_bags.cuh)
 
 struct __align__(16) Slot {
     unsigned long long kw;
@@ -166,6 +167,7 @@ struct BatchArgs {
     int probe_only;
     unsigned seq;                          // number of this batch on the handle (>= 1)
     unsigned pf_gen;                       // != 0: evs_prefetch staged rows for this batch (Params::pf_*), tagged with this generation
+    int bags;                              // 1: the batch holds slices of ragged bags; a negative index = no key at that position
     ShardArgs sh;
 };
 

@@ -140,3 +140,17 @@ def synth_table_pinned(table_id: int, rows: int, dim: int, device, chunk_rows: i
     if torch.device(device).type == "cuda":
         torch.cuda.synchronize(device)
     return out
+
+
+def synth_table_mapped(table_id: int, rows: int, dim: int, device, chunk_rows: int = 1 << 21):
+    """The same table in ``host_rows`` memory (evs_host_alloc: host memory the device maps with large pages); numpy [rows, dim]."""
+    import torch
+    from .cache_manager import host_rows
+    dev = torch.device(device)
+    out = host_rows((rows, dim), np.float32, dev.index or 0)
+    view = torch.from_numpy(out)
+    for r0 in range(0, rows, chunk_rows):
+        r1 = min(rows, r0 + chunk_rows)
+        ids = torch.arange(r0, r1, dtype=torch.int64, device=dev)
+        view[r0:r1].copy_(synth_rows(table_id, ids, dim, rows))
+    return out

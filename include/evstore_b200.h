@@ -134,6 +134,28 @@ int evs_version(void);
 int evs_lookup_batch(evs_handle h, const int64_t *idx_dev, int32_t B, float *out_dev, int64_t out_stride,
                      uint8_t *hit_dev, const uint8_t *agg_in, void *stream);
 
+/* Bags on the cached path (pooling factor > 1): the (lS_o, lS_i) pairs of apply_emb (dlrm_s_pytorch_C1_C2_C3.py:191-223;
+ * --data-generation=random draws up to 10 indices per bag, dlrm_data_pytorch.py:961-1007).
+ *   idx_dev  int64 [nnz]          all bags' indices, table 0's bags first
+ *   off_dev  int64 [n_tables*B+1] bag (t, s) = idx_dev[off[t*B+s] .. off[t*B+s+1]);  off[n_tables*B] = nnz
+ *   max_per_bag  P <= 32, B*P <= max_batch; a larger bag, a negative index or malformed offsets raise EVS_ERR_INDEX
+ *   out_dev  fp32 [B][n_tables][dim]: out[s][t] = sum over the bag's rows, j ascending, single fp32 adds (an empty bag
+ *            gives zeros) -- nn.EmbeddingBag(mode="sum") over the rows the cache serves (dequantised at the serving tier)
+ *   hit_dev  uint8 [nnz] hit code per index (as evs_lookup_batch), or NULL
+ * Policy: the batch is looked up as B*P slices -- slice s*P+j = the j-th index of every table's bag of sample s -- each one
+ * a request group in the reference's sense (its agg_hit counts the hits among its own keys). */
+int evs_lookup_bags(evs_handle h, const int64_t *idx_dev, const int64_t *off_dev, int32_t B, int64_t nnz, int32_t max_per_bag,
+                    float *out_dev, int64_t out_stride, uint8_t *hit_dev, void *stream);
+
+/* n consecutive batches of B samples in one call: exactly the results of n evs_lookup_batch calls in that order (the
+ * batches stay strictly ordered on the device), but groups of 4 batches go to the device as ONE captured graph, so only
+ * every fourth batch pays the graph-to-graph launch boundary, and the misses of batches 1..n-1 are staged by the
+ * look-ahead (evs_prefetch) without further calls.  A serving loop whose requests are queued uses this; announce the
+ * first batch of the next call with evs_prefetch.  idx_dev / out_dev / hit_dev: n pointers each (hit_dev or its entries
+ * may be NULL); the output buffers may alias each other if the caller consumes only the last one. */
+int evs_lookup_batches(evs_handle h, int32_t n, const int64_t *const *idx_dev, int32_t B, float *const *out_dev,
+                       int64_t out_stride, uint8_t *const *hit_dev, void *stream);
+
 /* Look-ahead: idx_dev is the index batch the NEXT evs_lookup_batch / evs_shard_lookup call on this handle will pass
  * (same pointer, same B).  The library probes it and stages the rows of its probable misses from the host-pinned
  * backing store into HBM on its own stream, under the kernels of the batch in flight; the next call then finds
@@ -238,6 +260,15 @@ int evs_embedding_bag_status(void);
 /* Device-visible alias of the handle's backing rows of (tier, table): the storage_manager no-cache
  * path (request_to_emb_storage, emb_storage/storage_manager.py:125) reads it with evs_embedding_bag. */
 int evs_store_ptr(evs_handle h, int tier, int table, const void **dev_ptr, int32_t *precision);
+
+/* ---- host memory for the backing rows (get_from_file's ev-table-N.bin contents, evlfu_32.cpp:283-316) --- *
+ * Any host array works as a backing store (pinned allocations are used as they are, pageable ones are
+ * page-locked by evs_create).  Memory from evs_host_alloc is additionally mapped into `device` with large
+ * pages: the zero-copy miss fetch over a multi-GB table runs at about twice the row rate (managed memory
+ * that lives in host memory and is never migrated; the host reads / writes / fread()s into it as usual).
+ * Free with evs_host_free after every handle created over it has been destroyed. */
+int evs_host_alloc(void **ptr, uint64_t bytes, int32_t device);
+int evs_host_free(void *ptr);
 
 /* ---- legacy libcachemanager.so surface (cache_manager.cpp) ------------------------ *
  * A process-global cache answers one sample per call.  Where the reference fixes its

@@ -175,14 +175,17 @@ class BatchEvLFU:
         T = self.T
         ent = self.entries
         gid = [table_base + t for t in range(Tl)] if table_ids is None else [int(g) for g in table_ids]
-        keys = [[make_key(gid[t], idx[t, s]) for t in range(Tl)] for s in range(B)]
-        hit0 = np.array([[k in ent for k in ks] for ks in keys], dtype=bool).reshape(B, Tl)
+        # a negative index = no key at this position (a slice of ragged bags, ``expand_bags``): it is not probed, counts
+        # for nothing and is reported as a miss with src_t = -1
+        keys = [[make_key(gid[t], idx[t, s]) if idx[t, s] >= 0 else None for t in range(Tl)] for s in range(B)]
+        hit0 = np.array([[k is not None and k in ent for k in ks] for ks in keys], dtype=bool).reshape(B, Tl)
         if agg is None:
             agg = hit0.sum(axis=1).astype(np.int64)
         agg = np.asarray(agg, dtype=np.int64)
         hit = hit0.copy()
         src_t = np.tile(np.asarray(gid, dtype=np.int32), (B, 1))
         src_r = np.ascontiguousarray(idx.T).astype(np.int64)
+        src_t[src_r < 0] = -1
 
         winners: dict[int, tuple[int, int]] = {}
         for s in range(B):
@@ -197,6 +200,8 @@ class BatchEvLFU:
             for t in range(Tl):
                 k = ks[t]
                 p = s * Tl + t
+                if k is None:
+                    continue
                 if hit0[s, t]:
                     last = t
                     if ent[k] >= a:
@@ -273,4 +278,32 @@ def gather_rows(tables, src_t, src_r, fill=0.0):
             continue
         m = src_t == t
         out[m] = tables[int(t)][src_r[m]]
+    return out
+
+
+def expand_bags(idx_lists, off_lists, B: int, P: int):
+    """Ragged bags -> slices.  idx_lists[t]: the indices of table t (all bags concatenated), off_lists[t]: int [B] start of
+    each bag (nn.EmbeddingBag's offsets; bag s ends where bag s+1 starts).  Returns int64 [T, B*P]: virtual sample
+    s*P + j holds the j-th index of every table's bag of sample s, -1 where the bag is shorter.  A batch of bags is
+    looked up as these B*P groups (each one a request group in the reference's sense: its agg_hit counts the hits among
+    its keys) and pooled per (sample, table) in ascending j -- the sum order of nn.EmbeddingBag(mode="sum")."""
+    T = len(idx_lists)
+    out = np.full((T, B * P), -1, dtype=np.int64)
+    for t in range(T):
+        off = list(off_lists[t]) + [len(idx_lists[t])]
+        for s in range(B):
+            n = off[s + 1] - off[s]
+            assert 0 <= n <= P, "bag larger than P"
+            out[t, s * P:s * P + n] = idx_lists[t][off[s]:off[s + 1]]
+    return out
+
+
+def pool_bags(rows_v, idx_v, B: int, P: int):
+    """rows_v fp32 [B*P, T, d] (the rows of the slices), idx_v [T, B*P] -> pooled [B, T, d]: sum over j ascending, fp32."""
+    BP, T, d = rows_v.shape
+    out = np.zeros((B, T, d), dtype=np.float32)
+    for j in range(P):
+        r = rows_v.reshape(B, P, T, d)[:, j]
+        m = (idx_v.reshape(T, B, P)[:, :, j] >= 0).T            # [B, T]
+        out = np.where(m[:, :, None], out + r, out).astype(np.float32)
     return out

@@ -46,6 +46,7 @@ import numpy as np
 from .evlfu import KEY_SHIFT, make_key, split_key
 
 HIT_MISS, HIT_C1, HIT_C2, HIT_C3, HIT_APPROX = 0, 1, 2, 3, 4
+ABSENT = 255        # no key at this position (a slice of ragged bags)
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
@@ -513,13 +514,14 @@ class BatchTiers:
                 w[tier][k] = (a, p)
 
         for s in range(B):
-            keys = [make_key(self.table_base + t, idx[t, s]) for t in range(Tl)]
-            h0 = [k in c1.entries for k in keys]
-            h1 = [two and (k in c2.entries) for k in keys]
+            # a negative index = no key at this position (slices of ragged bags, oracle.evlfu.expand_bags): code ABSENT
+            keys = [make_key(self.table_base + t, idx[t, s]) if idx[t, s] >= 0 else None for t in range(Tl)]
+            h0 = [k is not None and k in c1.entries for k in keys]
+            h1 = [two and k is not None and (k in c2.entries) for k in keys]
             c3src = {}
             if c3 is not None:
                 for t, k in enumerate(keys):
-                    if not h0[t] and not h1[t]:
+                    if k is not None and not h0[t] and not h1[t]:
                         akey = c3.find(k)
                         if akey is None:
                             continue
@@ -539,6 +541,10 @@ class BatchTiers:
             agg_out[s] = a
             for t, k in enumerate(keys):
                 p = s * Tl + t
+                if k is None:
+                    code[s, t] = ABSENT
+                    src_t[s, t] = -1
+                    continue
                 if h0[t]:
                     code[s, t] = HIT_C1
                     if c1.entries[k] < a:
@@ -578,6 +584,8 @@ def gather_tier_rows(dec_tables, val_tier, src_t, src_r, table_base: int = 0):
     out = np.zeros((B, Tl, d), dtype=np.float32)
     for tier in range(len(dec_tables)):
         for t in np.unique(src_t):
+            if t < 0:
+                continue
             m = (src_t == t) & (val_tier == tier)
             if m.any():
                 out[m] = dec_tables[tier][int(t) - table_base][src_r[m]]

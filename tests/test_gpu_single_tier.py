@@ -254,3 +254,44 @@ def test_fewer_tables_approx_threshold_and_quantised():
     rows = SMALL_ROWS[:6]
     run_single_tier_parity(rows, 16, 32, 300, [96, 7], 30, approx=4, check_state_every=3)
     run_single_tier_parity(SMALL_ROWS[3:7], 36, 8, 60, [130], 12, check_state_every=3)
+
+
+@pytest.mark.parametrize("prec,mapped", [(32, False), (32, True), (8, True)])
+def test_grouped_submission_equals_single_batches(prec, mapped):
+    """evs_lookup_batches: groups of 4 batches as one graph (+ look-ahead of the batches inside a call) deliver what the same
+    batches deliver one call each -- hit maps and rows of EVERY batch, the last batch's eviction stream, the final FIFO
+    state -- against the oracle; `mapped`: backing rows in evs_host_alloc memory (managed, resident on the host)."""
+    import torch
+    from helpers import decoded_tables
+    from oracle.evlfu import BatchEvLFU, gather_rows
+    p = pkg()
+    rows, dim, B = SKEW_ROWS, 16, 96
+    tables = p.workload.make_tables(rows, dim)
+    dec = decoded_tables(tables, prec)
+    total = 3000 * prec // 32
+    cfg = p.CacheConfig(n_layers=1, main_precision=prec, total_size=total, max_batch=B, record_events=True)
+    stores = {prec: [p.to_host_rows(p.codecs.encode_table(t, prec)) for t in tables]} if mapped else None
+    store = p.EvStore(tables, cfg, stores=stores)
+    oracle = BatchEvLFU(total * (32 // prec), n_tables=len(rows))
+    trace = p.workload.ZipfTrace(rows, seed=5)
+    try:
+        for call, n in enumerate([4, 9, 1, 8, 3, 12]):
+            idx = [trace.batch(B) for _ in range(n)]
+            dev = [torch.from_numpy(i).cuda() for i in idx]
+            torch.cuda.synchronize()
+            if call % 2 == 0:
+                store.prefetch(dev[0])                      # the first batch of a call announced by the caller, or not
+            outs, hits = store.lookup_many(dev)
+            torch.cuda.synchronize()
+            store.check()
+            for k in range(n):
+                o_hit, st, sr, _ = oracle.lookup_batch(idx[k])
+                assert (hits[k].cpu().numpy().astype(bool) == o_hit).all(), f"hit map, call {call} batch {k}"
+                assert (outs[k].cpu().numpy() == gather_rows(dec, st, sr)).all(), f"rows, call {call} batch {k}"
+            ev, fl = store.last_events()
+            assert ev.tolist() == oracle.evicted and fl.tolist() == oracle.flushed, f"eviction stream after call {call}"
+            state, n_perfect = store.dump_state()
+            assert state == oracle.state() and n_perfect == oracle.n_perfect, f"FIFO state after call {call}"
+        assert store.stats()["evictions"][0] > 0
+    finally:
+        store.close()

@@ -33,10 +33,10 @@ def main():
     pkg = importlib.import_module("ev-store-dlrm_b200")
     rows = pkg.workload.KAGGLE_ROWS
     B, T = a.batch, len(rows)
-    n_batches = a.warm + 12 + a.steps * a.repeat
+    n_batches = a.warm + 24 + a.steps * a.repeat
     _, tables, idx = bench.build_workload(a, n_batches, rows, a.dim, B)
     pinned = [torch.from_numpy(t).pin_memory() for t in tables]
-    stores = {32: [q.numpy() for q in pinned]}
+    stores_by_mem = {"pinned": {32: [q.numpy() for q in pinned]}}
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -47,6 +47,11 @@ def main():
         env = dict(kv.split("=", 1) for kv in var.split(",") if kv and kv != "default")
         pf = env.pop("PF", "1") == "1"               # pseudo-variables: PF=0 no look-ahead announcements, PTR=1 raw-pointer calls
         ptr = env.pop("PTR", "0") == "1"
+        many = int(env.pop("MANY", "0"))             # MANY=n: evs_lookup_batches over n batches per call
+        mem = env.pop("MEM", "pinned")               # MEM=mapped: backing rows in evs_host_alloc memory (large device pages)
+        if mem not in stores_by_mem:
+            stores_by_mem[mem] = {32: [pkg.to_host_rows(t) for t in tables]}
+        stores = stores_by_mem[mem]
         saved = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:
@@ -70,14 +75,22 @@ def main():
             base = a.warm + 10 + r * a.steps
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ptrs = [idx_dev[base + k].data_ptr() for k in range(a.steps + 1)]
+            ptrs = [idx_dev[base + k].data_ptr() for k in range(a.steps + 8)]
             op, hp, sp, os_ = out.data_ptr(), hit.data_ptr(), stream.cuda_stream, out.stride(0)
             if pf:
                 store.prefetch(idx_dev[base])
             torch.cuda.synchronize()
             e0.record()
             t0 = time.perf_counter()
-            if ptr:
+            if many:
+                import ctypes as C
+                ips = [(C.c_void_p * many)(*ptrs[k:k + many]) for k in range(0, a.steps, many)]
+                ops, hps = (C.c_void_p * many)(*([op] * many)), (C.c_void_p * many)(*([hp] * many))
+                for g, k in enumerate(range(0, a.steps, many)):
+                    store.lookup_many_ptr(many, ips[g], B, ops, os_, hps, sp)
+                    if pf:
+                        store.prefetch_ptr(ptrs[k + many], B)
+            elif ptr:
                 for k in range(a.steps):
                     store.lookup_ptr(ptrs[k], B, op, os_, hp, sp)
                     if pf:
@@ -105,7 +118,8 @@ def main():
         store.set_profiling(False)
         keys = ("avg_serve", "avg_gap1", "avg_update", "avg_gap2", "avg_evict", "evict_plan", "evict_chunks", "evict_wait_last",
                 "evict_writeback", "avg_fetch_since_evict_start", "evict_chunks_per_batch", "evict_last_chunk_avg", "evict_last_chunk_max")
-        print(json.dumps({"variant": var, "us_per_step": 1e3 * best, "host_us_per_step": host_us, "lookups_per_s": B * T / (best * 1e-3),
+        gap = 1e3 * best - sum(ph[k] for k in ("avg_serve", "avg_gap1", "avg_update", "avg_gap2", "avg_evict"))
+        print(json.dumps({"variant": var, "us_per_step": 1e3 * best, "batch_to_batch_gap_us": round(gap, 2), "host_us_per_step": host_us, "lookups_per_s": B * T / (best * 1e-3),
                           "evictions_per_step": st["evictions"][0] / (a.steps * a.repeat),
                           "phases_us": {k: round(ph[k], 3) for k in keys if k in ph}, "kernel_event_us": kt}), flush=True)
         store.close()
