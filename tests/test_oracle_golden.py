@@ -92,3 +92,28 @@ def test_batch_policy_empty_batch():
     p = BatchEvLFU(64, n_tables=4)
     hit, st, sr, agg = p.lookup_batch(np.zeros((4, 0), dtype=np.int64))
     assert hit.shape == (0, 4) and not p.evicted and not p.inserted
+
+
+def test_slices_of_bags_in_the_batch_oracle():
+    """oracle.evlfu.expand_bags / pool_bags and the absent-key handling of BatchEvLFU: with one index per bag the slices ARE
+    the batch (identical streams), absent positions are never probed or inserted, pooling sums in ascending j."""
+    from oracle.evlfu import BatchEvLFU, expand_bags, pool_bags
+    rng = np.random.default_rng(0)
+    rows = [40, 7, 300, 5]
+    a, b = BatchEvLFU(60, n_tables=4), BatchEvLFU(60, n_tables=4)
+    for _ in range(20):
+        idx = np.stack([rng.integers(0, n, size=16) for n in rows])
+        ha = a.lookup_batch(idx)[0]
+        v = expand_bags([idx[t] for t in range(4)], [np.arange(16) for _ in range(4)], 16, 1)
+        hb = b.lookup_batch(v)[0]
+        assert (ha == hb).all() and a.evicted == b.evicted and a.state() == b.state()
+    c = BatchEvLFU(60, n_tables=4)
+    idx_lists = [np.array([1, 2, 3]), np.array([], dtype=np.int64), np.array([5]), np.array([0, 0])]
+    off_lists = [np.array([0, 2]), np.array([0, 0]), np.array([0, 0]), np.array([0, 1])]
+    v = expand_bags(idx_lists, off_lists, 2, 2)
+    assert v.tolist() == [[1, 2, 3, -1], [-1, -1, -1, -1], [-1, -1, 5, -1], [0, -1, 0, -1]]
+    hit, st, sr, agg = c.lookup_batch(v)
+    assert not hit.any() and (st[v.T < 0] == -1).all() and len(c.entries) == 5
+    rows_v = np.arange(4 * 4 * 2, dtype=np.float32).reshape(4, 4, 2)
+    pooled = pool_bags(rows_v, v, 2, 2)
+    assert (pooled[0, 0] == rows_v[0, 0] + rows_v[1, 0]).all() and (pooled[1, 0] == rows_v[2, 0]).all() and (pooled[:, 1] == 0).all()
