@@ -693,7 +693,6 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
     if ((rc = dev_alloc(h->dev_allocs, &P.hist, static_cast<size_t>(kSeqs) * n_chunks_max))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.tot, kSeqs))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.done, 1))) return fail(rc);
-    if ((rc = dev_alloc(h->dev_allocs, &P.probe_done, 1))) return fail(rc);
     if ((rc = dev_alloc(h->dev_allocs, &P.dbg, 32))) return fail(rc);
 
     if ((rc = build_tier(h, h->tier[0], cfg->main_precision, h->caps.c1, cfg->store_main))) return fail(rc);
@@ -1483,8 +1482,7 @@ int evs_shard_create(evs_handle h, int32_t rank, int32_t world, int32_t batch_ma
     s->off_recv = 256;
     s->recv_bytes = (bl * s->t_total * h->cfg.dim * sizeof(float) + 255) & ~static_cast<size_t>(255);
     s->off_parts = s->off_recv + 2 * s->recv_bytes;
-    s->off_pflags = (s->off_parts + 2 * static_cast<size_t>(world) * batch_max + 255) & ~static_cast<size_t>(255);
-    s->off_oflags = s->off_pflags + 256;
+    s->off_oflags = (s->off_parts + 2 * sizeof(unsigned) * static_cast<size_t>(world) * batch_max + 255) & ~static_cast<size_t>(255);
     s->bytes = s->off_oflags + 256;
     void *q = nullptr;
     cudaError_t e = cudaMalloc(&q, s->bytes);
@@ -1599,15 +1597,13 @@ int evs_shard_lookup(evs_shard s, const int64_t *idx_dev, int32_t B, uint8_t *hi
     sh.T_total = s->t_total;
     sh.epoch = epoch;
     sh.fused = s->fused ? 1 : 0;
-    const size_t parts_par = s->off_parts + static_cast<size_t>(par) * s->world * s->batch_max;
+    const size_t parts_par = s->off_parts + sizeof(unsigned) * static_cast<size_t>(par) * s->world * s->batch_max;
     for (int r = 0; r < s->world; ++r) {
         sh.recv[r] = reinterpret_cast<float *>(s->peer[r] + s->off_recv + par * s->recv_bytes);
-        sh.parts[r] = s->peer[r] + parts_par + static_cast<size_t>(s->rank) * B;
-        sh.probe_flag[r] = reinterpret_cast<unsigned *>(s->peer[r] + s->off_pflags) + s->rank;
+        sh.parts[r] = reinterpret_cast<unsigned *>(s->peer[r] + parts_par) + static_cast<size_t>(s->rank) * B;
         sh.out_flag[r] = reinterpret_cast<unsigned *>(s->peer[r] + s->off_oflags) + s->rank;
     }
-    sh.my_parts = s->block + parts_par;
-    sh.my_probe_flags = reinterpret_cast<const unsigned *>(s->block + s->off_pflags);
+    sh.my_parts = reinterpret_cast<const unsigned *>(s->block + parts_par);
     sh.my_out_flags = reinterpret_cast<const unsigned *>(s->block + s->off_oflags);
 
     BatchArgs a{};

@@ -164,7 +164,7 @@ struct evs_shard_s {
     int batch_max = 0;                       // global batch
     int t_total = 0;
     unsigned char *block = nullptr;          // our exchange block (cudaMalloc, exported by CUDA IPC)
-    size_t bytes = 0, off_recv = 0, off_parts = 0, off_pflags = 0, off_oflags = 0, recv_bytes = 0;
+    size_t bytes = 0, off_recv = 0, off_parts = 0, off_oflags = 0, recv_bytes = 0;
     bool fused = true;                       // one-pass exchange inside k_serve (else a separate probe_only pass)
     unsigned char *peer[evs::kMaxPeers] = {};   // peer r's block in our address space (ours at [rank])
     bool opened[evs::kMaxPeers] = {};

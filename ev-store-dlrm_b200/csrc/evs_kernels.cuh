@@ -71,6 +71,7 @@ __device__ __forceinline__ void wait_flags(const unsigned *flags, int world, uns
                     set_error(p, 7u);
                     break;
                 }
+                __nanosleep(64);
             }
         }
         __threadfence();
@@ -459,23 +460,9 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
     const int local_agg = agg;
     const bool fused = SH && a.sh.world > 1 && a.sh.fused != 0 && a.agg_in == nullptr;
     if (SH && a.sh.world > 1 && (a.probe_only || fused)) {
-        // our count of every sample goes into every rank's count table; the last CTA of the batch raises the
-        // ranks' "counts of epoch e complete" words
+        // our count of every sample goes into every rank's count table (ours included), tagged with the batch's epoch
         if (sact)
-            for (int r = q.gl; r < a.sh.world; r += q.L) a.sh.parts[r][s] = static_cast<uint8_t>(local_agg);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            // one system-scope fence per CTA (cumulative over the CTA's stores, which the barrier ordered before it):
-            // the other warps go on to the gather while the counts travel
-            __threadfence_system();
-            const unsigned n_act = static_cast<unsigned>((B + spc - 1) / spc);
-            const bool last = atomicAdd(p.probe_done, 1u) == n_act - 1;
-            if (last) {
-                *p.probe_done = 0u;
-                __threadfence_system();
-                for (int r = 0; r < a.sh.world; ++r) *reinterpret_cast<volatile unsigned *>(a.sh.probe_flag[r]) = a.sh.epoch;
-            }
-        }
+            for (int r = q.gl; r < a.sh.world; r += q.L) a.sh.parts[r][s] = (a.sh.epoch << 5) | static_cast<unsigned>(local_agg);
     }
     if (a.probe_only) {
         if (!(SH && a.sh.world > 1) && q.gl == 0 && sact) a.agg_out[s] = static_cast<uint8_t>(local_agg);
@@ -513,12 +500,26 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
         if (sact) agg = a.agg_in[s];
     } else if (SH && a.sh.world > 1) {
         // exact groupability: agg_hit = sum over the ranks of their local hit counts
-        const unsigned long long tw0 = (blockIdx.x == 0 && threadIdx.x == 0) ? gtime() : 0ull;
-        wait_flags(a.sh.my_probe_flags, a.sh.world, a.sh.epoch, lane, p);
-        if (blockIdx.x == 0 && threadIdx.x == 0) p.dbg[30] += gtime() - tw0;      // CTA 0's wait for the peers' counts
+        // every sample waits for ITS counts only: the peers' warps that serve the same sample run at about the same
+        // time, so the words are usually there once the early gather above is done
+        const unsigned long long tw0 = gtime();
         int v = 0;
         if (sact)
-            for (int r = q.gl; r < a.sh.world; r += q.L) v += static_cast<int>(__ldcg(a.sh.my_parts + static_cast<size_t>(r) * a.B + s));
+            for (int r = q.gl; r < a.sh.world; r += q.L) {
+                const volatile unsigned *e = a.sh.my_parts + static_cast<size_t>(r) * a.B + s;
+                unsigned x = *e;
+                while ((x >> 5) != a.sh.epoch) {
+                    if (gtime() - tw0 > kPeerTimeoutNs) {
+                        set_error(p, 7u);
+                        x = a.sh.epoch << 5;
+                        break;
+                    }
+                    x = *e;
+                }
+                v += static_cast<int>(x & 31u);
+            }
+        __syncwarp();
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.dbg[30] += gtime() - tw0;      // CTA 0, warp 0: its wait for the peers' counts
         agg = grp_sum(v, q.L);
     }
     const bool approx = (P1 == 0) && (p.approx_thres > 0) && (agg >= p.approx_thres) && (m_h0 != 0u);

@@ -136,8 +136,9 @@ constexpr int kMaxPeers = 8;                 // GPUs of one NVSwitch box
 
 // Table-wise sharding over peer memory (evs_shard_*): every rank maps one exchange block of each
 // peer (CUDA IPC).  Pooled rows are stored straight into the batch-sharded buffer of the rank
-// that owns the sample, per-sample hit counts straight into every peer's count table; epochs in
-// flag words tell a peer when a batch's counts / rows are complete.  All pointers below are
+// that owns the sample, per-sample hit counts straight into every peer's count table.  A count is one 32-bit word
+// that carries its batch's epoch, so it is valid the moment it arrives (no flag, no fence: a sample waits only for
+// ITS counts, not for the peers' whole probe phase); an epoch word per peer says when a batch's rows are complete.  All pointers below are
 // addresses in THIS process (peer r's memory for index r, our own for index rank).
 struct ShardArgs {
     int world;                             // 0 = not sharded
@@ -146,11 +147,9 @@ struct ShardArgs {
     int T_total;                           // tables of the whole model
     unsigned epoch;                        // batch number, >= 1
     float *recv[kMaxPeers];                // peer r's receive buffer of this epoch's parity: [Bl][T_total][D]
-    uint8_t *parts[kMaxPeers];             // peer r's count table of this parity, OUR row: [B]
-    unsigned *probe_flag[kMaxPeers];       // peer r's "rank `rank` has written its counts of epoch e" word
+    unsigned *parts[kMaxPeers];            // peer r's count table of this parity, OUR row: [B] words epoch << 5 | hit count
     unsigned *out_flag[kMaxPeers];         // peer r's "rank `rank` has written its rows of epoch e" word
-    const uint8_t *my_parts;               // our count table of this parity: [world][B]
-    const unsigned *my_probe_flags;        // [world]
+    const unsigned *my_parts;              // our count table of this parity: [world][B]; an entry is valid once it carries this epoch
     const unsigned *my_out_flags;          // [world]
     int fused;                             // 1: k_serve sends its counts, gathers, THEN waits for the peers' counts (one pass);
                                            // 0: a probe_only pass sends the counts first (grids too large to be co-resident)
@@ -208,7 +207,6 @@ struct Params {
     unsigned int *tot;                     // [kSeqs] batch totals of the same (k_serve adds, k_evict clears)
     unsigned int stage_stride;             // max row_stride of the tiers (shared-memory staging of unaligned rows)
     unsigned int *done;                    // k_evict: tiers finished (C3 needs both tiers' victims)
-    unsigned int *probe_done;              // sharded probe: CTAs finished (the last one raises the peers' flags)
     unsigned int *miss_list;               // [N] position | tier << 31 of every miss of the batch in flight
     unsigned int *miss_ctl;                // [0] entries in miss_list, [1] fetch CTAs finished
     int evict_ctas;                        // CTAs per tier of the eviction roles of k_evict
