@@ -55,7 +55,7 @@ SYMBOLS = [
     "evs_memory_footprint", "evs_host_alloc", "evs_host_free",
     "evs_lookup_batch_host", "evs_submit_host", "evs_wait_host", "evs_sync", "evs_stats", "evs_last_events", "evs_dump_state", "evs_dump_c3",
     "evs_interact", "evs_embedding_bag", "evs_embedding_bag_status", "evs_store_ptr", "evs_shard_create", "evs_shard_export",
-    "evs_shard_connect", "evs_shard_lookup", "evs_shard_destroy", "evs_set_profiling", "evs_kernel_times", "evs_launch_count", "evs_phase_times", "evs_legacy_configure", "evs_legacy_handle", "ev_lookup", "get_ev_values", "print_perfect_hit",
+    "evs_shard_connect", "evs_shard_lookup", "evs_shard_lookup_many", "evs_shard_destroy", "evs_set_profiling", "evs_kernel_times", "evs_launch_count", "evs_phase_times", "evs_legacy_configure", "evs_legacy_handle", "ev_lookup", "get_ev_values", "print_perfect_hit",
     "test_arr", "ev_lookup_based_on_list_keys",
 ]
 
@@ -130,6 +130,8 @@ def load_library(path: str | None = None):
     lib.evs_shard_connect.restype = C.c_int
     lib.evs_shard_lookup.argtypes = [vp, vp, i32, vp, C.POINTER(vp), vp]
     lib.evs_shard_lookup.restype = C.c_int
+    lib.evs_shard_lookup_many.argtypes = [vp, i32, vp, i32, vp, vp, vp]
+    lib.evs_shard_lookup_many.restype = C.c_int
     lib.evs_shard_destroy.argtypes = [vp]
     lib.evs_shard_destroy.restype = C.c_int
     lib.evs_set_profiling.argtypes = [vp, C.c_int]

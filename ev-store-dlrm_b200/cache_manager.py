@@ -386,6 +386,26 @@ class EvStore:
         shape = (B // self._shard_world, self.cfg.n_tables_total or self.n_tables, self.dim)
         return _tensor_from_ptr(ptr.value, shape, lS_i.device), hit
 
+    def shard_lookup_many(self, lS_i_list, hits=None, stream=None):
+        """Consecutive global batches in one call (evs_shard_lookup_many; groups of 4 batches = one captured graph).  Returns
+        ([this rank's [B/world, n_tables_total, dim] rows per batch], hits); a buffer is valid until four batches later."""
+        import torch
+        n = len(lS_i_list)
+        T, B = lS_i_list[0].shape
+        dev = lS_i_list[0].device
+        assert all(x.is_cuda and x.dtype == torch.int64 and x.is_contiguous() and x.shape == (T, B) for x in lS_i_list) and T == self.n_tables
+        if hits is None:
+            hits = [torch.empty((B, T), dtype=torch.uint8, device=dev) for _ in range(n)]
+        elif torch.is_tensor(hits):
+            hits = [hits] * n
+        ip = (C.c_void_p * n)(*[x.data_ptr() for x in lS_i_list])
+        hp = (C.c_void_p * n)(*[x.data_ptr() for x in hits])
+        op = (C.c_void_p * n)()
+        st = _stream_handle(stream, dev)
+        _native.check(self.lib.evs_shard_lookup_many(self._shard, n, ip, B, hp, op, st), "evs_shard_lookup_many")
+        shape = (B // self._shard_world, self.cfg.n_tables_total or self.n_tables, self.dim)
+        return [_tensor_from_ptr(op[i], shape, dev) for i in range(n)], hits
+
     def shard_destroy(self):
         if getattr(self, "_shard", None):
             self.lib.evs_shard_destroy(self._shard)

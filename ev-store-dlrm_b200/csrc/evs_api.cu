@@ -1481,7 +1481,7 @@ int evs_shard_create(evs_handle h, int32_t rank, int32_t world, int32_t batch_ma
     const size_t bl = static_cast<size_t>(batch_max / world);
     s->off_recv = 256;
     s->recv_bytes = (bl * s->t_total * h->cfg.dim * sizeof(float) + 255) & ~static_cast<size_t>(255);
-    s->off_parts = s->off_recv + 2 * s->recv_bytes;
+    s->off_parts = s->off_recv + evs_shard_s::kRecvBufs * s->recv_bytes;
     s->off_oflags = (s->off_parts + 2 * sizeof(unsigned) * static_cast<size_t>(world) * batch_max + 255) & ~static_cast<size_t>(255);
     s->bytes = s->off_oflags + 256;
     void *q = nullptr;
@@ -1575,21 +1575,8 @@ int evs_shard_connect(evs_shard s, const void *handles) {
     return EVS_OK;
 }
 
-int evs_shard_lookup(evs_shard s, const int64_t *idx_dev, int32_t B, uint8_t *hit_dev, float **out_dev, void *stream) {
-    if (s == nullptr || idx_dev == nullptr || out_dev == nullptr || B < s->world || B > s->batch_max || B % s->world != 0) {
-        set_error("evs_shard_lookup: bad shard / pointers / B (B must be a multiple of world, <= batch_max)");
-        return EVS_ERR_INVALID;
-    }
-    evs_handle h = s->h;
-    for (int r = 0; r < s->world; ++r)
-        if (s->peer[r] == nullptr) {
-            set_error("evs_shard_lookup: evs_shard_connect has not been called");
-            return EVS_ERR_NOT_CONFIGURED;
-        }
-    DeviceGuard dg(h->cfg.device);
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
-    const unsigned epoch = ++s->epoch;
-    const unsigned par = epoch & 1u;
+// The exchange arguments of the batch with number `epoch`: receive buffer epoch % kRecvBufs of every rank, count table epoch % 2.
+static ShardArgs shard_args(evs_shard s, int32_t B, unsigned epoch) {
     ShardArgs sh{};
     sh.world = s->world;
     sh.rank = s->rank;
@@ -1597,21 +1584,47 @@ int evs_shard_lookup(evs_shard s, const int64_t *idx_dev, int32_t B, uint8_t *hi
     sh.T_total = s->t_total;
     sh.epoch = epoch;
     sh.fused = s->fused ? 1 : 0;
+    const unsigned par = epoch & 1u, buf = epoch % evs_shard_s::kRecvBufs;
     const size_t parts_par = s->off_parts + sizeof(unsigned) * static_cast<size_t>(par) * s->world * s->batch_max;
     for (int r = 0; r < s->world; ++r) {
-        sh.recv[r] = reinterpret_cast<float *>(s->peer[r] + s->off_recv + par * s->recv_bytes);
+        sh.recv[r] = reinterpret_cast<float *>(s->peer[r] + s->off_recv + buf * s->recv_bytes);
         sh.parts[r] = reinterpret_cast<unsigned *>(s->peer[r] + parts_par) + static_cast<size_t>(s->rank) * B;
         sh.out_flag[r] = reinterpret_cast<unsigned *>(s->peer[r] + s->off_oflags) + s->rank;
     }
     sh.my_parts = reinterpret_cast<const unsigned *>(s->block + parts_par);
     sh.my_out_flags = reinterpret_cast<const unsigned *>(s->block + s->off_oflags);
+    return sh;
+}
 
+static int shard_check(evs_shard s, const char *what, int32_t B) {
+    if (s == nullptr || B < s->world || B > s->batch_max || B % s->world != 0) {
+        set_error(std::string(what) + ": bad shard / B (B must be a multiple of world, <= batch_max)");
+        return EVS_ERR_INVALID;
+    }
+    for (int r = 0; r < s->world; ++r)
+        if (s->peer[r] == nullptr) {
+            set_error(std::string(what) + ": evs_shard_connect has not been called");
+            return EVS_ERR_NOT_CONFIGURED;
+        }
+    return EVS_OK;
+}
+
+int evs_shard_lookup(evs_shard s, const int64_t *idx_dev, int32_t B, uint8_t *hit_dev, float **out_dev, void *stream) {
+    if (idx_dev == nullptr || out_dev == nullptr) {
+        set_error("evs_shard_lookup: null pointer");
+        return EVS_ERR_INVALID;
+    }
+    int rc = shard_check(s, "evs_shard_lookup", B);
+    if (rc) return rc;
+    evs_handle h = s->h;
+    DeviceGuard dg(h->cfg.device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    const unsigned epoch = ++s->epoch;
     BatchArgs a{};
     a.idx = reinterpret_cast<const long long *>(idx_dev);
     a.B = B;
     a.agg_out = h->d_agg;
-    a.sh = sh;
-    int rc;
+    a.sh = shard_args(s, B, epoch);
     if (!s->fused) {
         a.probe_only = 1;
         if ((rc = run_batch(h, a, st))) return rc;
@@ -1622,7 +1635,56 @@ int evs_shard_lookup(evs_shard s, const int64_t *idx_dev, int32_t B, uint8_t *hi
     a.out_stride = static_cast<long long>(h->cfg.n_tables) * h->cfg.dim;
     rc = run_batch(h, a, st);
     if (rc) return rc;
-    *out_dev = reinterpret_cast<float *>(s->block + s->off_recv + par * s->recv_bytes);
+    *out_dev = reinterpret_cast<float *>(s->block + s->off_recv + (epoch % evs_shard_s::kRecvBufs) * s->recv_bytes);
+    return EVS_OK;
+}
+
+// n consecutive global batches in one call (evs_lookup_batches for a rank of a sharded cache): groups of 4 batches go to
+// the device as one captured graph on every rank.  out_dev[i] receives this rank's buffer of batch i; the receive buffers
+// rotate through kRecvBufs = 4, so a buffer is valid until four batches later.
+int evs_shard_lookup_many(evs_shard s, int32_t n, const int64_t *const *idx_dev, int32_t B, uint8_t *const *hit_dev, float **out_dev,
+                          void *stream) {
+    if (n < 0 || (n > 0 && (idx_dev == nullptr || out_dev == nullptr))) {
+        set_error("evs_shard_lookup_many: bad n / pointers");
+        return EVS_ERR_INVALID;
+    }
+    int rc = shard_check(s, "evs_shard_lookup_many", B);
+    if (rc) return rc;
+    evs_handle h = s->h;
+    DeviceGuard dg(h->cfg.device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    const int G = h->group;
+    const unsigned long long n_max = static_cast<unsigned long long>(h->cfg.max_batch) * h->cfg.n_tables;
+    int i = 0;
+    while (i < n) {
+        bool grouped = s->fused && h->use_graph && !h->prof.on && G > 1 && h->ggraph != nullptr && n - i >= G && h->pf_wait_mode == 0;
+        for (int t = 0; t < h->n_tiers && grouped; ++t) {
+            if (h->tier[t].ub_used + static_cast<unsigned long long>(G + 1) * n_max > h->tier[t].dev.ring_cap) {
+                if ((rc = maintain_rings(h, t, st, G + 1))) return rc;
+                grouped = h->tier[t].ub_used + static_cast<unsigned long long>(G + 1) * n_max <= h->tier[t].dev.ring_cap;
+            }
+        }
+        if (grouped) {
+            BatchArgs a[evs_handle_s::kGroup];
+            for (int k = 0; k < G; ++k) {
+                const unsigned epoch = ++s->epoch;
+                a[k] = BatchArgs{};
+                a[k].idx = reinterpret_cast<const long long *>(idx_dev[i + k]);
+                a[k].B = B;
+                a[k].agg_out = h->d_agg;
+                a[k].sh = shard_args(s, B, epoch);
+                a[k].hit = hit_dev ? hit_dev[i + k] : nullptr;
+                a[k].out_stride = static_cast<long long>(h->cfg.n_tables) * h->cfg.dim;
+                out_dev[i + k] = reinterpret_cast<float *>(s->block + s->off_recv + (epoch % evs_shard_s::kRecvBufs) * s->recv_bytes);
+            }
+            if ((rc = run_group(h, a, G, st))) return rc;
+            i += G;
+        } else {
+            if ((rc = evs_shard_lookup(s, idx_dev[i], B, hit_dev ? hit_dev[i] : nullptr, &out_dev[i], st))) return rc;
+            if (i + 1 < n && (rc = prefetch_next(h, idx_dev[i + 1], B, nullptr))) return rc;
+            i += 1;
+        }
+    }
     return EVS_OK;
 }
 

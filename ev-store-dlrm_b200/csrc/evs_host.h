@@ -161,6 +161,7 @@ struct evs_handle_s {
 struct evs_shard_s {
     evs_handle h = nullptr;
     int rank = 0, world = 1;
+    static constexpr unsigned kRecvBufs = 4; // receive buffers: batch e lands in buffer e % 4 of every rank (a group of 4 batches is one graph)
     int batch_max = 0;                       // global batch
     int t_total = 0;
     unsigned char *block = nullptr;          // our exchange block (cudaMalloc, exported by CUDA IPC)

@@ -135,6 +135,20 @@ class ShardedLookup:
             o += n
         return out, hit
 
+    def lookup_many(self, idx_list, next_idx=None, hits=None):
+        """Consecutive batches in one call: [(ly, hit)] as ``lookup`` on each in turn.  With the fused transport groups of 4
+        batches reach every rank's device as one captured graph (evs_shard_lookup_many) and a returned ``ly`` is valid until
+        four batches later; the other transports run the batches one by one."""
+        if self.transport == "p2p":
+            outs, hits = self.store.shard_lookup_many(idx_list, hits=hits)
+            if next_idx is not None:
+                self.store.prefetch(next_idx)
+            return list(zip(outs, hits))
+        res = []
+        for k, idx in enumerate(idx_list):
+            res.append(self.lookup(idx, next_idx=idx_list[k + 1] if k + 1 < len(idx_list) else next_idx))
+        return res
+
     def alltoall_bytes(self, B: int) -> int:
         """Bytes this rank sends to its peers per batch."""
         return B * self.T_local * self.dim * 4 * (self.world - 1) // self.world

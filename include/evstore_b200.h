@@ -238,12 +238,17 @@ int evs_interact(const float *x_dev, const float *ly_dev, float *r_dev, int32_t 
  *     sample, already in the [B/world][n_tables_total][dim] layout;
  *   - epoch words in peer memory order the two phases (no host synchronisation, no NCCL call).
  * evs_shard_lookup: idx_dev int64 [n_tables][B] for the whole global batch B (a multiple of world); *out_dev receives
- * this rank's [B/world][n_tables_total][dim] fp32 buffer, valid until the call after next (two alternate).  hit_dev as in
+ * this rank's [B/world][n_tables_total][dim] fp32 buffer, valid until four batches later (four alternate).  hit_dev as in
  * evs_lookup_batch.  Every rank must make the same sequence of calls. */
 int evs_shard_create(evs_handle h, int32_t rank, int32_t world, int32_t batch_max, evs_shard *out);
 int evs_shard_export(evs_shard s, void *handle64);
 int evs_shard_connect(evs_shard s, const void *handles /* world x 64 bytes, rank order */);
 int evs_shard_lookup(evs_shard s, const int64_t *idx_dev, int32_t B, uint8_t *hit_dev, float **out_dev, void *stream);
+/* n consecutive global batches in one call: what n evs_shard_lookup calls deliver, but groups of 4 batches reach the device
+ * as one captured graph on every rank (every rank must make the same calls).  out_dev[i] receives this rank's buffer of
+ * batch i; the buffers rotate through 4, so each stays valid until four batches later. */
+int evs_shard_lookup_many(evs_shard s, int32_t n, const int64_t *const *idx_dev, int32_t B, uint8_t *const *hit_dev,
+                          float **out_dev, void *stream);
 int evs_shard_destroy(evs_shard s);
 
 /* ---- sum pooling: nn.EmbeddingBag(mode="sum") of apply_emb_ori_dlrm ------------------- *

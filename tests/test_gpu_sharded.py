@@ -87,7 +87,17 @@ def _worker(rank, world, port, q, backend, transport, same_device, case, kind, p
         torch.cuda.synchronize()
         if prefetch:
             store.prefetch(dev[0])
-        for k in range(len(dev)):
+        if env.get("EVS_TEST_MANY"):
+            # grouped submission: calls of 4 batches (one captured graph on every rank), then the rest; a receive buffer
+            # is valid until four batches later, so each call's results are read before the next call
+            k = 0
+            while k < len(dev):
+                n = min(4, len(dev) - k)
+                for ly, hit in sh.lookup_many(dev[k:k + n], next_idx=dev[k + n] if (prefetch and k + n < len(dev)) else None):
+                    torch.cuda.synchronize()
+                    res.append((ly.cpu().numpy().copy(), hit.cpu().numpy().copy()))
+                k += n
+        for k in range(len(res), len(dev)):
             ly, hit = sh.lookup(dev[k], next_idx=dev[k + 1] if (prefetch and k + 1 < len(dev)) else None)
             torch.cuda.synchronize()
             res.append((ly.cpu().numpy().copy(), hit.cpu().numpy().copy()))
@@ -167,6 +177,18 @@ def test_sharded_lookup_p2p_two_gpus(kind, prefetch):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     assert _run_sharded(2, "nccl", "p2p", False, "skew", kind=kind, prefetch=prefetch) > 0
+
+
+def test_sharded_grouped_submission_two_processes_on_one_gpu():
+    """evs_shard_lookup_many: groups of 4 global batches as one graph per rank, four rotating receive buffers."""
+    assert _run_sharded(2, "gloo", "p2p", True, "small", kind="balanced", prefetch=True, env={"EVS_TEST_MANY": "1"}) > 0
+
+
+def test_sharded_grouped_submission_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    assert _run_sharded(2, "nccl", "p2p", False, "skew", kind="balanced", prefetch=True, env={"EVS_TEST_MANY": "1"}) > 0
 
 
 def test_shard_connect_refuses_a_peer_built_for_another_layout():
