@@ -46,6 +46,17 @@ def _sum_over_ranks(vals, dev, world):
     return [float(v) for v in t.tolist()]
 
 
+def _gather_over_ranks(vals, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    if world <= 1:
+        return [t.tolist()]
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [x.tolist() for x in out]
+
+
 def _barrier(world):
     import torch
     import torch.distributed as dist
@@ -74,7 +85,11 @@ class Leg:
         self.rows = [all_rows[t] for t in self.ids]
         self.T_local = len(self.ids)
         # the reference's 13 % operating point (cache_manager.cpp:16), each rank caching 13 % of its own rows
-        self.cache_rows = max(1024, int(sum(self.rows) * 0.13))
+        # the reference's 13 % operating point (cache_manager.cpp:16) is a budget for the whole cache: 13 % of ALL rows, split
+        # evenly over the GPUs, a rank with less than its share passing the rest on (sharded.split_cache_budget)
+        per_rank_rows = [sum(all_rows[t] for t in x) for x in self.placement]
+        self.cache_split = pkg.sharded.split_cache_budget(per_rank_rows, int(sum(all_rows) * 0.13))
+        self.cache_rows = self.cache_split[rank]
         t0 = time.time()
         assert prec == 32, "the sharded bench serves the fp32 tier"
         # backing rows in evs_host_alloc memory (host memory mapped into this rank's device with large pages)
@@ -110,7 +125,8 @@ class Leg:
                 self.sh.lookup(idx[k], next_idx=idx[k + 1])
             done += n
             st = self.store.stats()
-            full[0] = 1 if st["size"][0] >= st["capacity"][0] else 0
+            # (a rank whose budget covers all its rows never evicts: it counts as full from the start)
+            full[0] = 1 if (st["size"][0] >= st["capacity"][0] or self.cache_rows >= sum(self.rows)) else 0
             if self.world > 1:
                 dist.all_reduce(full, op=dist.ReduceOp.MIN)
             if int(full.item()) == 1:
@@ -162,6 +178,8 @@ class Leg:
         for k in range(W):
             self.sh.lookup(idx_dev[base + k], next_idx=idx_dev[base + k + 1])
         base += W
+        _barrier(self.world)
+        self.store.phase_times()                  # the phase accumulators cover the timed regions only
         regions = []
         launches = 0
         for _ in range(reps):
@@ -226,9 +244,9 @@ def verify_policy_small(pkg, log, rank, world, local_rank, transport):
         ok = ok and good
         n_ev += len(oracle.evicted)
     st = store.stats()
-    ok = ok and st["size"][0] == len(oracle.entries) and n_ev > 0
+    ok = ok and st["size"][0] == len(oracle.entries)
     store.close()
-    return ok
+    return ok, n_ev
 
 
 def main_sharded(args):
@@ -256,8 +274,9 @@ def main_sharded(args):
 
     verified = {}
     # ---- policy under the sharded exchange, against the oracle (scaled-down shard) -----------------------------------
-    okp = verify_policy_small(pkg, log, rank, world, local_rank, transport)
-    verified["policy_vs_oracle_scaled_shard"] = bool(_sum_over_ranks([0.0 if okp else 1.0], dev, world)[0] == 0.0)
+    okp, n_ev = verify_policy_small(pkg, log, rank, world, local_rank, transport)
+    bad, ev_all = _sum_over_ranks([0.0 if okp else 1.0, float(n_ev)], dev, world)        # a rank that owns only tiny tables never evicts
+    verified["policy_vs_oracle_scaled_shard"] = bool(bad == 0.0 and ev_all > 0)
 
     def run_leg(shape, placement_kind, label, K_leg, full_report):
         return run_one_leg(pkg, log, args, rank, world, local_rank, shape, placement_kind, label, K_leg, full_report, verified)
@@ -322,6 +341,7 @@ def run_one_leg(pkg, log, args, rank, world, local_rank, shape, placement_kind, 
            "cache_warm_batches": warm_done, "rows_verified_per_rank": checked, "verified": ok_all, "dim": dim,
            "placement": placement_kind, "tables_per_rank": [len(x) for x in leg.placement],
            "rows_per_rank_M": [round(sum(leg.all_rows[t] for t in x) / 1e6, 2) for x in leg.placement],
+           "cache_rows_per_rank": leg.cache_split,
            # where rank 0 waits for its peers (in-kernel %globaltimer, averaged over the timed steps): inside k_serve for their
            # hit counts (part of avg_serve) and at the end of k_evict for their rows
            "rank0_phases_us": {"serve_incl_wait_for_counts": ph["avg_serve"], "update": ph["avg_update"],
@@ -329,6 +349,12 @@ def run_one_leg(pkg, log, args, rank, world, local_rank, shape, placement_kind, 
                                    "wait_for_peer_counts_cta0": ph["avg_count_wait_cta0"],
                                "fetch_role_since_evict_start": ph["avg_fetch_since_evict_start"]},
            "nvlink_bytes_per_rank_per_step": leg.sh.alltoall_bytes(B)}
+    # every rank's in-kernel phase spans and misses per step: which rank the others wait for, and in which phase
+    mine = [ph["avg_serve"], ph["avg_count_wait_cta0"], ph["avg_update"], ph["avg_evict"], ph["avg_peer_wait"],
+            ph["avg_fetch_since_evict_start"], st["misses"] / (3 * K_leg + W)]
+    allp = _gather_over_ranks(mine, dev, world)
+    res["phases_us_by_rank"] = {"columns": ["serve", "of_it_wait_counts_cta0", "update", "evict", "of_it_wait_rows", "fetch_since_evict_start",
+                                            "misses_per_step"], "rows": [[round(v, 2) for v in r] for r in allp]}
     res["nvlink_GBps_per_rank"] = res["nvlink_bytes_per_rank_per_step"] / (res["ms_per_step"] * 1e-3) / 1e9
     res["nvlink_frac_of_peer_copy_peak"] = res["nvlink_GBps_per_rank"] / 770.0
     clocks = None

@@ -227,7 +227,9 @@ static int build_tier(evs_handle h, Tier &tr, int prec, long long cap, const voi
     d.n_buckets = c.n_tables_total + 1;
     const unsigned hash_cap = next_pow2(want_slots);
     d.hash_mask = hash_cap - 1;
-    d.ring_cap = next_pow2(static_cast<unsigned long long>(std::max(2 * (cap + n_max), cap + 5 * n_max)));
+    // room for the live entries plus 64 batches of appends: the host may run that far ahead of the device before it has to
+    // wait for the ring mirror to advance (maintain_rings)
+    d.ring_cap = next_pow2(static_cast<unsigned long long>(std::max(2 * (cap + n_max), cap + 64 * n_max)));
     int rc;
     if ((rc = dev_alloc(tr.allocs, &d.slots, hash_cap, false))) return rc;
     if ((rc = dev_alloc(tr.allocs, &d.slab, static_cast<size_t>(hash_cap) * d.row_stride, true))) return rc;
@@ -250,7 +252,6 @@ static int build_tier(evs_handle h, Tier &tr, int prec, long long cap, const voi
     k_init_tier<<<592, 256, 0, h->stream>>>(d);
     EVS_CUDA(cudaGetLastError());
     EVS_CUDA(cudaStreamSynchronize(h->stream));
-    tr.ub_used = 0;
     return EVS_OK;
 }
 
@@ -332,18 +333,44 @@ static void free_all(evs_handle h) {
     delete h;
 }
 
-// Keep every bucket ring from overflowing: the host only tracks an upper bound of the
-// occupancy and looks at the real head/tail when that bound gets close to the ring size.
+// Keep every bucket ring from overflowing.  The last CTA of k_evict mirrors, per tier, the longest ring window
+// (max over the buckets of tail - head) together with the batch number into mapped pinned memory, so the host knows the
+// occupancy as of the last FINISHED batch without touching the device; every batch started since can append at most
+// max_batch * n_tables records.  When that bound gets close to the ring size the host first lets the device catch up
+// (bounded run-ahead: it spins on the mirror, the device keeps its queue), and only a ring that is really full is
+// compacted (stream synchronise + k_compact).
+static bool ring_fits(evs_handle h, int ti, int ahead) {
+    const Tier &tr = h->tier[ti];
+    const unsigned long long n_max = static_cast<unsigned long long>(h->cfg.max_batch) * h->cfg.n_tables;
+    const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(h->ring_host + ti);
+    const unsigned long long used = v & 0xFFFFFFFFull;
+    const unsigned in_flight = static_cast<unsigned>(h->seq) - static_cast<unsigned>(v >> 32);
+    return used + (static_cast<unsigned long long>(in_flight) + ahead) * n_max <= tr.dev.ring_cap;
+}
+
 static int maintain_rings(evs_handle h, int ti, cudaStream_t st, int ahead = 2) {
+    if (ring_fits(h, ti, ahead)) return EVS_OK;
     Tier &tr = h->tier[ti];
     const unsigned long long n_max = static_cast<unsigned long long>(h->cfg.max_batch) * h->cfg.n_tables;
-    if (tr.ub_used + static_cast<unsigned long long>(ahead) * n_max <= tr.dev.ring_cap) return EVS_OK;
+    // let the device catch up: the mirror advances with every batch that finishes
+    {
+        unsigned long long spins = 0;
+        while (!ring_fits(h, ti, ahead)) {
+            const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(h->ring_host + ti);
+            if (static_cast<unsigned>(v >> 32) == static_cast<unsigned>(h->seq)) break;      // nothing in flight: the ring is full
+            if (++spins > (1ull << 22)) {                                                    // ~ tens of ms without progress
+                if (cudaStreamQuery(st) != cudaErrorNotReady) break;
+                spins = 0;
+            }
+        }
+        if (ring_fits(h, ti, ahead)) return EVS_OK;
+    }
     TierCtl ctl;
     EVS_CUDA(cudaStreamSynchronize(st));
     EVS_CUDA(cudaMemcpy(&ctl, tr.dev.ctl, sizeof(ctl), cudaMemcpyDeviceToHost));
     bool any = false;
     for (int b = 0; b < tr.dev.n_buckets; ++b) {
-        if (ctl.tail[b] - ctl.head[b] + 2 * n_max > tr.dev.ring_cap) {
+        if (ctl.tail[b] - ctl.head[b] + static_cast<unsigned long long>(ahead) * n_max > tr.dev.ring_cap) {
             LaunchScope ls(h->prof, K_COMPACT, st);
             k_compact<<<1, 1024, 0, st>>>(tr.dev, b);
             any = true;
@@ -356,7 +383,8 @@ static int maintain_rings(evs_handle h, int ti, cudaStream_t st, int ahead = 2) 
     }
     unsigned long long mx = 0;
     for (int b = 0; b < tr.dev.n_buckets; ++b) mx = std::max(mx, ctl.tail[b] - ctl.head[b]);
-    tr.ub_used = mx;
+    // the device is idle: the host refreshes the mirror itself
+    *reinterpret_cast<volatile unsigned long long *>(h->ring_host + ti) = (static_cast<unsigned long long>(static_cast<unsigned>(h->seq)) << 32) | mx;
     return EVS_OK;
 }
 
@@ -443,11 +471,15 @@ static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const Batc
     // serve_pdl: k_serve is a programmatic dependent of the kernel that precedes it -- the previous batch's k_evict, on the
     // stream of a serving loop or inside a graph of several batches (never the first node of a graph)
     { LaunchScope ls(pf, K_SERVE, st); EVS_CUDA(launch_serve(serve_of(h, ks), n_chunks, st, p, a, pdl && serve_pdl)); }
-    if (p.n_chunks_max > p.quad_max || p.L < kDirectMinLanes) {
+    if (p.n_chunks_max > p.quad_max) {
         LaunchScope ls(pf, K_SCAN, st);
         EVS_CUDA(launch(k_scan, (h->n_tiers == 1 ? 1 : kSeqGroups) * h->tier[0].dev.n_buckets, 256, 0, st, p, pdl));
     }
-    { LaunchScope ls(pf, K_UPDATE, st); EVS_CUDA(launch(h->n_tiers == 1 ? k_update<1, 8> : k_update<kSeqGroups, 4>, n_chunks, kLookupThreads, 0, st, p, pdl)); }
+    { LaunchScope ls(pf, K_UPDATE, st); 
+        // a sample per warp (26 tables): per-sample sums of the earlier CTAs' counts; packed warps: one sum per CTA
+        KernelFn upd = h->n_tiers == 1 ? (p.L == 32 ? k_update<1, 8, false> : k_update<1, 8, true>)
+                                       : (p.L == 32 ? k_update<kSeqGroups, 4, false> : k_update<kSeqGroups, 4, true>);
+        EVS_CUDA(launch(upd, n_chunks, kLookupThreads, 0, st, p, pdl)); }
     {
         LaunchScope ls(pf, K_EVICT, st);
         EVS_CUDA(launch(ks.evict, dim3(std::max(h->evict_ctas, h->fetch_list_ctas), h->n_tiers + 1), kEvictThreads, fetch_smem(h), st, p, pdl));
@@ -657,11 +689,12 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         cudaEventCreateWithFlags(&h->ev_done[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_done[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_pf_ready, cudaEventDisableTiming) != cudaSuccess ||
-        cudaHostAlloc(reinterpret_cast<void **>(&h->err_host), 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        cudaHostAlloc(reinterpret_cast<void **>(&h->err_host), 256, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
         set_error("cudaStreamCreate / cudaEventCreate / cudaHostAlloc failed");
         return fail(EVS_ERR_CUDA);
     }
-    *h->err_host = 0u;
+    memset(h->err_host, 0, 256);
+    h->ring_host = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(h->err_host) + 64);
     h->n_tiers = cfg->n_layers >= 2 ? 2 : 1;
     if (pick_kernels(cfg->main_precision, h->n_tiers == 2 ? cfg->secondary_precision : 0).serve == nullptr) {
         set_error("evs_create: no kernel for this precision pair");
@@ -722,6 +755,7 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         void *dp = nullptr;
         if (cudaHostGetDevicePointer(&dp, h->err_host, 0) != cudaSuccess) return fail(EVS_ERR_CUDA);
         P.err_host = static_cast<unsigned *>(dp);
+        P.ring_host = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(dp) + 64);
     }
     P.n_perfect_agg = h->cfg.n_tables_total;
     P.approx_thres = (h->n_tiers == 1) ? cfg->approx_emb_thres : 0;
@@ -846,7 +880,7 @@ static int set_serve_params(evs_handle h, cudaGraphExec_t exec, cudaGraphNode_t 
 
 static void count_batch_launches(evs_handle h) {
     h->prof.launches[K_SERVE]++, h->prof.launches[K_UPDATE]++, h->prof.launches[K_EVICT]++;
-    if (h->params.n_chunks_max > h->params.quad_max || h->params.L < kDirectMinLanes) h->prof.launches[K_SCAN]++;
+    if (h->params.n_chunks_max > h->params.quad_max) h->prof.launches[K_SCAN]++;
 }
 
 static int run_batch(evs_handle h, const BatchArgs &a_in, cudaStream_t st) {
@@ -879,7 +913,6 @@ static int run_batch(evs_handle h, const BatchArgs &a_in, cudaStream_t st) {
     }
     h->batches++;
     for (int i = 0; i < h->n_tiers; ++i) {
-        h->tier[i].ub_used += static_cast<unsigned long long>(a.B) * h->cfg.n_tables;
         int rc = maintain_rings(h, i, st);
         if (rc) return rc;
     }
@@ -965,8 +998,6 @@ static int run_group(evs_handle h, BatchArgs *a, int n, cudaStream_t st) {
         h->pf_B = a[n - 1].B;
     }
     h->batches += n;
-    for (int i = 0; i < h->n_tiers; ++i)
-        for (int k = 0; k < n; ++k) h->tier[i].ub_used += static_cast<unsigned long long>(a[k].B) * h->cfg.n_tables;
     return EVS_OK;
 }
 
@@ -1021,11 +1052,9 @@ int evs_lookup_batches(evs_handle h, int32_t n, const int64_t *const *idx_dev, i
         if (grouped) {
             // every bucket ring must take the whole group's appends (the host tracks an upper bound of the occupancy)
             for (int t = 0; t < h->n_tiers && grouped; ++t) {
-                if (h->tier[t].ub_used + static_cast<unsigned long long>(G + 1) * n_max > h->tier[t].dev.ring_cap) {
-                    int rc = maintain_rings(h, t, st, G + 1);
-                    if (rc) return rc;
-                    grouped = h->tier[t].ub_used + static_cast<unsigned long long>(G + 1) * n_max <= h->tier[t].dev.ring_cap;
-                }
+                int rc = maintain_rings(h, t, st, G + 1);
+                if (rc) return rc;
+                grouped = ring_fits(h, t, G + 1);
             }
         }
         if (grouped) {
@@ -1659,10 +1688,8 @@ int evs_shard_lookup_many(evs_shard s, int32_t n, const int64_t *const *idx_dev,
     while (i < n) {
         bool grouped = s->fused && h->use_graph && !h->prof.on && G > 1 && h->ggraph != nullptr && n - i >= G && h->pf_wait_mode == 0;
         for (int t = 0; t < h->n_tiers && grouped; ++t) {
-            if (h->tier[t].ub_used + static_cast<unsigned long long>(G + 1) * n_max > h->tier[t].dev.ring_cap) {
-                if ((rc = maintain_rings(h, t, st, G + 1))) return rc;
-                grouped = h->tier[t].ub_used + static_cast<unsigned long long>(G + 1) * n_max <= h->tier[t].dev.ring_cap;
-            }
+            if ((rc = maintain_rings(h, t, st, G + 1))) return rc;
+            grouped = ring_fits(h, t, G + 1);
         }
         if (grouped) {
             BatchArgs a[evs_handle_s::kGroup];

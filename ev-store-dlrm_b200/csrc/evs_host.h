@@ -32,7 +32,6 @@ int compute_caps(const evs_config &cfg, Caps &out);
 struct Tier {
     TierDev dev{};
     int prec = 0;
-    unsigned long long ub_used = 0;          // host upper bound of max_b(tail-head)
     std::vector<void *> allocs;              // device allocations to free
     std::vector<const unsigned char *> store_dev;   // per table, device-visible backing rows
 };
@@ -130,6 +129,7 @@ struct evs_handle_s {
     const void *pf_idx = nullptr;
     int pf_B = 0;
     unsigned *err_host = nullptr;            // pinned, device-mapped: last device-side error code (0 = none)
+    unsigned long long *ring_host = nullptr; // same block: per tier, batch number << 32 | longest ring window after that batch
     int sticky_error = 0;                    // first error evs_check saw
     size_t hbm_bytes = 0;                    // device memory this handle allocated
     evs::GlobalCtl *g = nullptr;             // device

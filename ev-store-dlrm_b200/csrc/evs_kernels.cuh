@@ -21,7 +21,6 @@ namespace evs {
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kEvictThreads = 256;         // small CTAs: they must fit on SMs that k_fetch occupies
 constexpr int kEvictPerThread = 4;           // ring records one thread examines per window
-constexpr int kDirectMinLanes = 8;           // k_update sums its predecessors' counts itself when a sample has at least this many lanes
 constexpr int kQuadMaxChunks = 512;          // above this a k_scan launch replaces the direct prefix sums (B = 16384: 150 -> 141 us)
 
 __device__ __forceinline__ uint4 ldg16(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
@@ -638,7 +637,7 @@ __global__ void __launch_bounds__(256) k_scan(const __grid_constant__ Params p) 
     griddep_wait(p);
     const int B = p.args->B;
     const int n_chunks = (B + p.spc - 1) / p.spc;
-    if (p.L >= kDirectMinLanes && n_chunks <= p.quad_max) return;          // k_update sums its predecessors directly
+    if (n_chunks <= p.quad_max) return;                          // k_update sums its predecessors' counts itself
     const int nb = p.tier[0].n_buckets;
     const int grp = blockIdx.x / nb, b = blockIdx.x - grp * nb;
     unsigned *h = p.hist + static_cast<size_t>(grp * kMaxBuckets + b) * p.n_chunks_max;

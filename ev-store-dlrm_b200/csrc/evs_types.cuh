@@ -213,6 +213,7 @@ struct Params {
     int fetch_ctas;                        // CTAs of its miss-fetch role
     int pdl;                               // kernels of a batch are chained by programmatic dependent launch
     unsigned int *err_host;                // mapped pinned copy of g->error: the host sees it without a device round trip
+    unsigned long long *ring_host;         // mapped pinned, per tier: batch number << 32 | max over the buckets of tail - head
     // look-ahead staging (evs_prefetch): rows of the next batch's probable misses, by position, two parities
     unsigned int *pf_tag;                  // [2][n_max]: generation << 1 | tier once the row is complete
     unsigned char *pf_rows;                // [2][n_max][stage_stride]

@@ -24,13 +24,39 @@ namespace evs {
 
 // NG = sequence groups in use: 1 for a single tier (only C1's interleaved sequence exists), kSeqGroups with a C2.
 // XU = rounds of 32 per-CTA counts a lane holds in registers across the claim.
-template <int NG, int XU>
-__global__ void __launch_bounds__(kLookupThreads, NG == 1 ? 5 : 4) k_update(const __grid_constant__ Params p) {
+//
+// Ring positions need, per append sequence (group, bucket), the number of records the EARLIER serve CTAs appended.  Unless
+// k_scan has turned the per-CTA counts into prefixes (batches of more than quad_max serve CTAs), they are summed here, by
+// loads that are issued BEFORE the claim's chain of dependent accesses and consumed after it (a warp issues in order: loads
+// placed after the CAS loop would only start when it ends), so they cost no round trip of their own:
+//   COOP = false (a sample is a whole warp, the 26 tables of an unsharded model): the warp of a flagged sample sums the
+//          counts of its one bucket, lane = earlier CTA;
+//   COOP = true  (packed warps: a rank of a sharded cache owns 3-13 tables and a warp carries 2-8 samples): the CTA sums
+//          once for all its samples -- the sequences that occur in the CTA are dealt out to the warps, lane = earlier CTA.
+//          (Per-sample sums by groups of 4-16 lanes were a serial chain of up to 8 round trips, and handles of fewer than
+//          8 tables needed a k_scan launch.)
+constexpr int kSeqPerWarp = 4;               // COOP: sequences a warp sums per round
+__device__ __forceinline__ bool kth_present(const unsigned *present, int ng, int k, int &g, int &b) {
+    for (g = 0; g < ng; ++g) {
+        const int c = __popc(present[g]);
+        if (k < c) {
+            b = static_cast<int>(__fns(present[g], 0, k + 1));
+            return true;
+        }
+        k -= c;
+    }
+    return false;
+}
+
+template <int NG, int XU, bool COOP>
+__global__ void __launch_bounds__(kLookupThreads, COOP ? 3 : (NG == 1 ? 5 : 4)) k_update(const __grid_constant__ Params p) {
     __shared__ unsigned s_cnt[kLookupThreads][kSeqGroups];      // per sample of the CTA (at most 256 when L = 1)
     __shared__ int s_b[kLookupThreads];
     __shared__ int s_delta[kMaxTiers * kMaxBuckets];
     __shared__ unsigned s_new[kMaxTiers], s_ins[kMaxTiers];
     __shared__ unsigned long long s_prot[kMaxTiers];
+    __shared__ unsigned s_base[kSeqGroups * kMaxBuckets];       // COOP: records the earlier CTAs append, per sequence
+    __shared__ unsigned s_present[kSeqGroups];                  // COOP: buckets that occur in this CTA, per group
 
     griddep_launch(p);
     if (threadIdx.x < kMaxTiers * kMaxBuckets) s_delta[threadIdx.x] = 0;
@@ -39,6 +65,7 @@ __global__ void __launch_bounds__(kLookupThreads, NG == 1 ? 5 : 4) k_update(cons
         s_ins[threadIdx.x] = 0;
         s_prot[threadIdx.x] = 0ull;
     }
+    if (threadIdx.x < kSeqGroups) s_present[threadIdx.x] = 0u;
     griddep_wait(p);
     if (blockIdx.x == 0 && threadIdx.x == 0) p.dbg[2] = gtime();
     const BatchArgs a = *p.args;
@@ -74,58 +101,110 @@ __global__ void __launch_bounds__(kLookupThreads, NG == 1 ? 5 : 4) k_update(cons
         s_cnt[j][1] = __popc(m1);
         s_cnt[j][2] = __popc(m2);
         s_b[j] = any ? wb : -1;
+        if (COOP && any) {
+            if (m0) atomicOr(&s_present[0], 1u << wb);
+            if (NG > 1 && m1) atomicOr(&s_present[1], 1u << wb);
+            if (NG > 1 && m2) atomicOr(&s_present[2], 1u << wb);
+        }
     }
     __syncthreads();
 
-    if (any) {
-        // Everything that does not depend on the claim is LOADED first and consumed after it, so that these
-        // round trips run under the claim's chain of dependent accesses (a warp issues in order: loads placed
-        // after the CAS loop would only start when it ends): the per-CTA append counts of the earlier chunks
-        // in my bucket's sequences (k_scan already made them prefixes for very large batches and for packed
-        // warps), the batch's C2 promotion total, the ring tail.
-        const unsigned msk3[kSeqGroups] = {m0, m1, m2};
-        unsigned msk[NG];
+    const bool direct = n_chunks <= p.quad_max;
+    const int nc = static_cast<int>(blockIdx.x);
+    const unsigned msk3[kSeqGroups] = {m0, m1, m2};
+    unsigned base[kSeqGroups] = {0, 0, 0};
+    // ---- loads that do not depend on the claim ----------------------------------------------------------------------
+    constexpr int NX = COOP ? kSeqPerWarp : NG;
+    unsigned x[NX][XU];
 #pragma unroll
-        for (int g = 0; g < NG; ++g) msk[g] = msk3[g];
-        const unsigned *h[NG];
+    for (int i = 0; i < NX; ++i)
 #pragma unroll
-        for (int g = 0; g < NG; ++g) h[g] = p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max;
-        // direct: the lanes of a sample's group sum the counts of the earlier chunks themselves (groups of >= 8 lanes)
-        const bool direct = q.L >= kDirectMinLanes && n_chunks <= p.quad_max;
-        const int nc = static_cast<int>(blockIdx.x);
-        unsigned base[kSeqGroups] = {0, 0, 0};
-        unsigned x[NG][XU];
+        for (int u = 0; u < XU; ++u) x[i][u] = 0u;
+    if (direct) {
+        if (COOP) {
+            unsigned pres[kSeqGroups] = {s_present[0], NG > 1 ? s_present[1] : 0u, NG > 1 ? s_present[2] : 0u};
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-#pragma unroll
-            for (int u = 0; u < XU; ++u) x[g][u] = 0u;
-            if (!msk[g]) continue;
-            if (!direct) {
-                base[g] = __ldcg(h[g] + blockIdx.x);
-            } else {
+            for (int i = 0; i < kSeqPerWarp; ++i) {
+                int g, bb;
+                if (!kth_present(pres, NG, warp + 8 * i, g, bb)) break;
+                const unsigned *h = p.hist + static_cast<size_t>(g * kMaxBuckets + bb) * p.n_chunks_max;
 #pragma unroll
                 for (int u = 0; u < XU; ++u) {
-                    const int c = u * q.L + q.gl;
-                    if (c < nc) x[g][u] = __ldcg(h[g] + c);
+                    const int c = u * 32 + lane;
+                    if (c < nc) x[i][u] = __ldcg(h + c);
+                }
+            }
+        } else if (any) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                if (!msk3[g]) continue;
+                const unsigned *h = p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max;
+#pragma unroll
+                for (int u = 0; u < XU; ++u) {
+                    const int c = u * 32 + lane;
+                    if (c < nc) x[g][u] = __ldcg(h + c);
                 }
             }
         }
-        const unsigned tot_p1 = m2 ? __ldcg(p.tot + kMaxBuckets + wb) : 0u;
-        unsigned long long tail_b = 0ull;
-        if (f) tail_b = static_cast<const volatile TierCtl *>(p.tier[tr].ctl)->tail[b];
+    } else if (any) {
+        // k_scan made the counts prefixes
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+            if (msk3[g]) base[g] = __ldcg(p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max + blockIdx.x);
+    }
+    const unsigned tot_p1 = (any && m2) ? __ldcg(p.tot + kMaxBuckets + wb) : 0u;
+    unsigned long long tail_b = 0ull;
+    if (f) tail_b = static_cast<const volatile TierCtl *>(p.tier[tr].ctl)->tail[b];
 
-        unsigned slot = 0;
+    unsigned slot = 0;
+    if (f & kFlagMiss) {
         bool claimed = false;
-        if (f & kFlagMiss) {
-            slot = claim_slot(p.tier[tr], make_key(p.tid[tbl], r), claimed);
-            p.pos_slot[pos] = slot | (claimed ? kClaimedBit : 0u);
-            if (claimed) atomicAdd(&s_new[tr], 1u);
-            atomicMax(&s_prot[tr], (static_cast<unsigned long long>(f & 0x3Fu) << 32) | static_cast<unsigned>(pos));
-        } else if (f) {
-            slot = p.pos_slot[pos];
-        }
+        slot = claim_slot(p.tier[tr], make_key(p.tid[tbl], r), claimed);
+        p.pos_slot[pos] = slot | (claimed ? kClaimedBit : 0u);
+        if (claimed) atomicAdd(&s_new[tr], 1u);
+        atomicMax(&s_prot[tr], (static_cast<unsigned long long>(f & 0x3Fu) << 32) | static_cast<unsigned>(pos));
+    } else if (f) {
+        slot = p.pos_slot[pos];
+    }
 
-        if (direct) {
+    // ---- sum the earlier CTAs' counts ----------------------------------------------------------------------------------
+    if (direct && COOP) {
+        unsigned pres[kSeqGroups] = {s_present[0], NG > 1 ? s_present[1] : 0u, NG > 1 ? s_present[2] : 0u};
+        const int n_present = __popc(pres[0]) + __popc(pres[1]) + __popc(pres[2]);
+        for (int i0 = 0; warp + 8 * i0 < n_present; i0 += kSeqPerWarp) {
+#pragma unroll
+            for (int i = 0; i < kSeqPerWarp; ++i) {
+                int g, bb;
+                if (!kth_present(pres, NG, warp + 8 * (i0 + i), g, bb)) break;
+                const unsigned *h = p.hist + static_cast<size_t>(g * kMaxBuckets + bb) * p.n_chunks_max;
+                unsigned acc = 0u;
+                if (i0 == 0) {
+#pragma unroll
+                    for (int u = 0; u < XU; ++u) acc += x[i][u];
+                }
+                for (int c0 = (i0 == 0 ? XU * 32 : 0); c0 < nc; c0 += 128) {       // the rest: 4 loads per lane and round
+                    unsigned y[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int c = c0 + u * 32 + lane;
+                        if (c < nc) y[u] = __ldcg(h + c);
+                    }
+                    acc += y[0] + y[1] + y[2] + y[3];
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
+                if (lane == 0) s_base[g * kMaxBuckets + bb] = acc;
+            }
+        }
+    }
+    if (COOP) __syncthreads();
+
+    if (any) {
+        if (direct && COOP) {
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+                if (msk3[g]) base[g] = s_base[g * kMaxBuckets + wb];
+        } else if (direct) {
             unsigned acc[NG];
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
@@ -133,23 +212,24 @@ __global__ void __launch_bounds__(kLookupThreads, NG == 1 ? 5 : 4) k_update(cons
 #pragma unroll
                 for (int u = 0; u < XU; ++u) acc[g] += x[g][u];
             }
-            for (int c0 = XU * q.L; c0 < nc; c0 += 4 * q.L) {       // the rest: 4 loads per lane, group and round
+            for (int c0 = XU * 32; c0 < nc; c0 += 128) {       // the rest: 4 loads per lane, group and round
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    if (!msk[g]) continue;
+                    if (!msk3[g]) continue;
+                    const unsigned *h = p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max;
                     unsigned y[4] = {0, 0, 0, 0};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int c = c0 + u * q.L + q.gl;
-                        if (c < nc) y[u] = __ldcg(h[g] + c);
+                        const int c = c0 + u * 32 + lane;
+                        if (c < nc) y[u] = __ldcg(h + c);
                     }
                     acc[g] += y[0] + y[1] + y[2] + y[3];
                 }
             }
-            // every lane of the group is here (`any` is uniform within a group), other groups of the warp may not be
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
-                for (int d = q.L >> 1; d > 0; d >>= 1) acc[g] += __shfl_xor_sync(q.mask, acc[g], d);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) acc[g] += __shfl_xor_sync(kFull, acc[g], d);
                 base[g] = acc[g];
             }
         }
@@ -549,6 +629,20 @@ __global__ void __launch_bounds__(kEvictThreads) k_evict(const __grid_constant__
             if (taken != P.need) c->error = 4u;
             atomicAdd(&p_dbg_appends, static_cast<unsigned long long>(P.appended));
         }
+    }
+    // the host's view of the ring occupancy (maintain_rings): one 8-byte store into mapped pinned memory
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long used = 0ull;
+        if (lane < tier.n_buckets) used = c->tail[lane] - c->head[lane];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(kFull, used, d);
+            used = o > used ? o : used;
+        }
+        if (lane == 0)
+            *reinterpret_cast<volatile unsigned long long *>(p.ring_host + t) =
+                (static_cast<unsigned long long>(p.args->seq) << 32) | (used & 0xFFFFFFFFull);
     }
     // per-batch scratch of the tier
     const unsigned n_tk = min(c->ticket + nev, tier.lb_cap);

@@ -51,6 +51,31 @@ def balanced_placement(rows, size: int):
     return [sorted(x) for x in out]
 
 
+def split_cache_budget(rows_per_rank, total_rows_cached: int, floor: int = 1024):
+    """The one cache's budget (TOTAL_SIZE, cache_manager.cpp:16: entries of the whole model) split over the ranks of a
+    table-wise sharded cache.  Every GPU contributes the same memory; a rank whose tables are smaller than its share caches
+    them whole and the rest of its share goes to the others (water filling): cap_r = min(rows_r, level), sum = budget.
+    Sizing every rank at the same FRACTION of its own rows instead leaves a rank that owns only small tables with a cache
+    far smaller than one batch's keys -- it thrashes, and the whole step waits for its miss fetches."""
+    rows = [int(r) for r in rows_per_rank]
+    budget = min(int(total_rows_cached), sum(rows))
+    caps = [0] * len(rows)
+    open_ranks = sorted(range(len(rows)), key=lambda r: rows[r])
+    left = budget
+    while open_ranks:
+        level = left // len(open_ranks)
+        r = open_ranks[0]
+        if rows[r] <= level:
+            caps[r] = rows[r]
+            left -= rows[r]
+            open_ranks.pop(0)
+        else:
+            for q in open_ranks:
+                caps[q] = level
+            break
+    return [max(floor, c) for c in caps]
+
+
 class ShardedLookup:
     """One rank's part of the sharded lookup.  ``store`` serves this rank's tables
     (``EvStore`` built with table_base / n_tables_total; any object with ``probe`` and ``lookup``

@@ -178,3 +178,18 @@ def test_latency_cdf_file_equals_the_reference_function(tmp_path, golden_dir):
     # fewer requests than CDF points: every latency is kept
     out = p.evstore_utils.calculate_and_write_cdf(str(tmp_path), "few", [0.0, 0.5, 0.75, 2.0, 9.0])
     assert open(out).read().splitlines() == ["y,latency_ms", "0.3333333333333333,250.0", "0.6666666666666666,500.0", "1.0,1250.0"]
+
+
+def test_split_cache_budget_water_filling():
+    """sharded.split_cache_budget: one budget over the ranks, equal shares, a rank smaller than its share is cached whole
+    and passes the rest on; the sum is the budget (up to the integer division) and never exceeds a rank's rows."""
+    from helpers import pkg
+    sh = pkg().sharded
+    assert sh.split_cache_budget([100, 100], 50, floor=0) == [25, 25]
+    assert sh.split_cache_budget([10, 1000, 1000], 410, floor=0) == [10, 200, 200]
+    assert sh.split_cache_budget([5, 8, 1000], 113, floor=0) == [5, 8, 100]
+    assert sh.split_cache_budget([5, 8], 1000, floor=0) == [5, 8]
+    rows = pkg().workload.KAGGLE_ROWS
+    per = [sum(rows[t] for t in x) for x in sh.balanced_placement(rows, 8)]
+    caps = sh.split_cache_budget(per, int(sum(rows) * 0.13))
+    assert all(c <= r for c, r in zip(caps, per)) and abs(sum(caps) - int(sum(rows) * 0.13)) < 8
