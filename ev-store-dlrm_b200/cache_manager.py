@@ -35,7 +35,7 @@ class CacheConfig:
     flush_rate: float = 0.0
     perfect_item_cap: float = 0.0
     high_agghit_threshold: int = 0
-    policy: str = "evlfu"             # "evlfu" (EvLFU_C1.py / mixed_precs_caching) or "lru" (cache_algo/LRU.py; one layer)
+    policy: str = "evlfu"             # "evlfu" (EvLFU_C1.py / mixed_precs_caching), "lru" (cache_algo/LRU.py) or "lfu" (cache_algo/LFU.py); the last two: one layer
     extra: dict = field(default_factory=dict)
 
     def proportions(self):
@@ -175,9 +175,9 @@ class EvStore:
             c.alt_keys = C.cast(self._alt_ptrs, C.POINTER(C.c_void_p))
         c.store_in_hbm = int(cfg.store_in_hbm)
         c.record_events = int(cfg.record_events)
-        if cfg.policy not in ("evlfu", "lru"):
-            raise ValueError(f"unknown policy {cfg.policy!r} (evlfu | lru)")
-        c.policy = 1 if cfg.policy == "lru" else 0
+        if cfg.policy not in ("evlfu", "lru", "lfu"):
+            raise ValueError(f"unknown policy {cfg.policy!r} (evlfu | lru | lfu)")
+        c.policy = {"evlfu": 0, "lru": 1, "lfu": 2}[cfg.policy]
         if cfg.table_ids:
             if len(cfg.table_ids) != self.n_tables:
                 raise ValueError("table_ids needs one global id per local table")

@@ -477,7 +477,8 @@ static int enqueue_batch(evs_handle h, cudaStream_t st, int n_chunks, const Batc
     }
     { LaunchScope ls(pf, K_UPDATE, st); 
         // a sample per warp (26 tables): per-sample sums of the earlier CTAs' counts; packed warps: one sum per CTA
-        KernelFn upd = h->n_tiers == 1 ? (p.L == 32 ? k_update<1, 8, false> : k_update<1, 8, true>)
+        KernelFn upd = p.policy == EVS_POLICY_LFU ? k_update<1, 8, true, true>
+                       : h->n_tiers == 1 ? (p.L == 32 ? k_update<1, 8, false> : k_update<1, 8, true>)
                                        : (p.L == 32 ? k_update<kSeqGroups, 4, false> : k_update<kSeqGroups, 4, true>);
         EVS_CUDA(launch(upd, n_chunks, kLookupThreads, 0, st, p, pdl)); }
     {
@@ -640,13 +641,13 @@ int evs_create(const evs_config *cfg, evs_handle *out) {
         }
     }
     if (h->cfg.high_agghit_threshold <= 0) h->cfg.high_agghit_threshold = 23;
-    if (cfg->policy != EVS_POLICY_EVLFU && cfg->policy != EVS_POLICY_LRU) {
+    if (cfg->policy != EVS_POLICY_EVLFU && cfg->policy != EVS_POLICY_LRU && cfg->policy != EVS_POLICY_LFU) {
         set_error("evs_create: unknown policy");
         delete h;
         return EVS_ERR_INVALID;
     }
-    if (cfg->policy == EVS_POLICY_LRU && (cfg->n_layers != 1 || cfg->approx_emb_thres > 0)) {
-        set_error("evs_create: the LRU policy (cache_algo/LRU.py) is single-layer and has no approximate substitution");
+    if (cfg->policy != EVS_POLICY_EVLFU && (cfg->n_layers != 1 || cfg->approx_emb_thres > 0)) {
+        set_error("evs_create: the LRU / LFU policies (cache_algo/LRU.py, LFU.py) are single-layer and have no approximate substitution");
         delete h;
         return EVS_ERR_INVALID;
     }

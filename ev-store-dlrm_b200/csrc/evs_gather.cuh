@@ -92,8 +92,11 @@ __global__ void __launch_bounds__(256) k_gather(const unsigned char *__restrict_
 #pragma unroll
                 for (int i = 0; i < EPC; ++i) acc[i] = 0.0f;
                 // U rows of the bag per round: the index loads, then the row loads, are all issued before the first
-                // add, so a bag costs ceil(P / U) dependent round trips instead of P; the sum still runs in ascending j
-                constexpr int U = 5;
+                // add, so a bag costs ceil(P / U) dependent round trips instead of P; the sum still runs in ascending j.
+                // fp32 rows: the reference's 10 indices per lookup (dlrm_data_pytorch.py:961-1007) in ONE round -- the
+                // kernel is a single wave of short-lived warps, so its time is the length of this chain (ncu,
+                // profiles/r2_gather_d64: DRAM 34 % busy, issue slots 31 %)
+                constexpr int U = 5;   // (10 in one round was slower: 80 registers, 18.5 vs 14.5 us at d = 64)
                 for (long long jb = j0; jb < j1; jb += U) {
                     long long rr[U];
                     uint4 v[U];

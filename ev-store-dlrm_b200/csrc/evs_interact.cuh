@@ -8,8 +8,9 @@
 //   * Z = T T^t as 32x32xd on the tensor cores with mma.sync.m16n8k8 TF32: T serves as the row-major A operand and,
 //     unchanged, as the "column-major" B operand (B[k][n] = T[n][k]), so a lane loads 8 values per k-step and uses
 //     them for both.  Only the 6 of 8 accumulator tiles that touch the strict lower triangle are computed;
-//   * fp32 accuracy from TF32 hardware: every operand is split hi + lo (cvt.rna.tf32) and a tile is the sum of
-//     hi*hi + hi*lo + lo*hi (the "3xTF32" scheme; the dropped lo*lo term is 2^-22 relative).  The kernel is bound
+//   * fp32 accuracy from TF32 hardware: every operand is split hi + lo (hi = the value masked to TF32's mantissa, lo = the
+//     exact remainder) and a tile is the sum of hi*hi + hi*lo + lo*hi (the "3xTF32" scheme; the dropped lo*lo term and the
+//     truncation of lo are 2^-20 relative).  The kernel is bound
 //     by HBM (7-11 FLOP/B), so the 3x tensor work is free;
 //   * the accumulators go back through shared memory so that the 351 packed outputs are written as consecutive floats.
 // k_interact (fp32 FMA) remains for shapes outside those limits.
@@ -82,41 +83,64 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// ld: floats between rows of the staged T (>= Dp, a multiple of 4, = 4 mod 8).  A warp owns two buffers of `region`
-// floats (region >= 32 * ld and >= 32 * 33): while it computes sample s out of one, cp.async fills the other with the
-// T of its next sample, so a warp always has a sample's worth of HBM reads in flight; the grid is sized to what is
-// resident at once and every warp walks the batch with the grid's stride.
-__global__ void __launch_bounds__(kMmaWarps * 32) k_interact_mma(const float *__restrict__ x, const float *__restrict__ ly,
+// ld: floats between rows of the staged T (>= Dp, = 8 mod 16: the 64-bit fragment reads below are bank-conflict free).
+// A warp owns two buffers of `region` floats (region >= 32 * ld and >= (n_f + 1) * kZld): while it computes sample s out
+// of one, cp.async fills the other with the T of its next sample, so a warp always has a sample's worth of HBM reads in
+// flight; the grid is sized to what is resident at once and every warp walks the batch with the grid's stride.
+// The kernel was issue-bound (ncu, profiles/r2_interact_*: 932 warp instructions per sample at d = 16, issue slots 64 % busy,
+// DRAM 12 %), so everything that does not depend on the sample is hoisted out of the sample loop: the (row, column) walk
+// of the staging copy is incremental (no division), the shared-memory offsets of a lane's packed pairs live in registers
+// (no pair table), and the fragments / accumulators move as 64-bit words.
+constexpr int kZld = 40;                     // row stride of the staged Z: the accumulators' 64-bit stores are conflict free
+constexpr int kPairSlots = 16;               // packed pairs per lane: 32 * 16 >= 31 * 32 / 2
+
+__global__ void __launch_bounds__(kMmaWarps * 32, 3) k_interact_mma(const float *__restrict__ x, const float *__restrict__ ly,
                                                                  float *__restrict__ r, int B, int n_f, int D, int Dp, int ld, int region) {
     extern __shared__ __align__(16) float s_t[];
-    __shared__ unsigned char s_pi[512], s_pj[512];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const int nt = n_f + 1;
     const int n_pairs = nt * (nt - 1) / 2;
     const int out_w = D + n_pairs;
-    // (i, j) of packed pair pr = i(i-1)/2 + j, 0 <= j < i, once per CTA
-    for (int pr = threadIdx.x; pr < n_pairs; pr += blockDim.x) {
-        int i = static_cast<int>((1.0f + sqrtf(1.0f + 8.0f * static_cast<float>(pr))) * 0.5f);
-        while (i * (i - 1) / 2 > pr) --i;
-        while ((i + 1) * i / 2 <= pr) ++i;
-        s_pi[pr] = static_cast<unsigned char>(i);
-        s_pj[pr] = static_cast<unsigned char>(pr - i * (i - 1) / 2);
+    // offset in the staged Z of packed pair pr = i(i-1)/2 + j (0 <= j < i) for the pairs lane + 32 k of this lane, two
+    // 16-bit offsets per register
+    unsigned poff[kPairSlots / 2];
+#pragma unroll
+    for (int k = 0; k < kPairSlots; ++k) {
+        const int pr = lane + 32 * k;
+        unsigned o = 0;
+        if (pr < n_pairs) {
+            int i = static_cast<int>((1.0f + sqrtf(1.0f + 8.0f * static_cast<float>(pr))) * 0.5f);
+            while (i * (i - 1) / 2 > pr) --i;
+            while ((i + 1) * i / 2 <= pr) ++i;
+            o = static_cast<unsigned>(i * kZld + (pr - i * (i - 1) / 2));
+        }
+        if (k & 1) poff[k >> 1] |= o << 16;
+        else poff[k >> 1] = o;
     }
-    __syncthreads();
     float *buf0 = s_t + static_cast<size_t>(warp) * 2 * region;
     const int g = lane >> 2, tq = lane & 3;
     const bool vec = ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(ly) & 15u) == 0);
     const int d4 = D >> 2, n4 = nt * d4;
     const int stride = gridDim.x * wpc;
+    // the staging walk of this lane: 16-byte piece e = lane + 32 i sits in row e / d4, column piece e % d4
+    const int row0 = vec ? lane / d4 : 0, c40 = vec ? lane - row0 * d4 : 0;
+    const int dr = vec ? 32 / d4 : 0, dc = vec ? 32 - dr * d4 : 0;
 
     // stage T = [x ; ly] of sample s into t (asynchronously when rows are 16-byte aligned)
     auto stage = [&](int s, float *t) {
         const float *xs = x + static_cast<size_t>(s) * D;
         const float *ls = ly + static_cast<size_t>(s) * n_f * D;
         if (vec) {
+            const float *lsm = ls - D;                        // row k >= 1 of T is row k - 1 of ly
+            int row = row0, c4 = c40;
             for (int e = lane; e < n4; e += 32) {
-                const int row = e / d4, c4 = e - row * d4;
-                cp_async16(t + row * ld + (c4 << 2), (row == 0 ? xs : ls + static_cast<size_t>(row - 1) * D) + (c4 << 2));
+                cp_async16(t + row * ld + (c4 << 2), (row == 0 ? xs : lsm + static_cast<size_t>(row) * D) + (c4 << 2));
+                c4 += dc;
+                row += dr;
+                if (c4 >= d4) {
+                    c4 -= d4;
+                    ++row;
+                }
             }
         } else {
             for (int e = lane; e < nt * D; e += 32) {
@@ -151,21 +175,27 @@ __global__ void __launch_bounds__(kMmaWarps * 32) k_interact_mma(const float *__
         // x goes to the head of the output row
         for (int e = lane; e < D; e += 32) rs[e] = t[e];
         // ---- Z = T T^t on the tensor cores (rows >= nt hold stale data: they only reach outputs nobody reads) ----
+        // The contraction index may be permuted as long as A and B agree: the fragment slots "k = tq" and "k = tq + 4"
+        // of a lane take the adjacent columns k0 + 2 tq and k0 + 2 tq + 1, so a lane reads one 64-bit word per row group.
         float acc[6][4];
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[i][k] = 0.0f;
+        const float *tl = t + g * ld + 2 * tq;
         for (int k0 = 0; k0 < Dp; k0 += 8) {
             unsigned hi[4][2], lo[4][2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float v = t[(g + 8 * j) * ld + k0 + tq + 4 * h];
-                    hi[j][h] = to_tf32(v);
-                    lo[j][h] = to_tf32(v - __uint_as_float(hi[j][h]));
-                }
+            for (int j = 0; j < 4; ++j) {
+                // hi = the value cut to TF32's 10 mantissa bits (a mask: cvt.rna runs at a quarter of the ALU rate, and at
+                // d = 64 its 256 conversions per sample were the longest pipe), lo = the exact remainder, which the tensor
+                // core itself cuts to TF32 on the way in: |v - hi - lo| <= 2^-20 |v|
+                const float2 v = *reinterpret_cast<const float2 *>(tl + 8 * j * ld + k0);
+                hi[j][0] = __float_as_uint(v.x) & 0xFFFFE000u;
+                lo[j][0] = __float_as_uint(v.x - __uint_as_float(hi[j][0]));
+                hi[j][1] = __float_as_uint(v.y) & 0xFFFFE000u;
+                lo[j][1] = __float_as_uint(v.y - __uint_as_float(hi[j][1]));
+            }
             // tile (m, n): rows 16m .. 16m+15 (A from row groups 2m, 2m+1), cols 8n .. 8n+7 (B from row group n)
 #define EVS_TILE(ti, m, n)                                                                                           \
     mma_tf32(acc[ti], hi[2 * m][0], hi[2 * m + 1][0], hi[2 * m][1], hi[2 * m + 1][1], hi[n][0], hi[n][1]);              \
@@ -180,21 +210,22 @@ __global__ void __launch_bounds__(kMmaWarps * 32) k_interact_mma(const float *__
 #undef EVS_TILE
         }
         __syncwarp();                                   // every lane has read its last fragment: T may be overwritten
-        // ---- accumulators -> Z[32][33] in the same buffer ---------------------------------------------------------
+        // ---- accumulators -> Z[nt][kZld] in the same buffer (rows >= nt are never read) ------------------------------
         {
             const int tm[6] = {0, 0, 1, 1, 1, 1}, tn[6] = {0, 1, 0, 1, 2, 3};
 #pragma unroll
             for (int ti = 0; ti < 6; ++ti) {
                 const int row = 16 * tm[ti] + g, col = 8 * tn[ti] + 2 * tq;
-                t[row * 33 + col] = acc[ti][0];
-                t[row * 33 + col + 1] = acc[ti][1];
-                t[(row + 8) * 33 + col] = acc[ti][2];
-                t[(row + 8) * 33 + col + 1] = acc[ti][3];
+                if (row < nt) *reinterpret_cast<float2 *>(t + row * kZld + col) = make_float2(acc[ti][0], acc[ti][1]);
+                if (row + 8 < nt) *reinterpret_cast<float2 *>(t + (row + 8) * kZld + col) = make_float2(acc[ti][2], acc[ti][3]);
             }
         }
         __syncwarp();
         // ---- strict lower triangle row-major behind x, consecutive lanes write consecutive floats ------------------
-        for (int pr = lane; pr < n_pairs; pr += 32) rs[D + pr] = t[s_pi[pr] * 33 + s_pj[pr]];
+        float *rp = rs + D + lane;
+#pragma unroll
+        for (int k = 0; k < kPairSlots; ++k)
+            if (lane + 32 * k < n_pairs) rp[32 * k] = t[(poff[k >> 1] >> (16 * (k & 1))) & 0xFFFFu];
         __syncwarp();
         cur ^= 1;
     }
@@ -209,8 +240,8 @@ inline int launch_interact(const float *x, const float *ly, float *r, int B, int
     }();
     if (n_f + 1 <= 32 && D <= 128 && !force_fma) {
         const int Dp = (D + 7) & ~7;
-        const int ld = Dp + 4;                                  // = 4 mod 8: conflict-free fragment reads
-        const int region = 32 * std::max(ld, 33);
+        const int ld = (Dp & 15) == 8 ? Dp : Dp + 8;            // = 8 mod 16: conflict-free 64-bit fragment reads
+        const int region = std::max(32 * ld, (n_f + 1) * kZld);
         // two buffers per warp; fewer warps per CTA when the rows are wide, so that several CTAs stay resident
         const int warps = (static_cast<size_t>(kMmaWarps) * 2 * region * sizeof(float) > 72 * 1024) ? 4 : kMmaWarps;
         const size_t smem = static_cast<size_t>(warps) * 2 * region * sizeof(float);

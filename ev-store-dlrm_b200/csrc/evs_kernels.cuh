@@ -524,13 +524,19 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
     const bool approx = (P1 == 0) && (p.approx_thres > 0) && (agg >= p.approx_thres) && (m_h0 != 0u);
     // LRU (cache_algo/LRU.py): one recency ring (bucket 0); every hit moves its key to the MRU end (:30)
     const bool lru = (P1 == 0) && (p.policy == 1);
-    const int bkt = lru ? 0 : agg;
+    // LFU (cache_algo/LFU.py): bucket = frequency - 1; a hit moves its key to the next frequency list (saturating at the last
+    // one), a miss enters list 1 -- the bucket is a property of the key, not of the sample (oracle.lru.BatchLFU)
+    const bool lfu = (P1 == 0) && (p.policy == 2);
+    const int bkt = (lru || lfu) ? 0 : agg;
 
     uint8_t f = 0;
     const int pos = s * T + tbl;
     if (act) {
         if (hc == kHitC1) {
-            if (lru || meta_bucket(m0) < agg) {
+            if (lfu) {
+                f = static_cast<uint8_t>(min(meta_bucket(m0) + 1, t0.n_buckets - 1) + 1);
+                p.pos_slot[pos] = slot0;
+            } else if (lru || meta_bucket(m0) < agg) {
                 f = static_cast<uint8_t>(bkt + 1);
                 p.pos_slot[pos] = slot0;
             }
@@ -578,7 +584,7 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
     if (q.gl == 0 && sact && m_miss) mbase = atomicAdd(p.miss_ctl, static_cast<unsigned>(__popc(m_miss)));
     if (q.gl == 0 && sact) {
         a.agg_out[s] = static_cast<uint8_t>(agg);
-        if (m_f0) atomicAdd(&s_hist[bkt], static_cast<unsigned>(__popc(m_f0)));
+        if (m_f0 && !lfu) atomicAdd(&s_hist[bkt], static_cast<unsigned>(__popc(m_f0)));
         if (m_p1) atomicAdd(&s_hist[kMaxBuckets + agg], static_cast<unsigned>(__popc(m_p1)));
         if (m_i1) atomicAdd(&s_hist[2 * kMaxBuckets + agg], static_cast<unsigned>(__popc(m_i1)));
         if (m_h0) atomicAdd(&s_stat[0], static_cast<unsigned>(__popc(m_h0)));
@@ -589,6 +595,8 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
         if (agg == p.n_perfect_agg) atomicAdd(&s_stat[5], 1u);
         if (m_abs) atomicAdd(&s_stat[6], static_cast<unsigned>(__popc(m_abs)));
     }
+
+    if (lfu && f != 0) atomicAdd(&s_hist[(f & 0x3Fu) - 1u], 1u);       // LFU: the appends of a sample go to different buckets
 
     if (!(SH && early)) {
         gather_tier<P0>(p, t0, 0, src_t, src_s, orow, sact, T, D, vec, q, &s_lut);
@@ -622,7 +630,7 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
         if (s_stat[4]) atomicAdd(&g->misses, static_cast<unsigned long long>(s_stat[4]));
         if (s_stat[5]) {
             atomicAdd(&g->perfect_hits, static_cast<unsigned long long>(s_stat[5]));
-            t0.ctl->any_perfect = 1u;                              // EvLFU_C1.py:163-165
+            if (p.policy != 2) t0.ctl->any_perfect = 1u;           // EvLFU_C1.py:163-165 (LFU has no perfect-item bookkeeping)
             if (P1 != 0 && full) t1.ctl->any_perfect = 1u;         // evlfu_8.cpp:439-441 (only when C2 is updated)
         }
     }

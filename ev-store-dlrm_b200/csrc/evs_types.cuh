@@ -196,7 +196,7 @@ struct Params {
     int high_thres;                        // high_agghit_threshold (evlfu_32.hpp:74)
     int n_chunks_max;
     int quad_max;                          // batches of more serve CTAs than this get their append offsets from k_scan
-    int policy;                            // 0 = EvLFU, 1 = LRU (single tier: one recency ring, every hit re-appends)
+    int policy;                            // 0 = EvLFU, 1 = LRU (single tier: one recency ring, every hit re-appends), 2 = LFU (single tier: bucket = frequency - 1)
     const long long *rows;                 // [T] cardinalities
     BatchArgs *args;
     GlobalCtl *g;

@@ -48,8 +48,13 @@ __device__ __forceinline__ bool kth_present(const unsigned *present, int ng, int
     return false;
 }
 
-template <int NG, int XU, bool COOP>
+// LFU (needs COOP, NG = 1): the appends of one sample go to different buckets (bucket = the key's own frequency), so a
+// position's rank inside the CTA is counted per bucket -- lanes of a warp that share a bucket find each other with
+// match.any, the warps of the CTA add up in sample order -- instead of per sample.
+template <int NG, int XU, bool COOP, bool LFU = false>
 __global__ void __launch_bounds__(kLookupThreads, COOP ? 3 : (NG == 1 ? 5 : 4)) k_update(const __grid_constant__ Params p) {
+    static_assert(!LFU || (COOP && NG == 1), "the LFU path is single-tier and sums per CTA");
+    __shared__ unsigned s_wcnt[LFU ? kSamplesPerCta : 1][kMaxBuckets];      // LFU: appends per warp and bucket
     __shared__ unsigned s_cnt[kLookupThreads][kSeqGroups];      // per sample of the CTA (at most 256 when L = 1)
     __shared__ int s_b[kLookupThreads];
     __shared__ int s_delta[kMaxTiers * kMaxBuckets];
@@ -66,6 +71,7 @@ __global__ void __launch_bounds__(kLookupThreads, COOP ? 3 : (NG == 1 ? 5 : 4)) 
         s_prot[threadIdx.x] = 0ull;
     }
     if (threadIdx.x < kSeqGroups) s_present[threadIdx.x] = 0u;
+    if (LFU) s_wcnt[threadIdx.x >> 5][threadIdx.x & 31] = 0u;
     griddep_wait(p);
     if (blockIdx.x == 0 && threadIdx.x == 0) p.dbg[2] = gtime();
     const BatchArgs a = *p.args;
@@ -96,12 +102,24 @@ __global__ void __launch_bounds__(kLookupThreads, COOP ? 3 : (NG == 1 ? 5 : 4)) 
     const unsigned m2 = __ballot_sync(kFull, grp == 2) & q.mask;
     const unsigned any = m0 | m1 | m2;
     const int wb = __shfl_sync(kFull, b, any ? (__ffs(any) - 1) : q.base);    // all flagged lanes of a sample share it
+    unsigned lfu_rank = 0;
+    if (LFU) {
+        const unsigned fm = __ballot_sync(kFull, f != 0u);
+        if (f) {
+            const unsigned peers = __match_any_sync(fm, b);
+            lfu_rank = __popc(peers & ((1u << lane) - 1u));
+            if (lfu_rank == 0) {
+                s_wcnt[warp][b] = __popc(peers);
+                atomicOr(&s_present[0], 1u << b);
+            }
+        }
+    }
     if (q.gl == 0) {
         s_cnt[j][0] = __popc(m0);
         s_cnt[j][1] = __popc(m1);
         s_cnt[j][2] = __popc(m2);
         s_b[j] = any ? wb : -1;
-        if (COOP && any) {
+        if (COOP && !LFU && any) {
             if (m0) atomicOr(&s_present[0], 1u << wb);
             if (NG > 1 && m1) atomicOr(&s_present[1], 1u << wb);
             if (NG > 1 && m2) atomicOr(&s_present[2], 1u << wb);
@@ -148,9 +166,13 @@ __global__ void __launch_bounds__(kLookupThreads, COOP ? 3 : (NG == 1 ? 5 : 4)) 
         }
     } else if (any) {
         // k_scan made the counts prefixes
+        if (LFU) {
+            if (f) base[0] = __ldcg(p.hist + static_cast<size_t>(b) * p.n_chunks_max + blockIdx.x);
+        } else {
 #pragma unroll
-        for (int g = 0; g < NG; ++g)
-            if (msk3[g]) base[g] = __ldcg(p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max + blockIdx.x);
+            for (int g = 0; g < NG; ++g)
+                if (msk3[g]) base[g] = __ldcg(p.hist + static_cast<size_t>(g * kMaxBuckets + wb) * p.n_chunks_max + blockIdx.x);
+        }
     }
     const unsigned tot_p1 = (any && m2) ? __ldcg(p.tot + kMaxBuckets + wb) : 0u;
     unsigned long long tail_b = 0ull;
@@ -199,7 +221,25 @@ __global__ void __launch_bounds__(kLookupThreads, COOP ? 3 : (NG == 1 ? 5 : 4)) 
     }
     if (COOP) __syncthreads();
 
-    if (any) {
+    if (LFU) {
+        if (f) {
+            unsigned bs = direct ? s_base[b] : base[0];
+            for (int w = 0; w < warp; ++w) bs += s_wcnt[w][b];
+            const TierDev &tier = p.tier[0];
+            const unsigned long long qq = tail_b + bs + lfu_rank;
+            tier.ring[static_cast<size_t>(b) * tier.ring_cap + (qq & (tier.ring_cap - 1))] = slot;
+            const unsigned long long mine = pack_meta(b, qq);
+            const unsigned long long old = atomicMax(&tier.slots[slot].meta, mine);
+            if (mine > old) {
+                const int ob = meta_bucket(old);
+                if (ob != b) {
+                    atomicAdd(&s_delta[b], 1);
+                    if (ob >= 0) atomicSub(&s_delta[ob], 1);
+                    else atomicAdd(&s_ins[0], 1u);
+                }
+            }
+        }
+    } else if (any) {
         if (direct && COOP) {
 #pragma unroll
             for (int g = 0; g < NG; ++g)

@@ -95,6 +95,7 @@ typedef struct {
 
 #define EVS_POLICY_EVLFU 0
 #define EVS_POLICY_LRU 1
+#define EVS_POLICY_LFU 2   /* cache_algo/LFU.py: one FIFO list per frequency, saturating at n_tables_total + 1 (n_layers == 1 only) */
 
 typedef struct {
     uint64_t lookups;            /* keys looked up */

@@ -114,19 +114,25 @@ class SeqLFU:
     dlrm_s_pytorch_C1_C2_C3.py:1294): per-frequency FIFO lists ``node_for_freq[f]`` (:9,33-34), ``node_for_key``
     key -> frequency (:11,31), a lazily maintained ``least_freq`` pointer (:25-28 advances it by ONE when its list
     empties, :50 resets it to 1 on every insert), eviction = the oldest key of ``node_for_freq[least_freq]``
-    (:40-44).  Sequential only: the frequency lists are unbounded, so this policy has no CUDA counterpart
-    (DESIGN.md section 5); it is here so that hit rates can be reported next to all three of the reference's
-    simulators (tools/hit_rate_compare.py).  Pinned by tests/golden/lfu_*.npz."""
+    (:40-44).  Pinned by tests/golden/lfu_*.npz.  The CUDA path (``policy="lfu"``) implements ``BatchLFU`` below, whose
+    frequencies saturate at n_tables + 1 (``freq_cap``)."""
 
-    def __init__(self, capacity: int, n_tables: int = 26):
+    def __init__(self, capacity: int, n_tables: int = 26, freq_cap: int = 0):
+        """freq_cap = 0: the reference (unbounded frequencies).  freq_cap = F: the frequency saturates at F -- a hit on a key
+        of frequency F re-appends it to list F -- which is the variant the CUDA path implements (F = n_tables + 1, one bucket
+        ring per frequency); identical to the reference as long as no key is hit more than F - 1 times."""
         self.cap, self.T = int(capacity), int(n_tables)
+        self.fcap = int(freq_cap)
         self.least = 1                                         # :7
         self.freq: list = [0, OrderedDict()]                   # :16-17 (index 0 unused)
         self.key: dict[int, int] = {}
         self.evicted: list[int] = []
+        self.corner = False
 
     def request(self, row_ids):
         self.evicted = []
+        self.corner = False
+        start = set(self.key) if self.cap <= 4096 else None
         hit = []
         for i, r in enumerate(row_ids):
             k = make_key(i, r)
@@ -135,12 +141,17 @@ class SeqLFU:
                 del self.freq[f][k]
                 if len(self.freq[self.least]) == 0:
                     self.least += 1
-                self.key[k] = f + 1
-                if f + 1 == len(self.freq):
+                nf = f + 1 if (self.fcap == 0 or f < self.fcap) else f
+                if nf == f and self.least > f:                 # saturated key re-appended to the list least_freq just left
+                    self.least = f
+                self.key[k] = nf
+                if nf == len(self.freq):
                     self.freq.append(OrderedDict())
-                self.freq[f + 1][k] = None
+                self.freq[nf][k] = None
                 hit.append(True)
             else:                                              # :62-66 -> set :36-50
+                if start is not None and k in start:
+                    self.corner = True
                 if len(self.key) >= self.cap:
                     ek, _ = self.freq[self.least].popitem(last=False)
                     del self.key[ek]
@@ -154,3 +165,74 @@ class SeqLFU:
     def state(self):
         """(least_freq, per-frequency key lists from frequency 1 up)."""
         return self.least, [list(d.keys()) for d in self.freq[1:]]
+
+
+class BatchLFU:
+    """The batch-granular LFU the CUDA path implements (``policy="lfu"``; same interface as BatchEvLFU / BatchLRU).
+
+    One FIFO list per frequency 1 .. F (F = n_tables + 1: the tier's bucket rings), bucket b = frequency - 1.  All keys of a
+    batch are probed against the state at batch start.  A key that hit moves to the end of the next list (a key already in
+    list F is re-appended to list F), a key that missed enters list 1; a key requested several times in a batch moves ONCE
+    -- its frequency counts the batches that asked for it -- and takes the place of its last occurrence (highest position,
+    sample-major / table-minor); moves are applied in position order.  Then the cache is evicted back down to capacity from
+    the lowest frequency up, oldest first, never the last key inserted (the reference evicts before it inserts,
+    LFU.py:40-50).  With one sample per batch this is ``SeqLFU(freq_cap=F)`` on every request that does not take the
+    same-request corner (a key resident at request start that an earlier insert of the same request evicted)."""
+
+    def __init__(self, capacity: int, n_tables: int = 26):
+        self.cap, self.T = int(capacity), int(n_tables)
+        self.entries: dict[int, int] = {}                      # key -> bucket
+        self.lists = [OrderedDict() for _ in range(self.T + 1)]
+        self.n_perfect = 0
+        self.evicted: list[int] = []
+        self.flushed: list[int] = []
+        self.inserted: list[int] = []
+
+    def lookup_batch(self, idx, approx_emb_thres: int = -1, agg=None, table_base: int = 0):
+        idx = np.asarray(idx)
+        Tl, B = idx.shape
+        ent = self.entries
+        top = self.T
+        hit = np.zeros((B, Tl), dtype=bool)
+        last: dict[int, int] = {}
+        for s in range(B):
+            for t in range(Tl):
+                k = make_key(table_base + t, idx[t, s])
+                hit[s, t] = k in ent
+                last[k] = s * Tl + t
+        self.inserted = []
+        prot = None
+        for k, _p in sorted(last.items(), key=lambda kv: kv[1]):
+            old = ent.get(k)
+            if old is not None:
+                del self.lists[old][k]
+                nb = min(old + 1, top)
+            else:
+                nb = 0
+                self.inserted.append(k)
+                prot = k
+            self.lists[nb][k] = None
+            ent[k] = nb
+        self.evicted = []
+        need = len(ent) - self.cap
+        b = 0
+        while need > 0 and b <= top:
+            victims = []
+            for k in self.lists[b]:
+                if k == prot:
+                    continue
+                victims.append(k)
+                if len(victims) == need:
+                    break
+            for k in victims:
+                del self.lists[b][k]
+                del ent[k]
+            self.evicted.extend(victims)
+            need -= len(victims)
+            b += 1
+        src_t = np.tile(np.arange(Tl, dtype=np.int32) + table_base, (B, 1))
+        src_r = np.ascontiguousarray(idx.T).astype(np.int64)
+        return hit, src_t, src_r, hit.sum(axis=1).astype(np.int64)
+
+    def state(self):
+        return [list(l.keys()) for l in self.lists]

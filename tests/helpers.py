@@ -5,7 +5,7 @@ import numpy as np
 
 from oracle import codecs as ocodecs
 from oracle.evlfu import BatchEvLFU, gather_rows
-from oracle.lru import BatchLRU
+from oracle.lru import BatchLFU, BatchLRU
 
 SMALL_ROWS = [50, 7, 400, 300, 9, 4, 60, 12, 3, 120, 30, 350, 40, 5, 45, 280, 4, 33, 21, 4, 390, 6, 5, 90, 11, 70]
 SKEW_ROWS = [3, 5, 4000, 2500, 7, 4, 60, 9, 3, 300, 50, 3500, 40, 4, 80, 3000, 5, 45, 30, 4, 3800, 6, 5, 600, 11, 400]
@@ -37,7 +37,7 @@ def run_single_tier_parity(rows, dim, prec, total_size, B_list, n_batches, seed=
     cfg = p.CacheConfig(n_layers=1, main_precision=prec, total_size=total_size, max_batch=max(B_list),
                         approx_emb_thres=approx, record_events=True, store_in_hbm=store_in_hbm, policy=policy)
     store = p.EvStore(tables, cfg)
-    oracle = BatchLRU(cap, n_tables=len(rows)) if policy == "lru" else BatchEvLFU(cap, n_tables=len(rows))
+    oracle = {"lru": BatchLRU, "lfu": BatchLFU, "evlfu": BatchEvLFU}[policy](cap, n_tables=len(rows))
     T = len(rows)
     totals = dict(hits=0, lookups=0, evicted=0, flushed=0)
     try:

@@ -83,3 +83,66 @@ def test_seq_lfu_equals_reference(golden_dir, name):
     least, lists = o.state()
     want = [list(g["state_keys"][g["state_off"][f]:g["state_off"][f + 1]]) for f in range(len(g["state_off"]) - 1)]
     assert least == int(g["least_freq"]) and lists == want
+
+
+def _clone_lfu(o, n_tables=T):
+    from oracle.lru import BatchLFU
+    p = BatchLFU(o.cap, n_tables=n_tables)
+    for f in range(1, len(o.freq)):
+        for k in o.freq[f]:
+            p.lists[f - 1][k] = None
+            p.entries[k] = f - 1
+    return p
+
+
+@pytest.mark.parametrize("name", ["lfu_small", "lfu_skew"])
+def test_batch_lfu_at_b1_equals_capped_sequential(golden_dir, name):
+    """BatchLFU (what policy="lfu" runs on the GPU) from the pre-state of SeqLFU(freq_cap = 27): the same hits, the same set
+    of victims and the same frequency lists after every request that does not take the same-request corner.  (The ORDER of a
+    request's victims may differ: the sequential policy alternates insert / evict and can evict a key it inserted a moment
+    ago before an older, more frequent one; the batch evicts lowest frequency first.)  And the capped sequential policy is the
+    reference's as long as no frequency reaches the cap."""
+    from oracle.lru import SeqLFU
+    g, hits = _load(golden_dir, name)
+    o = SeqLFU(int(g["cap"]), freq_cap=T + 1)
+    ref = SeqLFU(int(g["cap"]))
+    same_as_ref = True
+    corners = checked = 0
+    for i, req in enumerate(g["trace"]):
+        p = _clone_lfu(o)
+        h = o.request(req)
+        if same_as_ref:
+            hr = ref.request(req)
+            if len(ref.freq) - 1 > T + 1:
+                same_as_ref = False                     # a key went past the cap: from here on the two may part
+            else:
+                assert hr == h and ref.evicted == o.evicted, i
+        ph, _st, _sr, _agg = p.lookup_batch(np.asarray(req).reshape(T, 1))
+        if o.corner:
+            corners += 1
+            continue
+        assert list(ph[0]) == h, i
+        assert sorted(p.evicted) == sorted(o.evicted), i
+        _least, lists = o.state()
+        want = [l for l in lists] + [[] for _ in range(T + 1 - len(lists))]
+        assert p.state() == want[:T + 1], i
+        checked += 1
+    assert checked > len(g["trace"]) // 2
+
+
+def test_batch_lfu_frequency_counts_batches_and_saturates():
+    from oracle.lru import BatchLFU
+    p = BatchLFU(100, n_tables=3)
+    idx = np.array([[5, 5, 5], [1, 1, 2], [7, 8, 9]])          # table 0: the same key three times in one batch
+    for n in range(6):
+        hit, *_ = p.lookup_batch(idx)
+        assert p.entries[(0 << 40) | 5] == min(n, 3)            # one step per batch, saturating at bucket n_tables
+        assert hit[:, 0].all() == (n > 0)
+    # eviction: lowest frequency first, oldest first, the last insert survives
+    q = BatchLFU(4, n_tables=1)
+    q.lookup_batch(np.array([[1, 2, 3, 4]]))
+    q.lookup_batch(np.array([[1, 2]]))                          # 1, 2 -> frequency 2
+    q.lookup_batch(np.array([[9, 10]]))
+    assert q.evicted == [3, 4] and q.state()[0] == [9, 10] and q.state()[1] == [1, 2]
+    q.lookup_batch(np.array([[11, 12, 13, 14, 15]]))            # more new keys than the cache holds
+    assert 15 in q.entries and len(q.entries) == 4
