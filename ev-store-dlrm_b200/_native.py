@@ -51,7 +51,7 @@ class EvsStats(C.Structure):
 
 # every symbol include/evstore_b200.h declares
 SYMBOLS = [
-    "evs_create", "evs_destroy", "evs_last_error", "evs_version", "evs_lookup_batch", "evs_lookup_batches", "evs_lookup_bags", "evs_prefetch", "evs_probe_batch", "evs_check",
+    "evs_create", "evs_destroy", "evs_last_error", "evs_version", "evs_lookup_batch", "evs_lookup_batches", "evs_lookup_bags", "evs_note_replays", "evs_prefetch", "evs_probe_batch", "evs_check",
     "evs_memory_footprint", "evs_host_alloc", "evs_host_free",
     "evs_lookup_batch_host", "evs_submit_host", "evs_wait_host", "evs_sync", "evs_stats", "evs_last_events", "evs_dump_state", "evs_dump_c3",
     "evs_interact", "evs_embedding_bag", "evs_embedding_bag_status", "evs_store_ptr", "evs_shard_create", "evs_shard_export",
@@ -86,6 +86,8 @@ def load_library(path: str | None = None):
     lib.evs_lookup_batches.restype = C.c_int
     lib.evs_lookup_bags.argtypes = [vp, vp, vp, i32, i64, i32, vp, i64, vp, vp]
     lib.evs_lookup_bags.restype = C.c_int
+    lib.evs_note_replays.argtypes = [vp, i64, vp]
+    lib.evs_note_replays.restype = C.c_int
     lib.evs_prefetch.argtypes = [vp, vp, i32, vp]
     lib.evs_prefetch.restype = C.c_int
     lib.evs_check.argtypes = [vp, C.c_int]

@@ -222,6 +222,12 @@ class EvStore:
         _native.check(rc, "evs_lookup_batch")
         return out, hit
 
+    def note_replays(self, n: int = 1, stream=None):
+        """A CUDA graph the caller captured around ``lookup`` was launched ``n`` times (evs_note_replays)."""
+        import torch
+        st = _stream_handle(stream, torch.device("cuda", self.cfg.device))
+        _native.check(self.lib.evs_note_replays(self.handle, int(n), st), "evs_note_replays")
+
     def lookup_bags(self, lS_o, lS_i, max_per_bag: int = 10, out=None, stream=None):
         """Pooled lookup (evs_lookup_bags): lS_i / lS_o are the per-table index and offset tensors of apply_emb
         (lS_i[t] int64 CUDA [nnz_t], lS_o[t] int64 CUDA [B], nn.EmbeddingBag's offsets).  Returns (pooled fp32

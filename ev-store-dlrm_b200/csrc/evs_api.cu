@@ -344,7 +344,8 @@ static bool ring_fits(evs_handle h, int ti, int ahead) {
     const unsigned long long n_max = static_cast<unsigned long long>(h->cfg.max_batch) * h->cfg.n_tables;
     const unsigned long long v = *reinterpret_cast<volatile unsigned long long *>(h->ring_host + ti);
     const unsigned long long used = v & 0xFFFFFFFFull;
-    const unsigned in_flight = static_cast<unsigned>(h->seq) - static_cast<unsigned>(v >> 32);
+    unsigned in_flight = static_cast<unsigned>(h->seq) - static_cast<unsigned>(v >> 32);
+    if (static_cast<int>(in_flight) < 0) in_flight = 0;      // replays of a caller's graph not reported yet (evs_note_replays)
     return used + (static_cast<unsigned long long>(in_flight) + ahead) * n_max <= tr.dev.ring_cap;
 }
 
@@ -606,6 +607,8 @@ static int check_device_errors(evs_handle h) {
 using namespace evs;
 
 extern "C" {
+
+static int poll_error(evs_handle h);
 
 int evs_version(void) { return 100; }
 
@@ -891,6 +894,17 @@ static int run_batch(evs_handle h, const BatchArgs &a_in, cudaStream_t st) {
         EVS_CUDA(launch_serve(serve_of(h, ks), (a_in.B + h->params.spc - 1) / h->params.spc, st, h->params, a_in));
         return EVS_OK;
     }
+    // The caller is capturing its own graph (e.g. a whole sequential_forward): the batch goes in as plain kernels with frozen
+    // arguments; the device numbers each replay itself (BatchArgs::seq == 0) and the host is told by evs_note_replays.
+    {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (!h->capturing && cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) {
+            BatchArgs a = a_in;
+            a.seq = 0u;
+            a.pf_gen = 0u;
+            return enqueue_batch(h, st, (a.B + h->params.spc - 1) / h->params.spc, a, false);
+        }
+    }
     BatchArgs a = a_in;
     const uint64_t seq = ++h->seq;
     a.seq = static_cast<unsigned>(seq);
@@ -1147,6 +1161,19 @@ int evs_lookup_bags(evs_handle h, const int64_t *idx_dev, const int64_t *off_dev
     return EVS_OK;
 }
 
+int evs_note_replays(evs_handle h, int64_t n, void *stream) {
+    if (h == nullptr || n < 0) return EVS_ERR_INVALID;
+    DeviceGuard dg(h->cfg.device);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    h->seq += static_cast<uint64_t>(n);
+    h->batches += static_cast<uint64_t>(n);
+    for (int i = 0; i < h->n_tiers; ++i) {
+        int rc = maintain_rings(h, i, st);
+        if (rc) return rc;
+    }
+    return poll_error(h);
+}
+
 int evs_probe_batch(evs_handle h, const int64_t *idx_dev, int32_t B, uint8_t *agg_out_dev, void *stream) {
     if (h == nullptr || B < 0 || B > h->cfg.max_batch || idx_dev == nullptr || agg_out_dev == nullptr) return EVS_ERR_INVALID;
     if (B == 0) return EVS_OK;
@@ -1312,10 +1339,11 @@ int evs_stats(evs_handle h, evs_stats_t *out, int reset) {
         out->c3_capacity = h->params.c3.cap;
     }
     if (reset) {
-        const unsigned err = g.error, fds = g.fetch_done_seq;
+        const unsigned err = g.error, fds = g.fetch_done_seq, as = g.auto_seq;
         memset(&g, 0, sizeof(g));
         g.error = err;
         g.fetch_done_seq = fds;
+        g.auto_seq = as;
         EVS_CUDA(cudaMemcpy(h->g, &g, sizeof(g), cudaMemcpyHostToDevice));
     }
     return EVS_OK;

@@ -8,9 +8,9 @@
 //   * Z = T T^t as 32x32xd on the tensor cores with mma.sync.m16n8k8 TF32: T serves as the row-major A operand and,
 //     unchanged, as the "column-major" B operand (B[k][n] = T[n][k]), so a lane loads 8 values per k-step and uses
 //     them for both.  Only the 6 of 8 accumulator tiles that touch the strict lower triangle are computed;
-//   * fp32 accuracy from TF32 hardware: every operand is split hi + lo (hi = the value masked to TF32's mantissa, lo = the
-//     exact remainder) and a tile is the sum of hi*hi + hi*lo + lo*hi (the "3xTF32" scheme; the dropped lo*lo term and the
-//     truncation of lo are 2^-20 relative).  The kernel is bound
+//   * fp32 accuracy from TF32 hardware: every operand is split hi + lo (hi = the value rounded to TF32's mantissa, lo = the
+//     rounded remainder) and a tile is the sum of hi*hi + hi*lo + lo*hi (the "3xTF32" scheme; the dropped lo*lo term is
+//     2^-22 relative).  The kernel is bound
 //     by HBM (7-11 FLOP/B), so the 3x tensor work is free;
 //   * the accumulators go back through shared memory so that the 351 packed outputs are written as consecutive floats.
 // k_interact (fp32 FMA) remains for shapes outside those limits.
@@ -101,12 +101,11 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) k_interact_mma(const float 
     const int nt = n_f + 1;
     const int n_pairs = nt * (nt - 1) / 2;
     const int out_w = D + n_pairs;
-    // offset in the staged Z of packed pair pr = i(i-1)/2 + j (0 <= j < i) for the pairs lane + 32 k of this lane, two
-    // 16-bit offsets per register
-    unsigned poff[kPairSlots / 2];
-#pragma unroll
-    for (int k = 0; k < kPairSlots; ++k) {
-        const int pr = lane + 32 * k;
+    // offset in the staged Z of packed pair pr = i(i-1)/2 + j (0 <= j < i): a table built once by the CTA, from which a lane
+    // takes the pairs lane + 32 k it writes, two 16-bit offsets per register (a warp lives for only a handful of samples:
+    // per-lane square roots for all 16 slots cost as much as a whole sample)
+    __shared__ unsigned short s_off[32 * kPairSlots];
+    for (int pr = threadIdx.x; pr < 32 * kPairSlots; pr += blockDim.x) {
         unsigned o = 0;
         if (pr < n_pairs) {
             int i = static_cast<int>((1.0f + sqrtf(1.0f + 8.0f * static_cast<float>(pr))) * 0.5f);
@@ -114,27 +113,38 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) k_interact_mma(const float 
             while ((i + 1) * i / 2 <= pr) ++i;
             o = static_cast<unsigned>(i * kZld + (pr - i * (i - 1) / 2));
         }
-        if (k & 1) poff[k >> 1] |= o << 16;
-        else poff[k >> 1] = o;
+        s_off[pr] = static_cast<unsigned short>(o);
     }
+    __syncthreads();
+    unsigned poff[kPairSlots / 2];
+#pragma unroll
+    for (int k = 0; k < kPairSlots; k += 2)
+        poff[k >> 1] = static_cast<unsigned>(s_off[lane + 32 * k]) | (static_cast<unsigned>(s_off[lane + 32 * (k + 1)]) << 16);
     float *buf0 = s_t + static_cast<size_t>(warp) * 2 * region;
     const int g = lane >> 2, tq = lane & 3;
     const bool vec = ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(ly) & 15u) == 0);
     const int d4 = D >> 2, n4 = nt * d4;
     const int stride = gridDim.x * wpc;
-    // the staging walk of this lane: 16-byte piece e = lane + 32 i sits in row e / d4, column piece e % d4
+    // the staging walk of this lane: 16-byte piece e = lane + 32 i of [x ; ly] sits in row e / d4 of T.  x and the rows of
+    // ly are contiguous in global memory, so the source is a base pointer + 16 e; the destination is 16 e plus the row's
+    // padding, row * (ld - D) floats -- only the row is tracked (incrementally: no division in the loop), and shared-memory
+    // addresses are 32-bit
     const int row0 = vec ? lane / d4 : 0, c40 = vec ? lane - row0 * d4 : 0;
     const int dr = vec ? 32 / d4 : 0, dc = vec ? 32 - dr * d4 : 0;
+    const int pad = ld - D;
 
     // stage T = [x ; ly] of sample s into t (asynchronously when rows are 16-byte aligned)
     auto stage = [&](int s, float *t) {
         const float *xs = x + static_cast<size_t>(s) * D;
         const float *ls = ly + static_cast<size_t>(s) * n_f * D;
         if (vec) {
-            const float *lsm = ls - D;                        // row k >= 1 of T is row k - 1 of ly
+            const float *lsm = ls - D;                        // piece e >= d4 is at ls + 4 (e - d4)
+            const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(t));
             int row = row0, c4 = c40;
             for (int e = lane; e < n4; e += 32) {
-                cp_async16(t + row * ld + (c4 << 2), (row == 0 ? xs : lsm + static_cast<size_t>(row) * D) + (c4 << 2));
+                const float *src = (e < d4 ? xs : lsm) + (e << 2);
+                const unsigned dst = sa + (static_cast<unsigned>((e << 2) + row * pad) << 2);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
                 c4 += dc;
                 row += dr;
                 if (c4 >= d4) {
@@ -173,7 +183,8 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) k_interact_mma(const float 
             __syncwarp();
         }
         // x goes to the head of the output row
-        for (int e = lane; e < D; e += 32) rs[e] = t[e];
+        if (lane < D) rs[lane] = t[lane];
+        for (int e = lane + 32; e < D; e += 32) rs[e] = t[e];
         // ---- Z = T T^t on the tensor cores (rows >= nt hold stale data: they only reach outputs nobody reads) ----
         // The contraction index may be permuted as long as A and B agree: the fragment slots "k = tq" and "k = tq + 4"
         // of a lane take the adjacent columns k0 + 2 tq and k0 + 2 tq + 1, so a lane reads one 64-bit word per row group.
@@ -187,14 +198,14 @@ __global__ void __launch_bounds__(kMmaWarps * 32, 3) k_interact_mma(const float 
             unsigned hi[4][2], lo[4][2];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                // hi = the value cut to TF32's 10 mantissa bits (a mask: cvt.rna runs at a quarter of the ALU rate, and at
-                // d = 64 its 256 conversions per sample were the longest pipe), lo = the exact remainder, which the tensor
-                // core itself cuts to TF32 on the way in: |v - hi - lo| <= 2^-20 |v|
+                // hi = the value rounded to TF32's 10 mantissa bits with two integer instructions (add half an ulp, mask):
+                // cvt.rna.tf32 runs at a quarter of the ALU rate, and at d = 64 its 256 conversions per sample were the
+                // longest pipe.  lo = the exact remainder, rounded the same way: |v - hi - lo| <= 2^-22 |v|, as with cvt.rna
                 const float2 v = *reinterpret_cast<const float2 *>(tl + 8 * j * ld + k0);
-                hi[j][0] = __float_as_uint(v.x) & 0xFFFFE000u;
-                lo[j][0] = __float_as_uint(v.x - __uint_as_float(hi[j][0]));
-                hi[j][1] = __float_as_uint(v.y) & 0xFFFFE000u;
-                lo[j][1] = __float_as_uint(v.y - __uint_as_float(hi[j][1]));
+                hi[j][0] = (__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u;
+                lo[j][0] = (__float_as_uint(v.x - __uint_as_float(hi[j][0])) + 0x1000u) & 0xFFFFE000u;
+                hi[j][1] = (__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u;
+                lo[j][1] = (__float_as_uint(v.y - __uint_as_float(hi[j][1])) + 0x1000u) & 0xFFFFE000u;
             }
             // tile (m, n): rows 16m .. 16m+15 (A from row groups 2m, 2m+1), cols 8n .. 8n+7 (B from row group n)
 #define EVS_TILE(ti, m, n)                                                                                           \

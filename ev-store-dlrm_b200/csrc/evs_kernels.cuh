@@ -370,6 +370,8 @@ __global__ void __launch_bounds__(kLookupThreads, (P1 == 0) ? 5 : 1) k_serve(con
         p.dbg[0] = t_start;
         if (p.dbg[4] > p.dbg[6]) p.dbg[14] += 1ull;       // previous batch's k_evict has not finished (must stay 0)
         *p.args = a;                                       // the later kernels of this batch read the arguments here
+        if (a.seq != 0u) p.g->auto_seq = a.seq;
+        else p.args->seq = (p.g->auto_seq += 1u);          // replayed from a caller's graph: the device numbers the batch
     }
     griddep_launch(p);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -126,6 +126,8 @@ struct GlobalCtl {
     unsigned long long lookups, samples, hits[2], c3_hits, approx_subst, misses, perfect_hits, batches;
     unsigned int error;                    // 1 = index out of range, 7 = a peer did not answer in time
     unsigned int fetch_done_seq;           // number of the last batch whose miss-fetch role has finished (it no longer reads its staging rows)
+    unsigned int auto_seq;                 // number of the last batch started; a batch launched with BatchArgs::seq == 0 (a replay of a
+                                           // graph the CALLER captured: its arguments are frozen) takes the next number from here
 };
 constexpr unsigned long long kPeerTimeoutNs = 4000000000ull;   // spin-waits on peer flags give up after 4 s
 

@@ -173,3 +173,32 @@ class DLRMInference:
         if 0.0 < self.loss_threshold < 1.0:
             p = torch.clamp(p, min=self.loss_threshold, max=1.0 - self.loss_threshold)
         return p
+
+    # ---- the whole forward as one CUDA graph -----------------------------------------------------------------------
+    def capture(self, batch: int, n_dense: int | None = None):
+        """Capture ``sequential_forward`` for batches of ``batch`` samples into ONE CUDA graph: the bottom MLP branch, the
+        cache's serve / update / evict kernels, the interaction and the top MLP, with their dependencies -- a forward is then
+        a single graph launch instead of a dozen kernel launches and two stream joins.  Call ``replay(dense_x, lS_i)``."""
+        import torch
+        n_dense = n_dense or self.bot[0][0].shape[1]
+        self._g_dense = torch.zeros((batch, n_dense), dtype=torch.float32, device=self.device)
+        self._g_idx = torch.zeros((self.store.n_tables, batch), dtype=torch.int64, device=self.device)
+        # one eager pass on a side stream first (library handles, workspaces), as torch's capture rules ask
+        warm = torch.cuda.Stream(device=self.device)
+        warm.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(warm):
+            self.sequential_forward(self._g_dense, None, self._g_idx)
+        torch.cuda.current_stream(self.device).wait_stream(warm)
+        torch.cuda.synchronize(self.device)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_out = self.sequential_forward(self._g_dense, None, self._g_idx)
+        return self
+
+    def replay(self, dense_x, lS_i):
+        """One captured forward: fills the static inputs, launches the graph, returns the (static) probabilities [B, 1]."""
+        self._g_dense.copy_(dense_x, non_blocking=True)
+        self._g_idx.copy_(lS_i, non_blocking=True)
+        self._graph.replay()
+        self.store.note_replays(1)
+        return self._g_out

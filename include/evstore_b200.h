@@ -157,6 +157,13 @@ int evs_lookup_bags(evs_handle h, const int64_t *idx_dev, const int64_t *off_dev
 int evs_lookup_batches(evs_handle h, int32_t n, const int64_t *const *idx_dev, int32_t B, float *const *out_dev,
                        int64_t out_stride, uint8_t *const *hit_dev, void *stream);
 
+/* Capturing evs_lookup_batch into the CALLER's CUDA graph (e.g. a whole sequential_forward, dlrm_s_pytorch_C1_C2_C3.py:742-768):
+ * when `stream` is being captured the batch is recorded as plain kernels with its arguments frozen (same index / output
+ * buffers on every replay: refill them before each launch); the device numbers the replays itself.  After launching the
+ * captured graph n times call evs_note_replays(h, n, stream) -- it keeps the host's batch count and the ring bookkeeping
+ * in step (and returns a pending index / peer error).  Replays and direct calls may be mixed. */
+int evs_note_replays(evs_handle h, int64_t n, void *stream);
+
 /* Look-ahead: idx_dev is the index batch the NEXT evs_lookup_batch / evs_shard_lookup call on this handle will pass
  * (same pointer, same B).  The library probes it and stages the rows of its probable misses from the host-pinned
  * backing store into HBM on its own stream, under the kernels of the batch in flight; the next call then finds

@@ -92,3 +92,45 @@ def test_quantised_tier_predictions_within_the_stated_tolerance(golden_dir, prec
             assert float(np.abs(rows - tables[k][g["lS_i"][k]]).max()) <= tol_row
     finally:
         store.close()
+
+
+def test_captured_forward_equals_eager_forward(golden_dir):
+    """DLRMInference.capture: the whole sequential_forward (bottom MLP branch, the cache's three kernels, interaction, top MLP)
+    as ONE CUDA graph.  Replaying it over a stream of batches gives the eager path's probabilities, and the cache goes
+    through the same states (hit statistics, eviction counts, final FIFO lists) -- the device numbers the replays itself."""
+    import torch
+    p = pkg()
+    g = _golden(golden_dir)
+    tables = [np.ascontiguousarray(g[f"emb_{k}"]) for k in range(26)]
+    rows = [t.shape[0] for t in tables]
+    bot = [(g[f"bot_w{i}"], g[f"bot_b{i}"]) for i in range(4)]
+    top = [(g[f"top_w{i}"], g[f"top_b{i}"]) for i in range(3)]
+    B = 128
+    trace = p.workload.ZipfTrace(rows, seed=17)
+    batches = [trace.batch(B) for _ in range(12)]
+    dense = [torch.rand((B, 13), device="cuda", generator=torch.Generator(device="cuda").manual_seed(k)) for k in range(12)]
+    out = {}
+    for mode in ("eager", "graph"):
+        store = p.EvStore(tables, p.CacheConfig(total_size=500, max_batch=B, record_events=True))
+        net = p.dlrm_ops.DLRMInference(bot, top, store)
+        if mode == "graph":
+            net.capture(B)                                   # its warm-up pass looks batch-of-zeros up once, eagerly
+        else:
+            net.sequential_forward(torch.zeros((B, 13), device="cuda"), None, torch.zeros((26, B), dtype=torch.int64, device="cuda"))
+        probs = []
+        for k in range(12):
+            idx = torch.from_numpy(batches[k]).cuda()
+            z = net.replay(dense[k], idx) if mode == "graph" else net.sequential_forward(dense[k], None, idx)
+            torch.cuda.synchronize()
+            probs.append(z.cpu().numpy().copy())
+        store.sync()
+        st = store.stats()
+        state, n_perfect = store.dump_state()
+        out[mode] = (probs, st, state, n_perfect)
+        store.close()
+    for k in range(12):
+        assert np.allclose(out["eager"][0][k], out["graph"][0][k], rtol=0, atol=1e-6), k
+    se, sg = out["eager"][1], out["graph"][1]
+    assert sg["lookups"] == se["lookups"] and sg["hits"] == se["hits"] and sg["evictions"] == se["evictions"] and sg["batches"] == se["batches"]
+    assert se["evictions"][0] > 0
+    assert out["eager"][2] == out["graph"][2] and out["eager"][3] == out["graph"][3]
