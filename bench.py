@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="A/B: do not announce the next index batch (evs_prefetch)")
     ap.add_argument("--no-b16k", action="store_true", help="skip the batch-16384 roofline leg")
-    ap.add_argument("--op", default="", choices=["", "interact", "embedding_bag"],
+    ap.add_argument("--op", default="", choices=["", "interact", "embedding_bag", "knn"],
                     help="time one of the tensor ops either side of the cache alone (bench_ops.py) instead of the lookup path")
     ap.add_argument("--no-ops", action="store_true", help="skip the interact / embedding_bag legs of the default line")
     ap.add_argument("--no-configs4", action="store_true", help="N = 1: skip the Terabyte-shape (configs[4]) leg (48 GB of pinned host memory)")

@@ -99,6 +99,32 @@ def bench_embedding_bag(pkg, dev, B=16384, P=10, d=64, rows=4_000_000, prec=32, 
     return res
 
 
+def bench_knn(pkg, dev, n=262144, d=16, K=3):
+    """evs_knn, every row of an [n, d] matrix against all rows (the alt-key generator's inner loop).  FLOP = 2 d per pair (the
+    tensor cores execute 3x that for the hi / lo split); the kernel is bound by the selection's ALU work, not by the tensor pipe."""
+    import torch
+    x = torch.randn((n, d), device=dev)
+    nbr = pkg.altkeys.knn(x)                              # warm-up (and the result for the spot check)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        pkg.altkeys.knn(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    # spot check of 64 rows against torch's fp32 distances
+    rows = torch.arange(0, n, n // 64, device=dev)[:64]
+    d2 = torch.cdist(x[rows], x).pow(2)
+    want = d2.topk(11, dim=1, largest=False).indices[:, 1:]
+    agree = float((want == nbr[rows]).float().mean())
+    pairs = float(n) * n
+    return {"op": "knn", "kernel": "k_knn (mma.sync m16n8k8 TF32, operands split hi + lo; top-11 selection in registers) + k_knn_merge",
+            "rows": n, "dim": d, "k": 10, "ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "useful_TFLOPs": pairs * 2 * d / (ms * 1e-3) / 1e12,
+            "tensor_TFLOPs_executed": pairs * 2 * ((d + 7) // 8 * 8) * 3 / (ms * 1e-3) / 1e12, "agreement_with_torch_cdist_topk": agree,
+            "full_kaggle_estimate_s": (33.76e6 ** 2) / (pairs / (ms * 1e-3))}
+
+
 def main_ops(args):
     import torch
     from bench import measured_peak_hbm
@@ -109,6 +135,12 @@ def main_ops(args):
     peak, src = measured_peak_hbm()
     B = args.batch or 16384
     K = max(10, args.steps)
+    if args.op == "knn":
+        legs = [bench_knn(pkg, dev, n=(args.batch or 262144), d=d) for d in ([args.dim] if args.dim else [16, 64])]
+        line = {"metric": "knn_pairs_per_s", "op": "knn", "value": max(l["pairs_per_s"] for l in legs), "unit": "pairs/s", "n_gpus": 1,
+                "steps": 3, "legs": legs, "data": "synthetic"}
+        print(json.dumps(line), flush=True)
+        return 0
     if args.op == "interact":
         legs = [bench_interact(pkg, dev, B=B, d=d, K=K, peak=peak) for d in ([args.dim] if args.dim else [16, 64])]
     else:

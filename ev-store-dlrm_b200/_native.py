@@ -54,7 +54,7 @@ SYMBOLS = [
     "evs_create", "evs_destroy", "evs_last_error", "evs_version", "evs_lookup_batch", "evs_lookup_batches", "evs_lookup_bags", "evs_note_replays", "evs_prefetch", "evs_probe_batch", "evs_check",
     "evs_memory_footprint", "evs_host_alloc", "evs_host_free",
     "evs_lookup_batch_host", "evs_submit_host", "evs_wait_host", "evs_sync", "evs_stats", "evs_last_events", "evs_dump_state", "evs_dump_c3",
-    "evs_interact", "evs_embedding_bag", "evs_embedding_bag_status", "evs_store_ptr", "evs_shard_create", "evs_shard_export",
+    "evs_interact", "evs_knn", "evs_embedding_bag", "evs_embedding_bag_status", "evs_store_ptr", "evs_shard_create", "evs_shard_export",
     "evs_shard_connect", "evs_shard_lookup", "evs_shard_lookup_many", "evs_shard_destroy", "evs_set_profiling", "evs_kernel_times", "evs_launch_count", "evs_phase_times", "evs_legacy_configure", "evs_legacy_handle", "ev_lookup", "get_ev_values", "print_perfect_hit",
     "test_arr", "ev_lookup_based_on_list_keys",
 ]
@@ -118,6 +118,8 @@ def load_library(path: str | None = None):
     lib.evs_dump_c3.restype = C.c_int
     lib.evs_interact.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.evs_interact.restype = C.c_int
+    lib.evs_knn.argtypes = [vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, i32, vp, vp]
+    lib.evs_knn.restype = C.c_int
     lib.evs_embedding_bag.argtypes = [vp, i64, i32, i32, vp, vp, i64, i32, vp, vp, i64, vp]
     lib.evs_embedding_bag.restype = C.c_int
     lib.evs_embedding_bag_status.argtypes = []

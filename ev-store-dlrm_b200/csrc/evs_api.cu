@@ -17,6 +17,7 @@
 #include "evs_update.cuh"
 #include "evs_prefetch.cuh"
 #include "evs_bags.cuh"
+#include "evs_knn.cuh"
 
 namespace evs {
 
@@ -1824,6 +1825,28 @@ int evs_host_free(void *ptr) {
     if (ptr == nullptr) return EVS_OK;
     EVS_CUDA(cudaFree(ptr));
     return EVS_OK;
+}
+
+// ---- alt-key generation: brute-force k-NN over all embedding rows + most popular neighbour (evs_knn.cuh) ----------------
+int evs_knn(const float *x_dev, int64_t n, const float *q_dev, int64_t nq, int32_t dim, int32_t k, int64_t *nbr_dev, float *dist_dev,
+            const uint32_t *freq_dev, const int64_t *table_off_dev, int32_t n_tables, uint32_t *alt_dev, void *stream) {
+    if (nq < 0 || n < 1) return EVS_ERR_INVALID;
+    if (nq == 0) return EVS_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // few query blocks: split the database over CTAs so that the machine is full (the per-split lists are merged afterwards)
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long qblocks = (nq + kKnnQ - 1) / kKnnQ;
+    const long long tiles = (n + kKnnT - 1) / kKnnT;
+    int splits = static_cast<int>(std::max<long long>(1, std::min<long long>(std::min<long long>(tiles, 64), (2ll * sms + qblocks - 1) / qblocks)));
+    float2 *part = nullptr;
+    EVS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&part), static_cast<size_t>(nq) * splits * kKnnSel * sizeof(float2), st));
+    int rc = launch_knn(x_dev, n, q_dev, nq, dim, k, reinterpret_cast<long long *>(nbr_dev), dist_dev, freq_dev,
+                        reinterpret_cast<const long long *>(table_off_dev), n_tables, alt_dev, part, splits, st);
+    cudaFreeAsync(part, st);
+    if (rc == EVS_ERR_INVALID) set_error("evs_knn: bad pointers / n (< 2^31) / dim (1..64) / k (1..10)");
+    return rc;
 }
 
 int evs_store_ptr(evs_handle h, int tier, int table, const void **dev_ptr, int32_t *precision) {

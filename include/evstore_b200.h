@@ -274,6 +274,20 @@ int evs_embedding_bag_status(void);
  * path (request_to_emb_storage, emb_storage/storage_manager.py:125) reads it with evs_embedding_bag. */
 int evs_store_ptr(evs_handle h, int tier, int table, const void **dev_ptr, int32_t *precision);
 
+/* ---- alt-key generation for C3 (script/approximate_embedding/phase2_similarity_analysis/) ---------- *
+ * get_neighbors_GPU.ipynb: every embedding row of every table in one matrix, brute-force Euclidean k-NN (n_neighbors = 11,
+ * entry [0] -- the row itself -- dropped); most_popular_neighbor.ipynb: of those k = 10 the one with the highest workload
+ * frequency (first maximum, absent = 0) becomes the row's alternative key, alt_row * 100 + alt_table (tables 1-based,
+ * convert_altkeys_to_binary.py:50).  One fused tensor-core kernel (distances by 3xTF32 mma.sync: fp32-accurate) + a merge.
+ *   x_dev  fp32 [n][dim] the database (n < 2^31, dim <= 64);  q_dev fp32 [nq][dim] the query rows (may point into x_dev)
+ *   nbr_dev int64 [nq][k] global row ids, nearest first (ties by index), -1 where the database has fewer rows; or NULL
+ *   dist_dev fp32 [nq][k] squared distances, or NULL
+ *   alt_dev uint32 [nq] alt keys, or NULL; then table_off_dev int64 [n_tables + 1] = first global row of each table and
+ *           freq_dev uint32 [n] request counts per global row (or NULL: every neighbour counts 0, the nearest wins) */
+int evs_knn(const float *x_dev, int64_t n, const float *q_dev, int64_t nq, int32_t dim, int32_t k, int64_t *nbr_dev,
+            float *dist_dev, const uint32_t *freq_dev, const int64_t *table_off_dev, int32_t n_tables, uint32_t *alt_dev,
+            void *stream);
+
 /* ---- host memory for the backing rows (get_from_file's ev-table-N.bin contents, evlfu_32.cpp:283-316) --- *
  * Any host array works as a backing store (pinned allocations are used as they are, pageable ones are
  * page-locked by evs_create).  Memory from evs_host_alloc is additionally mapped into `device` with large
