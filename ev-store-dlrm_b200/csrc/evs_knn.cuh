@@ -14,10 +14,10 @@
 //     its near-ties, and plain TF32 (10 mantissa bits) reorders them.  The split of a database tile is done ONCE, by the
 //     thread that stages it (global -> registers -> hi / lo planes in shared memory, the next tile's loads in flight under
 //     the current tile's math); the queries' split fragments live in registers for d <= 16;
-//   * every thread keeps, for each of its two query rows, a sorted list of the 11 best (distance, index) pairs among the
-//     columns it sees; a candidate is compared with the list's worst first, so after the first tiles an element costs one
-//     FFMA and one compare.  At the end the four lists of a query row (the accumulator layout spreads a row over a quad) are
-//     merged through shared memory.
+//   * every thread keeps, for each of its two query rows, a sorted list (in shared memory) of the 11 best (distance, index)
+//     pairs among the columns it sees; a candidate is first compared with the row's threshold -- the smallest of the worst
+//     entries of the four lists of the row's quad -- so after the first tiles an element costs one FFMA and one compare.  At
+//     the end the four lists of a query row (the accumulator layout spreads a row over a quad) are merged.
 // With d = 16 there are only 2 x 16 multiply-adds per pair against ~4 selection instructions: the kernel is bound by the
 // ALU work of the selection, not by the tensor pipe (which is why the 3x split is free) and not by HBM (a tile is read once
 // per 128 queries).
@@ -37,34 +37,23 @@ constexpr int kKnnMaxD = 64;
 
 __device__ __forceinline__ unsigned tf32_rn(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
 
-struct KnnList {
-    float d[kKnnSel];
-    int id[kKnnSel];
-};
-__device__ __forceinline__ void knn_init(KnnList &l) {
-#pragma unroll
-    for (int i = 0; i < kKnnSel; ++i) {
-        l.d[i] = __int_as_float(0x7f800000);
-        l.id[i] = 0x7fffffff;
-    }
-}
 __device__ __forceinline__ bool knn_better(float a, int ia, float b, int ib) { return a < b || (a == b && ia < ib); }
-// insert (v, i) if it beats the worst entry; the list stays sorted ascending by (distance, index)
-__device__ __forceinline__ void knn_insert(KnnList &l, float v, int i) {
-    if (!knn_better(v, i, l.d[kKnnSel - 1], l.id[kKnnSel - 1])) return;
-    l.d[kKnnSel - 1] = v;
-    l.id[kKnnSel - 1] = i;
-#pragma unroll
-    for (int p = kKnnSel - 1; p > 0; --p) {
-        if (knn_better(l.d[p], l.id[p], l.d[p - 1], l.id[p - 1])) {
-            const float td = l.d[p];
-            const int ti = l.id[p];
-            l.d[p] = l.d[p - 1];
-            l.id[p] = l.id[p - 1];
-            l.d[p - 1] = td;
-            l.id[p - 1] = ti;
-        }
+// A thread's list of a query row: kKnnSel (distance, index) pairs in SHARED memory, sorted ascending.  Insertions are rare
+// once the lists have warmed up (a candidate must beat the row's threshold first), so the insertion is one out-of-line
+// routine: inlined at the 32 candidate sites of a tile, its unrolled register version was ~5000 instructions -- the kernel
+// spent its time fetching them -- and 44 registers per thread.  Returns the list's new worst distance.
+__device__ __noinline__ float knn_insert(float2 *list, float v, int i) {
+    float2 last = list[kKnnSel - 1];
+    if (!knn_better(v, i, last.x, __float_as_int(last.y))) return last.x;
+    int p = kKnnSel - 1;
+    while (p > 0) {
+        const float2 e = list[p - 1];
+        if (!knn_better(v, i, e.x, __float_as_int(e.y))) break;
+        list[p] = e;
+        --p;
     }
+    list[p] = make_float2(v, __int_as_float(i));
+    return list[kKnnSel - 1].x;
 }
 
 // x: database [n][D] fp32, q: queries [nq][D] fp32 (may alias x), part: [nq][splits][kKnnSel] (distance, index) pairs.
@@ -73,8 +62,9 @@ template <int KSR>
 __global__ void __launch_bounds__(kKnnThreads, 2) k_knn(const float *__restrict__ x, long long n, const float *__restrict__ q, long long nq,
                                                         int D, int Dp, int ld, long long rows_per_split, float2 *__restrict__ part) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    // layout: Qhi[128][ld] Qlo[128][ld] (AREG: only during set-up) | Xhi[64][ld] Xlo[64][ld] | norm[64] | cand (overlays Q/X at the end)
-    unsigned *s_qhi = reinterpret_cast<unsigned *>(s_raw);
+    // layout: lists[128 rows][4 threads of the row's quad][11] (distance, index) | Qhi[128][ld] Qlo[128][ld] | Xhi[64][ld] Xlo[64][ld] | norm[64]
+    float2 *s_cand = reinterpret_cast<float2 *>(s_raw);
+    unsigned *s_qhi = reinterpret_cast<unsigned *>(s_raw + static_cast<size_t>(kKnnQ) * 4 * kKnnSel * sizeof(float2));
     unsigned *s_qlo = s_qhi + kKnnQ * ld;
     unsigned *s_xhi = s_qlo + kKnnQ * ld;
     unsigned *s_xlo = s_xhi + kKnnT * ld;
@@ -116,9 +106,14 @@ __global__ void __launch_bounds__(kKnnThreads, 2) k_knn(const float *__restrict_
         }
     }
 
-    KnnList best[2];                                         // rows 16 warp + g and 16 warp + g + 8
-    knn_init(best[0]);
-    knn_init(best[1]);
+    // this thread's lists: rows 16 warp + g and 16 warp + g + 8; their worst distances are mirrored in registers
+    float2 *list[2] = {s_cand + ((16 * warp + g) * 4 + tq) * kKnnSel, s_cand + ((16 * warp + g + 8) * 4 + tq) * kKnnSel};
+    float worst[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        for (int i = 0; i < kKnnSel; ++i) list[r][i] = make_float2(__int_as_float(0x7f800000), __int_as_float(0x7fffffff));
+        worst[r] = __int_as_float(0x7f800000);
+    }
 
     // ---- staging: thread t owns float4 pieces t, t + 256, ... of a tile (64 rows x d4 pieces) ----------------------------------
     constexpr int PMAX = (KSR > 0 ? kKnnT * (KSR * 8 / 4) : kKnnT * (kKnnMaxD / 4)) / kKnnThreads;      // pieces per thread: 1 (d <= 16) or 4
@@ -146,37 +141,48 @@ __global__ void __launch_bounds__(kKnnThreads, 2) k_knn(const float *__restrict_
             }
         }
     };
+    // |x|^2 of a tile's rows: when a row's pieces sit in d4 neighbouring lanes (d4 = 2, 4, 8, 16) the lanes add up their pieces
+    // in a fixed butterfly (the same x gets the same norm in every CTA: the ranking must not depend on who computed it), else
+    // one thread per row walks the row in shared memory.  Rows past the end of the range get +inf: never selected.
+    const bool shfl_norm = (32 % d4) == 0;
     auto store_tile = [&](long long base) {
         __syncthreads();                                     // the previous tile's reads are over
 #pragma unroll
         for (int i = 0; i < PMAX; ++i) {
             const int e = threadIdx.x + i * kKnnThreads;
-            if (e < n_pieces) {
-                const int r = e / d4, c4 = e - r * d4;
-                const float v[4] = {stage[i].x, stage[i].y, stage[i].z, stage[i].w};
-                uint4 h, l;
-                unsigned *hp = &h.x, *lp = &l.x;
+            const bool on = e < n_pieces;
+            const int r = on ? e / d4 : 0, c4 = on ? e - r * d4 : 0;
+            const float v[4] = {stage[i].x, stage[i].y, stage[i].z, stage[i].w};
+            uint4 h, l;
+            unsigned *hp = &h.x, *lp = &l.x;
+            float nn = 0.0f;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    hp[k] = tf32_rn(v[k]);
-                    lp[k] = tf32_rn(v[k] - __uint_as_float(hp[k]));
-                }
+            for (int k = 0; k < 4; ++k) {
+                hp[k] = tf32_rn(v[k]);
+                lp[k] = tf32_rn(v[k] - __uint_as_float(hp[k]));
+                nn = fmaf(v[k], v[k], nn);
+            }
+            if (on) {
                 *reinterpret_cast<uint4 *>(s_xhi + r * ld + (c4 << 2)) = h;
                 *reinterpret_cast<uint4 *>(s_xlo + r * ld + (c4 << 2)) = l;
             }
-        }
-        __syncthreads();
-        // |x|^2 of every row of the tile, by one thread in a fixed order (the same x gets the same norm in every CTA); rows past
-        // the end of the range get +inf and can never displace a real candidate
-        if (threadIdx.x < kKnnT) {
-            float nn = 0.0f;
-            for (int c = 0; c < Dp; ++c) {
-                const float v = __uint_as_float(s_xhi[threadIdx.x * ld + c]) + __uint_as_float(s_xlo[threadIdx.x * ld + c]);
-                nn = fmaf(v, v, nn);
+            if (shfl_norm) {
+                for (int o = 1; o < d4; o <<= 1) nn += __shfl_xor_sync(0xFFFFFFFFu, nn, o);
+                if (on && c4 == 0) s_norm[r] = (base + r < n1) ? nn : __int_as_float(0x7f800000);
             }
-            s_norm[threadIdx.x] = (base + threadIdx.x < n1) ? nn : __int_as_float(0x7f800000);
         }
         __syncthreads();
+        if (!shfl_norm) {
+            if (threadIdx.x < kKnnT) {
+                float nn = 0.0f;
+                for (int c = 0; c < Dp; ++c) {
+                    const float v = __uint_as_float(s_xhi[threadIdx.x * ld + c]) + __uint_as_float(s_xlo[threadIdx.x * ld + c]);
+                    nn = fmaf(v, v, nn);
+                }
+                s_norm[threadIdx.x] = (base + threadIdx.x < n1) ? nn : __int_as_float(0x7f800000);
+            }
+            __syncthreads();
+        }
     };
 
     long long base = n0;
@@ -218,28 +224,34 @@ __global__ void __launch_bounds__(kKnnThreads, 2) k_knn(const float *__restrict_
                 }
             }
         }
-        // ---- selection: |x|^2 - 2 q.x against the worst entry of the row's list -----------------------------------------------
+        // ---- selection: |x|^2 - 2 q.x against the row's threshold -------------------------------------------------------------
+        // A query row is spread over the four threads of a quad, each with its own list.  Whatever a thread's list holds, 11
+        // candidates at or below its worst entry exist, so nothing above the SMALLEST of the quad's four worst entries can be
+        // among the row's 11 best: one threshold per row and tile (two shuffles) cuts the insertions -- the divergent, expensive
+        // part (ncu: 2/3 of the kernel's stall samples) -- by about four.
+        float thr[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float w = worst[r];
+            w = fminf(w, __shfl_xor_sync(0xFFFFFFFFu, w, 1));
+            w = fminf(w, __shfl_xor_sync(0xFFFFFFFFu, w, 2));
+            thr[r] = w;
+        }
 #pragma unroll
         for (int j = 0; j < kKnnT / 8; ++j) {
             const int c = 8 * j + 2 * tq;
             const float2 nn = *reinterpret_cast<const float2 *>(s_norm + c);
             const int id = static_cast<int>(base) + c;
-            knn_insert(best[0], fmaf(-2.0f, acc[j][0], nn.x), id);
-            knn_insert(best[0], fmaf(-2.0f, acc[j][1], nn.y), id + 1);
-            knn_insert(best[1], fmaf(-2.0f, acc[j][2], nn.x), id);
-            knn_insert(best[1], fmaf(-2.0f, acc[j][3], nn.y), id + 1);
+            const float v0 = fmaf(-2.0f, acc[j][0], nn.x), v1 = fmaf(-2.0f, acc[j][1], nn.y);
+            const float v2 = fmaf(-2.0f, acc[j][2], nn.x), v3 = fmaf(-2.0f, acc[j][3], nn.y);
+            if (v0 <= thr[0]) worst[0] = knn_insert(list[0], v0, id);
+            if (v1 <= thr[0]) worst[0] = knn_insert(list[0], v1, id + 1);
+            if (v2 <= thr[1]) worst[1] = knn_insert(list[1], v2, id);
+            if (v3 <= thr[1]) worst[1] = knn_insert(list[1], v3, id + 1);
         }
     }
 
-    // ---- merge the four lists of a query row (the quad's threads) through shared memory ----------------------------------------
-    __syncthreads();
-    float2 *s_cand = reinterpret_cast<float2 *>(s_raw);     // [128][4][11] pairs: 45 KB, over the query / tile planes
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int row = 16 * warp + g + 8 * r;
-#pragma unroll
-        for (int i = 0; i < kKnnSel; ++i) s_cand[(row * 4 + tq) * kKnnSel + i] = make_float2(best[r].d[i], __int_as_float(best[r].id[i]));
-    }
+    // ---- merge the four sorted lists of a query row (the quad's threads) ---------------------------------------------------------
     __syncthreads();
     if (threadIdx.x < kKnnQ && q0 + threadIdx.x < nq) {
         const float2 *c = s_cand + threadIdx.x * 4 * kKnnSel;
@@ -325,7 +337,7 @@ inline int launch_knn(const float *x, long long n, const float *q, long long nq,
     if (nq == 0) return EVS_OK;
     const int Dp = (D + 7) & ~7;
     const int ld = (Dp & 15) == 8 ? Dp : Dp + 8;             // = 8 mod 16: conflict-free 64-bit fragment reads
-    const size_t smem = std::max(static_cast<size_t>(2 * kKnnQ + 2 * kKnnT) * ld * 4 + kKnnT * 4, static_cast<size_t>(kKnnQ) * 4 * kKnnSel * 8);
+    const size_t smem = static_cast<size_t>(kKnnQ) * 4 * kKnnSel * 8 + static_cast<size_t>(2 * kKnnQ + 2 * kKnnT) * ld * 4 + kKnnT * 4;
     const long long tiles = (n + kKnnT - 1) / kKnnT;
     const long long rows_per_split = ((tiles + splits - 1) / splits) * kKnnT;
     const dim3 grid(static_cast<unsigned>((nq + kKnnQ - 1) / kKnnQ), static_cast<unsigned>(splits));
