@@ -162,12 +162,13 @@ def store_training_config(file_path, table_feature_map, nbatches, nbatches_test,
         f.write(str(m_den) + "\n")
 
 
-def open_model_dir(model_dir, precisions, dim=None, alt_path=None):
+def open_model_dir(model_dir, precisions, dim=None, alt_path=None, mapped_device=None):
     """Everything the GPU cache needs from the reference's stored model, unchanged on disk:
     <model_dir>/training_config.txt (cardinalities), <model_dir>/<ev-table[-16|-8|-4]>/binary/ev-table-N.bin per
     precision (evlfu_32.hpp:61, evlfu_16.hpp, evlfu_8.hpp:58, evlfu_4.hpp:61) and, for three layers, the alt-key
     directory.  Returns (rows, {precision: [raw tables]}, alt_keys | None) -- pass them to
-    ``EvStore.from_raw_stores``."""
+    ``EvStore.from_raw_stores``.  mapped_device: a CUDA device index -> the rows are moved into ``evs_host_alloc`` memory
+    (host memory that device maps with large pages: about twice the zero-copy miss-fetch rate over multi-GB tables)."""
     global ev_precs, ev_dimension, n_tables
     cfg = os.path.join(model_dir, "training_config.txt")
     rows = None
@@ -186,6 +187,11 @@ def open_model_dir(model_dir, precisions, dim=None, alt_path=None):
         ev_precs = keep
     rows = rows or list(_rows)
     alt = load_alt_keys(alt_path, rows) if alt_path else None
+    if mapped_device is not None:
+        from .cache_manager import to_host_rows
+        stores = {p: [to_host_rows(t, int(mapped_device)) for t in tabs] for p, tabs in stores.items()}
+        if alt is not None:
+            alt = [to_host_rows(a, int(mapped_device)) for a in alt]
     return rows, stores, alt
 
 
