@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--op", default="", choices=["", "interact", "embedding_bag", "knn"],
                     help="time one of the tensor ops either side of the cache alone (bench_ops.py) instead of the lookup path")
     ap.add_argument("--no-ops", action="store_true", help="skip the interact / embedding_bag legs of the default line")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short configs[2] / configs[3] legs of the default line")
     ap.add_argument("--no-configs4", action="store_true", help="N = 1: skip the Terabyte-shape (configs[4]) leg (48 GB of pinned host memory)")
     ap.add_argument("--only-main", action="store_true", help="N > 1: only the main leg (no contiguous-placement and configs[4] legs)")
     ap.add_argument("--store-in-hbm", action="store_true", help="debug: backing store copied into HBM (not the BASELINE config)")
@@ -283,6 +284,67 @@ def sharded_config(world: int, B: int, dim: int, transport: str = "p2p") -> dict
             "placement": "tables spread over the ranks by row count (sharded.balanced_placement; departs from ext_dist.get_my_slice, "
                          "whose contiguous slices are reported under placement_contiguous)",
             "l2": "no flush: index + slab working set exceeds the 126 MB L2 and every step reads a distinct index batch"}
+
+
+def extra_config_leg(pkg, dev, device, tables, idx, rows, dim, cache_rows, layers, p0, p1, prop, B, K, W, warm2048):
+    """One more BASELINE configuration on the tables and the trace of the main leg: configs[2] (C1 + C2 mixed precision) or
+    configs[3] (C1 + C2 + C3, batch 16384; alt keys = workload.make_alt_keys, the documented stand-in for the kNN tables).
+    Same memory budget as configs[1] (TOTAL_SIZE = cache_rows fp32-row units), same warm-up rule, 4 batches per call."""
+    import ctypes as C
+    import torch
+    T = len(rows)
+    g = B // 2048
+    n_need = (warm2048 // g + W + 3 * K + 8) if g > 1 else (warm2048 + W + 3 * K + 8)
+    if g > 1:
+        n = min(idx.shape[0] // g, n_need)
+        ib = np.ascontiguousarray(idx[:n * g].reshape(n, g, T, 2048).transpose(0, 2, 1, 3)).reshape(n, T, B)
+    else:
+        n = min(idx.shape[0], n_need)
+        ib = idx[:n]
+    warm = min(warm2048 // g, n - W - 3 * K - 5)
+    stores = {p: [pkg.to_host_rows(pkg.codecs.encode_table(t, p), device=device) for t in tables] for p in (p0, p1)}
+    alt = pkg.workload.make_alt_keys(rows) if layers == 3 else None
+    cfg = pkg.CacheConfig(n_layers=layers, main_precision=p0, secondary_precision=p1, size_proportion=prop, total_size=cache_rows,
+                          max_batch=B, device=device)
+    store = pkg.EvStore(tables, cfg, stores=stores, alt_keys=alt)
+    try:
+        idx_dev = torch.from_numpy(ib).to(dev)
+        out = torch.empty((B, T, dim), dtype=torch.float32, device=dev)
+        hit = torch.empty((B, T), dtype=torch.uint8, device=dev)
+        for k in range(warm + W):
+            store.lookup(idx_dev[k], out=out, hit=hit)
+            store.prefetch(idx_dev[k + 1])
+        store.sync()
+        store.stats(reset=True)
+        base = warm + W
+        st_ = torch.cuda.current_stream(dev).cuda_stream
+        outp, hitp = (C.c_void_p * 4)(*([out.data_ptr()] * 4)), (C.c_void_p * 4)(*([hit.data_ptr()] * 4))
+        regions = []
+        for rep in range(3):
+            calls = [(k, min(4, K - k), (C.c_void_p * 4)(*[idx_dev[base + k + j].data_ptr() for j in range(4)])) for k in range(0, K, 4)]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k, nb, ips in calls:
+                store.lookup_many_ptr(nb, ips, B, outp, out.stride(0), hitp, st_)
+                store.prefetch(idx_dev[base + k + nb])
+            e1.record()
+            torch.cuda.synchronize()
+            regions.append(e0.elapsed_time(e1))
+            base += K
+        store.check()
+        s = store.stats()
+        ms = sorted(regions)[1]
+        lk = max(1, s["lookups"])
+        return {"layers": layers, "main_precision": p0, "secondary_precision": p1, "size_proportion": prop, "batch": B, "steps": K,
+                "value": K * B * T / (ms * 1e-3), "unit": "lookups/s", "ms_per_step": ms / K, "value_regions_ms": regions,
+                "hit_rate_by_tier": {"c1": s["hits"][0] / lk, "c2": s["hits"][1] / lk, "c3": s["c3_hits"] / lk},
+                "capacity": s["capacity"], "c3_capacity": s["c3_capacity"], "cache_warm_batches": warm, "resident": s["size"],
+                "note": None if s["size"][0] >= s["capacity"][0] else
+                        "C1 is not full after the warm-up (its entries are %d-bit: the same budget holds %dx as many), so every key "
+                        "still goes to C1 (evlfu_8.cpp:590-602) and C2 / C3 see no traffic" % (p0, 32 // p0),
+                "alt_keys": "workload.make_alt_keys (a more popular row of the same table; the kNN generator is evs_knn)" if layers == 3 else None}
+    finally:
+        store.close()
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -585,6 +647,19 @@ def main_ours(args):
         except Exception as e:
             log("op legs failed:", repr(e))
 
+    # ---- BASELINE configs[2] and configs[3] on the same tables and trace (short legs; bench.py --layers ... for the full lines) ----
+    other = None
+    if (not args.no_other_configs and layers == 1 and prec == 32 and B == 2048 and args.scale == 1.0 and args.shape == "kaggle"
+            and not sliced and args.policy == "evlfu"):
+        other = {}
+        for name, (ly_, p0, p1, prop_, B3) in {"configs2_32_8": (2, 32, 8, "", 2048), "configs3_8_4_c3": (3, 8, 4, "48-48-4", 16384)}.items():
+            try:
+                other[name] = extra_config_leg(pkg, dev, local_rank, tables, idx, rows, dim, cache_rows, ly_, p0, p1, prop_, B3,
+                                               min(K, 20), W, warm)
+            except Exception as e:
+                log(name, "leg failed:", repr(e))
+            torch.cuda.empty_cache()
+
     # ---- CPU baseline: the reference's own library on this host -------------------------------
     cpu = None
     if (not args.no_cpu_baseline and args.scale == 1.0 and dim == 16 and prec == 32 and layers == 1 and args.policy == "evlfu"
@@ -661,7 +736,7 @@ def main_ours(args):
         "cache": {"fill": fill, "hbm_bytes": footprint, "budget_bytes": cache_rows * dim * prec // 8,
                   "note": "hbm_bytes = index (load factor <= 1/3) + slot-indexed slab + bucket rings + look-ahead staging; budget_bytes "
                           "= cache rows x row bytes, the reference's TOTAL_SIZE accounting (cache_manager.cpp:16)"},
-        "value_regions_ms": regions, "look_ahead": use_pf, "batches_per_call": GROUP, "configs4": configs4, "ops": ops,
+        "value_regions_ms": regions, "look_ahead": use_pf, "batches_per_call": GROUP, "configs4": configs4, "other_configs": other, "ops": ops,
         "e2e": {"value": e2e_value, "unit": "lookups/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / K, "api": "evs_submit_host/evs_wait_host (4 batches in flight)",
                 "sync_call_value": lookups / e2e_sync_s, "sync_call_ms_per_step": 1e3 * e2e_sync_s / K},
