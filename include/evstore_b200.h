@@ -10,7 +10,14 @@
  *
  *  (2) a runtime-configured, batched API that replaces the reference's
  *      compile-time #defines (cache_manager.cpp:13-20) and its one-sample-per-call
- *      limit.  Plain pointers and sizes only; no torch / C++ types.
+ *      limit.  Plain pointers and sizes only; no torch / C++ types.  Groups:
+ *        evs_create / evs_destroy / evs_stats / evs_check ...          handle life cycle and bookkeeping
+ *        evs_lookup_batch / _batches / _bags / _batch_host / evs_submit_host   the hot path (device or host buffers,
+ *                                                                      one batch, a queue of batches, bags with pooling)
+ *        evs_prefetch, evs_note_replays                                look-ahead; the lookup inside a caller's CUDA graph
+ *        evs_shard_*                                                   table-wise sharding over NVLink peer memory
+ *        evs_embedding_bag, evs_interact, evs_knn                      the ops either side of the cache; alt-key generation
+ *        evs_host_alloc / evs_host_free                                host memory for backing rows (large device pages)
  *
  * Conventions
  *  - table ids are 0-based here; the reference's keys are "<table+1>-<row>"
