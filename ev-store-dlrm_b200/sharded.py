@@ -171,7 +171,8 @@ class ShardedLookup:
             return list(zip(outs, hits))
         res = []
         for k, idx in enumerate(idx_list):
-            res.append(self.lookup(idx, next_idx=idx_list[k + 1] if k + 1 < len(idx_list) else next_idx))
+            ly, hit = self.lookup(idx, next_idx=idx_list[k + 1] if k + 1 < len(idx_list) else next_idx)
+            res.append((ly.clone(), hit.clone()))         # lookup() reuses its buffers from call to call
         return res
 
     def alltoall_bytes(self, B: int) -> int:

@@ -88,9 +88,15 @@ def _worker(rank, port, q, kind):
     store = OracleStore(tables, CAP, sl)
     sh = p.sharded.ShardedLookup(store, 26, DIM, rank, WORLD, placement=placement)
     res = []
-    for idx in batches:
-        ly, hit = sh.lookup(torch.from_numpy(np.ascontiguousarray(idx[sl])))
-        res.append((ly.numpy().copy(), hit.numpy().copy()))
+    local = [torch.from_numpy(np.ascontiguousarray(idx[sl])) for idx in batches]
+    if kind == "balanced":
+        # a queue of batches per call (ShardedLookup.lookup_many; with this transport the batches run one by one)
+        for k in range(0, len(local), 5):
+            res += [(ly.numpy().copy(), hit.numpy().copy()) for ly, hit in sh.lookup_many(local[k:k + 5])]
+    else:
+        for li in local:
+            ly, hit = sh.lookup(li)
+            res.append((ly.numpy().copy(), hit.numpy().copy()))
     q.put((rank, res))
     dist.barrier()
     dist.destroy_process_group()
