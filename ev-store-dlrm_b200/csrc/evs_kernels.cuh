@@ -1,17 +1,21 @@
 // Kernels of one batch of the embedding-lookup hot path, for one or two cache tiers (+ C3).
 //
-//   k_serve    probe both tiers -> per-sample agg_hit -> route (EvLFU promote / insert per tier) ->
-//              gather + dequantise every resident row into the fp32 output.  Read-only on the cache.
-//   k_update   (evs_update.cuh) claim index slots for missing keys (dedup by CAS), append promoted /
-//              inserted entries to their bucket's FIFO ring in position order, fetch the missing
-//              rows from the host-pinned backing store (zero-copy) into slab + output; the last
-//              CTA to finish then applies the flush rule, evicts in (bucket, FIFO) order down to
-//              capacity and feeds C3
-//   k_scan     only for batches of more than kQuadMaxChunks CTAs: per (tier, bucket) exclusive scan
-//              of the per-CTA append counts (smaller batches sum their predecessors directly)
+//   k_serve    probe both tiers -> per-sample agg_hit -> route (EvLFU promote / insert per tier; LRU / LFU variants) ->
+//              gather + dequantise every resident row into the fp32 output; writes the batch's flags, per-CTA append
+//              counts and compact miss list.  Read-only on the cache (C3 recency flags excepted).  As a rank of a
+//              table-wise sharded cache it also sends the per-sample hit counts to the peers, stores its rows into the
+//              owner ranks' receive buffers and waits for the peers' counts.
+//   k_scan     only for batches of more than kQuadMaxChunks serve CTAs: per (group, bucket) exclusive scan of the per-CTA
+//              append counts (smaller batches sum their predecessors in k_update)
+//   k_update   (evs_update.cuh) claim index slots for missing keys (dedup by CAS), append promoted / inserted entries to
+//              their bucket's FIFO ring in position order
+//   k_evict    (evs_update.cuh) roles of one grid: eviction of each tier down to capacity in (bucket, FIFO) order (flush
+//              rule first), and the miss fetch (fetch_list_body below) from the look-ahead's staging rows or zero-copy from
+//              the host backing store; the last role closes the batch (C3, peers)
+//   k_prefetch (evs_prefetch.cuh) look-ahead for the next batch on its own stream
 //   k_compact  squeeze dead records out of one bucket ring (rare, host-triggered)
-// Every kernel boundary costs ~2-4 us on this part while a dependent L2/HBM access costs 0.15/0.4 us,
-// so the batch is two launches.
+// The kernels of a batch (and the batches inside one graph) are joined by programmatic dependent launch: a kernel
+// boundary costs ~0.8 us that way, a dependent L2 / HBM access 0.3 - 0.8 us.
 #pragma once
 #include "evs_codec.cuh"
 #include "evs_types.cuh"

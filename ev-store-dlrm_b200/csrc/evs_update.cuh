@@ -2,20 +2,19 @@
 //
 //   k_update   same warp <-> sample, lane <-> table mapping as k_serve.  A flagged position
 //              (a) claims an index slot if it missed (CAS; same-batch duplicates converge on one slot),
-//              (b) appends a record to the FIFO ring of bucket agg_hit(sample) at the position its
-//                  rank among the flagged positions of the batch dictates (sample-major, table-minor:
-//                  the order EvLFU_C1.py processes them; in C2 all promotions come before all
-//                  inserts, as phase_2 does, evlfu_8.cpp:416-442), computed from k_serve's per-CTA counts,
-//              (c) atomicMax on the slot's meta picks the winning occurrence of a key (highest
-//                  (agg_hit, position)), bucket counters follow.
-//   k_evict    advances the ring tails, then evicts down to capacity in (bucket, FIFO) order with
-//              kTierCtas CTAs per tier: the candidate records form one virtual sequence that is cut
-//              into chunks of kEvictWindow records, chunks are handed out by ticket, and a chunk
-//              learns how many victims precede it by a decoupled look-back over its predecessors'
-//              counts.  A batch that triggers the flush rule (rare) takes the single-CTA path of
-//              evs_kernels.cuh instead.  The last CTA of the last tier inserts the victims into C3.
-// The rows of the missing keys are fetched by k_fetch on a side stream next to k_evict (into the
-// output and the slab rows of the slots k_update claimed).
+//              (b) appends a record to the FIFO ring of its bucket at the position its rank among the flagged positions of
+//                  the batch dictates (sample-major, table-minor: the order EvLFU_C1.py processes them; in C2 all
+//                  promotions come before all inserts, as phase_2 does, evlfu_8.cpp:416-442), computed from k_serve's
+//                  per-CTA counts,
+//              (c) atomicMax on the slot's meta picks the winning occurrence of a key (highest (bucket, position)), bucket
+//                  counters follow.
+//   k_evict    one grid, blockIdx.y = role.  Eviction roles (one per tier, p.evict_ctas CTAs): advance the ring tails, then
+//              evict down to capacity in (bucket, FIFO) order -- the candidate records form one virtual sequence cut into
+//              chunks of kEvictWindow records, a CTA's first chunk is its block index, further ones go by ticket, and a chunk
+//              learns how many victims precede it by a decoupled look-back over its predecessors' counts.  A batch that
+//              triggers the flush rule (rare) takes the single-CTA path of evs_kernels.cuh.  Miss-fetch role
+//              (p.fetch_ctas CTAs): fetch_list_body (evs_kernels.cuh).  The last role to finish inserts the victims into
+//              C3, mirrors the ring occupancy to the host and -- sharded -- exchanges the "rows delivered" words.
 #pragma once
 #include "evs_c3.cuh"
 #include "evs_kernels.cuh"
