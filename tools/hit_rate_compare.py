@@ -15,7 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle.evlfu import BatchEvLFU, SeqEvLFU  # noqa: E402
-from oracle.lru import BatchLRU, SeqLFU, SeqLRU  # noqa: E402
+from oracle.lru import BatchLFU, BatchLRU, SeqLFU, SeqLRU  # noqa: E402
 
 
 def main():
@@ -84,7 +84,7 @@ def main():
                 ev += len(o.evicted)
         out.append(f"| batch-granular LRU, B = {B} | {hits / (26 * (n - half)):.4f} | {perfect} | {ev} |")
         print(out[-1], f"({time.time() - t0:.0f}s)")
-    # and its plain LFU (cache_algo/LFU.py; sequential only, no CUDA counterpart)
+    # and its plain LFU (cache_algo/LFU.py), then the batch-granular LFU the CUDA path runs (frequencies saturate at 27)
     t0 = time.time()
     lfu = SeqLFU(cap)
     hits = perfect = ev = 0
@@ -96,6 +96,18 @@ def main():
             ev += len(lfu.evicted)
     out.append(f"| sequential LFU (LFU.py, 1 sample per request) | {hits / (26 * (n - half)):.4f} | {perfect} | {ev} |")
     print(out[-1], f"({time.time() - t0:.0f}s)")
+    for B in (1, 2048):
+        t0 = time.time()
+        o = BatchLFU(cap)
+        hits = perfect = ev = 0
+        for k in range(0, n, B):
+            h, _st, _sr, agg = o.lookup_batch(trace[:, k:k + B])
+            if k >= half:
+                hits += int(h.sum())
+                perfect += int((agg == 26).sum())
+                ev += len(o.evicted)
+        out.append(f"| batch-granular LFU (policy=\"lfu\"), B = {B} | {hits / (26 * (n - half)):.4f} | {perfect} | {ev} |")
+        print(out[-1], f"({time.time() - t0:.0f}s)")
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     open(os.path.join(ROOT, "profiles", f"{rnd}_hit_rate.md"), "w").write("\n".join(out) + "\n")
 
