@@ -69,8 +69,9 @@ def parse_args():
     ap.add_argument("--prop", default="", help='SIZE_PROPORTION "c1-c2-c3" (3 layers)')
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1 only: exchange fused into the kernels over NVLink peer memory, or NCCL all-reduce + all-to-all")
-    ap.add_argument("--policy", default="evlfu", choices=["evlfu", "lru"],
-                    help="replacement policy: evlfu = the reference's EvLFU (BASELINE configs), lru = its comparison policy cache_algo/LRU.py (1 layer)")
+    ap.add_argument("--policy", default="evlfu", choices=["evlfu", "lru", "lfu"],
+                    help="replacement policy: evlfu = the reference's EvLFU (BASELINE configs); lru / lfu = its comparison policies "
+                         "cache_algo/LRU.py / LFU.py (1 layer)")
     ap.add_argument("--shape", default="kaggle", choices=["kaggle", "terabyte"],
                     help="table shape: kaggle (configs[1-3]) or terabyte (configs[4]: dim 64, cardinalities capped at 40 M); N = 1 with "
                          "terabyte needs --table-slice (one rank's tables fit one host, all 48 GB of them do not)")
@@ -722,7 +723,8 @@ def main_ours(args):
         "samples_per_s": value / T, "hit_rate": hit_rate, "hit_rate_by_tier": tier_rates, "perfect_hit_rate": perfect_rate,
         "config": configs1_config(B, dim, cache_rows, warm) if std_cfg else
                   {"workload": ("%s: C1 %s fp%d tier" % ("configs[1]" if args.shape == "kaggle" else "configs[4], one GPU",
-                                                          "EvLFU" if args.policy == "evlfu" else "LRU (cache_algo/LRU.py, comparison policy)", prec) if layers == 1 else
+                                                          {"evlfu": "EvLFU", "lru": "LRU (cache_algo/LRU.py, comparison policy)",
+                                                           "lfu": "LFU (cache_algo/LFU.py, comparison policy)"}[args.policy], prec) if layers == 1 else
                                 "configs[%d]: C1 %d-bit + C2 %d-bit%s, TOTAL_SIZE %d fp32-row units%s" % (
                                     layers, prec, sec, " + C3" if layers == 3 else "", total_size, (" split " + args.prop) if args.prop else ""))
                                + ", %s %d tables (%.2fM rows), dim %d, Zipf(1.05), batch %d, cache %d rows, "
