@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--cache-warm", type=int, default=-1, help="untimed batches that fill the cache before warm-up")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=150.0, help="time budget of the CPU baseline's warm-up")
+    ap.add_argument("--cpu-replicas", type=int, default=0,
+                    help="leg (iii) of SURVEY 8(d): also time N independent processes of the reference library at once (4 threads "
+                         "each; adds about a minute and ~6 GB of host memory per replica)")
     ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="A/B: do not announce the next index batch (evs_prefetch)")
     ap.add_argument("--no-b16k", action="store_true", help="skip the batch-16384 roofline leg")
@@ -230,6 +233,25 @@ def run_cpu_reference(variant, tables_raw, idx, B, warm_batches, timed_batches, 
         "lookups_per_s": n_samples * idx.shape[1] / total, "warm_batches": warm_done, "warm_seconds": warm_s,
         "perfect_hits": int(perfect.value), "ms_per_step": 1e3 * total / max(1, len(per_step)),
     }
+
+
+def run_cpu_replicas(n: int, args):
+    """N concurrent `bench.py --impl reference` processes (the reference's library is process-global and single-caller, so
+    more host cores can only be used by more processes, each with its own cache): the sum of their lookups/s."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "40", "--warmup", "3"]
+    if args.cache_warm >= 0:
+        cmd += ["--cache-warm", str(args.cache_warm)]
+    t0 = time.time()
+    procs = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, cwd=ROOT) for _ in range(n)]
+    vals = []
+    for p in procs:
+        out, _ = p.communicate(timeout=1200)
+        lines = [ln for ln in out.splitlines() if ln.startswith("{")]
+        if p.returncode == 0 and lines:
+            vals.append(float(json.loads(lines[-1])["value"]))
+    return {"n": n, "finished": len(vals), "value": float(sum(vals)), "unit": "lookups/s", "cores": 4 * n, "per_replica": vals,
+            "wall_s": time.time() - t0, "kind": "reference",
+            "sample": "%d processes at once, each: 40 batches of 2048 samples after the full warm-up, 1 caller + 3 reader threads" % n}
 
 
 def main_reference(args):
@@ -691,6 +713,12 @@ def main_ours(args):
                                            "sample": "%d requests through oracle.evlfu.SeqEvLFU (EvLFU_C1.py restated; policy only, rows not copied), cold cache" % n_py}
                 except Exception as e:
                     log("python EvLFU leg failed:", repr(e))
+                # leg (iii): N independent processes, each the whole library with its own cache (replicas), all at once
+                if args.cpu_replicas > 0:
+                    try:
+                        cpu["replicas"] = run_cpu_replicas(args.cpu_replicas, args)
+                    except Exception as e:
+                        log("replica leg failed:", repr(e))
             else:
                 log("cpu_baseline: oracle/_ref not built")
         except Exception as e:                          # the baseline must not take the GPU number down
