@@ -193,3 +193,21 @@ def test_split_cache_budget_water_filling():
     per = [sum(rows[t] for t in x) for x in sh.balanced_placement(rows, 8)]
     caps = sh.split_cache_budget(per, int(sum(rows) * 0.13))
     assert all(c <= r for c, r in zip(caps, per)) and abs(sum(caps) - int(sum(rows) * 0.13)) < 8
+
+
+def test_placements_cover_every_table_once_and_keep_the_split_lengths():
+    from helpers import pkg
+    sh = pkg().sharded
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        n = int(rng.integers(1, 32))
+        size = int(rng.integers(1, 9))
+        if size > n:
+            continue
+        rows = rng.integers(1, 10 ** 7, size=n).tolist()
+        for pl in (sh.balanced_placement(rows, size), sh.contiguous_placement(n, size)):
+            assert sorted(t for x in pl for t in x) == list(range(n))
+            assert [len(x) for x in pl] == sh.get_split_lengths(n, size)
+            assert all(x == sorted(x) for x in pl)
+        caps = sh.split_cache_budget([sum(rows[t] for t in x) for x in sh.balanced_placement(rows, size)], int(sum(rows) * 0.13), floor=0)
+        assert sum(caps) <= int(sum(rows) * 0.13) and all(c >= 0 for c in caps)

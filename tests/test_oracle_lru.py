@@ -146,3 +146,28 @@ def test_batch_lfu_frequency_counts_batches_and_saturates():
     assert q.evicted == [3, 4] and q.state()[0] == [9, 10] and q.state()[1] == [1, 2]
     q.lookup_batch(np.array([[11, 12, 13, 14, 15]]))            # more new keys than the cache holds
     assert 15 in q.entries and len(q.entries) == 4
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_batch_lfu_random_configurations_against_the_sequential_policy(seed):
+    """Random table counts, capacities and skews: BatchLFU fed one request at a time tracks SeqLFU(freq_cap = T + 1) -- and, while no
+    frequency reaches the cap, the reference-exact SeqLFU -- request by request (state re-cloned after a same-request corner)."""
+    from oracle.lru import BatchLFU, SeqLFU
+    rng = np.random.default_rng(100 + seed)
+    Tn = int(rng.integers(2, 9))
+    rows = rng.integers(3, 60, size=Tn)
+    cap = int(rng.integers(6, 50))
+    o = SeqLFU(cap, n_tables=Tn, freq_cap=Tn + 1)
+    checked = 0
+    for i in range(400):
+        req = [int(rng.integers(0, rows[t]) if rng.random() < 0.7 else rng.integers(0, min(3, rows[t]))) for t in range(Tn)]
+        p = _clone_lfu(o, n_tables=Tn)
+        h = o.request(req)
+        ph, *_ = p.lookup_batch(np.asarray(req).reshape(Tn, 1))
+        if o.corner:
+            continue
+        assert list(ph[0]) == h and sorted(p.evicted) == sorted(o.evicted), (seed, i)
+        _least, lists = o.state()
+        assert p.state() == (lists + [[] for _ in range(Tn + 1 - len(lists))])[:Tn + 1], (seed, i)
+        checked += 1
+    assert checked > 150
