@@ -230,7 +230,10 @@ static int build_tier(evs_handle h, Tier &tr, int prec, long long cap, const voi
     d.hash_mask = hash_cap - 1;
     // room for the live entries plus 64 batches of appends: the host may run that far ahead of the device before it has to
     // wait for the ring mirror to advance (maintain_rings)
-    d.ring_cap = next_pow2(static_cast<unsigned long long>(std::max(2 * (cap + n_max), cap + 64 * n_max)));
+    long long slack = 64;
+    if (const char *rs = getenv("EVSTORE_B200_RING_SLACK"))         // testing aid: small rings, so that compaction runs within a few batches
+        if (atoi(rs) >= 5) slack = atoi(rs);
+    d.ring_cap = next_pow2(static_cast<unsigned long long>(std::max(2 * (cap + n_max), cap + slack * n_max)));
     int rc;
     if ((rc = dev_alloc(tr.allocs, &d.slots, hash_cap, false))) return rc;
     if ((rc = dev_alloc(tr.allocs, &d.slab, static_cast<size_t>(hash_cap) * d.row_stride, true))) return rc;

@@ -68,9 +68,13 @@ def test_empty_batch_and_bad_index():
     store.close()
 
 
-def test_ring_compaction_keeps_order():
-    """Many small batches on a tiny cache: the bucket rings wrap and get compacted."""
+def test_ring_compaction_keeps_order(monkeypatch):
+    """Many small batches on a tiny cache with the smallest rings the library makes: the bucket rings wrap and get compacted
+    (k_compact, host-triggered from the ring-occupancy mirror)."""
+    monkeypatch.setenv("EVSTORE_B200_RING_SLACK", "5")
     run_single_tier_parity(SMALL_ROWS, 16, 32, 64, [8], 700, check_state_every=50)
+    # every hit of an LRU cache appends a record: the one ring fills within a few batches
+    run_single_tier_parity(SMALL_ROWS, 16, 32, 400, [64], 60, check_state_every=10, policy="lru")
 
 
 def test_interaction_matches_torch_bmm():
